@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- megapixels/s of the fused categorise+clean hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over the whole synthetic sheet (SURVEY.md 8(d) generator).
+  N = 1 : BASELINE config 2 -- 20000 x 20000 RGB{N0f8}, 16-colour palette, clean window 5 (R = 2).
+  N > 1 : the same sheet shape per GPU (weak scaling): one 20000 x (20000*N) sheet split into N
+          row bands; every step does the RGB halo exchange (NCCL send/recv of R lines) and one
+          fused launch per rank.  --workload cfg3 / cfg5 select BASELINE configs 3 and 5 instead.
+`value` times device-resident inputs; `e2e` times the public host-buffer API (pinned host
+memory -> H2D -> kernel -> D2H) for the same sheet.  Prints ONE JSON line on rank 0.
+The CPU oracle (oracle/) is only used for the cpu_baseline leg and for --impl reference.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "megapixels/sec fused categorize+clean"
+UNIT = "Mpx/s"
+ALGO_BYTES_PER_PX = 4   # 3 B RGB{N0f8} in + 1 B UInt8 label out
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(workload):
+    """Per-launch DRAM bytes of the fused kernel from the committed ncu capture, or None."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(workload)
+        except Exception:
+            pass
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def workload_spec(args, world):
+    from maprast_b200 import synth
+    wl = args.workload
+    if wl == "auto":
+        wl = "cfg2"
+    cfg = int(wl[3])
+    seed, palrgb, stats, spec = synth.config_workload(cfg)
+    spec = dict(spec)
+    if args.workload == "auto" and world > 1:
+        spec["n2"] = spec["n2"] * world          # weak scaling: one config-2 sheet per GPU
+        name = (f"weak: {spec['n1']}x{spec['n2']} sheet = {world} row bands of BASELINE config 2 "
+                f"(20000x20000, K=16, window 5), RGB halo exchange of R=2 lines per step")
+        scaling = "weak"
+    else:
+        names = {1: "BASELINE config 1: 2000x2000, K=8, window 3",
+                 2: "BASELINE config 2: 20000x20000 sheet, K=16, clean window 5",
+                 3: "BASELINE config 3: 60000x40000 sheet (2.4 Gpx), K=16, window 5, row bands + halo exchange",
+                 4: "BASELINE config 4: 20000x20000, K=64 Lab distance + box, window 7",
+                 5: "BASELINE config 5: batch of 256 sheets 4096x4096, K=16, window 5, whole sheets per GPU"}
+        name = names[cfg]
+        scaling = "weak" if world == 1 else "strong"
+    return cfg, seed, palrgb, stats, spec, name, scaling
+
+
+# ------------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank, world):
+    """The reference's CPU path for this hot path.  The reference itself is Julia (not installed
+    in this image), so this arm times oracle/ -- the C restatement of
+    src/categories.jl:76-133 + Appendix A.3 -- with all host threads, on a bounded sample of the
+    same workload."""
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle import oracle as O
+    cfg, seed, palrgb, stats, spec, name, scaling = workload_spec(args, max(args.gpus, 1))
+    cores = O.max_threads()
+    cs = O.LAB if stats.colourspace == "lab" else O.RGB
+    n1 = spec["n1"]
+    # size the per-step sample so that warmup+steps stay within ~2 minutes
+    probe_lines = max(8, min(spec["n2"], (1 << 21) // n1))
+    scan = O.synth_scan(seed, 0, palrgb, n1, spec["n2"], 0, probe_lines)
+    t0 = time.perf_counter()
+    O.categorize_clean(scan, stats.mean, stats.lo, stats.hi, spec["R"], cs)
+    rate = n1 * probe_lines / (time.perf_counter() - t0)        # px/s
+    budget = 90.0 / max(1, args.steps + args.warmup)
+    lines = int(min(spec["n2"], max(probe_lines, rate * min(budget, 10.0) / n1)))
+    scan = O.synth_scan(seed, 0, palrgb, n1, spec["n2"], 0, lines)
+    for _ in range(args.warmup):
+        O.categorize_clean(scan, stats.mean, stats.lo, stats.hi, spec["R"], cs)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.categorize_clean(scan, stats.mean, stats.lo, stats.hi, spec["R"], cs)
+    dt = (time.perf_counter() - t0) / args.steps
+    mpx = n1 * lines / dt / 1e6
+    sample = f"first {lines} lines ({n1 * lines / 1e6:.1f} Mpx) of the sheet per step, {cores} OpenMP threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": mpx, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "K": spec["K"], "R": spec["R"], "colourspace": stats.colourspace},
+        "cpu_baseline": {"value": mpx, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": mpx, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference is pure Julia (no toolchain here): oracle/ C restatement timed on host cores",
+    }))
+
+
+# ------------------------------------------------------------------------------------ our arm
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import maprast_b200 as mr
+    D = mr.distributed
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ctx = mr.Context(local_rank)
+    cfg, seed, palrgb, stats, spec, name, scaling = workload_spec(args, world)
+    n1, n2, R, K = spec["n1"], spec["n2"], spec["R"], spec["K"]
+    ctx.set_palette(stats.mean, stats.lo, stats.hi, mr._lib.LAB if stats.colourspace == "lab" else mr._lib.RGB)
+    build_ms = ctx.palette_build_ms()
+    batch = spec["n_sheets"] > 1
+
+    # ---- synthetic input, generated in place on the device (untimed)
+    if batch:
+        s0, s1 = D.sheet_range(spec["n_sheets"], world, rank)
+        ns = s1 - s0
+        px = torch.empty((ns, n2, n1, 3), dtype=torch.uint8, device=dev)
+        for s in range(ns):
+            ctx.synth_scan_dev(seed, s0 + s, palrgb, n1, n2, 0, n2, px[s], n1 * 3)
+        out = torch.empty((ns, n2, n1), dtype=torch.uint8, device=dev)
+        my_px = ns * n1 * n2
+        total_px = spec["n_sheets"] * n1 * n2
+    else:
+        a, b = D.band_range(n2, world, rank)
+        nb = b - a
+        buf, own = D.alloc_band(n1, nb, R, device=dev)
+        ctx.synth_scan_dev(seed, 0, palrgb, n1, n2, a, nb, own, n1 * 3)
+        out = torch.empty((nb, n1), dtype=torch.uint8, device=dev)
+        my_px = nb * n1
+        total_px = n1 * n2
+    torch.cuda.synchronize()
+
+    def step():
+        if batch:
+            ctx.batch_categorize_clean_dev(ns, px, n1 * n2 * 3, n1, n2, n1 * 3, 3, R, out, n1 * n2, n1)
+        elif world > 1:
+            D.categorize_clean_band(ctx, buf, R, out, rank, world)
+        else:
+            ctx.categorize_clean_dev(own, n1, nb, n1 * 3, 3, R, out, n1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for k in range(args.steps):
+        step()
+        ev[k + 1].record()
+    barrier()
+    launches = ctx.launch_count() - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    ms_per_step = total_ms_max / args.steps
+    value = total_px / (ms_per_step * 1e-3) / 1e6
+
+    # ---- e2e: public host-buffer API, pinned host memory, H2D + D2H inside the timed region
+    e2e_steps = args.e2e_steps or min(args.steps, 5)
+    if batch:
+        host_in = torch.empty((ns * n2, n1, 3), dtype=torch.uint8, pin_memory=True)
+        host_in.copy_(px.view(ns * n2, n1, 3))
+        e_n2 = n2   # per-sheet calls below
+    else:
+        # the host holds the sheet: each rank uploads its band plus the halo lines straight from it
+        hl, hh = (min(R, a), min(R, n2 - b))
+        host_in = torch.empty((hl + nb + hh, n1, 3), dtype=torch.uint8, pin_memory=True)
+        host_in.copy_(buf[R - hl:R + nb + hh])     # halos are valid after the warm-up exchanges
+    host_out = torch.empty((ns * n2 if batch else nb, n1), dtype=torch.uint8, pin_memory=True)
+    hin, hout = host_in.numpy(), host_out.numpy()
+
+    def e2e_step():
+        if batch:
+            for s in range(ns):
+                ctx.categorize_clean_host(hin[s * n2:(s + 1) * n2], R, out=hout[s * n2:(s + 1) * n2])
+        else:
+            ctx.categorize_clean_host(hin, R, out=hout, halo_lo=hl, halo_hi=hh)
+        return int(hout[-1, -1])   # the step's result is read on the host
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = total_px / float(t.item()) / 1e6
+    # e2e labels must equal the device-resident labels (same code path, same bytes)
+    same = bool(torch.equal(host_out.to(dev).view(-1), out.view(-1)))
+
+    if rank != 0:
+        return
+    peak, peak_src = measured_peak()
+    kern_ms = statistics.mean(step_ms)      # one fused launch per step on this stream
+    launches_per_step = launches / args.steps
+    achieved = ALGO_BYTES_PER_PX * my_px / (kern_ms * 1e-3) / 1e9
+    wl_key = args.workload if args.workload != "auto" else "cfg2"
+    res = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": scaling, "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": name, "K": K, "R": R, "colourspace": stats.colourspace,
+                   "pixels_total": total_px, "pixels_per_gpu": my_px,
+                   "cache": "inputs larger than L2 (%.2f GB per GPU per step)" % (my_px * 4 / 1e9),
+                   "palette_table_build_ms": build_ms},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0,
+                     "peak_source": peak_src, "kernel": "fused categorise+clean", "kernel_ms": kern_ms,
+                     "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX * my_px,
+                     "traffic": ncu_traffic(wl_key) if world == 1 else None},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(total_px * 3),
+                "d2h_bytes_per_step": int(total_px), "steps": e2e_steps, "labels_equal_device_path": same},
+        "gpu_launches": int(launches), "gpu_launches_per_step": launches_per_step,
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import oracle as O
+        cs = O.LAB if stats.colourspace == "lab" else O.RGB
+        cores = O.max_threads()
+        src = px[0] if batch else own
+        probe = max(8, (1 << 21) // n1)
+        scan = src[:probe].contiguous().cpu().numpy()
+        t0 = time.perf_counter()
+        O.categorize_clean(scan, stats.mean, stats.lo, stats.hi, R, cs)
+        rate = scan.shape[0] * n1 / (time.perf_counter() - t0)
+        lines = int(min(src.shape[0], max(probe, rate * args.cpu_seconds / 2 / n1)))
+        scan = src[:lines].contiguous().cpu().numpy()
+        best = None
+        for _ in range(2):
+            t0 = time.perf_counter()
+            want = O.categorize_clean(scan, stats.mean, stats.lo, stats.hi, R, cs)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        # while the oracle output is at hand: the device labels of those lines must match it
+        # (lines whose window reaches past the sample are excluded)
+        got = (out[0] if batch else out)[:lines].cpu().numpy()
+        cut = lines if lines == src.shape[0] else lines - R
+        res["cpu_baseline"] = {"value": n1 * lines / best / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+                               "sample": f"first {lines} lines ({n1 * lines / 1e6:.1f} Mpx) of the same sheet, "
+                                         f"best of 2, C oracle + OpenMP ({cores} threads)",
+                               "label_mismatches_vs_gpu": int((got[:cut] != want[:cut]).sum())}
+    print(json.dumps(res))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,133 @@
+/*
+ * maprast.h -- C ABI of libmaprast.so: the B200 (sm_100a) implementation of the
+ * categorise + clean hot path of rafaqz/MapRasterization.jl.
+ *
+ * The reference has no FFI of its own (it is pure Julia); the entry points below
+ * are what a Julia `ccall` binding for this path needs.  Each one names the
+ * reference interface it replaces (paths under the reference checkout).
+ * INTEGRATION.md shows the Julia-side stubs.
+ *
+ * Conventions:
+ *   - image = Julia column-major Matrix, n1 = size(A,1) is the memory-fast axis;
+ *     a "line" is n1 consecutive pixels; stride2 = bytes between lines.
+ *   - pixels are packed RGB{N0f8} (bpp = 3) or RGBA{N0f8} (bpp = 4).
+ *   - labels are uint8: 0 = no match, 1..K = category (K <= 255).
+ *   - every function returns 0 (MR_OK) or a negative error code, never throws
+ *     or aborts; mr_last_error() gives the message.  There is NO CPU fallback:
+ *     without a usable CUDA device mr_create fails.
+ *   - one ctx = one GPU; calls on one ctx must be serialised by the caller;
+ *     different ctxs are independent.
+ */
+#ifndef MAPRAST_H
+#define MAPRAST_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MR_OK          0
+#define MR_ERR_ARG    (-1)   /* bad argument (Julia side: ArgumentError) */
+#define MR_ERR_CUDA   (-2)   /* CUDA runtime failure */
+#define MR_ERR_STATE  (-3)   /* call order (e.g. no palette set) */
+#define MR_ERR_NOMEM  (-4)
+
+#define MR_COLOURSPACE_RGB 0 /* match on RGB{Float64}: src/balance.jl:13-15 + src/blur.jl:8 */
+#define MR_COLOURSPACE_LAB 1 /* extension */
+
+typedef struct mr_ctx mr_ctx;
+
+/* Diagnostics the north_star asks to be "counted and reported". */
+typedef struct mr_counters {
+    uint64_t n_pixels;   /* pixels labelled */
+    uint64_t n_nomatch;  /* output labels equal to 0 */
+    uint64_t n_fine;     /* pixels whose colour fell in a mixed coarse cell and was resolved
+                            through the exact per-colour table (the "near-tie" path) */
+    uint64_t n_changed;  /* pixels whose label the clean filter changed */
+} mr_counters;
+
+int mr_version(void);
+
+/* Library/context.  Replaces nothing in the reference (it has no device state). */
+mr_ctx* mr_create(int device, int* err);
+void mr_destroy(mr_ctx* ctx);
+const char* mr_last_error(const mr_ctx* ctx); /* ctx may be NULL: last error of this thread */
+
+/* Palette = per-category statistics.  Replaces the `category_stats` value built at
+ * src/categories.jl:52 by _component_stats (:2-30) and consumed at :76-82.
+ * mean/lo/hi are K x channels Float64, row-major (category-major);
+ * lo = min - sd*tol, hi = max + sd*tol are precomputed by the host exactly as
+ * src/categories.jl:131-133 evaluates them.  A missing category (:6, :78) is
+ * passed as mean = +Inf.  NaN bounds are allowed (never accept).  channels = 3
+ * (RGB) or 4 (RGBA stats, alpha joins the distance, :92).  Builds the exact
+ * 2^24-entry label table on the GPU (channels == 3). */
+int mr_set_palette(mr_ctx* ctx, int K, const double* mean, const double* lo, const double* hi,
+                   int colourspace, int channels);
+
+/* Known-category plane, replaces _set_categories! (src/selectcolors.jl:670-681) feeding
+ * the override at src/categories.jl:110-112.  lin_idx = i + j*n1 (0-based). n = 0 clears. */
+int mr_set_known(mr_ctx* ctx, int64_t n, const int64_t* lin_idx, const uint8_t* cat);
+
+/* Introspection used by the parity tests (exhaustive 2^24 sweep) and reports. */
+int mr_get_lut(mr_ctx* ctx, uint8_t* lut_host /* 2^24 bytes, index r | g<<8 | b<<16 */);
+int mr_palette_build_ms(mr_ctx* ctx, float* ms);
+int mr_enable_counters(mr_ctx* ctx, int on);
+int mr_read_counters(mr_ctx* ctx, mr_counters* out, int reset); /* synchronises */
+int64_t mr_launch_count(const mr_ctx* ctx); /* kernels launched by this ctx so far */
+
+/* The fused hot path: labels = clean(categorize(px)).  Replaces
+ * _categorize(pixels, points; ...) non-segmented branch, src/categories.jl:49-52,68-73
+ * (call site src/selectcolors.jl:466-478), followed by the Window{R} majority filter
+ * (window kwarg shape of blur, src/blur.jl:6).  R = 0: categorise only.
+ * Host variant: caller-owned host buffers, copies inside. */
+int mr_categorize_clean_host(mr_ctx* ctx, const uint8_t* px, int64_t n1, int64_t n2,
+                             int64_t stride2_bytes, int bytes_per_px, int R,
+                             uint8_t* labels_out, int64_t out_stride2, mr_counters* counters);
+
+/* Host variant for one row band of a larger host-resident sheet (single-process multi-GPU or
+ * one rank of a multi-process job): px points at line 0 of the band and the halo_lo / halo_hi
+ * (0..R) lines before / after it are read straight from the caller's sheet -- no exchange. */
+int mr_categorize_clean_host_band(mr_ctx* ctx, const uint8_t* px, int64_t n1, int64_t n2,
+                                  int64_t stride2_bytes, int bytes_per_px, int R,
+                                  int halo_lo, int halo_hi,
+                                  uint8_t* labels_out, int64_t out_stride2, mr_counters* counters);
+
+/* Device variant (CuArray callers, band-sharded multi-GPU, benchmarking resident data).
+ * px_dev points at line 0 of this band.  halo_lo / halo_hi (0..R) say how many REAL image
+ * lines are readable before line 0 / after line n2-1 (the neighbour band's lines after a
+ * halo exchange); where they are 0 the window is clipped as at the image border.
+ * stream is a cudaStream_t (NULL = default stream).  Asynchronous. */
+int mr_categorize_clean_dev(mr_ctx* ctx, const uint8_t* px_dev, int64_t n1, int64_t n2,
+                            int64_t stride2_bytes, int bytes_per_px, int R,
+                            int halo_lo, int halo_hi,
+                            uint8_t* labels_dev, int64_t out_stride2, void* stream);
+
+/* Batch of independent sheets of identical shape (BASELINE config 5): one launch. */
+int mr_batch_categorize_clean_dev(mr_ctx* ctx, int n_sheets, const uint8_t* px_dev,
+                                  int64_t sheet_stride_bytes, int64_t n1, int64_t n2,
+                                  int64_t stride2_bytes, int bytes_per_px, int R,
+                                  uint8_t* labels_dev, int64_t out_sheet_stride,
+                                  int64_t out_stride2, void* stream);
+
+/* clean(labels; hood = Window{R}(), repeat): labels in -> labels out (Appendix A.3).
+ * Kwarg shape follows blur(A; hood, repeat), src/blur.jl:6-14. */
+int mr_clean_host(mr_ctx* ctx, const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2,
+                  int R, int repeat, uint8_t* out, int64_t out_stride2);
+int mr_clean_dev(mr_ctx* ctx, const uint8_t* labels_dev, int64_t n1, int64_t n2, int64_t stride2,
+                 int R, int halo_lo, int halo_hi, uint8_t* out_dev, int64_t out_stride2,
+                 void* stream);
+
+/* Pinned host staging (optional; pageable caller buffers also work, slower). */
+void* mr_host_alloc(size_t bytes);
+void mr_host_free(void* p);
+
+/* Bench/test utility (not part of the reference surface): deterministic synthetic scan,
+ * SURVEY 8(d).  Writes lines [line0, line0+nlines) of sheet `sheet_id` (3 B/px). */
+int mr_synth_scan_dev(mr_ctx* ctx, uint32_t seed, uint32_t sheet_id, int K,
+                      const uint8_t* palette_rgb_host, int64_t n1, int64_t n2, int64_t line0,
+                      int64_t nlines, int mode, uint8_t* out_dev, int64_t out_stride2,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,216 @@
+"""ctypes binding of libmaprast.so (the C ABI in include/maprast.h).
+
+This is the same surface a Julia `ccall` wrapper binds.  There is no CPU
+fallback: if the shared library is missing or no CUDA device is usable, loading / creating a
+context raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmaprast.so")
+
+MR_OK, MR_ERR_ARG, MR_ERR_CUDA, MR_ERR_STATE, MR_ERR_NOMEM = 0, -1, -2, -3, -4
+RGB, LAB = 0, 1
+LUT_SIZE = 1 << 24
+
+# every symbol include/maprast.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "mr_version", "mr_create", "mr_destroy", "mr_last_error", "mr_set_palette", "mr_set_known",
+    "mr_get_lut", "mr_palette_build_ms", "mr_enable_counters", "mr_read_counters", "mr_launch_count",
+    "mr_categorize_clean_host", "mr_categorize_clean_host_band", "mr_categorize_clean_dev", "mr_batch_categorize_clean_dev",
+    "mr_clean_host", "mr_clean_dev", "mr_host_alloc", "mr_host_free", "mr_synth_scan_dev",
+]
+
+
+class Counters(C.Structure):
+    _fields_ = [("n_pixels", C.c_uint64), ("n_nomatch", C.c_uint64), ("n_fine", C.c_uint64),
+                ("n_changed", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+class MapRastError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libmaprast error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load libmaprast.so or raise (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  maprast-b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i64, i32, u8p = C.c_void_p, C.c_int64, C.c_int, C.c_void_p
+    L.mr_version.restype = i32
+    L.mr_create.argtypes = [i32, C.POINTER(i32)]
+    L.mr_create.restype = vp
+    L.mr_destroy.argtypes = [vp]
+    L.mr_destroy.restype = None
+    L.mr_last_error.argtypes = [vp]
+    L.mr_last_error.restype = C.c_char_p
+    L.mr_set_palette.argtypes = [vp, i32, vp, vp, vp, i32, i32]
+    L.mr_set_known.argtypes = [vp, i64, vp, vp]
+    L.mr_get_lut.argtypes = [vp, u8p]
+    L.mr_palette_build_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.mr_enable_counters.argtypes = [vp, i32]
+    L.mr_read_counters.argtypes = [vp, C.POINTER(Counters), i32]
+    L.mr_launch_count.argtypes = [vp]
+    L.mr_launch_count.restype = i64
+    L.mr_categorize_clean_host.argtypes = [vp, u8p, i64, i64, i64, i32, i32, u8p, i64, C.POINTER(Counters)]
+    L.mr_categorize_clean_host_band.argtypes = [vp, u8p, i64, i64, i64, i32, i32, i32, i32, u8p, i64,
+                                                C.POINTER(Counters)]
+    L.mr_categorize_clean_dev.argtypes = [vp, u8p, i64, i64, i64, i32, i32, i32, i32, u8p, i64, vp]
+    L.mr_batch_categorize_clean_dev.argtypes = [vp, i32, u8p, i64, i64, i64, i64, i32, i32, u8p, i64, i64, vp]
+    L.mr_clean_host.argtypes = [vp, u8p, i64, i64, i64, i32, i32, u8p, i64]
+    L.mr_clean_dev.argtypes = [vp, u8p, i64, i64, i64, i32, i32, i32, u8p, i64, vp]
+    L.mr_host_alloc.argtypes = [C.c_size_t]
+    L.mr_host_alloc.restype = vp
+    L.mr_host_free.argtypes = [vp]
+    L.mr_host_free.restype = None
+    L.mr_synth_scan_dev.argtypes = [vp, C.c_uint32, C.c_uint32, i32, u8p, i64, i64, i64, i64, i32, u8p, i64, vp]
+    for name in ("mr_set_palette", "mr_set_known", "mr_get_lut", "mr_palette_build_ms", "mr_enable_counters",
+                 "mr_read_counters", "mr_categorize_clean_host", "mr_categorize_clean_host_band",
+                 "mr_categorize_clean_dev",
+                 "mr_batch_categorize_clean_dev", "mr_clean_host", "mr_clean_dev", "mr_synth_scan_dev"):
+        getattr(L, name).restype = i32
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    """Raw address of a numpy array / torch tensor / int."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()   # torch.Tensor
+
+
+class Context:
+    """One GPU.  Wraps mr_ctx; raises MapRastError on any non-zero return."""
+
+    def __init__(self, device=0):
+        L = load()
+        err = C.c_int(0)
+        self._h = L.mr_create(int(device), C.byref(err))
+        if not self._h:
+            raise MapRastError(err.value, L.mr_last_error(None).decode())
+        self._L = L
+        self.device = int(device)
+        self.palette = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.mr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise MapRastError(rc, self._L.mr_last_error(self._h).decode())
+
+    # -- palette -----------------------------------------------------------------------
+    def set_palette(self, mean, lo, hi, colourspace=RGB, channels=None):
+        mean = np.ascontiguousarray(mean, dtype=np.float64)
+        lo = np.ascontiguousarray(lo, dtype=np.float64)
+        hi = np.ascontiguousarray(hi, dtype=np.float64)
+        if mean.ndim != 2 or lo.shape != mean.shape or hi.shape != mean.shape:
+            raise ValueError("mean/lo/hi must be K x channels arrays of identical shape")
+        K, Cn = mean.shape
+        if channels is None:
+            channels = Cn
+        self._ck(self._L.mr_set_palette(self._h, K, _ptr(mean), _ptr(lo), _ptr(hi), int(colourspace), int(channels)))
+
+    def set_known(self, lin_idx=None, cat=None):
+        if lin_idx is None or len(lin_idx) == 0:
+            self._ck(self._L.mr_set_known(self._h, 0, None, None))
+            return
+        idx = np.ascontiguousarray(lin_idx, dtype=np.int64)
+        ct = np.ascontiguousarray(cat, dtype=np.uint8)
+        self._ck(self._L.mr_set_known(self._h, idx.size, _ptr(idx), _ptr(ct)))
+
+    def get_lut(self):
+        lut = np.empty(LUT_SIZE, dtype=np.uint8)
+        self._ck(self._L.mr_get_lut(self._h, _ptr(lut)))
+        return lut
+
+    def palette_build_ms(self):
+        ms = C.c_float(0)
+        self._ck(self._L.mr_palette_build_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def enable_counters(self, on=True):
+        self._ck(self._L.mr_enable_counters(self._h, 1 if on else 0))
+
+    def read_counters(self, reset=True):
+        c = Counters()
+        self._ck(self._L.mr_read_counters(self._h, C.byref(c), 1 if reset else 0))
+        return c.as_dict()
+
+    def launch_count(self):
+        return int(self._L.mr_launch_count(self._h))
+
+    # -- host buffers (numpy) ------------------------------------------------------------
+    def categorize_clean_host(self, px, R, out=None, counters=False, halo_lo=0, halo_hi=0):
+        """px: (halo_lo + n2 + halo_hi, n1, bpp) uint8 numpy (memory-identical to Julia's n1 x n2
+        Matrix{RGB{N0f8}}); with halos, the first/last lines are the neighbouring bands' lines."""
+        if px.dtype != np.uint8 or px.ndim != 3 or px.shape[2] not in (3, 4):
+            raise ValueError("px must be a (n2, n1, 3|4) uint8 array")
+        if px.strides[2] != 1 or px.strides[1] != px.shape[2]:
+            px = np.ascontiguousarray(px)
+        nt, n1, bpp = px.shape
+        n2 = nt - halo_lo - halo_hi
+        stride2 = px.strides[0] if nt > 1 else n1 * bpp
+        if out is None:
+            out = np.empty((n2, n1), dtype=np.uint8)
+        cnt = Counters() if counters else None
+        self._ck(self._L.mr_categorize_clean_host_band(
+            self._h, _ptr(px) + halo_lo * stride2, n1, n2, stride2, bpp, int(R), int(halo_lo), int(halo_hi),
+            _ptr(out), out.strides[0] if n2 > 1 else n1, C.byref(cnt) if counters else None))
+        return (out, cnt.as_dict()) if counters else out
+
+    def clean_host(self, labels, R, repeat=1):
+        labels = np.ascontiguousarray(labels, dtype=np.uint8)
+        n2, n1 = labels.shape
+        out = np.empty((n2, n1), dtype=np.uint8)
+        self._ck(self._L.mr_clean_host(self._h, _ptr(labels), n1, n2, n1, int(R), int(repeat), _ptr(out), n1))
+        return out
+
+    # -- device buffers (raw pointers / torch tensors) -------------------------------------
+    def categorize_clean_dev(self, px, n1, n2, stride2, bpp, R, out, out_stride2, halo_lo=0, halo_hi=0, stream=0):
+        self._ck(self._L.mr_categorize_clean_dev(self._h, _ptr(px), n1, n2, stride2, bpp, int(R), int(halo_lo),
+                                                 int(halo_hi), _ptr(out), out_stride2, stream or None))
+
+    def batch_categorize_clean_dev(self, n_sheets, px, sheet_stride, n1, n2, stride2, bpp, R, out,
+                                   out_sheet_stride, out_stride2, stream=0):
+        self._ck(self._L.mr_batch_categorize_clean_dev(self._h, int(n_sheets), _ptr(px), sheet_stride, n1, n2,
+                                                       stride2, bpp, int(R), _ptr(out), out_sheet_stride,
+                                                       out_stride2, stream or None))
+
+    def clean_dev(self, labels, n1, n2, stride2, R, out, out_stride2, halo_lo=0, halo_hi=0, stream=0):
+        self._ck(self._L.mr_clean_dev(self._h, _ptr(labels), n1, n2, stride2, int(R), int(halo_lo), int(halo_hi),
+                                      _ptr(out), out_stride2, stream or None))
+
+    def synth_scan_dev(self, seed, sheet_id, palette_rgb, n1, n2, line0, nlines, out, out_stride2, mode=0, stream=0):
+        pal = np.ascontiguousarray(palette_rgb, dtype=np.uint8)
+        self._ck(self._L.mr_synth_scan_dev(self._h, seed, sheet_id, pal.shape[0], _ptr(pal), n1, n2, line0, nlines,
+                                           mode, _ptr(out), out_stride2, stream or None))

@@ -1,0 +1,247 @@
+"""Host-side mirror of the reference's interface for the categorise + clean path.
+
+The reference is Julia (toolchain absent in this image), so this Python layer plays the role
+of the Julia wrapper in maprasterization.jl_b200/julia/: same names (minus the leading
+underscore), argument meaning and error behaviour as
+
+  * `_categorize(pixels, points; tolerances, match, segmented, scan_threshold)`
+       /root/reference/src/categories.jl:45-74  (call site src/selectcolors.jl:466-478)
+  * `_component_stats`   src/categories.jl:2-30, `_point_values` :155-157
+  * `blur(A; hood=Window{1}(), repeat=1)`  src/blur.jl:6  (kwarg shape of `clean`)
+
+All labels are produced by libmaprast.so (CUDA); nothing here computes labels on the CPU.
+Array convention: a Julia `Matrix{RGB{N0f8}}` of size n1 x n2 (column-major) is the numpy
+array of shape (n2, n1, 3) (C order) -- the same bytes.  Labels: (n2, n1).
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from ._lib import Context, MapRastError  # noqa: F401
+
+DEFAULT_CATEGORY_TOLERANCE = 2.0   # src/selectcolors.jl:1
+DEFAULT_MATCH = ("color", "std", "stripe")  # src/scan.jl:1 (the hot path supports ("color",) only)
+
+
+class Window:
+    """`Window{R}` of Neighborhoods.jl: square of side 2R+1, centre included (src/blur.jl:6)."""
+
+    def __init__(self, R=1):
+        R = int(R)
+        if R < 0:
+            raise ValueError("Window radius must be >= 0")
+        self.R = R
+
+    def __repr__(self):
+        return f"Window({self.R})"
+
+
+def component_stats(values):
+    """(mean, min, max, sd) per channel of an (n, C) array -- src/categories.jl:18-30.
+    sd is the sample standard deviation (n-1); one sample gives NaN, as in Julia."""
+    v = np.asarray(values, dtype=np.float64)
+    if v.ndim == 1:
+        v = v[:, None]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        sd = v.std(axis=0, ddof=1) if v.shape[0] > 1 else np.full(v.shape[1], np.nan)
+    return {"mean": v.mean(axis=0), "min": v.min(axis=0), "max": v.max(axis=0), "sd": sd}
+
+
+_SRGB_LIN = None
+
+
+def rgb8_to_lab(rgb):
+    """sRGB (D65) bytes -> Lab for HOST-SIDE palette statistics only.
+    The per-pixel conversion used for labelling happens inside the CUDA table build."""
+    global _SRGB_LIN
+    if _SRGB_LIN is None:
+        v = np.arange(256, dtype=np.float64) / 255.0
+        _SRGB_LIN = np.where(v <= 0.04045, v / 12.92, ((v + 0.055) / 1.055) ** 2.4)
+    rgb = np.asarray(rgb, dtype=np.uint8)
+    lin = _SRGB_LIN[rgb]
+    r, g, b = lin[..., 0], lin[..., 1], lin[..., 2]
+    X = (0.4124564390896921 * r + 0.357576077643909 * g) + 0.18043748326639894 * b
+    Y = (0.21267285140562248 * r + 0.715152155287818 * g) + 0.07217499330655958 * b
+    Z = (0.019333895582329317 * r + 0.119192025881303 * g) + 0.9503040785363677 * b
+
+    def f(t):
+        return np.where(t > 216.0 / 24389.0, np.cbrt(t), (24389.0 / 27.0 * t + 16.0) / 116.0)
+
+    fx, fy, fz = f(X / 0.95047), f(Y), f(Z / 1.08883)
+    return np.stack([116.0 * fy - 16.0, 500.0 * (fx - fy), 200.0 * (fy - fz)], axis=-1)
+
+
+@dataclass
+class Palette:
+    """Per-category statistics = `category_stats` of src/categories.jl:52.
+
+    mean/min/max/sd: (K, C) Float64; a category without points (`missing`, :6) has mean=+Inf.
+    tolerances: (K,) -- `tolerances[best]` of src/categories.jl:81."""
+    mean: np.ndarray
+    min: np.ndarray
+    max: np.ndarray
+    sd: np.ndarray
+    tolerances: np.ndarray = None
+    colourspace: str = "rgb"
+    lo: np.ndarray = field(init=False)
+    hi: np.ndarray = field(init=False)
+
+    def __post_init__(self):
+        self.mean = np.atleast_2d(np.asarray(self.mean, dtype=np.float64))
+        self.min = np.atleast_2d(np.asarray(self.min, dtype=np.float64))
+        self.max = np.atleast_2d(np.asarray(self.max, dtype=np.float64))
+        self.sd = np.atleast_2d(np.asarray(self.sd, dtype=np.float64))
+        K = self.mean.shape[0]
+        if self.tolerances is None:
+            self.tolerances = np.full(K, DEFAULT_CATEGORY_TOLERANCE)
+        self.tolerances = np.asarray(self.tolerances, dtype=np.float64).reshape(-1)
+        if self.tolerances.size != K:
+            raise ValueError("tolerances must have one entry per category")
+        if self.colourspace not in ("rgb", "lab"):
+            raise ValueError("colourspace must be 'rgb' or 'lab'")
+        # src/categories.jl:131-133: (s.min - s.sd * tol), (s.max + s.sd * tol): two rounded ops each
+        with np.errstate(invalid="ignore"):
+            w = self.sd * self.tolerances[:, None]
+            self.lo = self.min - w
+            self.hi = self.max + w
+
+    @property
+    def K(self):
+        return self.mean.shape[0]
+
+    @property
+    def channels(self):
+        return self.mean.shape[1]
+
+    @classmethod
+    def from_points(cls, img, points, tolerances=None, colourspace="rgb"):
+        """`_component_stats(A, pointvecs)` (src/categories.jl:2-9): sample img at the clicked
+        points (1-based (i, j), rounded like `round(Int, p)`, :155-157) per category."""
+        img = np.asarray(img)
+        n2, n1, bpp = img.shape
+        K = len(points)
+        C = 3 if colourspace == "lab" else bpp
+        mean = np.full((K, C), np.inf)
+        mn = np.full((K, C), np.nan)
+        mx = np.full((K, C), np.nan)
+        sd = np.full((K, C), np.nan)
+        for c, pts in enumerate(points):
+            pts = np.asarray(pts, dtype=np.float64).reshape(-1, 2)
+            if pts.shape[0] == 0:
+                continue   # `missing`
+            ij = np.rint(pts).astype(np.int64)   # Julia round(Int, x): ties to even
+            i, j = ij[:, 0] - 1, ij[:, 1] - 1
+            if (i < 0).any() or (i >= n1).any() or (j < 0).any() or (j >= n2).any():
+                raise IndexError("point outside the image (BoundsError in the reference)")
+            samples = img[j, i]
+            vals = rgb8_to_lab(samples[:, :3]) if colourspace == "lab" else samples.astype(np.float64) / 255.0
+            st = component_stats(vals)
+            mean[c], mn[c], mx[c], sd[c] = st["mean"], st["min"], st["max"], st["sd"]
+        return cls(mean, mn, mx, sd, tolerances, colourspace)
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+def _check_match(match, segmented):
+    m = tuple(match)
+    if m != ("color",):
+        raise ValueError(f"match={m!r} is not supported by the B200 hot path: only ('color',) "
+                         "(std/stripe texture planes are SURVEY 8(f) 'next' rows)")
+    if segmented:
+        raise ValueError("segmented=True (fast_scanning, src/categories.jl:53-67) is not supported")
+
+
+def _as_palette(img, points_or_palette, tolerances, colourspace):
+    if isinstance(points_or_palette, Palette):
+        return points_or_palette
+    return Palette.from_points(img, points_or_palette, tolerances, colourspace)
+
+
+def _upload_palette(ctx, pal):
+    if ctx.palette is not pal:
+        ctx.set_palette(pal.mean, pal.lo, pal.hi, _lib.LAB if pal.colourspace == "lab" else _lib.RGB)
+        ctx.palette = pal
+
+
+def _known_from_points(points, n1):
+    """`_set_categories!` (src/selectcolors.jl:670-681): later categories overwrite earlier ones."""
+    plane = {}
+    for c, pts in enumerate(points):
+        pts = np.asarray(pts, dtype=np.float64).reshape(-1, 2)
+        for p in np.rint(pts).astype(np.int64):
+            plane[(int(p[0]) - 1) + (int(p[1]) - 1) * n1] = c + 1
+    idx = np.fromiter(plane.keys(), dtype=np.int64, count=len(plane))
+    cat = np.fromiter(plane.values(), dtype=np.uint8, count=len(plane))
+    return idx, cat
+
+
+def _check_img(img):
+    if not isinstance(img, np.ndarray) or img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] not in (3, 4):
+        raise ValueError("img must be a (n2, n1, 3|4) uint8 array (RGB{N0f8} / RGBA{N0f8}); other element "
+                         "types are not supported by the B200 hot path")
+
+
+def categorize_clean_u8(img, points_or_palette, *, tolerances=None, hood=Window(1), match=("color",),
+                        segmented=False, scan_threshold=0.1, colourspace="rgb", use_known=False,
+                        ctx=None, counters=False):
+    """Fused clean(categorize(img)) returning uint8 labels (n2, n1)."""
+    del scan_threshold   # only used by the unsupported segmented branch
+    _check_match(match, segmented)
+    _check_img(img)
+    ctx = ctx or default_context()
+    pal = _as_palette(img, points_or_palette, tolerances, colourspace)
+    _upload_palette(ctx, pal)
+    if use_known and not isinstance(points_or_palette, Palette):
+        ctx.set_known(*_known_from_points(points_or_palette, img.shape[1]))
+    else:
+        ctx.set_known(None)
+    R = hood.R if isinstance(hood, Window) else int(hood)
+    return ctx.categorize_clean_host(img, R, counters=counters)
+
+
+def categorize_clean(img, points_or_palette, **kw):
+    """Same, eltype Int (Julia `Matrix{Int}`, src/categories.jl:69-73)."""
+    out = categorize_clean_u8(img, points_or_palette, **kw)
+    if isinstance(out, tuple):
+        return out[0].astype(np.int64), out[1]
+    return out.astype(np.int64)
+
+
+def categorize_u8(img, points_or_palette, **kw):
+    kw["hood"] = Window(0)
+    return categorize_clean_u8(img, points_or_palette, **kw)
+
+
+def categorize(img, points_or_palette, *, tolerances=None, match=("color",), segmented=False,
+               scan_threshold=0.1, **kw):
+    """`_categorize(pixels, points; tolerances, match, segmented, scan_threshold)`
+    (src/categories.jl:49-74) -> labels, eltype Int, same shape as the image."""
+    out = categorize_u8(img, points_or_palette, tolerances=tolerances, match=match, segmented=segmented,
+                        scan_threshold=scan_threshold, **kw)
+    if isinstance(out, tuple):
+        return out[0].astype(np.int64), out[1]
+    return out.astype(np.int64)
+
+
+def clean_u8(labels, *, hood=Window(1), repeat=1, ctx=None):
+    labels = np.asarray(labels)
+    if labels.ndim != 2 or not np.issubdtype(labels.dtype, np.integer):
+        raise ValueError("labels must be a 2-D integer array")
+    if labels.size and (labels.min() < 0 or labels.max() > 254):
+        raise ValueError("labels must be in 0..254")
+    ctx = ctx or default_context()
+    R = hood.R if isinstance(hood, Window) else int(hood)
+    return ctx.clean_host(labels.astype(np.uint8), R, repeat)
+
+
+def clean(labels, *, hood=Window(1), repeat=1, ctx=None):
+    """`clean(labels; hood=Window{1}(), repeat=1)`: Window majority filter, SURVEY Appendix A.3."""
+    return clean_u8(labels, hood=hood, repeat=repeat, ctx=ctx).astype(np.int64)

@@ -1,0 +1,543 @@
+// mr_api.cu -- the C ABI of libmaprast.so (include/maprast.h): context, palette upload,
+// host/device entry points, chunked H2D -> kernel -> D2H pipeline for host callers.
+// No CPU compute path exists: every label is produced by a CUDA kernel.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/maprast.h"
+#include "mr_internal.h"
+
+struct mr_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t s_main = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    // palette
+    bool palette_set = false;
+    MrPalette pal{};
+    double* d_pal = nullptr;        // mean | lo | hi | lin
+    uint8_t* d_lut = nullptr;
+    uint8_t* d_coarse = nullptr;
+    bool lut_valid = false;
+    float build_ms = 0.f;
+    // known-category plane (sparse)
+    int64_t n_known = 0;
+    int64_t* d_known_idx = nullptr;
+    uint8_t* d_known_cat = nullptr;
+    // counters
+    MrCountersDev* d_counters = nullptr;
+    bool count_on = false;
+    int64_t launches = 0;
+    // grow-only device scratch for the host entry points
+    uint8_t* d_in = nullptr;  size_t d_in_cap = 0;
+    uint8_t* d_out = nullptr; size_t d_out_cap = 0;
+    uint8_t* d_tmp = nullptr; size_t d_tmp_cap = 0;
+    std::vector<cudaEvent_t> ev_up, ev_done;
+    std::string err;
+};
+
+static thread_local std::string g_err;
+
+static int fail(mr_ctx* ctx, int code, const std::string& msg) {
+    g_err = msg;
+    if (ctx) ctx->err = msg;
+    return code;
+}
+static int fail_cuda(mr_ctx* ctx, cudaError_t e, const char* what) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "CUDA error in %s: %s", what, cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return fail(ctx, MR_ERR_CUDA, buf);
+}
+#define CK(call)                                                   \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return fail_cuda(ctx, e_, #call);   \
+    } while (0)
+
+extern "C" int mr_version(void) { return 100; }
+
+extern "C" const char* mr_last_error(const mr_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+extern "C" mr_ctx* mr_create(int device, int* err) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0 || device < 0 || device >= n) {
+        (void)cudaGetLastError();
+        fail(nullptr, MR_ERR_CUDA,
+             "mr_create: no usable CUDA device (libmaprast has no CPU fallback)");
+        if (err) *err = MR_ERR_CUDA;
+        return nullptr;
+    }
+    mr_ctx* ctx = new mr_ctx();
+    ctx->device = device;
+    bool ok = cudaSetDevice(device) == cudaSuccess;
+    cudaDeviceProp prop;
+    ok = ok && cudaGetDeviceProperties(&prop, device) == cudaSuccess;
+    if (ok && prop.major < 10) {
+        fail(nullptr, MR_ERR_CUDA, "mr_create: device is not sm_100+ (library is built for sm_100a only)");
+        ok = false;
+    }
+    ok = ok && cudaStreamCreateWithFlags(&ctx->s_main, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_lut, MR_LUT_SIZE) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_coarse, MR_COARSE_SIZE) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_counters, sizeof(MrCountersDev)) == cudaSuccess;
+    ok = ok && cudaMemset(ctx->d_counters, 0, sizeof(MrCountersDev)) == cudaSuccess;
+    if (!ok) {
+        if (g_err.empty()) fail(nullptr, MR_ERR_CUDA, "mr_create: CUDA initialisation failed");
+        if (err) *err = MR_ERR_CUDA;
+        mr_destroy(ctx);
+        return nullptr;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (err) *err = MR_OK;
+    return ctx;
+}
+
+extern "C" void mr_destroy(mr_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto e : ctx->ev_up) cudaEventDestroy(e);
+    for (auto e : ctx->ev_done) cudaEventDestroy(e);
+    cudaFree(ctx->d_pal); cudaFree(ctx->d_lut); cudaFree(ctx->d_coarse);
+    cudaFree(ctx->d_known_idx); cudaFree(ctx->d_known_cat); cudaFree(ctx->d_counters);
+    cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_tmp);
+    if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
+    if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+    (void)cudaGetLastError();
+    delete ctx;
+}
+
+extern "C" int mr_set_palette(mr_ctx* ctx, int K, const double* mean, const double* lo, const double* hi,
+                              int colourspace, int channels) {
+    if (!ctx) return fail(nullptr, MR_ERR_ARG, "mr_set_palette: null ctx");
+    if (K < 1 || K > 254) return fail(ctx, MR_ERR_ARG, "mr_set_palette: K must be in 1..254 (uint8 labels, 255 reserved)");
+    if (channels != 3 && channels != 4) return fail(ctx, MR_ERR_ARG, "mr_set_palette: channels must be 3 or 4");
+    if (colourspace != MR_COLOURSPACE_RGB && colourspace != MR_COLOURSPACE_LAB)
+        return fail(ctx, MR_ERR_ARG, "mr_set_palette: unknown colourspace");
+    if (colourspace == MR_COLOURSPACE_LAB && channels != 3)
+        return fail(ctx, MR_ERR_ARG, "mr_set_palette: Lab matching takes 3-channel statistics");
+    if (!mean || !lo || !hi) return fail(ctx, MR_ERR_ARG, "mr_set_palette: null statistics");
+    bool any_finite = false;
+    for (int c = 0; c < K; ++c) {
+        bool fin = true, inf = true;
+        for (int ch = 0; ch < channels; ++ch) {
+            double m = mean[c * channels + ch];
+            if (isnan(m)) return fail(ctx, MR_ERR_ARG, "mr_set_palette: NaN category mean");
+            fin = fin && isfinite(m);
+            inf = inf && (isinf(m) && m > 0);
+        }
+        if (!fin && !inf)
+            return fail(ctx, MR_ERR_ARG, "mr_set_palette: a category mean must be all finite or all +Inf (missing)");
+        any_finite = any_finite || fin;
+    }
+    // the reference indexes `missing` and throws when no category has points (categories.jl:80-81)
+    if (!any_finite) return fail(ctx, MR_ERR_ARG, "mr_set_palette: all categories are missing");
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)K * channels;
+    std::vector<double> h(3 * n + 256);
+    memcpy(h.data(), mean, n * 8);
+    memcpy(h.data() + n, lo, n * 8);
+    memcpy(h.data() + 2 * n, hi, n * 8);
+    for (int i = 0; i < 256; ++i) {   // sRGB inverse companding (Appendix A.4), host libm
+        double v = (double)i / 255.0;
+        h[3 * n + i] = (v <= 0.04045) ? v / 12.92 : pow((v + 0.055) / 1.055, 2.4);
+    }
+    CK(cudaStreamSynchronize(ctx->s_main));
+    cudaFree(ctx->d_pal);
+    ctx->d_pal = nullptr;
+    CK(cudaMalloc(&ctx->d_pal, h.size() * 8));
+    CK(cudaMemcpy(ctx->d_pal, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
+    ctx->pal.mean = ctx->d_pal;
+    ctx->pal.lo = ctx->d_pal + n;
+    ctx->pal.hi = ctx->d_pal + 2 * n;
+    ctx->pal.lin = ctx->d_pal + 3 * n;
+    ctx->pal.K = K;
+    ctx->pal.C = channels;
+    ctx->pal.colourspace = colourspace;
+    ctx->palette_set = true;
+    ctx->lut_valid = false;
+    ctx->build_ms = 0.f;
+    if (channels == 3) {
+        cudaEvent_t a, b;
+        CK(cudaEventCreate(&a));
+        CK(cudaEventCreate(&b));
+        int nl = 0;
+        CK(cudaEventRecord(a, ctx->s_main));
+        CK(mr_launch_build_lut(ctx->pal, ctx->d_lut, ctx->d_coarse, ctx->s_main, &nl));
+        CK(cudaEventRecord(b, ctx->s_main));
+        CK(cudaStreamSynchronize(ctx->s_main));
+        CK(cudaEventElapsedTime(&ctx->build_ms, a, b));
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+        ctx->launches += nl;
+        ctx->lut_valid = true;
+    }
+    return MR_OK;
+}
+
+extern "C" int mr_set_known(mr_ctx* ctx, int64_t n, const int64_t* lin_idx, const uint8_t* cat) {
+    if (!ctx) return fail(nullptr, MR_ERR_ARG, "mr_set_known: null ctx");
+    if (n < 0 || (n > 0 && (!lin_idx || !cat))) return fail(ctx, MR_ERR_ARG, "mr_set_known: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->s_main));
+    cudaFree(ctx->d_known_idx); ctx->d_known_idx = nullptr;
+    cudaFree(ctx->d_known_cat); ctx->d_known_cat = nullptr;
+    ctx->n_known = 0;
+    if (n == 0) return MR_OK;
+    CK(cudaMalloc(&ctx->d_known_idx, n * 8));
+    CK(cudaMalloc(&ctx->d_known_cat, n));
+    CK(cudaMemcpy(ctx->d_known_idx, lin_idx, n * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_known_cat, cat, n, cudaMemcpyHostToDevice));
+    ctx->n_known = n;
+    return MR_OK;
+}
+
+extern "C" int mr_get_lut(mr_ctx* ctx, uint8_t* lut_host) {
+    if (!ctx || !lut_host) return fail(ctx, MR_ERR_ARG, "mr_get_lut: null argument");
+    if (!ctx->lut_valid) return fail(ctx, MR_ERR_STATE, "mr_get_lut: no 3-channel palette set");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(lut_host, ctx->d_lut, MR_LUT_SIZE, cudaMemcpyDeviceToHost));
+    return MR_OK;
+}
+
+extern "C" int mr_palette_build_ms(mr_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return fail(ctx, MR_ERR_ARG, "mr_palette_build_ms: null argument");
+    *ms = ctx->build_ms;
+    return MR_OK;
+}
+
+extern "C" int mr_enable_counters(mr_ctx* ctx, int on) {
+    if (!ctx) return fail(nullptr, MR_ERR_ARG, "mr_enable_counters: null ctx");
+    ctx->count_on = on != 0;
+    return MR_OK;
+}
+
+extern "C" int mr_read_counters(mr_ctx* ctx, mr_counters* out, int reset) {
+    if (!ctx || !out) return fail(ctx, MR_ERR_ARG, "mr_read_counters: null argument");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    MrCountersDev h;
+    CK(cudaMemcpy(&h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+    out->n_pixels = h.n_pixels; out->n_nomatch = h.n_nomatch;
+    out->n_fine = h.n_fine; out->n_changed = h.n_changed;
+    if (reset) CK(cudaMemset(ctx->d_counters, 0, sizeof h));
+    return MR_OK;
+}
+
+extern "C" int64_t mr_launch_count(const mr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" void* mr_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void mr_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// ------------------------------------------------------------------ job plumbing
+static int check_image_args(mr_ctx* ctx, const char* fn, const void* in, const void* out, int64_t n1,
+                            int64_t n2, int64_t stride2, int bpp, int64_t out_stride2, int R,
+                            int halo_lo, int halo_hi) {
+    std::string f(fn);
+    if (!ctx) return fail(nullptr, MR_ERR_ARG, f + ": null ctx");
+    if (n1 < 0 || n2 < 0) return fail(ctx, MR_ERR_ARG, f + ": negative size");
+    if (n1 > 0 && n2 > 0 && (!in || !out)) return fail(ctx, MR_ERR_ARG, f + ": null buffer");
+    if (stride2 < n1 * bpp || out_stride2 < n1) return fail(ctx, MR_ERR_ARG, f + ": stride smaller than a line");
+    if (R < 0 || R > 7) return fail(ctx, MR_ERR_ARG, f + ": window radius R must be in 0..7");
+    if (halo_lo < 0 || halo_hi < 0 || halo_lo > R || halo_hi > R)
+        return fail(ctx, MR_ERR_ARG, f + ": halo_lo/halo_hi must be in 0..R");
+    return MR_OK;
+}
+
+static int check_palette(mr_ctx* ctx, const char* fn, int bpp) {
+    std::string f(fn);
+    if (!ctx->palette_set) return fail(ctx, MR_ERR_STATE, f + ": mr_set_palette has not been called");
+    if (bpp != 3 && bpp != 4) return fail(ctx, MR_ERR_ARG, f + ": bytes_per_px must be 3 (RGB{N0f8}) or 4 (RGBA{N0f8})");
+    if (bpp == 3 && ctx->pal.C != 3)
+        return fail(ctx, MR_ERR_ARG, f + ": 4-channel statistics need RGBA pixels");
+    if (bpp == 4 && ctx->pal.C != 4 && ctx->pal.colourspace == MR_COLOURSPACE_RGB)
+        return fail(ctx, MR_ERR_ARG, f + ": RGBA pixels need 4-channel statistics (categories.jl:92)");
+    return MR_OK;
+}
+
+static MrJob make_job(mr_ctx* ctx, const uint8_t* px, uint8_t* out, int64_t n1, int64_t n2, int64_t stride2,
+                      int bpp, int R, int halo_lo, int halo_hi, int64_t out_stride2) {
+    MrJob j{};
+    j.px = px; j.out = out; j.n1 = n1; j.n2 = n2; j.stride2 = stride2; j.out_stride2 = out_stride2;
+    j.sheet_stride = 0; j.out_sheet_stride = 0; j.n_sheets = 1; j.bpp = bpp; j.R = R;
+    j.halo_lo = halo_lo; j.halo_hi = halo_hi;
+    j.lut = (bpp == 3 && ctx->lut_valid) ? ctx->d_lut : nullptr;
+    j.coarse = ctx->d_coarse;
+    j.pal = ctx->pal;
+    j.counters = ctx->count_on ? ctx->d_counters : nullptr;
+    return j;
+}
+
+static int grow(mr_ctx* ctx, uint8_t** p, size_t* cap, size_t need) {
+    if (*cap >= need) return MR_OK;
+    cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    cudaError_t e = cudaMalloc(p, need);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, MR_ERR_NOMEM, "device allocation failed"); }
+    *cap = need;
+    return MR_OK;
+}
+
+// fused (or categorise-only) on device-resident data
+static int run_fused(mr_ctx* ctx, const MrJob& job, cudaStream_t s) {
+    if (job.n1 == 0 || job.n2 == 0 || job.n_sheets == 0) return MR_OK;
+    int nl = 0;
+    cudaError_t e = cudaErrorNotSupported;
+    if (mr_fast_supported(job)) e = mr_launch_fast(job, ctx->sm_count, s, &nl);
+    if (e == cudaErrorNotSupported) e = mr_launch_generic(job, false, ctx->sm_count, s, &nl);
+    ctx->launches += nl;
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "fused kernel launch");
+    return MR_OK;
+}
+
+static int run_clean(mr_ctx* ctx, const MrJob& job, cudaStream_t s) {
+    if (job.n1 == 0 || job.n2 == 0) return MR_OK;
+    int nl = 0;
+    cudaError_t e = mr_launch_generic(job, true, ctx->sm_count, s, &nl);
+    ctx->launches += nl;
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "clean kernel launch");
+    return MR_OK;
+}
+
+// whole-image path with the sparse known-category plane: categorise -> fix-up -> clean
+static int run_with_known(mr_ctx* ctx, MrJob job, cudaStream_t s) {
+    const int R = job.R;
+    uint8_t* final_out = job.out;
+    const int64_t final_stride = job.out_stride2;
+    if (R > 0) {
+        int rc = grow(ctx, &ctx->d_tmp, &ctx->d_tmp_cap, (size_t)job.n1 * job.n2);
+        if (rc) return rc;
+        job.out = ctx->d_tmp;
+        job.out_stride2 = job.n1;
+    }
+    job.R = 0;
+    MrCountersDev* cnt = job.counters;
+    if (R > 0) job.counters = nullptr;
+    int rc = run_fused(ctx, job, s);
+    if (rc) return rc;
+    int nl = 0;
+    cudaError_t e = mr_launch_known_fixup(job, ctx->n_known, ctx->d_known_idx, ctx->d_known_cat, job.out,
+                                          job.out_stride2, s, &nl);
+    ctx->launches += nl;
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "known-category fix-up");
+    if (R > 0) {
+        MrJob c = job;
+        c.px = ctx->d_tmp; c.stride2 = job.n1; c.bpp = 1; c.R = R; c.out = final_out;
+        c.out_stride2 = final_stride; c.counters = cnt;
+        return run_clean(ctx, c, s);
+    }
+    return MR_OK;
+}
+
+extern "C" int mr_categorize_clean_dev(mr_ctx* ctx, const uint8_t* px_dev, int64_t n1, int64_t n2,
+                                       int64_t stride2, int bpp, int R, int halo_lo, int halo_hi,
+                                       uint8_t* labels_dev, int64_t out_stride2, void* stream) {
+    int rc = check_image_args(ctx, "mr_categorize_clean_dev", px_dev, labels_dev, n1, n2, stride2, bpp,
+                              out_stride2, R, halo_lo, halo_hi);
+    if (rc) return rc;
+    if ((rc = check_palette(ctx, "mr_categorize_clean_dev", bpp))) return rc;
+    CK(cudaSetDevice(ctx->device));
+    MrJob job = make_job(ctx, px_dev, labels_dev, n1, n2, stride2, bpp, R, halo_lo, halo_hi, out_stride2);
+    if (ctx->n_known > 0) {
+        if (halo_lo || halo_hi)
+            return fail(ctx, MR_ERR_ARG, "mr_categorize_clean_dev: known-category points need a whole-image call (no halos)");
+        return run_with_known(ctx, job, (cudaStream_t)stream);
+    }
+    return run_fused(ctx, job, (cudaStream_t)stream);
+}
+
+extern "C" int mr_batch_categorize_clean_dev(mr_ctx* ctx, int n_sheets, const uint8_t* px_dev,
+                                             int64_t sheet_stride, int64_t n1, int64_t n2, int64_t stride2,
+                                             int bpp, int R, uint8_t* labels_dev, int64_t out_sheet_stride,
+                                             int64_t out_stride2, void* stream) {
+    int rc = check_image_args(ctx, "mr_batch_categorize_clean_dev", px_dev, labels_dev, n1, n2, stride2, bpp,
+                              out_stride2, R, 0, 0);
+    if (rc) return rc;
+    if ((rc = check_palette(ctx, "mr_batch_categorize_clean_dev", bpp))) return rc;
+    if (n_sheets < 0 || sheet_stride < stride2 * n2 || out_sheet_stride < out_stride2 * n2)
+        return fail(ctx, MR_ERR_ARG, "mr_batch_categorize_clean_dev: bad sheet count/strides");
+    if (ctx->n_known > 0)
+        return fail(ctx, MR_ERR_ARG, "mr_batch_categorize_clean_dev: known-category points are per-sheet; clear them (mr_set_known n=0)");
+    CK(cudaSetDevice(ctx->device));
+    MrJob job = make_job(ctx, px_dev, labels_dev, n1, n2, stride2, bpp, R, 0, 0, out_stride2);
+    job.n_sheets = n_sheets;
+    job.sheet_stride = sheet_stride;
+    job.out_sheet_stride = out_sheet_stride;
+    return run_fused(ctx, job, (cudaStream_t)stream);
+}
+
+extern "C" int mr_clean_dev(mr_ctx* ctx, const uint8_t* labels_dev, int64_t n1, int64_t n2, int64_t stride2,
+                            int R, int halo_lo, int halo_hi, uint8_t* out_dev, int64_t out_stride2,
+                            void* stream) {
+    int rc = check_image_args(ctx, "mr_clean_dev", labels_dev, out_dev, n1, n2, stride2, 1, out_stride2, R,
+                              halo_lo, halo_hi);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    MrJob job = make_job(ctx, labels_dev, out_dev, n1, n2, stride2, 1, R, halo_lo, halo_hi, out_stride2);
+    job.lut = nullptr;
+    return run_clean(ctx, job, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ host entry points
+static int ensure_events(mr_ctx* ctx, size_t n) {
+    while (ctx->ev_up.size() < n) {
+        cudaEvent_t a, b;
+        CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        ctx->ev_up.push_back(a);
+        ctx->ev_done.push_back(b);
+    }
+    return MR_OK;
+}
+
+// Chunked pipeline: every input line crosses PCIe once (into one resident device image);
+// chunk c's kernel waits for the upload of the last line its windows read, its labels go back
+// on a third stream.  H2D, kernel and D2H of different chunks overlap.
+// px points at line 0 of the band; lines [-halo_lo, n2 + halo_hi) are read from the host.
+static int host_impl(mr_ctx* ctx, const char* fn, const uint8_t* px, int64_t n1, int64_t n2, int64_t stride2,
+                     int bpp, int R, int halo_lo, int halo_hi, uint8_t* labels_out, int64_t out_stride2,
+                     mr_counters* counters) {
+    int rc = check_image_args(ctx, fn, px, labels_out, n1, n2, stride2, bpp, out_stride2, R, halo_lo, halo_hi);
+    if (rc) return rc;
+    if ((rc = check_palette(ctx, fn, bpp))) return rc;
+    if (n1 == 0 || n2 == 0) {
+        if (counters) memset(counters, 0, sizeof *counters);
+        return MR_OK;
+    }
+    if (ctx->n_known > 0 && (halo_lo || halo_hi))
+        return fail(ctx, MR_ERR_ARG, std::string(fn) + ": known-category points need a whole-image call (no halos)");
+    CK(cudaSetDevice(ctx->device));
+    const int64_t T = n2 + halo_lo + halo_hi;            // lines resident on the device
+    const int64_t line_in = (n1 * bpp + 15) / 16 * 16;   // 16-byte aligned device lines
+    const int64_t line_out = (n1 + 15) / 16 * 16;
+    if ((rc = grow(ctx, &ctx->d_in, &ctx->d_in_cap, (size_t)line_in * T))) return rc;
+    if ((rc = grow(ctx, &ctx->d_out, &ctx->d_out_cap, (size_t)line_out * n2))) return rc;
+    const bool saved_count = ctx->count_on;
+    if (counters) {
+        ctx->count_on = true;
+        CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(MrCountersDev), ctx->s_main));
+    }
+    int64_t chunk_lines = T;
+    if (ctx->n_known == 0) {
+        const int64_t target = (int64_t)48 << 20;   // ~48 MiB of input per chunk
+        chunk_lines = target / line_in;
+        if (chunk_lines < 4 * (R + 1)) chunk_lines = 4 * (R + 1);
+        if (chunk_lines > T) chunk_lines = T;
+    }
+    const int64_t n_up = (T + chunk_lines - 1) / chunk_lines;      // upload pieces over [0, T)
+    const int64_t n_k = (n2 + chunk_lines - 1) / chunk_lines;      // kernel chunks over [0, n2)
+    if ((rc = ensure_events(ctx, (size_t)(n_up > n_k ? n_up : n_k)))) { ctx->count_on = saved_count; return rc; }
+    const uint8_t* host0 = px - (int64_t)halo_lo * stride2;        // device line 0
+    uint8_t* d_own = ctx->d_in + (int64_t)halo_lo * line_in;
+    rc = MR_OK;
+    for (int64_t c = 0; c < n_up && rc == MR_OK; ++c) {
+        const int64_t a = c * chunk_lines, b = (a + chunk_lines < T) ? a + chunk_lines : T;
+        cudaError_t e = cudaMemcpy2DAsync(ctx->d_in + a * line_in, line_in, host0 + a * stride2, stride2,
+                                          n1 * bpp, b - a, cudaMemcpyHostToDevice, ctx->s_h2d);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_up[c], ctx->s_h2d);
+        if (e != cudaSuccess) rc = fail_cuda(ctx, e, "H2D copy");
+    }
+    for (int64_t c = 0; c < n_k && rc == MR_OK; ++c) {
+        const int64_t a = c * chunk_lines, b = (a + chunk_lines < n2) ? a + chunk_lines : n2;
+        const int hl = (int)((a + halo_lo < R) ? a + halo_lo : R);
+        const int hh = (int)((n2 + halo_hi - b < R) ? n2 + halo_hi - b : R);
+        const int64_t last_dev_line = halo_lo + b + hh - 1;         // last line this chunk's windows read
+        cudaError_t e = cudaStreamWaitEvent(ctx->s_main, ctx->ev_up[last_dev_line / chunk_lines], 0);
+        if (e != cudaSuccess) { rc = fail_cuda(ctx, e, "stream wait"); break; }
+        MrJob job = make_job(ctx, d_own + a * line_in, ctx->d_out + a * line_out, n1, b - a, line_in, bpp,
+                             R, hl, hh, line_out);
+        rc = (ctx->n_known > 0) ? run_with_known(ctx, job, ctx->s_main) : run_fused(ctx, job, ctx->s_main);
+        if (rc) break;
+        e = cudaEventRecord(ctx->ev_done[c], ctx->s_main);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_done[c], 0);
+        if (e == cudaSuccess)
+            e = cudaMemcpy2DAsync(labels_out + a * out_stride2, out_stride2, ctx->d_out + a * line_out, line_out,
+                                  n1, b - a, cudaMemcpyDeviceToHost, ctx->s_d2h);
+        if (e != cudaSuccess) rc = fail_cuda(ctx, e, "D2H copy");
+    }
+    cudaError_t e1 = cudaStreamSynchronize(ctx->s_h2d);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->s_main);
+    cudaError_t e3 = cudaStreamSynchronize(ctx->s_d2h);
+    ctx->count_on = saved_count;
+    if (rc) return rc;
+    if (e1 != cudaSuccess) return fail_cuda(ctx, e1, "H2D stream");
+    if (e2 != cudaSuccess) return fail_cuda(ctx, e2, "kernel stream");
+    if (e3 != cudaSuccess) return fail_cuda(ctx, e3, "D2H stream");
+    if (counters) return mr_read_counters(ctx, counters, 1);
+    return MR_OK;
+}
+
+extern "C" int mr_categorize_clean_host(mr_ctx* ctx, const uint8_t* px, int64_t n1, int64_t n2,
+                                        int64_t stride2, int bpp, int R, uint8_t* labels_out,
+                                        int64_t out_stride2, mr_counters* counters) {
+    return host_impl(ctx, "mr_categorize_clean_host", px, n1, n2, stride2, bpp, R, 0, 0, labels_out,
+                     out_stride2, counters);
+}
+
+extern "C" int mr_categorize_clean_host_band(mr_ctx* ctx, const uint8_t* px, int64_t n1, int64_t n2,
+                                             int64_t stride2, int bpp, int R, int halo_lo, int halo_hi,
+                                             uint8_t* labels_out, int64_t out_stride2, mr_counters* counters) {
+    return host_impl(ctx, "mr_categorize_clean_host_band", px, n1, n2, stride2, bpp, R, halo_lo, halo_hi,
+                     labels_out, out_stride2, counters);
+}
+
+extern "C" int mr_clean_host(mr_ctx* ctx, const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2,
+                             int R, int repeat, uint8_t* out, int64_t out_stride2) {
+    int rc = check_image_args(ctx, "mr_clean_host", labels, out, n1, n2, stride2, 1, out_stride2, R, 0, 0);
+    if (rc) return rc;
+    if (repeat < 0) return fail(ctx, MR_ERR_ARG, "mr_clean_host: repeat must be >= 0");
+    if (n1 == 0 || n2 == 0) return MR_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)n1 * n2;
+    if ((rc = grow(ctx, &ctx->d_out, &ctx->d_out_cap, bytes))) return rc;
+    if ((rc = grow(ctx, &ctx->d_tmp, &ctx->d_tmp_cap, bytes))) return rc;
+    uint8_t* a = ctx->d_out;
+    uint8_t* b = ctx->d_tmp;
+    CK(cudaMemcpy2DAsync(a, n1, labels, stride2, n1, n2, cudaMemcpyHostToDevice, ctx->s_main));
+    const int passes = (R == 0) ? 0 : repeat;
+    for (int p = 0; p < passes; ++p) {
+        MrJob job = make_job(ctx, a, b, n1, n2, n1, 1, R, 0, 0, n1);
+        job.lut = nullptr;
+        if ((rc = run_clean(ctx, job, ctx->s_main))) return rc;
+        uint8_t* t = a; a = b; b = t;
+    }
+    CK(cudaMemcpy2DAsync(out, out_stride2, a, n1, n1, n2, cudaMemcpyDeviceToHost, ctx->s_main));
+    CK(cudaStreamSynchronize(ctx->s_main));
+    return MR_OK;
+}
+
+// ------------------------------------------------------------------ bench/test utility
+extern "C" int mr_synth_scan_dev(mr_ctx* ctx, uint32_t seed, uint32_t sheet_id, int K,
+                                 const uint8_t* palette_rgb_host, int64_t n1, int64_t n2, int64_t line0,
+                                 int64_t nlines, int mode, uint8_t* out_dev, int64_t out_stride2, void* stream) {
+    if (!ctx) return fail(nullptr, MR_ERR_ARG, "mr_synth_scan_dev: null ctx");
+    if (K < 1 || K > 254 || !palette_rgb_host || n1 < 0 || nlines < 0 || out_stride2 < 3 * n1 || line0 < 0 ||
+        line0 + nlines > n2)
+        return fail(ctx, MR_ERR_ARG, "mr_synth_scan_dev: bad arguments");
+    if (n1 == 0 || nlines == 0) return MR_OK;
+    CK(cudaSetDevice(ctx->device));
+    uint8_t* d_pal = nullptr;
+    CK(cudaMalloc(&d_pal, (size_t)K * 3));
+    CK(cudaMemcpy(d_pal, palette_rgb_host, (size_t)K * 3, cudaMemcpyHostToDevice));
+    int nl = 0;
+    cudaError_t e = mr_launch_synth(seed, sheet_id, K, d_pal, n1, line0, nlines, mode, out_dev, out_stride2,
+                                    (cudaStream_t)stream, &nl);
+    ctx->launches += nl;
+    cudaError_t e2 = cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(d_pal);
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "synth launch");
+    if (e2 != cudaSuccess) return fail_cuda(ctx, e2, "synth kernel");
+    return MR_OK;
+}

@@ -1,0 +1,193 @@
+// mr_generic.cu -- table build + the general-purpose fused kernel.
+//
+//  * k_build_lut / k_build_coarse: per palette, evaluate the reference arithmetic
+//    (mr_device.cuh) once for each of the 2^24 N0f8 colours -> exact 16 MiB label table,
+//    then reduce it to a 32 KiB table of 8x8x8-colour cells (label, or MIXED).
+//    With match = (:color,) the label is a pure function of the 24-bit colour
+//    (src/categories.jl:76-95), so a table lookup is bit-exact by construction.
+//  * k_generic: any stride/alignment, RGB or RGBA (direct Float64 evaluation), any R <= 7,
+//    label input (clean only).  It is the on-GPU general path; mr_fast.cu holds the
+//    tuned packed-RGB path.  There is no CPU path.
+#include "mr_device.cuh"
+
+// ------------------------------------------------------------------ table build
+__global__ void __launch_bounds__(256) k_build_lut(MrPalette pal, uint8_t* __restrict__ lut) {
+    unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;   // r | g<<8 | b<<16
+    if (idx >= MR_LUT_SIZE) return;
+    int r = idx & 255, g = (idx >> 8) & 255, b = (idx >> 16) & 255;
+    lut[idx] = (uint8_t)mr_eval_px(pal, r, g, b, 255, false, 0);
+}
+
+// One thread per coarse cell c = (r>>3) | (g>>3)<<5 | (b>>3)<<10: uniform label or MIXED.
+__global__ void __launch_bounds__(128) k_build_coarse(const uint8_t* __restrict__ lut,
+                                                      uint8_t* __restrict__ coarse) {
+    unsigned c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= MR_COARSE_SIZE) return;
+    unsigned r0 = (c & 31u) << 3, g0 = ((c >> 5) & 31u) << 3, b0 = ((c >> 10) & 31u) << 3;
+    unsigned first = lut[r0 | (g0 << 8) | (b0 << 16)];
+    unsigned long long want = 0x0101010101010101ull * first;
+    bool uniform = true;
+    for (unsigned b = 0; b < 8; ++b)
+        for (unsigned g = 0; g < 8; ++g) {
+            unsigned long long v = *reinterpret_cast<const unsigned long long*>(
+                lut + (r0 | ((g0 + g) << 8) | ((b0 + b) << 16)));
+            uniform = uniform && (v == want);
+        }
+    coarse[c] = (uniform && first != MR_MIXED) ? (uint8_t)first : (uint8_t)MR_MIXED;
+}
+
+cudaError_t mr_launch_build_lut(const MrPalette& pal, uint8_t* lut, uint8_t* coarse, cudaStream_t s,
+                                int* n_launches) {
+    k_build_lut<<<MR_LUT_SIZE / 256, 256, 0, s>>>(pal, lut);
+    k_build_coarse<<<MR_COARSE_SIZE / 128, 128, 0, s>>>(lut, coarse);
+    *n_launches += 2;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ generic fused kernel
+#define G_TW 128
+#define G_TH 16
+#define G_MAXR 7
+#define G_VOID 0xFFu   // outside the image (window clipping); never a real label in smem
+
+// Label of one input element.  labels_in: the input already is a label plane (bpp == 1).
+__device__ __forceinline__ unsigned g_label(const MrJob& job, const uint8_t* __restrict__ p,
+                                            const uint8_t* __restrict__ s_coarse, bool labels_in,
+                                            bool direct, unsigned& fine) {
+    if (labels_in) return p[0];
+    if (direct) return (unsigned)mr_eval_px(job.pal, p[0], p[1], p[2], job.bpp == 4 ? p[3] : 255,
+                                            job.bpp == 4, 0);
+    unsigned r = p[0], g = p[1], b = p[2];
+    unsigned v = s_coarse[(r >> 3) | ((g >> 3) << 5) | ((b >> 3) << 10)];
+    if (v == MR_MIXED) {
+        v = __ldg(job.lut + (r | (g << 8) | (b << 16)));
+        ++fine;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_generic(MrJob job, bool labels_in, bool direct) {
+    __shared__ uint8_t s_coarse[MR_COARSE_SIZE];
+    __shared__ uint8_t s_lab[(G_TH + 2 * G_MAXR) * (G_TW + 2 * G_MAXR)];
+    const int R = job.R;
+    const int SW = G_TW + 2 * R;
+    const bool use_coarse = !labels_in && !direct;
+    if (use_coarse) {
+        const uint4* src = reinterpret_cast<const uint4*>(job.coarse);
+        uint4* dst = reinterpret_cast<uint4*>(s_coarse);
+        for (int i = threadIdx.x; i < (int)(MR_COARSE_SIZE / 16); i += blockDim.x) dst[i] = src[i];
+    }
+    const int64_t tiles_x = (job.n1 + G_TW - 1) / G_TW;
+    const int64_t tiles_y = (job.n2 + G_TH - 1) / G_TH;
+    const int64_t tiles = tiles_x * tiles_y * job.n_sheets;
+    unsigned c_nomatch = 0, c_fine = 0, c_changed = 0, c_pix = 0;
+
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int64_t sheet = t / (tiles_x * tiles_y);
+        const int64_t rem = t - sheet * tiles_x * tiles_y;
+        const int64_t ty = rem / tiles_x, tx = rem - ty * tiles_x;
+        const int64_t i0 = tx * G_TW, j0 = ty * G_TH;
+        const uint8_t* px = job.px + sheet * job.sheet_stride;
+        uint8_t* out = job.out + sheet * job.out_sheet_stride;
+        __syncthreads();   // previous tile's votes are done; also publishes s_coarse
+        // phase 1: labels of the tile + halo
+        const int region = SW * (G_TH + 2 * R);
+        for (int e = threadIdx.x; e < region; e += blockDim.x) {
+            const int ly = e / SW, lx = e - ly * SW;
+            const int64_t i = i0 + lx - R, j = j0 + ly - R;
+            unsigned v = G_VOID;
+            if (i >= 0 && i < job.n1 && j >= -(int64_t)job.halo_lo && j < job.n2 + job.halo_hi) {
+                unsigned fine = 0;
+                v = g_label(job, px + j * job.stride2 + i * job.bpp, s_coarse, labels_in, direct, fine);
+                // count the near-tie path once per owned pixel (not for halo re-reads)
+                if (lx >= R && lx < R + G_TW && ly >= R && ly < R + G_TH && j >= 0 && j < job.n2)
+                    c_fine += fine;
+            }
+            s_lab[e] = (uint8_t)v;
+        }
+        __syncthreads();
+        // phase 2: Window{R} majority, ties -> lowest label (Appendix A.3)
+        for (int e = threadIdx.x; e < G_TW * G_TH; e += blockDim.x) {
+            const int oy = e / G_TW, ox = e - oy * G_TW;
+            const int64_t i = i0 + ox, j = j0 + oy;
+            if (i >= job.n1 || j >= job.n2) continue;
+            const uint8_t* w = s_lab + oy * SW + ox;   // top-left of the window
+            const unsigned centre = w[R * SW + R];
+            unsigned best = centre;
+            if (R > 0) {
+                int bc = 0;
+                unsigned prev = G_VOID;
+                best = G_VOID;
+                const int side = 2 * R + 1;
+                for (int a = 0; a < side * side; ++a) {
+                    const unsigned c = w[(a / side) * SW + (a % side)];
+                    if (c == G_VOID || c == prev) continue;
+                    prev = c;
+                    if (c == best) continue;
+                    int cnt = 0;
+                    for (int y = 0; y < side; ++y)
+                        for (int x = 0; x < side; ++x) cnt += (w[y * SW + x] == c);
+                    if (cnt > bc || (cnt == bc && c < best)) { bc = cnt; best = c; }
+                }
+            }
+            out[j * job.out_stride2 + i] = (uint8_t)best;
+            ++c_pix;
+            c_nomatch += (best == 0);
+            c_changed += (best != centre);
+        }
+    }
+    if (job.counters) {
+        // warp-aggregate, one atomic per warp and counter
+        for (int o = 16; o > 0; o >>= 1) {
+            c_pix += __shfl_xor_sync(0xffffffffu, c_pix, o);
+            c_nomatch += __shfl_xor_sync(0xffffffffu, c_nomatch, o);
+            c_fine += __shfl_xor_sync(0xffffffffu, c_fine, o);
+            c_changed += __shfl_xor_sync(0xffffffffu, c_changed, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&job.counters->n_pixels, (unsigned long long)c_pix);
+            atomicAdd(&job.counters->n_nomatch, (unsigned long long)c_nomatch);
+            atomicAdd(&job.counters->n_fine, (unsigned long long)c_fine);
+            atomicAdd(&job.counters->n_changed, (unsigned long long)c_changed);
+        }
+    }
+}
+
+cudaError_t mr_launch_generic(const MrJob& job, bool labels_in, int sm_count, cudaStream_t s,
+                              int* n_launches) {
+    if (job.R > G_MAXR) return cudaErrorInvalidValue;
+    const bool direct = !labels_in && job.lut == nullptr;
+    const int64_t tiles = ((job.n1 + G_TW - 1) / G_TW) * ((job.n2 + G_TH - 1) / G_TH) * job.n_sheets;
+    if (tiles == 0) return cudaSuccess;
+    int64_t grid = (int64_t)sm_count * 4;
+    if (grid > tiles) grid = tiles;
+    k_generic<<<(unsigned)grid, 256, 0, s>>>(job, labels_in, direct);
+    *n_launches += 1;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ known-category fix-up
+// src/categories.jl:110-112 + src/selectcolors.jl:670-681: a clicked pixel with known
+// category k is labelled (best == k) ? best : 0, skipping the box test.  Sparse (<= a few
+// hundred pixels), so it runs as its own tiny kernel on the categorised plane.
+__global__ void k_known_fixup(MrJob job, int64_t n_known, const int64_t* __restrict__ idx,
+                              const uint8_t* __restrict__ cat, uint8_t* __restrict__ labels,
+                              int64_t labels_stride2) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= n_known) return;
+    const int64_t i = idx[k] % job.n1, j = idx[k] / job.n1;
+    if (cat[k] == 0 || j >= job.n2) return;
+    const uint8_t* p = job.px + j * job.stride2 + i * job.bpp;
+    labels[j * labels_stride2 + i] =
+        (uint8_t)mr_eval_px(job.pal, p[0], p[1], p[2], job.bpp == 4 ? p[3] : 255, job.bpp == 4, cat[k]);
+}
+
+cudaError_t mr_launch_known_fixup(const MrJob& job, int64_t n_known, const int64_t* idx,
+                                  const uint8_t* cat, uint8_t* labels, int64_t labels_stride2,
+                                  cudaStream_t s, int* n_launches) {
+    if (n_known <= 0) return cudaSuccess;
+    k_known_fixup<<<(unsigned)((n_known + 127) / 128), 128, 0, s>>>(job, n_known, idx, cat, labels,
+                                                                     labels_stride2);
+    *n_launches += 1;
+    return cudaGetLastError();
+}

@@ -1,0 +1,57 @@
+// mr_internal.h -- shared declarations between the kernel and API translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define MR_LUT_SIZE (1u << 24)      // exact per-colour label table, index r | g<<8 | b<<16
+#define MR_COARSE_SIZE (1u << 15)   // 32^3 cells of 8^3 colours; 0xFF = mixed cell
+#define MR_MIXED 0xFFu
+
+// Device-resident palette (global memory; read uniformly -> broadcast loads).
+struct MrPalette {
+    const double* mean;   // K x C
+    const double* lo;     // K x C
+    const double* hi;     // K x C
+    const double* lin;    // 256-entry sRGB inverse companding table (Lab only)
+    int K;
+    int C;                // 3 | 4
+    int colourspace;      // 0 RGB | 1 Lab
+};
+
+struct MrCountersDev {
+    unsigned long long n_pixels, n_nomatch, n_fine, n_changed;
+};
+
+// One fused launch = n_sheets independent sheets (a band is one sheet with halos).
+struct MrJob {
+    const uint8_t* px;        // line 0 of sheet 0
+    uint8_t* out;             // line 0 of sheet 0
+    int64_t n1, n2;
+    int64_t stride2;          // bytes between input lines
+    int64_t out_stride2;
+    int64_t sheet_stride;     // bytes between sheets (input)
+    int64_t out_sheet_stride;
+    int n_sheets;
+    int bpp;                  // 3 | 4 (fused) ; 1 for label input (clean only)
+    int R;
+    int halo_lo, halo_hi;     // real lines available outside [0, n2)
+    const uint8_t* lut;       // 2^24 exact table (nullptr when direct evaluation is used)
+    const uint8_t* coarse;    // 2^15 coarse table
+    MrPalette pal;
+    MrCountersDev* counters;  // nullptr = do not count
+};
+
+cudaError_t mr_launch_build_lut(const MrPalette& pal, uint8_t* lut, uint8_t* coarse, cudaStream_t s,
+                                int* n_launches);
+cudaError_t mr_launch_generic(const MrJob& job, bool labels_in, int sm_count, cudaStream_t s,
+                              int* n_launches);
+// Fast path (packed RGB, 16-byte aligned lines, R in 0..3).  Returns cudaErrorNotSupported
+// when the job does not qualify (caller then uses the generic kernel).
+cudaError_t mr_launch_fast(const MrJob& job, int sm_count, cudaStream_t s, int* n_launches);
+bool mr_fast_supported(const MrJob& job);
+cudaError_t mr_launch_known_fixup(const MrJob& job, int64_t n_known, const int64_t* idx,
+                                  const uint8_t* cat, uint8_t* labels, int64_t labels_stride2,
+                                  cudaStream_t s, int* n_launches);
+cudaError_t mr_launch_synth(uint32_t seed, uint32_t sheet, int K, const uint8_t* pal_dev, int64_t n1,
+                            int64_t line0, int64_t nlines, int mode, uint8_t* out, int64_t out_stride2,
+                            cudaStream_t s, int* n_launches);

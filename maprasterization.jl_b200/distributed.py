@@ -1,0 +1,62 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink on the GPU box,
+gloo in the CPU tests).  SURVEY.md 8(e):
+
+  * a large sheet is split into contiguous bands over the slow axis n2 ("row bands"); the only
+    data-path exchange is the R clean-window halo lines of packed RGB between band neighbours
+    (grouped isend/irecv = ncclSend/ncclRecv), after which every rank runs ONE fused launch;
+  * a batch of sheets (config 5) is split into whole sheets per rank, no communication.
+
+The reference has no distributed code at all (single-threaded Julia); this module only exists
+for the new path.  Band buffers have shape (R + nb + R, n1, bpp): own lines in the middle, halo
+slots at both ends, so received halos land exactly where the kernel reads them.
+"""
+import torch
+import torch.distributed as dist
+
+
+def band_range(n2, world, rank):
+    """Lines [a, b) owned by `rank` (balanced contiguous split of the slow axis)."""
+    return (rank * n2) // world, ((rank + 1) * n2) // world
+
+
+def sheet_range(n_sheets, world, rank):
+    return (rank * n_sheets) // world, ((rank + 1) * n_sheets) // world
+
+
+def alloc_band(n1, nb, R, bpp=3, device="cuda"):
+    """Band buffer with halo slots; `own` is the view of the rank's own lines."""
+    buf = torch.empty((nb + 2 * R, n1, bpp), dtype=torch.uint8, device=device)
+    return buf, buf[R:R + nb]
+
+
+def exchange_halos(buf, R, rank=None, world=None, group=None):
+    """Fill the halo slots of `buf` with the neighbours' edge lines.  Returns (halo_lo, halo_hi):
+    the number of real lines now readable before / after the own lines (0 at the sheet border)."""
+    rank = dist.get_rank(group) if rank is None else rank
+    world = dist.get_world_size(group) if world is None else world
+    nb = buf.shape[0] - 2 * R
+    if R == 0 or world == 1:
+        return 0, 0
+    if nb < R:
+        raise ValueError(f"band of {nb} lines is thinner than the window radius {R}")
+    ops = []
+    if rank > 0:
+        ops.append(dist.P2POp(dist.isend, buf[R:2 * R].contiguous(), rank - 1, group))
+        ops.append(dist.P2POp(dist.irecv, buf[0:R], rank - 1, group))
+    if rank < world - 1:
+        ops.append(dist.P2POp(dist.isend, buf[nb:nb + R].contiguous(), rank + 1, group))
+        ops.append(dist.P2POp(dist.irecv, buf[nb + R:nb + 2 * R], rank + 1, group))
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+    return (R if rank > 0 else 0), (R if rank < world - 1 else 0)
+
+
+def categorize_clean_band(ctx, buf, R, out, rank=None, world=None, group=None, stream=0):
+    """Halo exchange + one fused launch on this rank's band.  buf: (R+nb+R, n1, bpp) uint8 CUDA
+    tensor, out: (nb, n1) uint8 CUDA tensor.  Asynchronous on `stream` (after the exchange)."""
+    nb = buf.shape[0] - 2 * R
+    n1, bpp = buf.shape[1], buf.shape[2]
+    halo_lo, halo_hi = exchange_halos(buf, R, rank, world, group)
+    own = buf[R:R + nb]
+    ctx.categorize_clean_dev(own, n1, nb, n1 * bpp, bpp, R, out, n1, halo_lo, halo_hi, stream)
+    return halo_lo, halo_hi

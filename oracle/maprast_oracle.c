@@ -1,0 +1,348 @@
+/*
+ * maprast_oracle.c -- CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
+ * See maprast_oracle.h for scope and parity status.  Build: oracle/Makefile
+ * (gcc -O2 -ffp-contract=off -fopenmp): every Float64 operation below is an
+ * individually rounded IEEE-754 binary64 operation, no FMA, no reassociation,
+ * exactly as Julia executes the reference.
+ *
+ * Each function cites the reference file:line (under /root/reference) it follows.
+ */
+#include "maprast_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+int mro_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+static int clamp_threads(int nthreads) {
+    int m = mro_max_threads();
+    if (nthreads <= 0 || nthreads > m) nthreads = m;
+    return nthreads;
+}
+
+/* ---- src/categories.jl:131-133: (s.min - s.sd * tol), (s.max + s.sd * tol) ---- */
+void mro_bounds(int n, const double* mn, const double* mx, const double* sd,
+                const double* tol, double* lo, double* hi) {
+    for (int i = 0; i < n; ++i) {
+        volatile double w = sd[i] * tol[i];   /* rounded product first */
+        lo[i] = mn[i] - w;
+        hi[i] = mx[i] + w;
+    }
+}
+
+/* ---- src/categories.jl:28-30: (mean, minimum, maximum, std) ; std = sample sd (n-1).
+ * Summation is a plain left-to-right loop (Julia's pairwise/@simd order is not
+ * reproducible here: SURVEY Appendix C.5 -- stats are host-side inputs anyway). ---- */
+void mro_component_stats(const double* v, int n, double out4[4]) {
+    double s = 0.0, mn = v[0], mx = v[0];
+    for (int i = 0; i < n; ++i) {
+        s += v[i];
+        if (v[i] < mn) mn = v[i];
+        if (v[i] > mx) mx = v[i];
+    }
+    double mean = s / (double)n;
+    double ss = 0.0;
+    for (int i = 0; i < n; ++i) {
+        double d = v[i] - mean;
+        ss += d * d;
+    }
+    out4[0] = mean;
+    out4[1] = mn;
+    out4[2] = mx;
+    out4[3] = (n > 1) ? sqrt(ss / (double)(n - 1)) : NAN;
+}
+
+/* ---- Appendix A.0: Float64(::N0f8) adopted as the correctly rounded i/255.0 ---- */
+double mro_n0f8(int i) { return (double)i / 255.0; }
+
+/* ---- Appendix A.4 (extension, no reference body): hand-written FMA-free cbrt ----
+ * Bit-hack seed on the high word, then five Newton steps y <- (2y + t/y^2)/3,
+ * each step a fixed sequence of IEEE mul/div/add.  Valid for t > 0 normal. */
+double mro_cbrt(double t) {
+    uint64_t bits;
+    memcpy(&bits, &t, 8);
+    uint32_t hi = (uint32_t)(bits >> 32);
+    hi = hi / 3u + 715094163u;
+    bits = (uint64_t)hi << 32;
+    double y;
+    memcpy(&y, &bits, 8);
+    for (int it = 0; it < 5; ++it) {
+        double yy = y * y;
+        double q = t / yy;
+        double s = y + y;
+        s = s + q;
+        y = s / 3.0;
+    }
+    return y;
+}
+
+static double g_lin[256];
+static int g_lin_ready = 0;
+static void init_lin(void) {
+    if (g_lin_ready) return;
+#pragma omp critical(mro_lin)
+    {
+        if (!g_lin_ready) {
+            for (int i = 0; i < 256; ++i) {
+                double v = (double)i / 255.0;
+                g_lin[i] = (v <= 0.04045) ? v / 12.92 : pow((v + 0.055) / 1.055, 2.4);
+            }
+            g_lin_ready = 1;
+        }
+    }
+}
+
+static double lab_f(double v) {
+    const double eps = 216.0 / 24389.0;
+    const double kappa = 24389.0 / 27.0;
+    if (v > eps) return mro_cbrt(v);
+    double t = kappa * v;
+    t = t + 16.0;
+    return t / 116.0;
+}
+
+/* sRGB (D65) -> CIE L*a*b*, constants as remembered from Colors.jl
+ * ("unverified against Colors.jl"). */
+void mro_rgb8_to_lab(int r8, int g8, int b8, double lab[3]) {
+    init_lin();
+    double r = g_lin[r8], g = g_lin[g8], b = g_lin[b8];
+    double X = (0.4124564390896921 * r + 0.357576077643909 * g) + 0.18043748326639894 * b;
+    double Y = (0.21267285140562248 * r + 0.715152155287818 * g) + 0.07217499330655958 * b;
+    double Z = (0.019333895582329317 * r + 0.119192025881303 * g) + 0.9503040785363677 * b;
+    double fx = lab_f(X / 0.95047);
+    double fy = lab_f(Y / 1.0);
+    double fz = lab_f(Z / 1.08883);
+    lab[0] = 116.0 * fy - 16.0;
+    lab[1] = 500.0 * (fx - fy);
+    lab[2] = 200.0 * (fy - fz);
+}
+
+/* ---- src/categories.jl:76-82 (argmin + accept), :91-95 (distance),
+ *      :106-121,131-133 (box test / known override / alpha rule) ---- */
+int mro_categorize_f64(const double* x, int C, int K, const double* mean,
+                       const double* lo, const double* hi, int known) {
+    int best = 0;
+    double beste = 0.0;
+    for (int c = 0; c < K; ++c) {
+        const double* m = mean + (int64_t)c * C;
+        /* categories.jl:92-94: sum(map((v - mean)^2)) over (r,g,b[,alpha]), left fold */
+        double d0 = x[0] - m[0], d1 = x[1] - m[1], d2 = x[2] - m[2];
+        double q0 = d0 * d0, q1 = d1 * d1, q2 = d2 * d2;
+        double e = q0 + q1;
+        e = e + q2;
+        if (C == 4) {
+            double d3 = x[3] - m[3];
+            double q3 = d3 * d3;
+            e = e + q3;
+        }
+        /* categories.jl:86: mean over the 1-tuple of matched properties = e/1 (exact).
+         * categories.jl:80: findmin -> first minimum (strict <). */
+        if (c == 0 || e < beste) { beste = e; best = c; }
+    }
+    /* categories.jl:110-112: known-category override skips the box test */
+    if (known != 0) return (best + 1 == known) ? best + 1 : 0;
+    /* categories.jl:116: transparent pixel never matches */
+    if (C == 4 && x[3] == 0.0) return 0;
+    /* categories.jl:119-121,131-133: box on r,g,b of the winner only; NaN -> false */
+    const double* l = lo + (int64_t)best * C;
+    const double* h = hi + (int64_t)best * C;
+    for (int ch = 0; ch < 3; ++ch)
+        if (!(x[ch] >= l[ch] && x[ch] <= h[ch])) return 0;
+    return best + 1;
+}
+
+int mro_categorize_px(const uint8_t* px, int bpp, int channels, int colourspace, int K,
+                      const double* mean, const double* lo, const double* hi, int known) {
+    double x[4];
+    if (colourspace == MRO_LAB) {
+        mro_rgb8_to_lab(px[0], px[1], px[2], x);
+        /* transparent pixel rule still applies to RGBA storage */
+        if (bpp == 4 && px[3] == 0 && known == 0) return 0;
+        return mro_categorize_f64(x, 3, K, mean, lo, hi, known);
+    }
+    x[0] = mro_n0f8(px[0]);
+    x[1] = mro_n0f8(px[1]);
+    x[2] = mro_n0f8(px[2]);
+    if (bpp == 4) {
+        x[3] = mro_n0f8(px[3]);
+        if (channels == 4) return mro_categorize_f64(x, 4, K, mean, lo, hi, known);
+        if (px[3] == 0 && known == 0) return 0;
+    }
+    return mro_categorize_f64(x, 3, K, mean, lo, hi, known);
+}
+
+/* ---- src/categories.jl:68-72: map over all pixels (non-segmented branch) ---- */
+void mro_categorize_u8(const uint8_t* px, int64_t n1, int64_t n2, int64_t stride2,
+                       int bpp, int channels, int colourspace, int K,
+                       const double* mean, const double* lo, const double* hi,
+                       int64_t n_known, const int64_t* known_idx, const uint8_t* known_cat,
+                       uint8_t* out, int64_t out_stride2, int nthreads) {
+    nthreads = clamp_threads(nthreads);
+    init_lin();
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+    for (int64_t j = 0; j < n2; ++j) {
+        const uint8_t* line = px + j * stride2;
+        uint8_t* o = out + j * out_stride2;
+        for (int64_t i = 0; i < n1; ++i)
+            o[i] = (uint8_t)mro_categorize_px(line + i * bpp, bpp, channels, colourspace, K,
+                                              mean, lo, hi, 0);
+    }
+    /* src/selectcolors.jl:670-681 known plane: linear index = i + j*n1 (0-based) */
+    for (int64_t k = 0; k < n_known; ++k) {
+        int64_t i = known_idx[k] % n1, j = known_idx[k] / n1;
+        if (known_cat[k] == 0) continue;
+        out[j * out_stride2 + i] = (uint8_t)mro_categorize_px(
+            px + j * stride2 + i * bpp, bpp, channels, colourspace, K, mean, lo, hi, known_cat[k]);
+    }
+}
+
+void mro_build_lut(int colourspace, int K, const double* mean, const double* lo,
+                   const double* hi, uint8_t* lut, int nthreads) {
+    nthreads = clamp_threads(nthreads);
+    init_lin();
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+    for (int b = 0; b < 256; ++b)
+        for (int g = 0; g < 256; ++g)
+            for (int r = 0; r < 256; ++r) {
+                uint8_t p[3] = {(uint8_t)r, (uint8_t)g, (uint8_t)b};
+                lut[(size_t)r | ((size_t)g << 8) | ((size_t)b << 16)] =
+                    (uint8_t)mro_categorize_px(p, 3, 3, colourspace, K, mean, lo, hi, 0);
+            }
+}
+
+/* ---- SURVEY Appendix A.3 (north_star-defined; conventions from src/clean.jl:21-22
+ * (findmax => first/lowest on ties), :96,121 (0 is an ordinary label here),
+ * src/blur.jl:6 (Window{R} includes the centre, side 2R+1)).  Naive histogram. ---- */
+void mro_majority(const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2,
+                  int R, int tie_rule, int64_t halo_lo, int64_t halo_hi,
+                  uint8_t* out, int64_t out_stride2, int nthreads) {
+    nthreads = clamp_threads(nthreads);
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+    for (int64_t j = 0; j < n2; ++j) {
+        for (int64_t i = 0; i < n1; ++i) {
+            int cnt[256];
+            int maxl = 0;
+            memset(cnt, 0, sizeof(cnt));
+            for (int64_t dj = -R; dj <= R; ++dj) {
+                int64_t jj = j + dj;
+                if (jj < -halo_lo || jj >= n2 + halo_hi) continue;
+                const uint8_t* line = labels + jj * stride2;
+                for (int64_t di = -R; di <= R; ++di) {
+                    int64_t ii = i + di;
+                    if (ii < 0 || ii >= n1) continue;
+                    int l = line[ii];
+                    cnt[l]++;
+                    if (l > maxl) maxl = l;
+                }
+            }
+            /* first maximum in label order = lowest label on ties (findmax, clean.jl:21-22) */
+            int best = 0, bc = cnt[0];
+            for (int l = 1; l <= maxl; ++l)
+                if (cnt[l] > bc) { bc = cnt[l]; best = l; }
+            if (tie_rule == MRO_TIE_CENTRE_IF_MODAL) {
+                int c = labels[j * stride2 + i];
+                if (cnt[c] == bc) best = c;
+            }
+            out[j * out_stride2 + i] = (uint8_t)best;
+        }
+    }
+}
+
+void mro_categorize_clean(const uint8_t* px, int64_t n1, int64_t n2, int64_t stride2,
+                          int bpp, int channels, int colourspace, int K,
+                          const double* mean, const double* lo, const double* hi,
+                          int R, int tie_rule, uint8_t* out, int64_t out_stride2,
+                          int nthreads) {
+    if (R <= 0) {
+        mro_categorize_u8(px, n1, n2, stride2, bpp, channels, colourspace, K, mean, lo, hi,
+                          0, 0, 0, out, out_stride2, nthreads);
+        return;
+    }
+    uint8_t* tmp = (uint8_t*)malloc((size_t)n1 * (size_t)n2);
+    mro_categorize_u8(px, n1, n2, stride2, bpp, channels, colourspace, K, mean, lo, hi,
+                      0, 0, 0, tmp, n1, nthreads);
+    mro_majority(tmp, n1, n2, n1, R, tie_rule, 0, 0, out, out_stride2, nthreads);
+    free(tmp);
+}
+
+/* ------------------------------------------------------------------------- *
+ * Synthetic scans, SURVEY.md 8(d).  Integer-only (Philox4x32-10 + Irwin-Hall
+ * noise) so the CUDA generator in the product library yields identical bytes.
+ * ------------------------------------------------------------------------- */
+void mro_philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                    uint32_t k0, uint32_t k1, uint32_t out[4]) {
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+static inline int synth_noise(uint32_t w) {
+    int s = (int)(w & 255u) + (int)((w >> 8) & 255u) + (int)((w >> 16) & 255u) + (int)(w >> 24) - 510;
+    /* sigma(sum of 4 U[0,255]) = 147.8; * 333/8192 -> sigma ~ 6 (N0f8 units), rounded */
+    return ((s * 333 + 4096 + (1 << 20)) >> 13) - 128;
+}
+
+static inline int clamp255(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
+
+static void synth_pixel(uint32_t seed, uint32_t sheet, int K, const uint8_t* pal,
+                        int64_t i, int64_t j, int mode, uint8_t* o) {
+    uint32_t w[4];
+    mro_philox4x32((uint32_t)i, (uint32_t)j, 0x50495845u, 0u, seed, sheet, w);
+    if (mode == 1) { /* uniform random RGB: worst case for any colour-table cache */
+        o[0] = (uint8_t)(w[0] & 255u); o[1] = (uint8_t)(w[1] & 255u); o[2] = (uint8_t)(w[2] & 255u);
+        return;
+    }
+    /* Voronoi label field: one jittered site per 64x64 cell, nearest of the 3x3 cells */
+    int64_t ci = i >> 6, cj = j >> 6;
+    int64_t bestd = -1;
+    int idx = 0;
+    for (int di = -1; di <= 1; ++di)
+        for (int dj = -1; dj <= 1; ++dj) {
+            uint32_t s[4];
+            int64_t a = ci + di, b = cj + dj;
+            mro_philox4x32((uint32_t)a, (uint32_t)b, 0x53495445u, 0u, seed, sheet, s);
+            int64_t sx = a * 64 + (int64_t)(s[0] & 63u), sy = b * 64 + (int64_t)(s[1] & 63u);
+            int64_t d = (i - sx) * (i - sx) + (j - sy) * (j - sy);
+            if (bestd < 0 || d < bestd) { bestd = d; idx = (int)(s[2] % (uint32_t)K); }
+        }
+    uint32_t sel = w[3] & 0xFFFFu;
+    if (K > 1 && sel < 1311u) {            /* 2 % speckle: a different palette colour */
+        idx = (int)(((uint32_t)idx + 1u + ((w[3] >> 16) % (uint32_t)(K - 1))) % (uint32_t)K);
+    } else if (sel >= 1311u && sel < 1639u) { /* 0.5 % stray: uniform RGB */
+        o[0] = (uint8_t)(w[0] & 255u); o[1] = (uint8_t)(w[1] & 255u); o[2] = (uint8_t)(w[2] & 255u);
+        return;
+    }
+    for (int ch = 0; ch < 3; ++ch)
+        o[ch] = (uint8_t)clamp255((int)pal[idx * 3 + ch] + synth_noise(w[ch]));
+}
+
+void mro_synth_scan(uint32_t seed, uint32_t sheet_id, int K, const uint8_t* palette_rgb,
+                    int64_t n1, int64_t n2, int64_t line0, int64_t nlines,
+                    int mode, uint8_t* out, int64_t out_stride2, int nthreads) {
+    (void)n2;
+    nthreads = clamp_threads(nthreads);
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+    for (int64_t jj = 0; jj < nlines; ++jj) {
+        uint8_t* o = out + jj * out_stride2;
+        for (int64_t i = 0; i < n1; ++i)
+            synth_pixel(seed, sheet_id, K, palette_rgb, i, line0 + jj, mode, o + 3 * i);
+    }
+}

@@ -1,0 +1,95 @@
+/*
+ * maprast_oracle.h -- CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
+ *
+ * Plain-C restatement of the hot path of rafaqz/MapRasterization.jl
+ * (per-pixel categorise + the north_star-defined Window{R} majority filter).
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this library.  The product library
+ * (libmaprast.so) never links, loads or calls anything in oracle/.
+ *
+ * Parity status (see DESIGN.md "Oracle"):
+ *   - categorise (RGB, Float64):   PINNED by the reference's own four
+ *     known-answer vectors, test/runtests.jl:6-20 (tests/golden/).
+ *   - N0f8 -> Float64 conversion:  parity unpinned (FixedPointNumbers is not
+ *     in /root/reference); adopted: correctly rounded i/255.0.
+ *   - majority ("clean") filter:   parity unpinned (north_star-defined; the
+ *     reference has no window-majority body), SURVEY.md Appendix A.3.
+ *   - Lab variant:                 parity unpinned (extension, Appendix A.4).
+ *
+ * Conventions: image is column-major n1 x n2, n1 is the memory-fast axis
+ * ("line" = n1 contiguous pixels), stride2 = bytes between consecutive lines.
+ * Labels: 0 = no match, 1..K = category.  K <= 255.
+ */
+#ifndef MAPRAST_ORACLE_H
+#define MAPRAST_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { MRO_RGB = 0, MRO_LAB = 1 };
+enum { MRO_TIE_LOWEST = 0, MRO_TIE_CENTRE_IF_MODAL = 1 };
+
+/* categories.jl:131-133 -- lo = min - sd*tol, hi = max + sd*tol (two rounded ops) */
+void mro_bounds(int n, const double* mn, const double* mx, const double* sd,
+                const double* tol_per_entry, double* lo, double* hi);
+
+/* categories.jl:28-30 -- (mean, min, max, sd[n-1]) of n values; n==1 -> sd = NaN */
+void mro_component_stats(const double* v, int n, double out4[4]);
+
+/* categories.jl:76-82 with Float64 colour input (C = 3 or 4 channels).
+ * known != 0 selects the known-category override of categories.jl:110-112. */
+int mro_categorize_f64(const double* x, int C, int K, const double* mean,
+                       const double* lo, const double* hi, int known);
+
+/* correctly rounded i/255.0 table (Appendix A.0) and the sRGB->Lab map (A.4) */
+double mro_n0f8(int i);
+void mro_rgb8_to_lab(int r, int g, int b, double lab[3]);
+double mro_cbrt(double t);
+
+/* one pixel given as bytes; colourspace MRO_RGB|MRO_LAB; bpp 3|4.
+ * For bpp==4 and channels==4 the alpha term joins the distance (categories.jl:92),
+ * alpha==0 forces 0 (categories.jl:116).  known as above. */
+int mro_categorize_px(const uint8_t* px, int bpp, int channels, int colourspace, int K,
+                      const double* mean, const double* lo, const double* hi, int known);
+
+/* whole image (OpenMP over lines).  out_stride2 in bytes. */
+void mro_categorize_u8(const uint8_t* px, int64_t n1, int64_t n2, int64_t stride2,
+                       int bpp, int channels, int colourspace, int K,
+                       const double* mean, const double* lo, const double* hi,
+                       int64_t n_known, const int64_t* known_idx, const uint8_t* known_cat,
+                       uint8_t* out, int64_t out_stride2, int nthreads);
+
+/* full 2^24 label table, index = r | g<<8 | b<<16 */
+void mro_build_lut(int colourspace, int K, const double* mean, const double* lo,
+                   const double* hi, uint8_t* lut, int nthreads);
+
+/* Appendix A.3 majority filter, windows clipped at the image border.
+ * halo_lo/halo_hi: number of real lines available before line 0 / after line
+ * n2-1 of `labels` (used for band-seam tests; 0 for a whole image). */
+void mro_majority(const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2,
+                  int R, int tie_rule, int64_t halo_lo, int64_t halo_hi,
+                  uint8_t* out, int64_t out_stride2, int nthreads);
+
+/* A.5: clean(categorize(img)) computed as two whole-image passes. */
+void mro_categorize_clean(const uint8_t* px, int64_t n1, int64_t n2, int64_t stride2,
+                          int bpp, int channels, int colourspace, int K,
+                          const double* mean, const double* lo, const double* hi,
+                          int R, int tie_rule, uint8_t* out, int64_t out_stride2,
+                          int nthreads);
+
+/* ---- deterministic synthetic scans; integer-only so that the
+ * GPU generator in the product library produces identical bytes. ---- */
+void mro_philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                    uint32_t k0, uint32_t k1, uint32_t out[4]);
+/* lines [line0, line0+nlines) of the n1 x n2 sheet `sheet_id` into out (3 B/px) */
+void mro_synth_scan(uint32_t seed, uint32_t sheet_id, int K, const uint8_t* palette_rgb,
+                    int64_t n1, int64_t n2, int64_t line0, int64_t nlines,
+                    int mode, uint8_t* out, int64_t out_stride2, int nthreads);
+
+int mro_max_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,169 @@
+"""ctypes loader for the CPU ORACLE (test infrastructure, not product code).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module.  It wraps oracle/libmaprast_oracle.so (built by
+oracle/Makefile from oracle/maprast_oracle.c, the plain-C restatement of
+/root/reference/src/categories.jl:76-133 + SURVEY.md Appendix A.3/A.4).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libmaprast_oracle.so")
+
+RGB, LAB = 0, 1
+TIE_LOWEST, TIE_CENTRE_IF_MODAL = 0, 1
+
+_f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_u8p = C.c_void_p
+_i64 = C.c_int64
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "maprast_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        L.mro_bounds.argtypes = [C.c_int, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p]
+        L.mro_component_stats.argtypes = [_f64p, C.c_int, _f64p]
+        L.mro_categorize_f64.argtypes = [_f64p, C.c_int, C.c_int, _f64p, _f64p, _f64p, C.c_int]
+        L.mro_categorize_f64.restype = C.c_int
+        L.mro_n0f8.argtypes = [C.c_int]
+        L.mro_n0f8.restype = C.c_double
+        L.mro_cbrt.argtypes = [C.c_double]
+        L.mro_cbrt.restype = C.c_double
+        L.mro_rgb8_to_lab.argtypes = [C.c_int, C.c_int, C.c_int, _f64p]
+        L.mro_categorize_u8.argtypes = [_u8p, _i64, _i64, _i64, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        _f64p, _f64p, _f64p, _i64, C.c_void_p, C.c_void_p,
+                                        _u8p, _i64, C.c_int]
+        L.mro_build_lut.argtypes = [C.c_int, C.c_int, _f64p, _f64p, _f64p, _u8p, C.c_int]
+        L.mro_majority.argtypes = [_u8p, _i64, _i64, _i64, C.c_int, C.c_int, _i64, _i64,
+                                   _u8p, _i64, C.c_int]
+        L.mro_categorize_clean.argtypes = [_u8p, _i64, _i64, _i64, C.c_int, C.c_int, C.c_int,
+                                           C.c_int, _f64p, _f64p, _f64p, C.c_int, C.c_int,
+                                           _u8p, _i64, C.c_int]
+        L.mro_philox4x32.argtypes = [C.c_uint32] * 6 + [C.c_void_p]
+        L.mro_synth_scan.argtypes = [C.c_uint32, C.c_uint32, C.c_int, _u8p, _i64, _i64, _i64, _i64,
+                                     C.c_int, _u8p, _i64, C.c_int]
+        L.mro_max_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def max_threads():
+    return int(lib().mro_max_threads())
+
+
+def bounds(mn, mx, sd, tol):
+    """lo = min - sd*tol, hi = max + sd*tol (categories.jl:131-133); arrays broadcast to K x C."""
+    mn, mx, sd = _f64(mn), _f64(mx), _f64(sd)
+    tol = _f64(np.broadcast_to(np.asarray(tol, dtype=np.float64).reshape(-1, *([1] * (mn.ndim - 1))), mn.shape))
+    lo, hi = np.empty_like(mn), np.empty_like(mn)
+    lib().mro_bounds(mn.size, mn.ravel(), mx.ravel(), sd.ravel(), tol.ravel(), lo.ravel(), hi.ravel())
+    return lo, hi
+
+
+def component_stats(v):
+    v = _f64(v).ravel()
+    out = np.empty(4, dtype=np.float64)
+    lib().mro_component_stats(v, v.size, out)
+    return out
+
+
+def categorize_f64(x, mean, lo, hi, known=0):
+    x, mean, lo, hi = _f64(x), _f64(mean), _f64(lo), _f64(hi)
+    K, Cn = mean.shape
+    return int(lib().mro_categorize_f64(x, Cn, K, mean, lo, hi, known))
+
+
+def rgb8_to_lab(r, g, b):
+    out = np.empty(3, dtype=np.float64)
+    lib().mro_rgb8_to_lab(int(r), int(g), int(b), out)
+    return out
+
+
+def _img(px):
+    """px: (n2, n1, bpp) uint8 C-contiguous (line-major view of Julia's n1 x n2 column-major)."""
+    px = np.ascontiguousarray(px, dtype=np.uint8)
+    assert px.ndim == 3 and px.shape[2] in (3, 4)
+    return px
+
+
+def categorize_u8(px, mean, lo, hi, colourspace=RGB, channels=3, known_idx=None, known_cat=None,
+                  nthreads=0):
+    px = _img(px)
+    n2, n1, bpp = px.shape
+    mean, lo, hi = _f64(mean), _f64(lo), _f64(hi)
+    out = np.empty((n2, n1), dtype=np.uint8)
+    nk = 0
+    ki = kc = None
+    if known_idx is not None and len(known_idx):
+        ki = np.ascontiguousarray(known_idx, dtype=np.int64)
+        kc = np.ascontiguousarray(known_cat, dtype=np.uint8)
+        nk = ki.size
+    lib().mro_categorize_u8(px.ctypes.data, n1, n2, n1 * bpp, bpp, channels, colourspace,
+                            mean.shape[0], mean, lo, hi, nk,
+                            ki.ctypes.data if nk else None, kc.ctypes.data if nk else None,
+                            out.ctypes.data, n1, nthreads)
+    return out
+
+
+def build_lut(mean, lo, hi, colourspace=RGB, nthreads=0):
+    mean, lo, hi = _f64(mean), _f64(lo), _f64(hi)
+    lut = np.empty(1 << 24, dtype=np.uint8)
+    lib().mro_build_lut(colourspace, mean.shape[0], mean, lo, hi, lut.ctypes.data, nthreads)
+    return lut
+
+
+def majority(labels, R, tie_rule=TIE_LOWEST, halo_lo=0, halo_hi=0, nthreads=0):
+    """labels: (n2 + halo_lo + halo_hi, n1) uint8; returns the (n2, n1) filtered core."""
+    labels = np.ascontiguousarray(labels, dtype=np.uint8)
+    nt, n1 = labels.shape
+    n2 = nt - halo_lo - halo_hi
+    out = np.empty((n2, n1), dtype=np.uint8)
+    base = labels.ctypes.data + halo_lo * n1
+    lib().mro_majority(base, n1, n2, n1, R, tie_rule, halo_lo, halo_hi, out.ctypes.data, n1, nthreads)
+    return out
+
+
+def categorize_clean(px, mean, lo, hi, R, colourspace=RGB, channels=3, tie_rule=TIE_LOWEST, nthreads=0):
+    px = _img(px)
+    n2, n1, bpp = px.shape
+    mean, lo, hi = _f64(mean), _f64(lo), _f64(hi)
+    out = np.empty((n2, n1), dtype=np.uint8)
+    lib().mro_categorize_clean(px.ctypes.data, n1, n2, n1 * bpp, bpp, channels, colourspace,
+                               mean.shape[0], mean, lo, hi, R, tie_rule, out.ctypes.data, n1, nthreads)
+    return out
+
+
+def philox4x32(c, k):
+    out = (C.c_uint32 * 4)()
+    lib().mro_philox4x32(c[0], c[1], c[2], c[3], k[0], k[1], out)
+    return [int(v) for v in out]
+
+
+def synth_scan(seed, sheet_id, palette_rgb, n1, n2, line0=0, nlines=None, mode=0, nthreads=0):
+    pal = np.ascontiguousarray(palette_rgb, dtype=np.uint8)
+    if nlines is None:
+        nlines = n2 - line0
+    out = np.empty((nlines, n1, 3), dtype=np.uint8)
+    lib().mro_synth_scan(seed, sheet_id, pal.shape[0], pal.ctypes.data, n1, n2, line0, nlines,
+                         mode, out.ctypes.data, n1 * 3, nthreads)
+    return out

@@ -1,0 +1,259 @@
+"""GPU (-m gpu): parity of libmaprast.so (called through its C ABI) against the CPU oracle.
+Bit-exact: every comparison is array equality of uint8 labels / bytes; mismatch target is 0."""
+import numpy as np
+import pytest
+import torch
+
+from util import golden_palette, mismatches, random_palette
+
+pytestmark = pytest.mark.gpu
+
+
+def _workload(mr, cfg, colourspace=None):
+    from maprast_b200 import synth
+    seed, pal, stats, spec = synth.config_workload(cfg)
+    return seed, pal, stats, spec
+
+
+def _set(ctx, mr, stats):
+    ctx.set_known(None)
+    ctx.set_palette(stats.mean, stats.lo, stats.hi, mr._lib.LAB if stats.colourspace == "lab" else mr._lib.RGB)
+    ctx.palette = stats
+
+
+def _ocs(oracle, stats):
+    return oracle.LAB if stats.colourspace == "lab" else oracle.RGB
+
+
+# ---------------------------------------------------------------- exhaustive colour sweep
+@pytest.mark.parametrize("cfg", [1, 2, 4])
+def test_exhaustive_2p24_colour_sweep(ctx, mr, oracle, cfg):
+    """all 2^24 colours x benchmark palette, device table vs oracle."""
+    _, _, stats, _ = _workload(mr, cfg)
+    _set(ctx, mr, stats)
+    got = ctx.get_lut()
+    want = oracle.build_lut(stats.mean, stats.lo, stats.hi, _ocs(oracle, stats))
+    assert mismatches(got, want) == 0
+    assert 0 < ctx.palette_build_ms() < 1000
+
+
+def test_exhaustive_sweep_adversarial_palettes(ctx, mr, oracle):
+    from maprast_b200 import synth
+    lat = synth.make_palette(11, 16, "lattice")
+    st = synth.make_stats(11, lat, exact_means=True)          # exact distance ties everywhere
+    _set(ctx, mr, st)
+    assert mismatches(ctx.get_lut(), oracle.build_lut(st.mean, st.lo, st.hi)) == 0
+    rng = np.random.default_rng(5)
+    mean, mn, mx, sd, tol = random_palette(rng, 37, spread=0.3)
+    mean[3] = np.inf                                          # a missing category
+    sd[5] = np.nan                                            # a one-point category
+    pal = mr.Palette(mean, mn, mx, sd, tol)
+    _set(ctx, mr, pal)
+    assert mismatches(ctx.get_lut(), oracle.build_lut(pal.mean, pal.lo, pal.hi)) == 0
+
+
+def test_reference_golden_vectors_on_device(ctx, mr, oracle):
+    """The reference's four known-answer colours are Float64, not N0f8; the nearest N0f8 colours
+    of vectors 3 and 4 (exactly representable cases aside) must agree with the oracle, and the
+    whole golden palette table must match."""
+    mean, mn, mx, sd, tol, vectors = golden_palette()
+    pal = mr.Palette(mean, mn, mx, sd, [tol, tol])
+    _set(ctx, mr, pal)
+    lut = ctx.get_lut()
+    assert mismatches(lut, oracle.build_lut(pal.mean, pal.lo, pal.hi)) == 0
+    for v in vectors:
+        b = [int(round(c * 255)) for c in v["rgb"]]
+        x = [c / 255.0 for c in b]
+        assert lut[b[0] | b[1] << 8 | b[2] << 16] == oracle.categorize_f64(x, pal.mean, pal.lo, pal.hi)
+
+
+# ---------------------------------------------------------------- fused image parity
+@pytest.mark.parametrize("cfg,n1,n2", [(1, 2000, 2000), (2, 1531, 777), (4, 1024, 300), (5, 512, 512)])
+def test_fused_matches_oracle(ctx, mr, oracle, cfg, n1, n2):
+    """config 1 in full; crops (incl. all four borders) of configs 2/4/5."""
+    seed, palrgb, stats, spec = _workload(mr, cfg)
+    _set(ctx, mr, stats)
+    scan = oracle.synth_scan(seed, 0, palrgb, n1, n2)
+    got, cnt = ctx.categorize_clean_host(scan, spec["R"], counters=True)
+    want = oracle.categorize_clean(scan, stats.mean, stats.lo, stats.hi, spec["R"], _ocs(oracle, stats))
+    assert mismatches(got, want) == 0
+    pre = oracle.categorize_u8(scan, stats.mean, stats.lo, stats.hi, _ocs(oracle, stats))
+    assert cnt["n_pixels"] == n1 * n2
+    assert cnt["n_nomatch"] == int((want == 0).sum())
+    assert cnt["n_changed"] == int((want != pre).sum())
+    assert cnt["n_fine"] <= n1 * n2
+
+
+@pytest.mark.parametrize("R", [0, 1, 2, 3, 5, 7])
+@pytest.mark.parametrize("shape", [(1, 1), (1, 9), (9, 1), (3, 5), (16, 16), (17, 31), (130, 67), (257, 129)])
+def test_ragged_and_tiny_shapes(ctx, mr, oracle, R, shape):
+    n1, n2 = shape
+    seed, palrgb, stats, _ = _workload(mr, 2)
+    _set(ctx, mr, stats)
+    scan = oracle.synth_scan(seed + R, 3, palrgb, n1, n2)
+    got = ctx.categorize_clean_host(scan, R)
+    want = oracle.categorize_clean(scan, stats.mean, stats.lo, stats.hi, R)
+    assert mismatches(got, want) == 0
+
+
+def test_empty_inputs(ctx, mr):
+    _, _, stats, _ = _workload(mr, 1)
+    _set(ctx, mr, stats)
+    assert ctx.categorize_clean_host(np.zeros((0, 5, 3), np.uint8), 1).shape == (0, 5)
+    assert ctx.categorize_clean_host(np.zeros((5, 0, 3), np.uint8), 1).shape == (5, 0)
+    assert ctx.clean_host(np.zeros((0, 0), np.uint8), 1).shape == (0, 0)
+
+
+def test_uniform_random_colours_and_lattice(ctx, mr, oracle):
+    """Adversarial sets: worst case for the coarse-cell filter (every colour distinct) and the
+    lattice palette (exact ties)."""
+    from maprast_b200 import synth
+    seed, palrgb, stats, _ = _workload(mr, 2)
+    _set(ctx, mr, stats)
+    scan = oracle.synth_scan(seed, 0, palrgb, 640, 480, mode=1)
+    assert mismatches(ctx.categorize_clean_host(scan, 2),
+                      oracle.categorize_clean(scan, stats.mean, stats.lo, stats.hi, 2)) == 0
+    lat = synth.make_palette(11, 16, "lattice")
+    st = synth.make_stats(11, lat, exact_means=True)
+    _set(ctx, mr, st)
+    scan = oracle.synth_scan(seed, 0, lat, 640, 480)
+    assert mismatches(ctx.categorize_clean_host(scan, 1),
+                      oracle.categorize_clean(scan, st.mean, st.lo, st.hi, 1)) == 0
+
+
+def test_strided_and_unaligned_views(ctx, mr, oracle):
+    seed, palrgb, stats, _ = _workload(mr, 1)
+    _set(ctx, mr, stats)
+    big = oracle.synth_scan(seed, 0, palrgb, 333, 100)
+    view = big[5:90, 7:300]                     # line stride != n1*3, start not 16-byte aligned
+    got = ctx.categorize_clean_host(view, 1)
+    want = oracle.categorize_clean(np.ascontiguousarray(view), stats.mean, stats.lo, stats.hi, 1)
+    assert mismatches(got, want) == 0
+
+
+def test_rgba_direct_path(ctx, mr, oracle):
+    rng = np.random.default_rng(8)
+    mean, mn, mx, sd, tol = random_palette(rng, 5, C=4, spread=0.4)
+    pal = mr.Palette(mean, mn, mx, sd, tol)
+    ctx.set_known(None)
+    ctx.set_palette(pal.mean, pal.lo, pal.hi, mr._lib.RGB, 4)
+    ctx.palette = None
+    px = rng.integers(0, 256, size=(60, 77, 4), dtype=np.uint8)
+    px[::7, ::5, 3] = 0                         # transparent pixels never match (categories.jl:116)
+    got = ctx.categorize_clean_host(px, 1)
+    want = oracle.categorize_clean(px, pal.mean, pal.lo, pal.hi, 1, channels=4)
+    assert mismatches(got, want) == 0
+    with pytest.raises(mr.MapRastError):        # RGB pixels with RGBA statistics
+        ctx.categorize_clean_host(px[..., :3].copy(), 1)
+
+
+def test_known_category_override(ctx, mr, oracle):
+    seed, palrgb, stats, _ = _workload(mr, 1)
+    _set(ctx, mr, stats)
+    n1, n2 = 200, 150
+    scan = oracle.synth_scan(seed, 0, palrgb, n1, n2)
+    rng = np.random.default_rng(2)
+    idx = rng.choice(n1 * n2, size=300, replace=False).astype(np.int64)
+    cat = rng.integers(0, 9, size=300).astype(np.uint8)
+    ctx.set_known(idx, cat)
+    for R in (0, 2):
+        got = ctx.categorize_clean_host(scan, R)
+        pre = oracle.categorize_u8(scan, stats.mean, stats.lo, stats.hi, known_idx=idx, known_cat=cat)
+        want = pre if R == 0 else oracle.majority(pre, R)
+        assert mismatches(got, want) == 0
+    ctx.set_known(None)
+
+
+@pytest.mark.parametrize("R,repeat", [(1, 1), (2, 3), (3, 2), (1, 0), (0, 4)])
+def test_clean_standalone_and_repeat(ctx, mr, oracle, R, repeat):
+    rng = np.random.default_rng(R * 10 + repeat)
+    L = rng.integers(0, 6, size=(90, 141), dtype=np.uint8)
+    L[20:60, 30:100] = 3
+    want = L.copy()
+    for _ in range(repeat if R > 0 else 0):
+        want = oracle.majority(want, R)
+    assert mismatches(ctx.clean_host(L, R, repeat), want) == 0
+    assert mr.clean(L, hood=mr.Window(R), repeat=repeat, ctx=ctx).dtype == np.int64
+
+
+def test_reference_shaped_api(ctx, mr, oracle):
+    """categorize(img, points; tolerances, match) -> Int labels, like _categorize (categories.jl:49-74)."""
+    seed, palrgb, _, _ = _workload(mr, 1)
+    n1, n2 = 160, 120
+    scan = oracle.synth_scan(seed, 0, palrgb, n1, n2)
+    rng = np.random.default_rng(4)
+    points = [[(float(rng.integers(1, n1 + 1)), float(rng.integers(1, n2 + 1))) for _ in range(12)] for _ in range(4)]
+    points.append([])                                       # a category without points: `missing`
+    tol = [2.0, 1.0, 3.5, 0.5, 2.0]
+    pal = mr.Palette.from_points(scan, points, tol)
+    want_pre = oracle.categorize_u8(scan, pal.mean, pal.lo, pal.hi)
+    got = mr.categorize(scan, points, tolerances=tol, ctx=ctx)
+    assert got.dtype == np.int64 and got.shape == (n2, n1) and mismatches(got, want_pre) == 0
+    got2 = mr.categorize_clean(scan, points, tolerances=tol, hood=mr.Window(2), ctx=ctx)
+    assert mismatches(got2, oracle.majority(want_pre, 2)) == 0
+    # known-category plane from the clicked points (selectcolors.jl:670-681)
+    got3 = mr.categorize_u8(scan, points, tolerances=tol, use_known=True, ctx=ctx)
+    idx, cat = mr.api._known_from_points(points, n1)
+    want3 = oracle.categorize_u8(scan, pal.mean, pal.lo, pal.hi, known_idx=idx, known_cat=cat)
+    assert mismatches(got3, want3) == 0
+
+
+# ---------------------------------------------------------------- device API: bands, batch, synth
+def test_device_bands_equal_whole(ctx, mr, oracle):
+    """band-sharded launches (with halos) are byte-identical to one launch."""
+    seed, palrgb, stats, spec = _workload(mr, 2)
+    _set(ctx, mr, stats)
+    n1, n2, R = 1000, 403, 2
+    scan = oracle.synth_scan(seed, 0, palrgb, n1, n2)
+    want = oracle.categorize_clean(scan, stats.mean, stats.lo, stats.hi, R)
+    d = torch.from_numpy(scan).cuda()
+    whole = torch.empty((n2, n1), dtype=torch.uint8, device="cuda")
+    ctx.categorize_clean_dev(d, n1, n2, n1 * 3, 3, R, whole, n1)
+    banded = torch.empty_like(whole)
+    for k in range(5):
+        a, b = mr.distributed.band_range(n2, 5, k)
+        ctx.categorize_clean_dev(d[a:], n1, b - a, n1 * 3, 3, R, banded[a:], n1,
+                                 halo_lo=min(R, a), halo_hi=min(R, n2 - b))
+    torch.cuda.synchronize()
+    assert mismatches(whole.cpu().numpy(), want) == 0
+    assert torch.equal(whole, banded)
+
+
+def test_batch_of_sheets(ctx, mr, oracle):
+    seed, palrgb, stats, spec = _workload(mr, 5)
+    _set(ctx, mr, stats)
+    n1 = n2 = 256
+    sheets = np.stack([oracle.synth_scan(seed, s, palrgb, n1, n2) for s in range(5)])
+    d = torch.from_numpy(sheets).cuda()
+    out = torch.empty((5, n2, n1), dtype=torch.uint8, device="cuda")
+    ctx.batch_categorize_clean_dev(5, d, n1 * n2 * 3, n1, n2, n1 * 3, 3, 2, out, n1 * n2, n1)
+    torch.cuda.synchronize()
+    for s in range(5):   # independent sheets: no bleeding across sheet borders
+        want = oracle.categorize_clean(sheets[s], stats.mean, stats.lo, stats.hi, 2)
+        assert mismatches(out[s].cpu().numpy(), want) == 0
+
+
+def test_device_synth_matches_oracle_bytes(ctx, mr, oracle):
+    seed, palrgb, _, _ = _workload(mr, 2)
+    n1, n2 = 700, 300
+    for mode in (0, 1):
+        d = torch.empty((100, n1, 3), dtype=torch.uint8, device="cuda")
+        ctx.synth_scan_dev(seed, 2, palrgb, n1, n2, 150, 100, d, n1 * 3, mode=mode)
+        want = oracle.synth_scan(seed, 2, palrgb, n1, n2, line0=150, nlines=100, mode=mode)
+        assert np.array_equal(d.cpu().numpy(), want)
+
+
+def test_argument_errors(ctx, mr):
+    _, _, stats, _ = _workload(mr, 1)
+    _set(ctx, mr, stats)
+    with pytest.raises(mr.MapRastError):
+        ctx.categorize_clean_host(np.zeros((4, 4, 3), np.uint8), 9)           # R too large
+    with pytest.raises(mr.MapRastError):
+        ctx.set_palette(np.full((2, 3), np.inf), np.zeros((2, 3)), np.ones((2, 3)))   # all missing
+    with pytest.raises(mr.MapRastError):
+        ctx.set_palette(np.zeros((300, 3)), np.zeros((300, 3)), np.ones((300, 3)))    # K > 254
+    fresh = mr.Context(0)
+    with pytest.raises(mr.MapRastError, match="mr_set_palette"):
+        fresh.categorize_clean_host(np.zeros((4, 4, 3), np.uint8), 1)
+    fresh.close()
+    _set(ctx, mr, stats)

@@ -1,0 +1,90 @@
+"""CPU: host-side logic of the reference-interface mirror and the C-ABI surface (no compute)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(mr):
+    hdr = open(os.path.join(ROOT, "include", "maprast.h")).read()
+    declared = sorted(set(re.findall(r"\b(mr_[a-z_0-9]+)\s*\(", hdr)))
+    assert declared, "no declarations parsed"
+    L = C.CDLL(mr.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), f"libmaprast.so does not export {name}"
+    assert sorted(mr._lib.SYMBOLS) == declared
+    assert mr._lib.load().mr_version() >= 100
+
+
+def test_no_cpu_fallback_without_gpu(mr):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(mr.MapRastError, match="no usable CUDA device"):
+        mr.Context(0)
+    img = np.zeros((4, 4, 3), dtype=np.uint8)
+    pal = mr.Palette([[0.5] * 3], [[0.4] * 3], [[0.6] * 3], [[0.1] * 3])
+    with pytest.raises(mr.MapRastError):
+        mr.categorize(img, pal)
+
+
+def test_palette_bounds_match_oracle(mr, oracle):
+    rng = np.random.default_rng(0)
+    mean, mn, mx, sd, tol = __import__("util").random_palette(rng, 9)
+    pal = mr.Palette(mean, mn, mx, sd, tol)
+    lo, hi = oracle.bounds(mn, mx, sd, tol)
+    assert np.array_equal(pal.lo, lo) and np.array_equal(pal.hi, hi)
+    assert pal.K == 9 and pal.channels == 3
+    assert np.array_equal(mr.Palette(mean, mn, mx, sd).tolerances, np.full(9, 2.0))   # selectcolors.jl:1
+
+
+def test_component_stats_and_from_points(mr, oracle):
+    rng = np.random.default_rng(1)
+    img = rng.integers(0, 256, size=(20, 30, 3), dtype=np.uint8)   # n2=20, n1=30
+    # 1-based (i, j) points; 2.5 rounds to 2, 3.5 to 4 (Julia round(Int, x): ties to even)
+    pts = [[(2.5, 3.5), (10.2, 7.9), (30.0, 20.0)], [], [(1.0, 1.0)]]
+    pal = mr.Palette.from_points(img, pts)
+    samples = np.stack([img[4 - 1, 2 - 1], img[8 - 1, 10 - 1], img[20 - 1, 30 - 1]]).astype(np.float64) / 255.0
+    for ch in range(3):
+        st = oracle.component_stats(samples[:, ch])
+        assert np.allclose([pal.mean[0, ch], pal.min[0, ch], pal.max[0, ch], pal.sd[0, ch]], st, rtol=1e-15, atol=0)
+    assert np.all(np.isinf(pal.mean[1]))                 # `missing` category
+    assert np.all(np.isnan(pal.sd[2])) and np.all(np.isnan(pal.lo[2]))   # one point -> sd NaN
+    with pytest.raises(IndexError):
+        mr.Palette.from_points(img, [[(31.0, 1.0)]])
+
+
+def test_unsupported_options_raise(mr):
+    img = np.zeros((4, 4, 3), dtype=np.uint8)
+    pal = mr.Palette([[0.5] * 3], [[0.4] * 3], [[0.6] * 3], [[0.1] * 3])
+    with pytest.raises(ValueError, match="match"):
+        mr.categorize(img, pal, match=("color", "std", "stripe"))
+    with pytest.raises(ValueError, match="segmented"):
+        mr.categorize(img, pal, segmented=True)
+    with pytest.raises(ValueError, match="uint8"):
+        mr.categorize(img.astype(np.float64), pal)
+    with pytest.raises(ValueError):
+        mr.clean(np.zeros((3, 3)))
+    with pytest.raises(ValueError):
+        mr.Window(-1)
+    with pytest.raises(ValueError):
+        mr.Palette([[0.5] * 3], [[0.4] * 3], [[0.6] * 3], [[0.1] * 3], tolerances=[1.0, 2.0])
+
+
+def test_workload_definitions(mr):
+    from maprast_b200 import synth
+    for cfg, spec in synth.CONFIGS.items():
+        seed, pal, stats, spec = synth.config_workload(cfg)
+        assert seed == 0x4D520000 + cfg and pal.shape == (spec["K"], 3) and stats.K == spec["K"]
+        d = ((pal[:, None].astype(int) - pal[None].astype(int)) ** 2).sum(-1)
+        np.fill_diagonal(d, 1 << 30)
+        assert np.sqrt(d.min()) >= 24            # min pairwise distance >= 24/255
+        assert np.all(np.isfinite(stats.lo)) and np.all(stats.lo < stats.hi)
+    lat = synth.make_palette(7, 16, "lattice")
+    assert set(np.unique(lat)) <= {32, 96, 160, 224}
+    st = synth.make_stats(7, lat, exact_means=True)
+    assert np.array_equal(st.mean, lat / 255.0)
