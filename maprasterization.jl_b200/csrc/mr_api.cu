@@ -272,7 +272,7 @@ static MrJob make_job(mr_ctx* ctx, const uint8_t* px, uint8_t* out, int64_t n1, 
     MrJob j{};
     j.px = px; j.out = out; j.n1 = n1; j.n2 = n2; j.stride2 = stride2; j.out_stride2 = out_stride2;
     j.sheet_stride = 0; j.out_sheet_stride = 0; j.n_sheets = 1; j.bpp = bpp; j.R = R;
-    j.halo_lo = halo_lo; j.halo_hi = halo_hi;
+    j.halo_lo = halo_lo; j.halo_hi = halo_hi; j.padded = 0;
     j.lut = (bpp == 3 && ctx->lut_valid) ? ctx->d_lut : nullptr;
     j.coarse = ctx->d_coarse;
     j.pal = ctx->pal;
@@ -458,6 +458,7 @@ static int host_impl(mr_ctx* ctx, const char* fn, const uint8_t* px, int64_t n1,
         if (e != cudaSuccess) { rc = fail_cuda(ctx, e, "stream wait"); break; }
         MrJob job = make_job(ctx, d_own + a * line_in, ctx->d_out + a * line_out, n1, b - a, line_in, bpp,
                              R, hl, hh, line_out);
+        job.padded = 1;   // d_in / d_out lines are padded to 16 bytes by construction
         rc = (ctx->n_known > 0) ? run_with_known(ctx, job, ctx->s_main) : run_fused(ctx, job, ctx->s_main);
         if (rc) break;
         e = cudaEventRecord(ctx->ev_done[c], ctx->s_main);

@@ -35,6 +35,7 @@ struct MrJob {
     int bpp;                  // 3 | 4 (fused) ; 1 for label input (clean only)
     int R;
     int halo_lo, halo_hi;     // real lines available outside [0, n2)
+    int padded;               // in/out lines are readable/writable up to the next multiple of 16 bytes
     const uint8_t* lut;       // 2^24 exact table (nullptr when direct evaluation is used)
     const uint8_t* coarse;    // 2^15 coarse table
     MrPalette pal;
