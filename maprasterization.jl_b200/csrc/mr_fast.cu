@@ -64,13 +64,15 @@ struct Smem {
     uint8_t* stage;     // [NWARPS][1024]
     uint16_t* sent;     // codes slot<<10 | wx
     uint16_t* fb;
-    int* misc;          // [0] n_sent [1] n_fb [2] item [3] fb overflow [8 .. 8+RING) line of slot
+    uint16_t* w2code;   // round-2 word list: slot<<5 | vote lane
+    uint32_t* w2mask;   //                    undecided pixels of that word
+    int* misc;          // [0] n_sent [1] n_fb [2] item [3] fb overflow [4] n_w2 [8 .. 8+RING) line of slot
 };
 
 template <int R, int NB>
 __host__ __device__ constexpr size_t smem_bytes() {
     return MR_COARSE_SIZE + (size_t)(TH + 2 * R) * (R > 0 ? NB : 0) * 128 + (size_t)(TH + 2 * R) * 1024 +
-           (R > 0 ? NWARPS * 1024 : 0) + SENT_CAP * 2 + FB_CAP * 2 + (8 + TH + 2 * R) * 4 + 16;
+           (R > 0 ? NWARPS * 1024 : 0) + SENT_CAP * 2 + FB_CAP * 2 + TH * 32 * 6 + (8 + TH + 2 * R) * 4 + 16;
 }
 
 __device__ __forceinline__ uint4 ldg16(const uint8_t* p) {
@@ -213,37 +215,65 @@ __device__ __forceinline__ void categorize_line(const FastParams& P, const Smem&
 }
 
 // ---------------------------------------------------------------------------------------------
-// exact vote of one pixel from the pristine byte ring (phase C / overflow path)
-template <int R>
+// exact vote of one pixel (phase C): plane words of the pixel's vote word, one popcount pass per
+// distinct label in the window; stops as soon as no unseen label can still win or tie.
+template <int R, int NB>
 __device__ __forceinline__ unsigned exact_vote(const Smem& S, int slot_of_y, int wx, int ring) {
+    using G = Geo<R>;
     constexpr int SIDE = 2 * R + 1;
-    int best = 0x100, bc = 0;
-    unsigned prev = VOIDB;
-    for (int a = 0; a < SIDE * SIDE; ++a) {
-        const int ay = a / SIDE, ax = a - ay * SIDE;
-        int sl = slot_of_y + ay - R; sl += (sl < 0) ? ring : 0; sl -= (sl >= ring) ? ring : 0;
-        const unsigned c = S.bytes[sl * 1024 + wx + ax - R];
-        if (c == VOIDB || c == prev) continue;
-        prev = c;
-        if ((int)c == best) continue;
-        int cnt = 0;
-        for (int by = 0; by < SIDE; ++by) {
-            int sb = slot_of_y + by - R; sb += (sb < 0) ? ring : 0; sb -= (sb >= ring) ? ring : 0;
-            const uint8_t* row = S.bytes + sb * 1024 + wx - R;
-            for (int bx = 0; bx < SIDE; ++bx) cnt += (row[bx] == c);
+    const int vl = (wx - 32 * G::HW) / G::U;            // vote word that owns wx as an output pixel
+    const int q = wx - G::O0 - vl * G::U;               // bit of the pixel, in [R, R+U)
+    const uint32_t wm = ((1u << SIDE) - 1u) << (q - R);
+    uint32_t Pl[SIDE][NB], rem[SIDE];
+    int left = 0;
+#pragma unroll
+    for (int d = 0; d < SIDE; ++d) {
+        int sl = slot_of_y + d - R; sl += (sl < 0) ? ring : 0; sl -= (sl >= ring) ? ring : 0;
+        uint32_t vd = ~0u;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            Pl[d][b] = S.planes[(sl * NB + b) * 32 + vl];
+            vd &= Pl[d][b];
         }
-        if (cnt > bc || (cnt == bc && (int)c < best)) { bc = cnt; best = (int)c; }
+        rem[d] = wm & ~vd;                               // real (non-VOID) window pixels not yet counted
+        left += __popc(rem[d]);
+    }
+    int best = 0x100, bc = 0;
+#pragma unroll
+    for (int d = 0; d < SIDE; ++d) {
+        while (rem[d] && left >= bc) {
+            const int i = __ffs(rem[d]) - 1;
+            unsigned c = 0;
+            uint32_t L[NB];
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                const uint32_t bit = (Pl[d][b] >> i) & 1u;
+                c |= bit << b;
+                L[b] = 0u - bit;
+            }
+            int cnt = 0;
+#pragma unroll
+            for (int e = 0; e < SIDE; ++e) {
+                uint32_t m = rem[e];
+#pragma unroll
+                for (int b = 0; b < NB; ++b) m &= ~(Pl[e][b] ^ L[b]);
+                cnt += __popc(m);
+                rem[e] &= ~m;
+            }
+            left -= cnt;
+            if (cnt > bc || (cnt == bc && (int)c < best)) { bc = cnt; best = (int)c; }
+        }
     }
     return (unsigned)best;
 }
 
-template <int R, bool COUNT>
+template <int R, int NB, bool COUNT>
 __device__ __forceinline__ void fallback_pixel(const FastParams& P, const Smem& S, uint8_t* out_sheet,
                                                long long xw0, int code, int ring, unsigned& c_nomatch,
                                                unsigned& c_changed) {
     const int slot = code >> 10, wx = code & 1023;
     const int y = S.misc[8 + slot];
-    const unsigned best = exact_vote<R>(S, slot, wx, ring);
+    const unsigned best = exact_vote<R, NB>(S, slot, wx, ring);
     out_sheet[(long long)y * P.job.out_stride2 + xw0 + wx] = (uint8_t)best;
     if (COUNT) {
         c_nomatch += (best == 0);
@@ -274,16 +304,106 @@ __device__ __forceinline__ void store_word(const FastParams& P, uint8_t* dst, lo
 }
 
 // ---------------------------------------------------------------------------------------------
-// phase B: one warp votes one line.  vvalid: output pixels owned by this lane's vote word;
-// avalid: output pixels of this lane's aligned word (for the final store).
+// bit-sliced two-candidate vote of one 32-pixel vote word.  Pl = plane words of lines y-R..y+R.
+// decided: pixels whose mode is certainly the better of {A, B}; selA: that winner is A.
+template <int R, int NB>
+__device__ __forceinline__ void vote_core(const uint32_t (&Pl)[2 * R + 1][NB], unsigned a_lab, unsigned b_lab,
+                                          uint32_t& decided, uint32_t& selA, uint32_t& diff, uint32_t& zero) {
+    using G = Geo<R>;
+    constexpr int SIDE = 2 * R + 1;
+    constexpr int N = SIDE * SIDE;
+    constexpr int WV = G::WV, WC = G::WC;
+    constexpr unsigned VOIDL = (1u << NB) - 1u;
+    const uint32_t nbm = (b_lab != a_lab && b_lab != VOIDL) ? ~0u : 0u;   // B == A -> B's masks are empty
+    const uint32_t avm = (a_lab != VOIDL) ? ~0u : 0u;     // a bitwise majority can alias the VOID code
+    uint32_t LA[NB], LB[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        LA[b] = 0u - ((a_lab >> b) & 1u);
+        LB[b] = 0u - ((b_lab >> b) & 1u);
+    }
+    // ---- match masks + vertical sums
+    uint32_t mA[SIDE], mB[SIDE];
+#pragma unroll
+    for (int d = 0; d < SIDE; ++d) {
+        uint32_t ma = avm, mb = nbm;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            ma &= ~(Pl[d][b] ^ LA[b]);
+            mb &= ~(Pl[d][b] ^ LB[b]);
+        }
+        mA[d] = ma;
+        mB[d] = mb;
+    }
+    Bs<WV> VA, VB;
+    if constexpr (R == 1) { VA = bs_sum3(mA[0], mA[1], mA[2]); VB = bs_sum3(mB[0], mB[1], mB[2]); }
+    if constexpr (R == 2) {
+        VA = bs_sum5(mA[0], mA[1], mA[2], mA[3], mA[4]);
+        VB = bs_sum5(mB[0], mB[1], mB[2], mB[3], mB[4]);
+    }
+    if constexpr (R == 3) {
+        VA = bs_sum7(mA[0], mA[1], mA[2], mA[3], mA[4], mA[5], mA[6]);
+        VB = bs_sum7(mB[0], mB[1], mB[2], mB[3], mB[4], mB[5], mB[6]);
+    }
+    // ---- horizontal sums: the word carries its own R-pixel halo on both sides
+    Bs<WV> zz;
+#pragma unroll
+    for (int k = 0; k < WV; ++k) zz.b[k] = 0u;
+    const Bs<WC> cA = bs_hsum<R, WV, WC>(zz, VA, zz);
+    const Bs<WC> cB = bs_hsum<R, WV, WC>(zz, VB, zz);
+    // ---- decide: winner of {A, B} is the mode iff max(cA, cB) > N - cA - cB
+    uint32_t eq;
+    const uint32_t bgt = bs_gt<WC>(cB, cA, &eq);
+    const uint32_t a_lower = (a_lab < b_lab) ? ~0u : 0u;
+    selA = ~bgt & (~eq | a_lower);
+    const Bs<WC> mx = bs_sel<WC>(bgt, cB, cA), mn = bs_sel<WC>(bgt, cA, cB);
+    Bs<WC + 1> mx2;
+    mx2.b[0] = 0u;
+#pragma unroll
+    for (int k = 0; k < WC; ++k) mx2.b[k + 1] = mx.b[k];
+    const Bs<WC + 2> u = bs_add<WC + 1, WC, WC + 2>(mx2, mn);
+    decided = bs_gt_const<WC + 2>(u, (unsigned)N);
+    diff = 0u;
+    zero = ~0u;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const uint32_t o = (LA[b] & selA) | (LB[b] & ~selA);
+        diff |= o ^ Pl[R][b];
+        zero &= ~o;
+    }
+}
+
+template <int R, int NB>
+__device__ __forceinline__ void load_planes(const Smem& S, int slot, int ring, int vl, uint32_t (&Pl)[2 * R + 1][NB]) {
+#pragma unroll
+    for (int d = 0; d < 2 * R + 1; ++d) {
+        int sl = slot + d - R; sl += (sl < 0) ? ring : 0; sl -= (sl >= ring) ? ring : 0;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) Pl[d][b] = S.planes[(sl * NB + b) * 32 + vl];
+    }
+}
+
+// label at bit `pos`: vertical bitwise majority of the three centre lines (robust to isolated
+// speckle) unless the line above / below is outside the sheet
+template <int R, int NB>
+__device__ __forceinline__ unsigned label_maj3(const uint32_t (&Pl)[2 * R + 1][NB], bool vedge, int pos) {
+    unsigned l = 0;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const uint32_t m = vedge ? Pl[R][b] : mr_maj(Pl[R - 1][b], Pl[R][b], Pl[R + 1][b]);
+        l |= ((m >> pos) & 1u) << b;
+    }
+    return l;
+}
+
+// phase B, round 1: one warp votes one line.  vvalid: output pixels owned by this lane's vote
+// word; avalid: output pixels of this lane's aligned word (for the final store).
 template <int R, int NB, bool COUNT>
 __device__ __forceinline__ void vote_line(const FastParams& P, const Smem& S, uint8_t* out_sheet, long long xw0,
                                           int y, int slot, int ring, int lane, int warp, unsigned vvalid,
                                           unsigned avalid, unsigned& c_nomatch, unsigned& c_changed) {
     using G = Geo<R>;
     constexpr int SIDE = 2 * R + 1;
-    constexpr int N = SIDE * SIDE;
-    constexpr int WV = G::WV, WC = G::WC;
     constexpr unsigned VOIDL = (1u << NB) - 1u;
     const uint8_t* by = S.bytes + slot * 1024;
     uint8_t* st = S.stage + warp * 1024;
@@ -297,88 +417,27 @@ __device__ __forceinline__ void vote_line(const FastParams& P, const Smem& S, ui
     __syncwarp();
     if (vvalid) {
         uint32_t Pl[SIDE][NB];
-#pragma unroll
-        for (int d = 0; d < SIDE; ++d) {
-            int sl = slot + d - R; sl += (sl < 0) ? ring : 0; sl -= (sl >= ring) ? ring : 0;
-#pragma unroll
-            for (int b = 0; b < NB; ++b) Pl[d][b] = S.planes[(sl * NB + b) * 32 + lane];
-        }
-        // ---- candidate labels (heuristic only).  A / B: last / first output pixel of the word, each
-        // the bitwise vertical majority of 3 lines (kills isolated speckle); if they agree, B comes
-        // from the top / bottom line of the window instead.
+        load_planes<R, NB>(S, slot, ring, lane, Pl);
+        // ---- candidate labels (heuristic only).  A / B: last / first output pixel of the word; if
+        // they agree, B comes from the top / bottom line of the window instead.
         const bool vedge = (y - 1 < -P.job.halo_lo) || (y + 1 >= P.job.n2 + P.job.halo_hi);   // warp-uniform
         const int posA = 31 - __clz(vvalid), posB = __ffs(vvalid) - 1;
         const int posM = ((vvalid >> 16) & 1u) ? 16 : posA;
-        unsigned a_lab = 0, e_lab = 0, t_lab = 0, u_lab = 0;
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            const uint32_t m = vedge ? Pl[R][b] : mr_maj(Pl[R - 1][b], Pl[R][b], Pl[R + 1][b]);
-            a_lab |= ((m >> posA) & 1u) << b;
-            e_lab |= ((m >> posB) & 1u) << b;
-            t_lab |= ((Pl[0][b] >> posM) & 1u) << b;
-            u_lab |= ((Pl[SIDE - 1][b] >> posM) & 1u) << b;
-        }
-        unsigned b_lab = e_lab;
-        if (b_lab == a_lab) b_lab = (t_lab != a_lab && t_lab != VOIDL) ? t_lab : u_lab;
-        if (b_lab == VOIDL) b_lab = a_lab;
-        const uint32_t nbm = (b_lab != a_lab) ? ~0u : 0u;     // B == A -> B's masks are empty
-        const uint32_t avm = (a_lab != VOIDL) ? ~0u : 0u;     // a bitwise majority can alias the VOID code
-        uint32_t LA[NB], LB[NB];
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            LA[b] = 0u - ((a_lab >> b) & 1u);
-            LB[b] = 0u - ((b_lab >> b) & 1u);
-        }
-        // ---- match masks + vertical sums
-        uint32_t mA[SIDE], mB[SIDE];
-#pragma unroll
-        for (int d = 0; d < SIDE; ++d) {
-            uint32_t ma = avm, mb = nbm;
+        const unsigned a_lab = label_maj3<R, NB>(Pl, vedge, posA);
+        unsigned b_lab = label_maj3<R, NB>(Pl, vedge, posB);
+        if (b_lab == a_lab) {
+            unsigned t_lab = 0, u_lab = 0;
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
-                ma &= ~(Pl[d][b] ^ LA[b]);
-                mb &= ~(Pl[d][b] ^ LB[b]);
+                t_lab |= ((Pl[0][b] >> posM) & 1u) << b;
+                u_lab |= ((Pl[SIDE - 1][b] >> posM) & 1u) << b;
             }
-            mA[d] = ma;
-            mB[d] = mb;
+            b_lab = (t_lab != a_lab && t_lab != VOIDL) ? t_lab : u_lab;
         }
-        Bs<WV> VA, VB;
-        if constexpr (R == 1) { VA = bs_sum3(mA[0], mA[1], mA[2]); VB = bs_sum3(mB[0], mB[1], mB[2]); }
-        if constexpr (R == 2) {
-            VA = bs_sum5(mA[0], mA[1], mA[2], mA[3], mA[4]);
-            VB = bs_sum5(mB[0], mB[1], mB[2], mB[3], mB[4]);
-        }
-        if constexpr (R == 3) {
-            VA = bs_sum7(mA[0], mA[1], mA[2], mA[3], mA[4], mA[5], mA[6]);
-            VB = bs_sum7(mB[0], mB[1], mB[2], mB[3], mB[4], mB[5], mB[6]);
-        }
-        // ---- horizontal sums: the word carries its own R-pixel halo on both sides
-        Bs<WV> zz;
-#pragma unroll
-        for (int k = 0; k < WV; ++k) zz.b[k] = 0u;
-        const Bs<WC> cA = bs_hsum<R, WV, WC>(zz, VA, zz);
-        const Bs<WC> cB = bs_hsum<R, WV, WC>(zz, VB, zz);
-        // ---- decide: winner of {A, B} is the mode iff max(cA, cB) > N - cA - cB
-        uint32_t eq;
-        const uint32_t bgt = bs_gt<WC>(cB, cA, &eq);
-        const uint32_t a_lower = (a_lab < b_lab) ? ~0u : 0u;
-        const uint32_t selA = ~bgt & (~eq | a_lower);
-        const Bs<WC> mx = bs_sel<WC>(bgt, cB, cA), mn = bs_sel<WC>(bgt, cA, cB);
-        Bs<WC + 1> mx2;
-        mx2.b[0] = 0u;
-#pragma unroll
-        for (int k = 0; k < WC; ++k) mx2.b[k + 1] = mx.b[k];
-        const Bs<WC + 2> u = bs_add<WC + 1, WC, WC + 2>(mx2, mn);
-        const uint32_t decided = bs_gt_const<WC + 2>(u, (unsigned)N);
-        uint32_t diff = 0u, zero = ~0u;
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            const uint32_t o = (LA[b] & selA) | (LB[b] & ~selA);
-            diff |= o ^ Pl[R][b];
-            zero &= ~o;
-        }
+        uint32_t decided, selA, diff, zero;
+        vote_core<R, NB>(Pl, a_lab, b_lab, decided, selA, diff, zero);
         uint32_t changed = decided & vvalid & diff;
-        uint32_t undec = ~decided & vvalid;
+        const uint32_t undec = ~decided & vvalid;
         if (COUNT) {
             c_changed += __popc(changed);
             c_nomatch += __popc(decided & vvalid & zero);
@@ -389,14 +448,10 @@ __device__ __forceinline__ void vote_line(const FastParams& P, const Smem& S, ui
             changed &= changed - 1;
             st[o0 + q] = (uint8_t)(((selA >> q) & 1u) ? a_lab : b_lab);
         }
-        // undecided pixels -> dense exact pass (their provisional bytes are overwritten in phase C)
-        while (undec) {
-            const int q = __ffs(undec) - 1;
-            undec &= undec - 1;
-            const int code = (slot << 10) | (o0 + q);
-            const int pos = atomicAdd(&S.misc[1], 1);
-            if (pos < FB_CAP) S.fb[pos] = (uint16_t)code;
-            else S.misc[3] = 1;   // list full: phase C re-votes the whole step exactly
+        if (undec) {   // second round with candidates taken from the undecided pixels (dense list)
+            const int pos = atomicAdd(&S.misc[4], 1);
+            S.w2code[pos] = (uint16_t)((slot << 5) | lane);
+            S.w2mask[pos] = undec;
         }
     }
     __syncwarp();
@@ -407,6 +462,48 @@ __device__ __forceinline__ void vote_line(const FastParams& P, const Smem& S, ui
         store_word(P, out_sheet + (long long)y * P.job.out_stride2 + x0, x0, v0, v1);
     }
     __syncwarp();   // staging is reused by this warp's next line
+}
+
+// phase B, round 2: one thread re-votes one word whose round-1 candidates left pixels undecided.
+// Candidates are the labels at the last / first undecided pixel.  Newly decided pixels go
+// straight to global memory; the rest is queued for the exact per-pixel vote.
+template <int R, int NB, bool COUNT>
+__device__ __forceinline__ void vote_word2(const FastParams& P, const Smem& S, uint8_t* out_sheet, long long xw0,
+                                           int code, uint32_t undec, int ring, unsigned& c_nomatch,
+                                           unsigned& c_changed) {
+    using G = Geo<R>;
+    constexpr int SIDE = 2 * R + 1;
+    const int slot = code >> 5, vl = code & 31;
+    const int y = S.misc[8 + slot];
+    uint32_t Pl[SIDE][NB];
+    load_planes<R, NB>(S, slot, ring, vl, Pl);
+    const bool vedge = (y - 1 < -P.job.halo_lo) || (y + 1 >= P.job.n2 + P.job.halo_hi);
+    const int posA = 31 - __clz(undec), posB = __ffs(undec) - 1;
+    const unsigned a_lab = label_maj3<R, NB>(Pl, vedge, posA);
+    const unsigned b_lab = label_maj3<R, NB>(Pl, vedge, posB);
+    uint32_t decided, selA, diff, zero;
+    vote_core<R, NB>(Pl, a_lab, b_lab, decided, selA, diff, zero);
+    const int o0 = G::O0 + vl * G::U;
+    uint8_t* orow = out_sheet + (long long)y * P.job.out_stride2 + xw0 + o0;
+    uint32_t now = undec & decided;
+    if (COUNT) {
+        c_changed += __popc(now & diff);
+        c_nomatch += __popc(now & zero);
+    }
+    now &= diff;   // unchanged pixels already hold the right (pristine) label
+    while (now) {
+        const int q = __ffs(now) - 1;
+        now &= now - 1;
+        orow[q] = (uint8_t)(((selA >> q) & 1u) ? a_lab : b_lab);
+    }
+    uint32_t still = undec & ~decided;
+    while (still) {
+        const int q = __ffs(still) - 1;
+        still &= still - 1;
+        const int pos = atomicAdd(&S.misc[1], 1);
+        if (pos < FB_CAP) S.fb[pos] = (uint16_t)((slot << 10) | (o0 + q));
+        else S.misc[3] = 1;   // list full: phase C re-votes the whole step exactly
+    }
 }
 
 // R == 0: categorise only -- emit the byte ring line
@@ -447,7 +544,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_fast(const FastParams P) {
     S.stage = S.bytes + RING * 1024;
     S.sent = reinterpret_cast<uint16_t*>(S.stage + (R > 0 ? NWARPS * 1024 : 0));
     S.fb = S.sent + SENT_CAP;
-    S.misc = reinterpret_cast<int*>(S.fb + FB_CAP);
+    S.w2mask = reinterpret_cast<uint32_t*>(S.fb + FB_CAP);
+    S.w2code = reinterpret_cast<uint16_t*>(S.w2mask + TH * 32);
+    S.misc = reinterpret_cast<int*>(S.w2code + TH * 32);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     {
         const uint4* src = reinterpret_cast<const uint4*>(P.job.coarse);
@@ -514,7 +613,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_fast(const FastParams P) {
                 const int n = min(S.misc[0], SENT_CAP);
                 for (int e = tid; e < n; e += NTHREADS)
                     fix_sentinel<R, NB>(P, S, px_sheet, xw0, S.sent[e], y0, y1, c_fine);
-                if (tid == 0) { S.misc[1] = 0; S.misc[3] = 0; }
+                if (tid == 0) { S.misc[1] = 0; S.misc[3] = 0; S.misc[4] = 0; }
             }
             __syncthreads();
             // ---- phase B
@@ -525,13 +624,21 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_fast(const FastParams P) {
                     vote_line<R, NB, COUNT>(P, S, out_sheet, xw0, y, (y - ybase) % RING, RING, lane, warp, vvalid,
                                             avalid, t_nomatch, t_changed);
                 __syncthreads();
-                // ---- phase C: exact vote of the undecided pixels
+                // ---- phase B2: words with undecided pixels, new candidates (dense)
+                {
+                    const int n = S.misc[4];
+                    for (int e = tid; e < n; e += NTHREADS)
+                        vote_word2<R, NB, COUNT>(P, S, out_sheet, xw0, S.w2code[e], S.w2mask[e], RING, t_nomatch,
+                                                 t_changed);
+                }
+                __syncthreads();
+                // ---- phase C: exact vote of the still undecided pixels
                 if (S.misc[3] == 0) {
                     c_nomatch += t_nomatch;
                     c_changed += t_changed;
                     const int n = S.misc[1];
                     for (int e = tid; e < n; e += NTHREADS)
-                        fallback_pixel<R, COUNT>(P, S, out_sheet, xw0, S.fb[e], RING, c_nomatch, c_changed);
+                        fallback_pixel<R, NB, COUNT>(P, S, out_sheet, xw0, S.fb[e], RING, c_nomatch, c_changed);
                 } else {
                     // work list overflowed (adversarial input): all pixels of the step are re-voted
                     // and re-counted exactly (the step's bit-sliced counts are dropped)
@@ -540,7 +647,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_fast(const FastParams P) {
                         const int ly = e / G::SW, wx = 32 * G::HW + (e - ly * G::SW);
                         if (xw0 + wx >= n1) continue;
                         const int yy = a + ly, sl = (yy - ybase) % RING;
-                        const unsigned best = exact_vote<R>(S, sl, wx, RING);
+                        const unsigned best = exact_vote<R, NB>(S, sl, wx, RING);
                         uint8_t* o = out_sheet + (long long)yy * P.job.out_stride2 + xw0 + wx;
                         if (COUNT) {
                             c_nomatch += (best == 0);
