@@ -151,24 +151,36 @@ __device__ __forceinline__ LaneMasks lane_masks(const FastParams& P, long long x
     return m;
 }
 
-// TMA: bring the packed RGB of line y into the warp's staging buffer.  Returns false if the line
-// needs no load (outside the sheet).
+// TMA extents of a strip window: which bytes of a line are copied, and where they land
+struct CopyPlan {
+    const uint8_t* src0;   // sheet base + first byte of the window part that is loaded
+    uint32_t dst;          // shared address the first loaded byte goes to
+    uint32_t bytes;        // 0: nothing to load
+};
+
 template <int R>
-__device__ __forceinline__ bool issue_line_copy(const FastParams& P, const Item& it, int y, uint32_t stage,
-                                                uint32_t bar, int lane) {
+__device__ __forceinline__ CopyPlan copy_plan(const FastParams& P, const Item& it, uint32_t stage) {
     using G = Geo<R>;
-    if (y < -P.job.halo_lo || y >= P.job.n2 + P.job.halo_hi) return false;
     const long long limit = P.padded ? ((P.job.n1 * 3 + 15) / 16) * 16 : P.job.n1 * 3;
     const long long w0 = it.xw0 * 3;                      // byte offset of the window in the line
     long long lo = w0 + (R > 0 ? 80 : 0);                 // halo words: only the chunk next to the interior
     long long hi = w0 + (long long)G::AW * 96 - (R > 0 ? 80 : 0);
     lo = lo < 0 ? 0 : lo;
     hi = hi > limit ? limit : hi;
-    if (hi <= lo) return false;
+    CopyPlan c;
+    c.src0 = it.px + lo;
+    c.dst = stage + (uint32_t)(lo - w0);
+    c.bytes = hi > lo ? (uint32_t)(hi - lo) : 0u;
+    return c;
+}
+
+// TMA: bring the packed RGB of line y into the warp's staging buffer.  Returns false if the line
+// needs no load (outside the sheet).
+__device__ __forceinline__ bool issue_line_copy(const FastParams& P, const CopyPlan& c, int y, uint32_t bar, int lane) {
+    if (y < -P.job.halo_lo || y >= P.job.n2 + P.job.halo_hi || c.bytes == 0u) return false;
     if (lane == 0) {
-        const uint32_t bytes = (uint32_t)(hi - lo);
-        mbar_expect_tx(bar, bytes);
-        tma_load_1d(stage + (uint32_t)(lo - w0), it.px + (long long)y * P.job.stride2 + lo, bytes, bar);
+        mbar_expect_tx(bar, c.bytes);
+        tma_load_1d(c.dst, c.src0 + (long long)y * P.job.stride2, c.bytes, bar);
     }
     return true;
 }
@@ -244,7 +256,7 @@ __device__ __forceinline__ void categorize_line(const FastParams& P, const uint8
         const uint2 v1 = *reinterpret_cast<const uint2*>(mine + 24 * h + 8);
         const uint2 v2 = *reinterpret_cast<const uint2*>(mine + 24 * h + 16);
         const uint32_t w[6] = {v0.x, v0.y, v1.x, v1.y, v2.x, v2.y};
-        const int sh8 = 8 * h;
+        const uint32_t mul8 = 1u << (8 * h);   // label bytes are disjoint: l << 8h accumulates as l * 2^8h (IMAD)
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
             const uint32_t w0 = w[3 * g], w1 = w[3 * g + 1], w2 = w[3 * g + 2];
@@ -259,7 +271,7 @@ __device__ __forceinline__ void categorize_line(const FastParams& P, const uint8
                 const uint32_t t = (a & 0x1Fu) | (b & ~0x1Fu);
                 const uint32_t idx = (t & 0x3FFu) | (c & ~0x3FFu);     // r5 | g5<<5 | b5<<10
                 const uint32_t l = coarse[idx];
-                Wp[4 * g + i] |= l << sh8;
+                Wp[4 * g + i] = l * mul8 + Wp[4 * g + i];
             }
         }
     }
@@ -615,7 +627,8 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
         const LaneMasks M = lane_masks<R>(P, it.xw0, lane);
         const int cat_last = it.y1 + R;                       // lines [y0-R, y1+R) are categorised
         int ycat = it.y0 - R;                                 // next line to categorise
-        bool pend = issue_line_copy<R>(P, it, ycat, stage_u32, bar, lane);
+        const CopyPlan plan = copy_plan<R>(P, it, stage_u32);
+        bool pend = issue_line_copy(P, plan, ycat, bar, lane);
 #pragma unroll 1
         for (int a = it.y0; a < it.y1; a += C::B) {
             const int vend = min(a + C::B, it.y1);
@@ -630,7 +643,7 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
                 categorize_line<R, NB, COUNT>(P, coarse, ws, it, ycat, blk_y, lane, M, pend ? stage : nullptr,
                                               c_nomatch);
                 __syncwarp();   // every lane is done with the staging buffer
-                pend = (ycat + 1 < cat_last) ? issue_line_copy<R>(P, it, ycat + 1, stage_u32, bar, lane) : false;
+                pend = (ycat + 1 < cat_last) ? issue_line_copy(P, plan, ycat + 1, bar, lane) : false;
             }
             // ---- resolve the MIXED-cell pixels of these lines, densely over the lanes
             {
