@@ -186,43 +186,77 @@ __device__ __forceinline__ bool issue_line_copy(const FastParams& P, const CopyP
 }
 
 // ---------------------------------------------------------------------------------------------
-// exact resolution of the MIXED-cell pixels of one aligned word.  code = line-in-block << 5 | word
-template <int R, int NB>
-__device__ __forceinline__ void fix_word(const FastParams& P, uint8_t* ws, const Item& it, int code, uint32_t mask,
-                                         int blk_y, unsigned& c_fine, unsigned& c_nomatch) {
-    using G = Geo<R>;
-    using C = Cfg<R, NB>;
-    const int y = blk_y + (code >> 5), aw = code & 31;
-    const uint8_t* line = it.px + (long long)y * P.job.stride2;
-    const bool own_line = (y >= it.y0) && (y < it.y1);
-    const int slot = (y - (it.y0 - R)) % C::RL;
-    uint32_t* planes = reinterpret_cast<uint32_t*>(ws + C::W_PLANES) + slot * NB * 32;
+// Work lists hold one entry per 32-pixel word (code + pixel mask).  The rare per-pixel jobs are
+// spread evenly over the lanes: 32 entries at a time, inclusive scan of their pixel counts, every
+// lane then finds "its" pixel (entry by binary search over the scan, bit by skipping set bits).
+// f(code, bit) is called once per (entry, set bit).  Whole warp, converged.
+template <typename F>
+__device__ __forceinline__ void for_each_pixel(const uint16_t* codes, const uint32_t* masks, int n, int lane, F f) {
 #pragma unroll 1
-    while (mask) {
-        const int wx = aw * 32 + __ffs(mask) - 1;
-        mask &= mask - 1;
-        const long long x = it.xw0 + wx;
-        const uint8_t* p = line + x * 3;
-        const unsigned rgb = (unsigned)__ldg(p) | ((unsigned)__ldg(p + 1) << 8) | ((unsigned)__ldg(p + 2) << 16);
-        const unsigned l = __ldg(P.job.lut + rgb);
-        if (R > 0 && wx >= G::O0) {
-            // the pixel lives in up to two overlapped vote words
-            const int lh = (wx - G::O0) / G::U;
+    for (int e0 = 0; e0 < n; e0 += 32) {
+        const int e = e0 + lane;
+        const uint32_t my_mask = e < n ? masks[e] : 0u;
+        const int my_code = e < n ? codes[e] : 0;
+        const int c = __popc(my_mask);
+        int S = c;   // inclusive scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, S, o);
+            if (lane >= o) S += v;
+        }
+        const int T = __shfl_sync(0xffffffffu, S, 31);
 #pragma unroll 1
-            for (int t = 0; t < 2; ++t) {
-                const int vl = lh - t;
-                const int q = wx - G::O0 - vl * G::U;
-                if (vl < 0 || vl > 31 || q > 31) continue;
-#pragma unroll 1
-                for (int b = 0; b < NB; ++b)
-                    if (!((l >> b) & 1u)) atomicAnd(&planes[b * 32 + vl], ~(1u << q));
+        for (int t0 = 0; t0 < T; t0 += 32) {
+            const int t = t0 + lane;
+            int idx = 0;   // number of entries whose inclusive scan is <= t  (= entry that owns task t)
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const int v = __shfl_sync(0xffffffffu, S, (idx + step - 1) & 31);
+                if (v <= t) idx += step;
+            }
+            idx &= 31;
+            const int before = __shfl_sync(0xffffffffu, S - c, idx);
+            uint32_t m = __shfl_sync(0xffffffffu, my_mask, idx);
+            const int code = __shfl_sync(0xffffffffu, my_code, idx);
+            if (t < T) {
+                for (int r = t - before; r > 0; --r) m &= m - 1;   // skip r set bits
+                f(code, __ffs(m) - 1);
             }
         }
-        if (own_line && wx >= 32 * G::HW && wx < 32 * G::HW + G::SW) {              // owned pixel
-            it.out[(long long)y * P.job.out_stride2 + x] = (uint8_t)l;               // provisional label
-            ++c_fine;
-            if (R == 0) c_nomatch += (l == 0);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact resolution of one MIXED-cell pixel.  code = line-in-block << 5 | aligned word, q = pixel
+template <int R, int NB>
+__device__ __forceinline__ void fix_pixel(const FastParams& P, uint8_t* ws, const Item& it, int code, int q,
+                                          int blk_y, unsigned& c_fine, unsigned& c_nomatch) {
+    using G = Geo<R>;
+    using C = Cfg<R, NB>;
+    const int y = blk_y + (code >> 5), wx = (code & 31) * 32 + q;
+    const long long x = it.xw0 + wx;
+    const uint8_t* p = it.px + (long long)y * P.job.stride2 + x * 3;
+    const unsigned rgb = (unsigned)__ldg(p) | ((unsigned)__ldg(p + 1) << 8) | ((unsigned)__ldg(p + 2) << 16);
+    const unsigned l = __ldg(P.job.lut + rgb);
+    if (R > 0 && wx >= G::O0) {
+        // the pixel lives in up to two overlapped vote words
+        const int slot = (y - (it.y0 - R)) % C::RL;
+        uint32_t* planes = reinterpret_cast<uint32_t*>(ws + C::W_PLANES) + slot * NB * 32;
+        const int lh = (wx - G::O0) / G::U;
+#pragma unroll 1
+        for (int t = 0; t < 2; ++t) {
+            const int vl = lh - t;
+            const int qq = wx - G::O0 - vl * G::U;
+            if (vl < 0 || vl > 31 || qq > 31) continue;
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
+                if (!((l >> b) & 1u)) atomicAnd(&planes[b * 32 + vl], ~(1u << qq));
         }
+    }
+    if (y >= it.y0 && y < it.y1 && wx >= 32 * G::HW && wx < 32 * G::HW + G::SW) {   // owned pixel
+        it.out[(long long)y * P.job.out_stride2 + x] = (uint8_t)l;                   // provisional label
+        ++c_fine;
+        if (R == 0) c_nomatch += (l == 0);
     }
 }
 
@@ -548,28 +582,23 @@ __device__ __forceinline__ void vote_word(const FastParams& P, uint8_t* ws, cons
     }
 }
 
-// exact vote of the still undecided pixels of one word
+// exact vote of one still undecided pixel.  code = line-in-block << 5 | vote word, q = bit
 template <int R, int NB, bool COUNT>
-__device__ __forceinline__ void exact_word(const FastParams& P, uint8_t* ws, const Item& it, int blk_a, int code,
-                                           uint32_t mask, unsigned& c_nomatch, unsigned& c_changed) {
+__device__ __forceinline__ void exact_pixel(const FastParams& P, uint8_t* ws, const Item& it, int blk_a, int code,
+                                            int q, unsigned& c_nomatch, unsigned& c_changed) {
     using G = Geo<R>;
     const int y = blk_a + (code >> 5), vl = code & 31;
     uint32_t Pl[2 * R + 1][NB];
     load_planes<R, NB>(ws, it, y, vl, Pl);
-    uint8_t* orow = it.out + (long long)y * P.job.out_stride2 + it.xw0 + G::O0 + vl * G::U;
-#pragma unroll 1
-    while (mask) {
-        const int q = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const unsigned best = exact_vote<R, NB>(Pl, q);
-        unsigned centre = 0;
+    const unsigned best = exact_vote<R, NB>(Pl, q);
+    unsigned centre = 0;
 #pragma unroll
-        for (int b = 0; b < NB; ++b) centre |= ((Pl[R][b] >> q) & 1u) << b;
-        if (best != centre) orow[q] = (uint8_t)best;   // the provisional label is the centre label
-        if (COUNT) {
-            c_nomatch += (best == 0);
-            c_changed += (best != centre);
-        }
+    for (int b = 0; b < NB; ++b) centre |= ((Pl[R][b] >> q) & 1u) << b;
+    if (best != centre)   // the provisional label is the centre label
+        it.out[(long long)y * P.job.out_stride2 + it.xw0 + G::O0 + vl * G::U + q] = (uint8_t)best;
+    if (COUNT) {
+        c_nomatch += (best == 0);
+        c_changed += (best != centre);
     }
 }
 
@@ -645,13 +674,13 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
                 __syncwarp();   // every lane is done with the staging buffer
                 pend = (ycat + 1 < cat_last) ? issue_line_copy(P, plan, ycat + 1, bar, lane) : false;
             }
-            // ---- resolve the MIXED-cell pixels of these lines, densely over the lanes
+            // ---- resolve the MIXED-cell pixels of these lines, spread evenly over the lanes
             {
+                __syncwarp();
                 const int n = cnt[0];
-                const uint16_t* code = reinterpret_cast<const uint16_t*>(ws + C::W_SENTCODE);
-                const uint32_t* mask = reinterpret_cast<const uint32_t*>(ws + C::W_SENTMASK);
-#pragma unroll 1
-                for (int e = lane; e < n; e += 32) fix_word<R, NB>(P, ws, it, code[e], mask[e], blk_y, c_fine, c_nomatch);
+                for_each_pixel(reinterpret_cast<const uint16_t*>(ws + C::W_SENTCODE),
+                               reinterpret_cast<const uint32_t*>(ws + C::W_SENTMASK), n, lane,
+                               [&](int code, int q) { fix_pixel<R, NB>(P, ws, it, code, q, blk_y, c_fine, c_nomatch); });
                 __syncwarp();
                 if (lane == 0) cnt[0] = 0;
                 __syncwarp();
@@ -684,13 +713,12 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
                     if (mask) vote_word<R, NB, COUNT>(P, ws, it, y, a, vl, mask, round2, c_nomatch, c_changed);
                 }
                 __syncwarp();
-                {   // ---- exact votes of what is still undecided
+                {   // ---- exact votes of what is still undecided, spread evenly over the lanes
                     const int n = cnt[2];
-                    const uint16_t* code = reinterpret_cast<const uint16_t*>(ws + C::W_FBCODE);
-                    const uint32_t* mask = reinterpret_cast<const uint32_t*>(ws + C::W_FBMASK);
-#pragma unroll 1
-                    for (int e = lane; e < n; e += 32)
-                        exact_word<R, NB, COUNT>(P, ws, it, a, code[e], mask[e], c_nomatch, c_changed);
+                    for_each_pixel(reinterpret_cast<const uint16_t*>(ws + C::W_FBCODE),
+                                   reinterpret_cast<const uint32_t*>(ws + C::W_FBMASK), n, lane, [&](int code, int q) {
+                                       exact_pixel<R, NB, COUNT>(P, ws, it, a, code, q, c_nomatch, c_changed);
+                                   });
                 }
                 __syncwarp();
                 if (lane == 0) { cnt[1] = 0; cnt[2] = 0; }
