@@ -284,29 +284,28 @@ __device__ __forceinline__ void categorize_line(const FastParams& P, const uint8
 #pragma unroll
     for (int j = 0; j < 8; ++j) Wp[j] = 0u;
     const uint8_t* mine = staged + lane * 96;
+    // rounds run from the last 8 pixels to the first so that "Wp = Wp * 256 + label" (one IMAD on
+    // the FMA pipe) leaves round h in byte h.  Two pixels share the index arithmetic: their r / g / b
+    // bytes are gathered into 16-bit lanes (PRMT) and quantised together.
 #pragma unroll 1
-    for (int h = 0; h < 4; ++h) {
+    for (int h = 3; h >= 0; --h) {
         const uint2 v0 = *reinterpret_cast<const uint2*>(mine + 24 * h);
         const uint2 v1 = *reinterpret_cast<const uint2*>(mine + 24 * h + 8);
         const uint2 v2 = *reinterpret_cast<const uint2*>(mine + 24 * h + 16);
         const uint32_t w[6] = {v0.x, v0.y, v1.x, v1.y, v2.x, v2.y};
-        const uint32_t mul8 = 1u << (8 * h);   // label bytes are disjoint: l << 8h accumulates as l * 2^8h (IMAD)
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-            const uint32_t w0 = w[3 * g], w1 = w[3 * g + 1], w2 = w[3 * g + 2];
-            uint32_t p[4];
-            p[0] = w0 & 0xFFFFFFu;
-            p[1] = __funnelshift_r(w0, w1, 24) & 0xFFFFFFu;
-            p[2] = __funnelshift_r(w1, w2, 16) & 0xFFFFFFu;
-            p[3] = w2 >> 8;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint32_t a = p[i] >> 3, b = p[i] >> 6, c = p[i] >> 9;
-                const uint32_t t = (a & 0x1Fu) | (b & ~0x1Fu);
-                const uint32_t idx = (t & 0x3FFu) | (c & ~0x3FFu);     // r5 | g5<<5 | b5<<10
-                const uint32_t l = coarse[idx];
-                Wp[4 * g + i] = l * mul8 + Wp[4 * g + i];
-            }
+        for (int m = 0; m < 4; ++m) {
+            // pixels 2m, 2m+1 of the round = bytes 6m .. 6m+5 = words (3m)/2, (3m)/2 + 1
+            const uint32_t wa = w[(3 * m) >> 1], wb = w[((3 * m) >> 1) + 1];
+            const uint32_t R2 = __byte_perm(wa, wb, (m & 1) ? 0x5522 : 0x3300);
+            const uint32_t G2 = __byte_perm(wa, wb, (m & 1) ? 0x6633 : 0x4411);
+            const uint32_t B2 = __byte_perm(wa, wb, (m & 1) ? 0x7744 : 0x5522);
+            // idx = r5 | g5<<5 | b5<<10 in each 16-bit half
+            const uint32_t X = ((R2 >> 3) & 0x001F001Fu) | ((G2 * 4u) & 0x03E003E0u) | ((B2 * 128u) & 0x7C007C00u);
+            const uint32_t la = coarse[X & 0xFFFFu];
+            const uint32_t lb = coarse[X >> 16];
+            Wp[2 * m] = Wp[2 * m] * 256u + la;
+            Wp[2 * m + 1] = Wp[2 * m + 1] * 256u + lb;
         }
     }
     if (it.edge) {   // warp-uniform: force VOID outside [0, n1)
