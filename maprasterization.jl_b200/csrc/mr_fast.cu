@@ -262,15 +262,18 @@ __device__ __forceinline__ void fix_pixel(const FastParams& P, uint8_t* ws, cons
 
 // ---------------------------------------------------------------------------------------------
 // categorise one line of the strip window (whole warp) from the TMA staging buffer
-template <int R, int NB, bool COUNT>
+// after_read() is called as soon as the staging buffer has been consumed (the caller uses it to
+// issue the TMA copy of the next line, so that the copy overlaps the rest of this line's work).
+template <int R, int NB, bool COUNT, typename F>
 __device__ __forceinline__ void categorize_line(const FastParams& P, const uint8_t* coarse, uint8_t* ws,
                                                 const Item& it, int y, int blk_y, int lane, const LaneMasks& M,
-                                                const uint8_t* staged, unsigned& c_nomatch) {
+                                                const uint8_t* staged, F after_read, unsigned& c_nomatch) {
     using G = Geo<R>;
     using C = Cfg<R, NB>;
     const int slot = (y - (it.y0 - R)) % C::RL;
     uint32_t* pl = reinterpret_cast<uint32_t*>(ws + C::W_PLANES) + slot * NB * 32;
     if (!staged) {   // outside the sheet: VOID everywhere (warp-uniform)
+        after_read();
         if (R > 0) {
 #pragma unroll
             for (int b = 0; b < NB; ++b) pl[b * 32 + lane] = ~0u;
@@ -308,6 +311,7 @@ __device__ __forceinline__ void categorize_line(const FastParams& P, const uint8
             Wp[2 * m + 1] = Wp[2 * m + 1] * 256u + lb;
         }
     }
+    after_read();
     if (it.edge) {   // warp-uniform: force VOID outside [0, n1)
 #pragma unroll
         for (int j = 0; j < 8; ++j) Wp[j] |= ((~M.vmask >> j) & 0x01010101u) * 0xFFu;
@@ -448,13 +452,15 @@ template <int R, int NB>
 __device__ __forceinline__ void load_planes(const uint8_t* ws, const Item& it, int y, int vl,
                                             uint32_t (&Pl)[2 * R + 1][NB]) {
     using C = Cfg<R, NB>;
-    const uint32_t* planes = reinterpret_cast<const uint32_t*>(ws + C::W_PLANES);
-    int sl = (y - it.y0) % C::RL;   // slot of line y - R
+    constexpr int LINE = NB * 128, RING = C::RL * LINE;
+    const uint8_t* base = ws + C::W_PLANES + vl * 4;
+    int off = ((y - it.y0) % C::RL) * LINE;   // slot of line y - R
 #pragma unroll
     for (int d = 0; d < 2 * R + 1; ++d) {
 #pragma unroll
-        for (int b = 0; b < NB; ++b) Pl[d][b] = planes[(sl * NB + b) * 32 + vl];
-        sl = (sl + 1 == C::RL) ? 0 : sl + 1;
+        for (int b = 0; b < NB; ++b) Pl[d][b] = *reinterpret_cast<const uint32_t*>(base + off + b * 128);
+        off += LINE;
+        if (off == RING) off = 0;
     }
 }
 
@@ -668,10 +674,15 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
                     mbar_wait(bar, parity);
                     parity ^= 1u;
                 }
-                categorize_line<R, NB, COUNT>(P, coarse, ws, it, ycat, blk_y, lane, M, pend ? stage : nullptr,
-                                              c_nomatch);
-                __syncwarp();   // every lane is done with the staging buffer
-                pend = (ycat + 1 < cat_last) ? issue_line_copy(P, plan, ycat + 1, bar, lane) : false;
+                bool nxt = false;
+                categorize_line<R, NB, COUNT>(
+                    P, coarse, ws, it, ycat, blk_y, lane, M, pend ? stage : nullptr,
+                    [&]() {
+                        __syncwarp();   // every lane is done with the staging buffer
+                        nxt = (ycat + 1 < cat_last) ? issue_line_copy(P, plan, ycat + 1, bar, lane) : false;
+                    },
+                    c_nomatch);
+                pend = nxt;
             }
             // ---- resolve the MIXED-cell pixels of these lines, spread evenly over the lanes
             {
