@@ -102,6 +102,35 @@ MR_HD Bs<3> bs_sum7(uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3, uint32_t
     return o;
 }
 
+// out = a - b (per pixel), WA >= WB, caller guarantees a >= b.
+template <int WA, int WB>
+MR_HD Bs<WA> bs_sub(const Bs<WA>& a, const Bs<WB>& b) {
+    Bs<WA> o;
+    uint32_t borrow = 0;
+#pragma unroll
+    for (int k = 0; k < WA; ++k) {
+        const uint32_t x = a.b[k];
+        const uint32_t y = k < WB ? b.b[k] : 0u;
+        o.b[k] = x ^ y ^ borrow;
+        borrow = (~x & (y | borrow)) | (y & borrow);
+    }
+    return o;
+}
+
+// Horizontal window sum of a ONE-bit plane: out(x) = sum over dx in [-R, R] of m(x + dx); bits that
+// fall off the word count as 0 (the vote words carry their own R-pixel halo, see mr_fast.cu).
+// R=1: 0..3 (2 bits), R=2: 0..5 (3 bits), R=3: 0..7 (3 bits).
+template <int R>
+MR_HD Bs<(R == 1 ? 2 : 3)> bs_hsum1(uint32_t m) {
+    if constexpr (R == 1) {
+        return bs_sum3(m << 1, m, m >> 1);
+    } else if constexpr (R == 2) {
+        return bs_sum5(m << 2, m << 1, m, m >> 1, m >> 2);
+    } else {
+        return bs_sum7(m << 3, m << 2, m << 1, m, m >> 1, m >> 2, m >> 3);
+    }
+}
+
 // funnel shifts over the (left | centre | right) triple of neighbouring words:
 // value of pixel i+d (d > 0: towards the right neighbour word) delivered at bit i.
 MR_HD uint32_t mr_take_right(uint32_t centre, uint32_t right, int d) {

@@ -587,6 +587,146 @@ __device__ __forceinline__ void vote_word(const FastParams& P, uint8_t* ws, cons
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Round 1 of the vote for a whole block of nl output lines [a, a + nl) of vote word `lane`.
+// The two candidate labels are chosen ONCE per (vote word, block), so every line's match masks
+// and their horizontal window sums are computed once and shared by the 2R+1 output lines that
+// see the line: the box counts slide down the block (add the line entering the window, subtract
+// the line leaving it).  Decision test and tie rule as in vote_core.  Words with undecided pixels
+// go to the round-2 list (candidates per word there).
+template <int R, int NB, bool COUNT>
+__device__ __forceinline__ void block_vote(const FastParams& P, uint8_t* ws, const Item& it, int a, int nl, int vl,
+                                           uint32_t mask, unsigned& c_nomatch, unsigned& c_changed) {
+    using G = Geo<R>;
+    using C = Cfg<R, NB>;
+    constexpr int SIDE = 2 * R + 1;
+    constexpr int N = SIDE * SIDE;
+    constexpr int WH = R == 1 ? 2 : 3, WC = G::WC;
+    constexpr unsigned VOIDL = (1u << NB) - 1u;
+    constexpr int LINE = NB * 128, RING = C::RL * LINE;
+    if (mask == 0u) return;   // this vote word has no output pixels (right sheet border)
+    const uint8_t* base = ws + C::W_PLANES + vl * 4;
+    // ---- candidates (heuristic only): A = label at the centre of the block, B = the label farthest
+    // from the centre among the pixels of the centre / first / last line that differ from A.  Labels
+    // are read through a vertical bitwise majority of three lines, which hides isolated speckle.
+    unsigned a_lab = 0, b_lab = 0;
+    {
+        bool found = false;
+#pragma unroll 1
+        for (int t = 0; t < 3 && !found; ++t) {
+            const int yy = t == 0 ? a + (nl >> 1) : (t == 1 ? a : a + nl - 1);
+            int off = ((yy - 1 - (it.y0 - R)) % C::RL) * LINE;
+            uint32_t Q[NB];
+            {
+                uint32_t X[3][NB];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) X[d][b] = *reinterpret_cast<const uint32_t*>(base + off + b * 128);
+                    off += LINE;
+                    if (off == RING) off = 0;
+                }
+#pragma unroll
+                for (int b = 0; b < NB; ++b) Q[b] = mr_maj(X[0][b], X[1][b], X[2][b]);
+            }
+            if (t == 0) {
+#pragma unroll
+                for (int b = 0; b < NB; ++b) a_lab |= ((Q[b] >> 16) & 1u) << b;
+                b_lab = a_lab;
+            }
+            uint32_t nota = 0u, isvoid = ~0u;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                nota |= Q[b] ^ (0u - ((a_lab >> b) & 1u));
+                isvoid &= Q[b];
+            }
+            nota &= mask & ~isvoid;
+            if (nota) {
+                const int pf = __ffs(nota) - 1, pl = 31 - __clz(nota);
+                const int pos = (pl - 16 > 16 - pf) ? pl : pf;
+                b_lab = 0;
+#pragma unroll
+                for (int b = 0; b < NB; ++b) b_lab |= ((Q[b] >> pos) & 1u) << b;
+                found = true;
+            }
+        }
+    }
+    const uint32_t nbm = (b_lab != a_lab && b_lab != VOIDL) ? ~0u : 0u;   // B == A -> B's masks are empty
+    const uint32_t avm = (a_lab != VOIDL) ? ~0u : 0u;
+    const uint32_t a_lower = (a_lab < b_lab) ? ~0u : 0u;
+    uint32_t LA[NB], LB[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        LA[b] = 0u - ((a_lab >> b) & 1u);
+        LB[b] = 0u - ((b_lab >> b) & 1u);
+    }
+    // ---- slide down the block.  hA / hB: match masks of the last 2R+1 lines (oldest first)
+    Bs<WC> SA, SB;
+#pragma unroll
+    for (int k = 0; k < WC; ++k) SA.b[k] = SB.b[k] = 0u;
+    uint32_t hA[SIDE], hB[SIDE];
+#pragma unroll
+    for (int d = 0; d < SIDE; ++d) hA[d] = hB[d] = 0u;
+    int off = ((a - it.y0) % C::RL) * LINE;   // slot of line a - R
+    uint8_t* orow = it.out + (long long)a * P.job.out_stride2 + it.xw0 + G::O0 + vl * G::U;
+#pragma unroll 1
+    for (int i = 0; i < nl + 2 * R; ++i) {
+        uint32_t ma = avm, mb = nbm;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const uint32_t p = *reinterpret_cast<const uint32_t*>(base + off + b * 128);
+            ma &= ~(p ^ LA[b]);
+            mb &= ~(p ^ LB[b]);
+        }
+        off += LINE;
+        if (off == RING) off = 0;
+        SA = bs_add<WC, WH, WC>(SA, bs_hsum1<R>(ma));
+        SB = bs_add<WC, WH, WC>(SB, bs_hsum1<R>(mb));
+#pragma unroll
+        for (int d = 0; d < SIDE - 1; ++d) {
+            hA[d] = hA[d + 1];
+            hB[d] = hB[d + 1];
+        }
+        hA[SIDE - 1] = ma;
+        hB[SIDE - 1] = mb;
+        if (i >= 2 * R) {
+            // ---- decide output line a + i - 2R: winner of {A, B} is the mode iff max > N - cA - cB
+            uint32_t eq;
+            const uint32_t bgt = bs_gt<WC>(SB, SA, &eq);
+            const uint32_t selA = ~bgt & (~eq | a_lower);
+            const Bs<WC> mx = bs_sel<WC>(bgt, SB, SA), mn = bs_sel<WC>(bgt, SA, SB);
+            Bs<WC + 1> mx2;
+            mx2.b[0] = 0u;
+#pragma unroll
+            for (int k = 0; k < WC; ++k) mx2.b[k + 1] = mx.b[k];
+            const Bs<WC + 2> u = bs_add<WC + 1, WC, WC + 2>(mx2, mn);
+            const uint32_t decided = bs_gt_const<WC + 2>(u, (unsigned)N);
+            const uint32_t now = decided & mask;
+            uint32_t changed = now & ~((selA & hA[R]) | (~selA & hB[R]));   // centre label != winner
+            const uint32_t undec = ~decided & mask;
+            if (COUNT) {
+                c_changed += __popc(changed);
+                c_nomatch += __popc(now & ((a_lab == 0 ? selA : 0u) | (b_lab == 0 ? ~selA : 0u)));
+            }
+#pragma unroll 1
+            while (changed) {   // the provisional labels are already in global memory: patch only changes
+                const int q = __ffs(changed) - 1;
+                changed &= changed - 1;
+                orow[q] = (uint8_t)(((selA >> q) & 1u) ? a_lab : b_lab);
+            }
+            if (undec) {
+                int* cnt = reinterpret_cast<int*>(ws + C::W_CNT);
+                const int e = atomicAdd(cnt + 1, 1);
+                reinterpret_cast<uint16_t*>(ws + C::W_W2CODE)[e] = (uint16_t)(((i - 2 * R) << 5) | vl);
+                reinterpret_cast<uint32_t*>(ws + C::W_W2MASK)[e] = undec;
+            }
+            orow += P.job.out_stride2;
+            SA = bs_sub<WC, WH>(SA, bs_hsum1<R>(hA[0]));
+            SB = bs_sub<WC, WH>(SB, bs_hsum1<R>(hB[0]));
+        }
+    }
+}
+
 // exact vote of one still undecided pixel.  code = line-in-block << 5 | vote word, q = bit
 template <int R, int NB, bool COUNT>
 __device__ __forceinline__ void exact_pixel(const FastParams& P, uint8_t* ws, const Item& it, int blk_a, int code,
@@ -696,31 +836,18 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
                 __syncwarp();
             }
             if constexpr (R > 0) {
-                // ---- votes: round 1 (lane = vote word, one line per pass), then round 2 over the
-                // word list round 1 produced -- one copy of the vote code serves both
-                const int nl = vend - a;
-                int n2 = 0;
+                // ---- votes: round 1 per block (lane = vote word), then round 2 over the word list
+                // round 1 produced, densely over the lanes
+                block_vote<R, NB, COUNT>(P, ws, it, a, vend - a, lane, M.vvalid, c_nomatch, c_changed);
+                __syncwarp();
+                const int n2 = cnt[1];
 #pragma unroll 1
-                for (int e = 0;; ++e) {
-                    int y = a + e, vl = lane;
-                    uint32_t mask = M.vvalid;
-                    const bool round2 = e >= nl;
-                    if (round2) {
-                        if (e == nl) {
-                            __syncwarp();
-                            n2 = cnt[1];
-                        }
-                        const int base = (e - nl) * 32;
-                        if (base >= n2) break;
-                        mask = 0u;
-                        if (base + lane < n2) {
-                            const int code = reinterpret_cast<const uint16_t*>(ws + C::W_W2CODE)[base + lane];
-                            mask = reinterpret_cast<const uint32_t*>(ws + C::W_W2MASK)[base + lane];
-                            y = a + (code >> 5);
-                            vl = code & 31;
-                        }
+                for (int base = 0; base < n2; base += 32) {
+                    if (base + lane < n2) {
+                        const int code = reinterpret_cast<const uint16_t*>(ws + C::W_W2CODE)[base + lane];
+                        const uint32_t mask = reinterpret_cast<const uint32_t*>(ws + C::W_W2MASK)[base + lane];
+                        vote_word<R, NB, COUNT>(P, ws, it, a + (code >> 5), a, code & 31, mask, true, c_nomatch, c_changed);
                     }
-                    if (mask) vote_word<R, NB, COUNT>(P, ws, it, y, a, vl, mask, round2, c_nomatch, c_changed);
                 }
                 __syncwarp();
                 {   // ---- exact votes of what is still undecided, spread evenly over the lanes
