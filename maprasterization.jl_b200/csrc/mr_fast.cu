@@ -280,35 +280,41 @@ __device__ __forceinline__ void categorize_line(const FastParams& P, const uint8
         }
         return;
     }
-    // labels, packed so that register j holds pixels {j, 8+j, 16+j, 24+j} in bytes 0..3: the bit
-    // transpose below then needs no final gather.  Four rounds of 8 pixels (24 bytes) keep the code
-    // small (instruction cache) -- unloaded parts of halo words give garbage that is never used.
+    // labels, packed so that register j holds pixels {j, 8+j, 16+j, 24+j} in bytes 0..3 (the layout
+    // the bit transpose below wants).  Two rounds of 16 pixels (48 bytes = three 16-byte reads);
+    // unloaded parts of halo words give garbage that is never used.
+    // Cell index r5 | g5<<5 | b5<<10 of a pixel = byte dot product (IDP.4A, off the ALU pipe) of the
+    // quantised words with the weights (1, 32, 128): r and g bytes are quantised to x>>3, b bytes to
+    // x & 0xF8 (= 8*b5), the byte masks depend only on the position of the word in its 12-byte group.
+    extern __shared__ __align__(128) uint8_t sm_coarse[];   // the coarse table sits at offset 0
     uint32_t Wp[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) Wp[j] = 0u;
     const uint8_t* mine = staged + lane * 96;
-    // rounds run from the last 8 pixels to the first so that "Wp = Wp * 256 + label" (one IMAD on
-    // the FMA pipe) leaves round h in byte h.  Two pixels share the index arithmetic: their r / g / b
-    // bytes are gathered into 16-bit lanes (PRMT) and quantised together.
+    // rounds run from the last 16 pixels to the first so that "Wp = Wp * 256 + label" (one IMAD on
+    // the FMA pipe) leaves pixels 8k+j in byte k of register j.
 #pragma unroll 1
-    for (int h = 3; h >= 0; --h) {
-        const uint2 v0 = *reinterpret_cast<const uint2*>(mine + 24 * h);
-        const uint2 v1 = *reinterpret_cast<const uint2*>(mine + 24 * h + 8);
-        const uint2 v2 = *reinterpret_cast<const uint2*>(mine + 24 * h + 16);
-        const uint32_t w[6] = {v0.x, v0.y, v1.x, v1.y, v2.x, v2.y};
+    for (int h = 1; h >= 0; --h) {
+        const uint4 v0 = *reinterpret_cast<const uint4*>(mine + 48 * h);
+        const uint4 v1 = *reinterpret_cast<const uint4*>(mine + 48 * h + 16);
+        const uint4 v2 = *reinterpret_cast<const uint4*>(mine + 48 * h + 32);
+        const uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            // pixels 2m, 2m+1 of the round = bytes 6m .. 6m+5 = words (3m)/2, (3m)/2 + 1
-            const uint32_t wa = w[(3 * m) >> 1], wb = w[((3 * m) >> 1) + 1];
-            const uint32_t R2 = __byte_perm(wa, wb, (m & 1) ? 0x5522 : 0x3300);
-            const uint32_t G2 = __byte_perm(wa, wb, (m & 1) ? 0x6633 : 0x4411);
-            const uint32_t B2 = __byte_perm(wa, wb, (m & 1) ? 0x7744 : 0x5522);
-            // idx = r5 | g5<<5 | b5<<10 in each 16-bit half
-            const uint32_t X = ((R2 >> 3) & 0x001F001Fu) | ((G2 * 4u) & 0x03E003E0u) | ((B2 * 128u) & 0x7C007C00u);
-            const uint32_t la = coarse[X & 0xFFFFu];
-            const uint32_t lb = coarse[X >> 16];
-            Wp[2 * m] = Wp[2 * m] * 256u + la;
-            Wp[2 * m + 1] = Wp[2 * m + 1] * 256u + lb;
+        for (int g = 3; g >= 0; --g) {   // 4 pixels = 12 bytes: [r0 g0 b0 r1] [g1 b1 r2 g2] [b2 r3 g3 b3]
+            const uint32_t w0 = w[3 * g], w1 = w[3 * g + 1], w2 = w[3 * g + 2];
+            const uint32_t q0 = ((w0 >> 3) & 0x1F001F1Fu) | (w0 & 0x00F80000u);
+            const uint32_t q1 = ((w1 >> 3) & 0x1F1F001Fu) | (w1 & 0x0000F800u);
+            const uint32_t q2 = ((w2 >> 3) & 0x001F1F00u) | (w2 & 0xF80000F8u);
+            const uint32_t i0 = __dp4a(q0, 0x00802001u, 0u);
+            const uint32_t i1 = __dp4a(q1, 0x00008020u, __dp4a(q0, 0x01000000u, 0u));
+            const uint32_t i2 = __dp4a(q2, 0x00000080u, __dp4a(q1, 0x20010000u, 0u));
+            const uint32_t i3 = __dp4a(q2, 0x80200100u, 0u);
+            // pixel 16h + 4g + t -> register (4g + t) & 7, byte order by descending pixel index
+            const int j = (4 * g) & 7;
+            Wp[j + 0] = Wp[j + 0] * 256u + sm_coarse[i0];
+            Wp[j + 1] = Wp[j + 1] * 256u + sm_coarse[i1];
+            Wp[j + 2] = Wp[j + 2] * 256u + sm_coarse[i2];
+            Wp[j + 3] = Wp[j + 3] * 256u + sm_coarse[i3];
         }
     }
     after_read();
@@ -346,18 +352,29 @@ __device__ __forceinline__ void categorize_line(const FastParams& P, const uint8
     }
     uint32_t s_all = ~0u;   // pixels whose label byte has all NB low bits set: MIXED (0xFF) or VOID
     if (R > 0) {
+        // bit transpose (three delta-swap stages between register pairs): T[b] bit q = bit b of the
+        // label of pixel q of aligned word `lane`
+        uint32_t T[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) T[j] = Wp[j];
+#pragma unroll
+        for (int st = 0; st < 3; ++st) {
+            const int d = 1 << st;
+            const uint32_t m = st == 0 ? 0x55555555u : (st == 1 ? 0x33333333u : 0x0F0F0F0Fu);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (j & d) continue;
+                const uint32_t x = T[j], y = T[j + d];
+                T[j] = (x & m) | ((y << d) & ~m);
+                T[j + d] = ((x >> d) & m) | (y & ~m);
+            }
+        }
         // vote word `lane` starts at wx = O0 + lane*U: funnel of aligned words k, k+1
         const int o = G::O0 + lane * G::U;
         const int k = o >> 5, sh = o & 31;
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
-            uint32_t t = 0u;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const uint32_t s = (j >= b) ? (Wp[j] << (j - b)) : (Wp[j] >> (b - j));
-                t |= s & (0x01010101u << j);
-            }
-            // t: bit q = bit b of the label of pixel q of aligned word `lane`
+            const uint32_t t = T[b];
             s_all &= t;
             const uint32_t lo = __shfl_sync(0xffffffffu, t, k);
             const uint32_t hi = __shfl_sync(0xffffffffu, t, (k + 1) & 31);
