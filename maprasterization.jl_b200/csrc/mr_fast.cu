@@ -59,18 +59,16 @@ template <int R, int NB> struct Cfg {
     static constexpr int WARPS = (R > 0 && NB >= 6) ? 12 : 16;
     static constexpr int B = R == 0 ? 8 : ((NB <= 5) ? (R == 3 ? 4 : 6) : 4);   // lines voted per block
     static constexpr int RL = B + 2 * R;                                       // plane ring, lines
-    static constexpr int N_SENT = RL * 32, N_W2 = B * 32;                      // list capacities
+    static constexpr int N_W2 = B * 32;                                        // list capacity
     // per-warp slice (byte offsets)
     static constexpr int W_PLANES = 0;                                 // uint32 [RL][NB][32]
     static constexpr int W_STAGE = W_PLANES + RL * NBP * 128;          // uint8  [STAGE_BYTES]
-    static constexpr int W_LISTS = W_STAGE + STAGE_BYTES;              // MIXED list, later w2 + fb lists
-    static constexpr int W_SENTMASK = W_LISTS;                         // uint32 [N_SENT]
-    static constexpr int W_SENTCODE = W_SENTMASK + N_SENT * 4;         // uint16 [N_SENT]
+    static constexpr int W_LISTS = W_STAGE + STAGE_BYTES;              // round-2 and exact-vote word lists
     static constexpr int W_W2MASK = W_LISTS;                           // uint32 [N_W2]
     static constexpr int W_FBMASK = W_W2MASK + N_W2 * 4;               // uint32 [N_W2]
     static constexpr int W_W2CODE = W_FBMASK + N_W2 * 4;               // uint16 [N_W2]
     static constexpr int W_FBCODE = W_W2CODE + N_W2 * 2;               // uint16 [N_W2]
-    static constexpr int W_CNT = W_LISTS + cmax(N_SENT * 6, N_W2 * 12);   // int [4]: n_sent, n_w2, n_fb
+    static constexpr int W_CNT = W_LISTS + N_W2 * 12;                  // int [4]: -, n_w2, n_fb
     static constexpr int W_MBAR = W_CNT + 16;                          // uint64
     static constexpr int W_BYTES = (W_MBAR + 8 + 127) / 128 * 128;
     static constexpr int SLICES = (int)MR_COARSE_SIZE;                 // CTA layout: coarse | slices
@@ -174,13 +172,21 @@ __device__ __forceinline__ CopyPlan copy_plan(const FastParams& P, const Item& i
     return c;
 }
 
-// TMA: bring the packed RGB of line y into the warp's staging buffer.  Returns false if the line
-// needs no load (outside the sheet).
-__device__ __forceinline__ bool issue_line_copy(const FastParams& P, const CopyPlan& c, int y, uint32_t bar, int lane) {
-    if (y < -P.job.halo_lo || y >= P.job.n2 + P.job.halo_hi || c.bytes == 0u) return false;
+// TMA: bring the packed RGB of line y into the warp's staging buffer, and pull the line PF lines
+// further down into L2 (the next copy then completes at L2 latency instead of DRAM latency).
+// Returns false if the line needs no load (outside the sheet).  ylo / yhi: loadable lines.
+constexpr int PF_LINES = 3;
+__device__ __forceinline__ bool issue_line_copy(const FastParams& P, const CopyPlan& c, int y, int ylo, int yhi,
+                                                uint32_t bar, int lane) {
+    if (y < ylo || y >= yhi) return false;
     if (lane == 0) {
+        const uint8_t* src = c.src0 + (long long)y * P.job.stride2;
         mbar_expect_tx(bar, c.bytes);
-        tma_load_1d(c.dst, c.src0 + (long long)y * P.job.stride2, c.bytes, bar);
+        tma_load_1d(c.dst, src, c.bytes, bar);
+        if (y + PF_LINES < yhi) {
+            const uint8_t* pf = src + (long long)PF_LINES * P.job.stride2;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf), "r"(c.bytes) : "memory");
+        }
     }
     return true;
 }
@@ -227,47 +233,14 @@ __device__ __forceinline__ void for_each_pixel(const uint16_t* codes, const uint
 }
 
 // ---------------------------------------------------------------------------------------------
-// exact resolution of one MIXED-cell pixel.  code = line-in-block << 5 | aligned word, q = pixel
-template <int R, int NB>
-__device__ __forceinline__ void fix_pixel(const FastParams& P, uint8_t* ws, const Item& it, int code, int q,
-                                          int blk_y, unsigned& c_fine, unsigned& c_nomatch) {
-    using G = Geo<R>;
-    using C = Cfg<R, NB>;
-    const int y = blk_y + (code >> 5), wx = (code & 31) * 32 + q;
-    const long long x = it.xw0 + wx;
-    const uint8_t* p = it.px + (long long)y * P.job.stride2 + x * 3;
-    const unsigned rgb = (unsigned)__ldg(p) | ((unsigned)__ldg(p + 1) << 8) | ((unsigned)__ldg(p + 2) << 16);
-    const unsigned l = __ldg(P.job.lut + rgb);
-    if (R > 0 && wx >= G::O0) {
-        // the pixel lives in up to two overlapped vote words
-        const int slot = (y - (it.y0 - R)) % C::RL;
-        uint32_t* planes = reinterpret_cast<uint32_t*>(ws + C::W_PLANES) + slot * NB * 32;
-        const int lh = (wx - G::O0) / G::U;
-#pragma unroll 1
-        for (int t = 0; t < 2; ++t) {
-            const int vl = lh - t;
-            const int qq = wx - G::O0 - vl * G::U;
-            if (vl < 0 || vl > 31 || qq > 31) continue;
-#pragma unroll
-            for (int b = 0; b < NB; ++b)
-                if (!((l >> b) & 1u)) atomicAnd(&planes[b * 32 + vl], ~(1u << qq));
-        }
-    }
-    if (y >= it.y0 && y < it.y1 && wx >= 32 * G::HW && wx < 32 * G::HW + G::SW) {   // owned pixel
-        it.out[(long long)y * P.job.out_stride2 + x] = (uint8_t)l;                   // provisional label
-        ++c_fine;
-        if (R == 0) c_nomatch += (l == 0);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
 // categorise one line of the strip window (whole warp) from the TMA staging buffer
 // after_read() is called as soon as the staging buffer has been consumed (the caller uses it to
 // issue the TMA copy of the next line, so that the copy overlaps the rest of this line's work).
 template <int R, int NB, bool COUNT, typename F>
 __device__ __forceinline__ void categorize_line(const FastParams& P, const uint8_t* coarse, uint8_t* ws,
-                                                const Item& it, int y, int blk_y, int lane, const LaneMasks& M,
-                                                const uint8_t* staged, F after_read, unsigned& c_nomatch) {
+                                                const Item& it, int y, int lane, const LaneMasks& M,
+                                                const uint8_t* staged, F after_read, unsigned& c_fine,
+                                                unsigned& c_nomatch) {
     using G = Geo<R>;
     using C = Cfg<R, NB>;
     const int slot = (y - (it.y0 - R)) % C::RL;
@@ -317,7 +290,6 @@ __device__ __forceinline__ void categorize_line(const FastParams& P, const uint8
             Wp[j + 3] = Wp[j + 3] * 256u + sm_coarse[i3];
         }
     }
-    after_read();
     if (it.edge) {   // warp-uniform: force VOID outside [0, n1)
 #pragma unroll
         for (int j = 0; j < 8; ++j) Wp[j] |= ((~M.vmask >> j) & 0x01010101u) * 0xFFu;
@@ -350,11 +322,11 @@ __device__ __forceinline__ void categorize_line(const FastParams& P, const uint8
         *reinterpret_cast<uint4*>(dst) = make_uint4(nat[0], nat[1], nat[2], nat[3]);
         if (x0 + 16 < P.job.n1) *reinterpret_cast<uint4*>(dst + 16) = make_uint4(nat[4], nat[5], nat[6], nat[7]);
     }
-    uint32_t s_all = ~0u;   // pixels whose label byte has all NB low bits set: MIXED (0xFF) or VOID
+    // bit transpose (three delta-swap stages between register pairs): T[b] bit q = bit b of the
+    // label of pixel q of aligned word `lane`
+    uint32_t T[8];
+    uint32_t s_all;   // pixels whose label has all NB low bits set: MIXED (0xFF) or VOID
     if (R > 0) {
-        // bit transpose (three delta-swap stages between register pairs): T[b] bit q = bit b of the
-        // label of pixel q of aligned word `lane`
-        uint32_t T[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) T[j] = Wp[j];
 #pragma unroll
@@ -369,28 +341,78 @@ __device__ __forceinline__ void categorize_line(const FastParams& P, const uint8
                 T[j + d] = ((x >> d) & m) | (y & ~m);
             }
         }
-        // vote word `lane` starts at wx = O0 + lane*U: funnel of aligned words k, k+1
-        const int o = G::O0 + lane * G::U;
-        const int k = o >> 5, sh = o & 31;
+        s_all = ~0u;
 #pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            const uint32_t t = T[b];
-            s_all &= t;
-            const uint32_t lo = __shfl_sync(0xffffffffu, t, k);
-            const uint32_t hi = __shfl_sync(0xffffffffu, t, (k + 1) & 31);
-            pl[b * 32 + lane] = __funnelshift_r(lo, hi, sh);
-        }
+        for (int b = 0; b < NB; ++b) s_all &= T[b];
     } else {
         s_all = 0u;
 #pragma unroll
         for (int j = 0; j < 8; ++j) s_all |= ((Wp[j] >> 7) & 0x01010101u) << j;
     }
-    // MIXED-cell pixels (real, loaded pixels only) -> the warp's work list, one entry per word
-    const uint32_t s7 = s_all & M.smask;
-    if (s7) {
-        const int e = atomicAdd(reinterpret_cast<int*>(ws + C::W_CNT), 1);
-        reinterpret_cast<uint16_t*>(ws + C::W_SENTCODE)[e] = (uint16_t)(((y - blk_y) << 5) | lane);
-        reinterpret_cast<uint32_t*>(ws + C::W_SENTMASK)[e] = s7;
+    // ---- MIXED-cell pixels (real, loaded pixels only; ~1 %): exact label from the 2^24-entry table
+    // (L2 resident), colour bytes from the staging line.  The colours of the first two MIXED pixels
+    // of every word are captured first, so that the staging line can be released (next TMA copy)
+    // before the table loads are issued; words with more than two (rare) take the loop.
+    {
+        uint32_t s = s_all & M.smask;
+        uint8_t* orow = it.out + (long long)y * P.job.out_stride2 + it.xw0 + (long long)lane * 32;
+        const uint32_t ownmask = own_line ? M.avalid : 0u;
+        auto colour = [&](int q) {
+            const uint8_t* c3 = mine + 3 * q;
+            return (unsigned)c3[0] | ((unsigned)c3[1] << 8) | ((unsigned)c3[2] << 16);
+        };
+        auto apply = [&](int q, unsigned l) {
+            const uint32_t bitq = 1u << q;
+            if (R > 0) {
+#pragma unroll
+                for (int b = 0; b < NB; ++b)
+                    if (!((l >> b) & 1u)) T[b] &= ~bitq;
+            }
+            if (ownmask & bitq) {   // owned pixel: fix the provisional label too
+                orow[q] = (uint8_t)l;
+                ++c_fine;
+                if (COUNT && R == 0) c_nomatch += (l == 0);
+            }
+        };
+        int q0 = 0, q1 = 0;
+        unsigned rgb0 = 0, rgb1 = 0;
+        const bool h0 = s != 0u;
+        if (h0) {
+            q0 = __ffs(s) - 1;
+            s &= s - 1;
+            rgb0 = colour(q0);
+        }
+        const bool h1 = s != 0u;
+        if (h1) {
+            q1 = __ffs(s) - 1;
+            s &= s - 1;
+            rgb1 = colour(q1);
+        }
+#pragma unroll 1
+        while (__any_sync(0xffffffffu, s != 0u)) {
+            if (s) {
+                const int q = __ffs(s) - 1;
+                s &= s - 1;
+                apply(q, __ldg(P.job.lut + colour(q)));
+            }
+        }
+        after_read();
+        unsigned l0 = 0, l1 = 0;
+        if (h0) l0 = __ldg(P.job.lut + rgb0);
+        if (h1) l1 = __ldg(P.job.lut + rgb1);
+        if (h0) apply(q0, l0);
+        if (h1) apply(q1, l1);
+    }
+    if (R > 0) {
+        // vote word `lane` starts at wx = O0 + lane*U: funnel of aligned words k, k+1
+        const int o = G::O0 + lane * G::U;
+        const int k = o >> 5, sh = o & 31;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const uint32_t lo = __shfl_sync(0xffffffffu, T[b], k);
+            const uint32_t hi = __shfl_sync(0xffffffffu, T[b], (k + 1) & 31);
+            pl[b * 32 + lane] = __funnelshift_r(lo, hi, sh);
+        }
     }
 }
 
@@ -819,11 +841,13 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
         const int cat_last = it.y1 + R;                       // lines [y0-R, y1+R) are categorised
         int ycat = it.y0 - R;                                 // next line to categorise
         const CopyPlan plan = copy_plan<R>(P, it, stage_u32);
-        bool pend = issue_line_copy(P, plan, ycat, bar, lane);
+        // loadable lines of this item (none if the strip window has no bytes inside the sheet)
+        const int ylo = max(ycat, -P.job.halo_lo);
+        const int yhi = plan.bytes ? min(cat_last, (int)P.job.n2 + P.job.halo_hi) : ylo;
+        bool pend = issue_line_copy(P, plan, ycat, ylo, yhi, bar, lane);
 #pragma unroll 1
         for (int a = it.y0; a < it.y1; a += C::B) {
             const int vend = min(a + C::B, it.y1);
-            const int blk_y = ycat;                           // first line categorised in this block
             // ---- categorise lines [ycat, vend + R); each arrives by TMA, issued one line ahead
 #pragma unroll 1
             for (; ycat < vend + R; ++ycat) {
@@ -833,24 +857,13 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
                 }
                 bool nxt = false;
                 categorize_line<R, NB, COUNT>(
-                    P, coarse, ws, it, ycat, blk_y, lane, M, pend ? stage : nullptr,
+                    P, coarse, ws, it, ycat, lane, M, pend ? stage : nullptr,
                     [&]() {
                         __syncwarp();   // every lane is done with the staging buffer
-                        nxt = (ycat + 1 < cat_last) ? issue_line_copy(P, plan, ycat + 1, bar, lane) : false;
+                        nxt = issue_line_copy(P, plan, ycat + 1, ylo, yhi, bar, lane);
                     },
-                    c_nomatch);
+                    c_fine, c_nomatch);
                 pend = nxt;
-            }
-            // ---- resolve the MIXED-cell pixels of these lines, spread evenly over the lanes
-            {
-                __syncwarp();
-                const int n = cnt[0];
-                for_each_pixel(reinterpret_cast<const uint16_t*>(ws + C::W_SENTCODE),
-                               reinterpret_cast<const uint32_t*>(ws + C::W_SENTMASK), n, lane,
-                               [&](int code, int q) { fix_pixel<R, NB>(P, ws, it, code, q, blk_y, c_fine, c_nomatch); });
-                __syncwarp();
-                if (lane == 0) cnt[0] = 0;
-                __syncwarp();
             }
             if constexpr (R > 0) {
                 // ---- votes: round 1 per block (lane = vote word), then round 2 over the word list
