@@ -63,12 +63,11 @@ template <int R, int NB> struct Cfg {
     // per-warp slice (byte offsets)
     static constexpr int W_PLANES = 0;                                 // uint32 [RL][NB][32]
     static constexpr int W_STAGE = W_PLANES + RL * NBP * 128;          // uint8  [STAGE_BYTES]
-    static constexpr int W_LISTS = W_STAGE + STAGE_BYTES;              // round-2 and exact-vote word lists
-    static constexpr int W_W2MASK = W_LISTS;                           // uint32 [N_W2]
-    static constexpr int W_FBMASK = W_W2MASK + N_W2 * 4;               // uint32 [N_W2]
-    static constexpr int W_W2CODE = W_FBMASK + N_W2 * 4;               // uint16 [N_W2]
-    static constexpr int W_FBCODE = W_W2CODE + N_W2 * 2;               // uint16 [N_W2]
-    static constexpr int W_CNT = W_LISTS + N_W2 * 12;                  // int [4]: -, n_w2, n_fb
+    static constexpr int W_LISTS = W_STAGE + STAGE_BYTES;              // round-2 word list; the exact-vote list
+    static constexpr int W_W2MASK = W_LISTS;                           // uint32 [N_W2]   overwrites it in place
+    static constexpr int W_W2CODE = W_W2MASK + N_W2 * 4;               // uint16 [N_W2]
+    static constexpr int W_OUT = W_W2CODE + N_W2 * 2;                  // uint8 [32 * U]: final labels of one line
+    static constexpr int W_CNT = W_OUT + (R > 0 ? 32 * (32 - 2 * R) : 0);   // int [4]: -, n_w2, n_fb
     static constexpr int W_MBAR = W_CNT + 16;                          // uint64
     static constexpr int W_BYTES = (W_MBAR + 8 + 127) / 128 * 128;
     static constexpr int SLICES = (int)MR_COARSE_SIZE;                 // CTA layout: coarse | slices
@@ -294,39 +293,92 @@ __device__ __forceinline__ void categorize_line(const FastParams& P, const uint8
 #pragma unroll
         for (int j = 0; j < 8; ++j) Wp[j] |= ((~M.vmask >> j) & 0x01010101u) * 0xFFu;
     }
-    // provisional output: the categorised labels of the words / lines this item owns
     const bool own_line = (y >= it.y0) && (y < it.y1);
-    if (own_line && M.avalid) {
-        uint32_t nat[8];
+    const uint32_t ownmask = own_line ? M.avalid : 0u;
+    // ---- MIXED-cell pixels (real, loaded pixels only; ~1 %) get their exact label from the
+    // 2^24-entry table (L2 resident).  Bit 7 of a label byte is set for MIXED (and VOID) only.
+    // The colours of the first two MIXED pixels of every word are captured from the staging line
+    // right away, so that the line can be released (next TMA copy) and the table loads fly while
+    // the labels are transposed; words with more than two (rare) keep the line a little longer.
+    uint32_t s = 0u;
 #pragma unroll
-        for (int n = 0; n < 8; ++n) {   // natural order: pixel 4n+k in byte k of register n
-            const int k = n >> 1, base = 4 * (n & 1);
-            const uint32_t sel = (uint32_t)k | ((uint32_t)(4 + k) << 4);
-            const uint32_t lo = __byte_perm(Wp[base + 0], Wp[base + 1], sel);
-            const uint32_t hi = __byte_perm(Wp[base + 2], Wp[base + 3], sel);
-            nat[n] = __byte_perm(lo, hi, 0x5410);
-        }
-        if (COUNT && R == 0) {
-#pragma unroll
-            for (int n = 0; n < 8; ++n) {
-                const uint32_t nz = (nat[n] | (nat[n] >> 4)) & 0x0F0F0F0Fu;
-                const uint32_t nz2 = (nz | (nz >> 1) | (nz >> 2) | (nz >> 3)) & 0x01010101u;   // byte != 0
-                const uint32_t v4 = (M.avalid >> (4 * n)) & 0xFu;
-                const uint32_t vm = (v4 & 1u) | ((v4 & 2u) << 7) | ((v4 & 4u) << 14) | ((v4 & 8u) << 21);
-                c_nomatch += __popc(vm & ~nz2);
-            }
-        }
-        // mr_fast_supported guarantees n1 % 16 == 0 or padded lines: whole 16-byte chunks only
-        const long long x0 = it.xw0 + (long long)lane * 32;
-        uint8_t* dst = it.out + (long long)y * P.job.out_stride2 + x0;
-        *reinterpret_cast<uint4*>(dst) = make_uint4(nat[0], nat[1], nat[2], nat[3]);
-        if (x0 + 16 < P.job.n1) *reinterpret_cast<uint4*>(dst + 16) = make_uint4(nat[4], nat[5], nat[6], nat[7]);
+    for (int j = 0; j < 8; ++j) s |= (Wp[j] >> (7 - j)) & (0x01010101u << j);
+    s &= M.smask;
+    auto colour = [&](int q) {
+        const uint8_t* c3 = mine + 3 * q;
+        return (unsigned)c3[0] | ((unsigned)c3[1] << 8) | ((unsigned)c3[2] << 16);
+    };
+    int q0 = 0, q1 = 0;
+    unsigned rgb0 = 0, rgb1 = 0;
+    const bool h0 = s != 0u;
+    if (h0) {
+        q0 = __ffs(s) - 1;
+        s &= s - 1;
+        rgb0 = colour(q0);
     }
-    // bit transpose (three delta-swap stages between register pairs): T[b] bit q = bit b of the
-    // label of pixel q of aligned word `lane`
-    uint32_t T[8];
-    uint32_t s_all;   // pixels whose label has all NB low bits set: MIXED (0xFF) or VOID
-    if (R > 0) {
+    const bool h1 = s != 0u;
+    if (h1) {
+        q1 = __ffs(s) - 1;
+        s &= s - 1;
+        rgb1 = colour(q1);
+    }
+    const bool more = __any_sync(0xffffffffu, s != 0u);
+    if (!more) after_read();
+    unsigned l0 = 0, l1 = 0;
+    if (h0) l0 = __ldg(P.job.lut + rgb0);
+    if (h1) l1 = __ldg(P.job.lut + rgb1);
+    if constexpr (R == 0) {
+        // ---- no clean: the categorised labels are the output
+        uint8_t* orow = it.out + (long long)y * P.job.out_stride2 + it.xw0 + (long long)lane * 32;
+        if (ownmask) {
+            uint32_t nat[8];
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {   // natural order: pixel 4n+k in byte k of register n
+                const int k = n >> 1, base = 4 * (n & 1);
+                const uint32_t sel = (uint32_t)k | ((uint32_t)(4 + k) << 4);
+                const uint32_t lo = __byte_perm(Wp[base + 0], Wp[base + 1], sel);
+                const uint32_t hi = __byte_perm(Wp[base + 2], Wp[base + 3], sel);
+                nat[n] = __byte_perm(lo, hi, 0x5410);
+            }
+            if (COUNT) {
+#pragma unroll
+                for (int n = 0; n < 8; ++n) {
+                    const uint32_t nz = (nat[n] | (nat[n] >> 4)) & 0x0F0F0F0Fu;
+                    const uint32_t nz2 = (nz | (nz >> 1) | (nz >> 2) | (nz >> 3)) & 0x01010101u;   // byte != 0
+                    const uint32_t v4 = (ownmask >> (4 * n)) & 0xFu;
+                    const uint32_t vm = (v4 & 1u) | ((v4 & 2u) << 7) | ((v4 & 4u) << 14) | ((v4 & 8u) << 21);
+                    c_nomatch += __popc(vm & ~nz2);
+                }
+            }
+            // mr_fast_supported guarantees n1 % 16 == 0 or padded lines: whole 16-byte chunks only
+            *reinterpret_cast<uint4*>(orow) = make_uint4(nat[0], nat[1], nat[2], nat[3]);
+            if (it.xw0 + (long long)lane * 32 + 16 < P.job.n1)
+                *reinterpret_cast<uint4*>(orow + 16) = make_uint4(nat[4], nat[5], nat[6], nat[7]);
+        }
+        auto patch = [&](int q, unsigned l) {
+            if ((ownmask >> q) & 1u) {
+                orow[q] = (uint8_t)l;
+                ++c_fine;
+                if (COUNT) c_nomatch += (l == 0);
+            }
+        };
+        if (more) {
+#pragma unroll 1
+            while (__any_sync(0xffffffffu, s != 0u)) {
+                if (s) {
+                    const int q = __ffs(s) - 1;
+                    s &= s - 1;
+                    patch(q, __ldg(P.job.lut + colour(q)));
+                }
+            }
+            after_read();
+        }
+        if (h0) patch(q0, l0);
+        if (h1) patch(q1, l1);
+    } else {
+        // ---- bit transpose (three delta-swap stages between register pairs): T[b] bit q = bit b of
+        // the label of pixel q of aligned word `lane`
+        uint32_t T[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) T[j] = Wp[j];
 #pragma unroll
@@ -336,74 +388,31 @@ __device__ __forceinline__ void categorize_line(const FastParams& P, const uint8
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 if (j & d) continue;
-                const uint32_t x = T[j], y = T[j + d];
-                T[j] = (x & m) | ((y << d) & ~m);
-                T[j + d] = ((x >> d) & m) | (y & ~m);
+                const uint32_t x = T[j], y2 = T[j + d];
+                T[j] = (x & m) | ((y2 << d) & ~m);
+                T[j + d] = ((x >> d) & m) | (y2 & ~m);
             }
         }
-        s_all = ~0u;
-#pragma unroll
-        for (int b = 0; b < NB; ++b) s_all &= T[b];
-    } else {
-        s_all = 0u;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s_all |= ((Wp[j] >> 7) & 0x01010101u) << j;
-    }
-    // ---- MIXED-cell pixels (real, loaded pixels only; ~1 %): exact label from the 2^24-entry table
-    // (L2 resident), colour bytes from the staging line.  The colours of the first two MIXED pixels
-    // of every word are captured first, so that the staging line can be released (next TMA copy)
-    // before the table loads are issued; words with more than two (rare) take the loop.
-    {
-        uint32_t s = s_all & M.smask;
-        uint8_t* orow = it.out + (long long)y * P.job.out_stride2 + it.xw0 + (long long)lane * 32;
-        const uint32_t ownmask = own_line ? M.avalid : 0u;
-        auto colour = [&](int q) {
-            const uint8_t* c3 = mine + 3 * q;
-            return (unsigned)c3[0] | ((unsigned)c3[1] << 8) | ((unsigned)c3[2] << 16);
-        };
-        auto apply = [&](int q, unsigned l) {
+        auto apply = [&](int q, unsigned l) {   // MIXED = all ones: clear the zero bits of the label
             const uint32_t bitq = 1u << q;
-            if (R > 0) {
 #pragma unroll
-                for (int b = 0; b < NB; ++b)
-                    if (!((l >> b) & 1u)) T[b] &= ~bitq;
-            }
-            if (ownmask & bitq) {   // owned pixel: fix the provisional label too
-                orow[q] = (uint8_t)l;
-                ++c_fine;
-                if (COUNT && R == 0) c_nomatch += (l == 0);
-            }
+            for (int b = 0; b < NB; ++b)
+                if (!((l >> b) & 1u)) T[b] &= ~bitq;
+            c_fine += (ownmask >> q) & 1u;
         };
-        int q0 = 0, q1 = 0;
-        unsigned rgb0 = 0, rgb1 = 0;
-        const bool h0 = s != 0u;
-        if (h0) {
-            q0 = __ffs(s) - 1;
-            s &= s - 1;
-            rgb0 = colour(q0);
-        }
-        const bool h1 = s != 0u;
-        if (h1) {
-            q1 = __ffs(s) - 1;
-            s &= s - 1;
-            rgb1 = colour(q1);
-        }
+        if (more) {
 #pragma unroll 1
-        while (__any_sync(0xffffffffu, s != 0u)) {
-            if (s) {
-                const int q = __ffs(s) - 1;
-                s &= s - 1;
-                apply(q, __ldg(P.job.lut + colour(q)));
+            while (__any_sync(0xffffffffu, s != 0u)) {
+                if (s) {
+                    const int q = __ffs(s) - 1;
+                    s &= s - 1;
+                    apply(q, __ldg(P.job.lut + colour(q)));
+                }
             }
+            after_read();
         }
-        after_read();
-        unsigned l0 = 0, l1 = 0;
-        if (h0) l0 = __ldg(P.job.lut + rgb0);
-        if (h1) l1 = __ldg(P.job.lut + rgb1);
         if (h0) apply(q0, l0);
         if (h1) apply(q1, l1);
-    }
-    if (R > 0) {
         // vote word `lane` starts at wx = O0 + lane*U: funnel of aligned words k, k+1
         const int o = G::O0 + lane * G::U;
         const int k = o >> 5, sh = o & 31;
@@ -578,8 +587,7 @@ __device__ __forceinline__ unsigned exact_vote(const uint32_t (&Pl)[2 * R + 1][N
 // Pixels still undecided are appended (word entry: code + mask) to the next list.
 template <int R, int NB, bool COUNT>
 __device__ __forceinline__ void vote_word(const FastParams& P, uint8_t* ws, const Item& it, int y, int blk_a,
-                                          int vl, uint32_t mask, bool round2, unsigned& c_nomatch,
-                                          unsigned& c_changed) {
+                                          int vl, uint32_t mask, unsigned& c_nomatch, unsigned& c_changed) {
     using G = Geo<R>;
     using C = Cfg<R, NB>;
     constexpr int SIDE = 2 * R + 1;
@@ -604,25 +612,24 @@ __device__ __forceinline__ void vote_word(const FastParams& P, uint8_t* ws, cons
     }
     uint32_t decided, selA, diff, zero;
     vote_core<R, NB>(Pl, a_lab, b_lab, decided, selA, diff, zero);
-    const uint32_t now = decided & mask;
-    uint32_t changed = now & diff;
+    uint32_t now = decided & mask;
     const uint32_t undec = ~decided & mask;
     if (COUNT) {
-        c_changed += __popc(changed);
+        c_changed += __popc(now & diff);
         c_nomatch += __popc(now & zero);
     }
     uint8_t* orow = it.out + (long long)y * P.job.out_stride2 + it.xw0 + G::O0 + vl * G::U;
 #pragma unroll 1
-    while (changed) {   // the provisional labels are already in global memory: patch only changes
-        const int q = __ffs(changed) - 1;
-        changed &= changed - 1;
+    while (now) {   // round 1 stored a guess for these pixels: overwrite it with the decision
+        const int q = __ffs(now) - 1;
+        now &= now - 1;
         orow[q] = (uint8_t)(((selA >> q) & 1u) ? a_lab : b_lab);
     }
-    if (undec) {
+    if (undec) {   // -> exact-vote list (in place: at most one entry per round-2 entry already read)
         int* cnt = reinterpret_cast<int*>(ws + C::W_CNT);
-        const int e = atomicAdd(cnt + (round2 ? 2 : 1), 1);
-        reinterpret_cast<uint16_t*>(ws + (round2 ? C::W_FBCODE : C::W_W2CODE))[e] = (uint16_t)(((y - blk_a) << 5) | vl);
-        reinterpret_cast<uint32_t*>(ws + (round2 ? C::W_FBMASK : C::W_W2MASK))[e] = undec;
+        const int e = atomicAdd(cnt + 2, 1);
+        reinterpret_cast<uint16_t*>(ws + C::W_W2CODE)[e] = (uint16_t)(((y - blk_a) << 5) | vl);
+        reinterpret_cast<uint32_t*>(ws + C::W_W2MASK)[e] = undec;
     }
 }
 
@@ -633,9 +640,14 @@ __device__ __forceinline__ void vote_word(const FastParams& P, uint8_t* ws, cons
 // see the line: the box counts slide down the block (add the line entering the window, subtract
 // the line leaving it).  Decision test and tie rule as in vote_core.  Words with undecided pixels
 // go to the round-2 list (candidates per word there).
+//
+// Output: the labels of every output line are final here except for the undecided pixels (which get
+// a guess that round 2 / the exact vote overwrite): each vote word writes its U bytes into the warp's
+// line buffer and one TMA bulk store (shared -> global, 32*U contiguous bytes) sends the line out.
 template <int R, int NB, bool COUNT>
 __device__ __forceinline__ void block_vote(const FastParams& P, uint8_t* ws, const Item& it, int a, int nl, int vl,
-                                           uint32_t mask, unsigned& c_nomatch, unsigned& c_changed) {
+                                           uint32_t mask, uint32_t obytes, unsigned& c_nomatch,
+                                           unsigned& c_changed) {
     using G = Geo<R>;
     using C = Cfg<R, NB>;
     constexpr int SIDE = 2 * R + 1;
@@ -643,7 +655,6 @@ __device__ __forceinline__ void block_vote(const FastParams& P, uint8_t* ws, con
     constexpr int WH = R == 1 ? 2 : 3, WC = G::WC;
     constexpr unsigned VOIDL = (1u << NB) - 1u;
     constexpr int LINE = NB * 128, RING = C::RL * LINE;
-    if (mask == 0u) return;   // this vote word has no output pixels (right sheet border)
     const uint8_t* base = ws + C::W_PLANES + vl * 4;
     // ---- candidates (heuristic only): A = label at the centre of the block, B = the label farthest
     // from the centre among the pixels of the centre / first / last line that differ from A.  Labels
@@ -707,7 +718,10 @@ __device__ __forceinline__ void block_vote(const FastParams& P, uint8_t* ws, con
 #pragma unroll
     for (int d = 0; d < SIDE; ++d) hA[d] = hB[d] = 0u;
     int off = ((a - it.y0) % C::RL) * LINE;   // slot of line a - R
-    uint8_t* orow = it.out + (long long)a * P.job.out_stride2 + it.xw0 + G::O0 + vl * G::U;
+    uint8_t* gline = it.out + (long long)a * P.job.out_stride2 + it.xw0 + 32 * G::HW;   // strip start, line a
+    uint8_t* obuf = ws + C::W_OUT + vl * G::U;
+    const uint32_t obuf0 = smem_u32(ws + C::W_OUT);
+    const uint32_t AB = a_lab ^ b_lab, B4 = b_lab * 0x01010101u;
 #pragma unroll 1
     for (int i = 0; i < nl + 2 * R; ++i) {
         uint32_t ma = avm, mb = nbm;
@@ -741,25 +755,40 @@ __device__ __forceinline__ void block_vote(const FastParams& P, uint8_t* ws, con
             const Bs<WC + 2> u = bs_add<WC + 1, WC, WC + 2>(mx2, mn);
             const uint32_t decided = bs_gt_const<WC + 2>(u, (unsigned)N);
             const uint32_t now = decided & mask;
-            uint32_t changed = now & ~((selA & hA[R]) | (~selA & hB[R]));   // centre label != winner
             const uint32_t undec = ~decided & mask;
             if (COUNT) {
-                c_changed += __popc(changed);
+                c_changed += __popc(now & ~((selA & hA[R]) | (~selA & hB[R])));   // centre label != winner
                 c_nomatch += __popc(now & ((a_lab == 0 ? selA : 0u) | (b_lab == 0 ? ~selA : 0u)));
             }
-#pragma unroll 1
-            while (changed) {   // the provisional labels are already in global memory: patch only changes
-                const int q = __ffs(changed) - 1;
-                changed &= changed - 1;
-                orow[q] = (uint8_t)(((selA >> q) & 1u) ? a_lab : b_lab);
+            // ---- the line buffer is free once the previous line's bulk store has read it
+            if (vl == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+            {   // labels of the U output pixels: B ^ (selA ? A ^ B : 0), GP pixels (bytes) per step
+                const uint32_t sel = selA >> R;
+                constexpr int GP = (G::U % 4 == 0) ? 4 : 2;
+#pragma unroll
+                for (int k = 0; k < G::U / GP; ++k) {
+                    const uint32_t nib = (sel >> (GP * k)) & ((1u << GP) - 1u);
+                    const uint32_t m = (nib * 0x00204081u) & 0x01010101u;   // bit j -> byte j
+                    const uint32_t v = B4 ^ (m * AB);
+                    if (GP == 4) *reinterpret_cast<uint32_t*>(obuf + 4 * k) = v;
+                    else *reinterpret_cast<uint16_t*>(obuf + 2 * k) = (uint16_t)v;
+                }
             }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (vl == 0 && obytes) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gline), "r"(obuf0),
+                             "r"(obytes) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            gline += P.job.out_stride2;
             if (undec) {
                 int* cnt = reinterpret_cast<int*>(ws + C::W_CNT);
                 const int e = atomicAdd(cnt + 1, 1);
                 reinterpret_cast<uint16_t*>(ws + C::W_W2CODE)[e] = (uint16_t)(((i - 2 * R) << 5) | vl);
                 reinterpret_cast<uint32_t*>(ws + C::W_W2MASK)[e] = undec;
             }
-            orow += P.job.out_stride2;
             SA = bs_sub<WC, WH>(SA, bs_hsum1<R>(hA[0]));
             SB = bs_sub<WC, WH>(SB, bs_hsum1<R>(hB[0]));
         }
@@ -778,8 +807,7 @@ __device__ __forceinline__ void exact_pixel(const FastParams& P, uint8_t* ws, co
     unsigned centre = 0;
 #pragma unroll
     for (int b = 0; b < NB; ++b) centre |= ((Pl[R][b] >> q) & 1u) << b;
-    if (best != centre)   // the provisional label is the centre label
-        it.out[(long long)y * P.job.out_stride2 + it.xw0 + G::O0 + vl * G::U + q] = (uint8_t)best;
+    it.out[(long long)y * P.job.out_stride2 + it.xw0 + G::O0 + vl * G::U + q] = (uint8_t)best;   // over round 1's guess
     if (COUNT) {
         c_nomatch += (best == 0);
         c_changed += (best != centre);
@@ -845,6 +873,13 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
         const int ylo = max(ycat, -P.job.halo_lo);
         const int yhi = plan.bytes ? min(cat_last, (int)P.job.n2 + P.job.halo_hi) : ylo;
         bool pend = issue_line_copy(P, plan, ycat, ylo, yhi, bar, lane);
+        // bytes of one output line of the strip (whole 16-byte chunks, see mr_fast_supported)
+        uint32_t obytes = 0;
+        if (R > 0) {
+            const long long olimit = P.padded ? ((P.job.n1 + 15) / 16) * 16 : P.job.n1;
+            const long long ob = olimit - (it.xw0 + 32 * Geo<R>::HW);
+            obytes = (uint32_t)(ob < 0 ? 0 : (ob > Geo<R>::SW ? Geo<R>::SW : ob));
+        }
 #pragma unroll 1
         for (int a = it.y0; a < it.y1; a += C::B) {
             const int vend = min(a + C::B, it.y1);
@@ -868,22 +903,30 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
             if constexpr (R > 0) {
                 // ---- votes: round 1 per block (lane = vote word), then round 2 over the word list
                 // round 1 produced, densely over the lanes
-                block_vote<R, NB, COUNT>(P, ws, it, a, vend - a, lane, M.vvalid, c_nomatch, c_changed);
+                block_vote<R, NB, COUNT>(P, ws, it, a, vend - a, lane, M.vvalid, obytes, c_nomatch, c_changed);
                 __syncwarp();
                 const int n2 = cnt[1];
+                if (n2) {   // byte patches follow: the bulk stores of this block must have landed
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                    __syncwarp();
+                }
 #pragma unroll 1
                 for (int base = 0; base < n2; base += 32) {
-                    if (base + lane < n2) {
-                        const int code = reinterpret_cast<const uint16_t*>(ws + C::W_W2CODE)[base + lane];
-                        const uint32_t mask = reinterpret_cast<const uint32_t*>(ws + C::W_W2MASK)[base + lane];
-                        vote_word<R, NB, COUNT>(P, ws, it, a + (code >> 5), a, code & 31, mask, true, c_nomatch, c_changed);
+                    const bool have = base + lane < n2;
+                    int code = 0;
+                    uint32_t mask = 0u;
+                    if (have) {
+                        code = reinterpret_cast<const uint16_t*>(ws + C::W_W2CODE)[base + lane];
+                        mask = reinterpret_cast<const uint32_t*>(ws + C::W_W2MASK)[base + lane];
                     }
+                    __syncwarp();   // entries are in registers: the exact-vote list may overwrite them
+                    if (have) vote_word<R, NB, COUNT>(P, ws, it, a + (code >> 5), a, code & 31, mask, c_nomatch, c_changed);
                 }
                 __syncwarp();
                 {   // ---- exact votes of what is still undecided, spread evenly over the lanes
                     const int n = cnt[2];
-                    for_each_pixel(reinterpret_cast<const uint16_t*>(ws + C::W_FBCODE),
-                                   reinterpret_cast<const uint32_t*>(ws + C::W_FBMASK), n, lane, [&](int code, int q) {
+                    for_each_pixel(reinterpret_cast<const uint16_t*>(ws + C::W_W2CODE),
+                                   reinterpret_cast<const uint32_t*>(ws + C::W_W2MASK), n, lane, [&](int code, int q) {
                                        exact_pixel<R, NB, COUNT>(P, ws, it, a, code, q, c_nomatch, c_changed);
                                    });
                 }
@@ -893,6 +936,7 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
             }
         }
     }
+    if (R > 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // line buffer still in use
     if (COUNT && P.job.counters) {
         for (int o = 16; o > 0; o >>= 1) {
             c_fine += __shfl_xor_sync(0xffffffffu, c_fine, o);
