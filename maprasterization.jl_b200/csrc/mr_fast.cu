@@ -54,10 +54,19 @@ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 // kernel configuration per (R, NB): warps per CTA and lines per block, sized so that one CTA
 // (coarse table + per-warp slices) fits the 227 KiB of shared memory of an SM.
 // All work lists hold one entry per 32-pixel WORD (code + pixel mask), so they cannot overflow.
+constexpr int warp_bytes(int R, int NB, int B) {   // per-warp slice for B lines per block
+    const int raw = (B + 2 * R) * (R > 0 ? NB : 0) * 128 + STAGE_BYTES + B * 32 * 6 + (R > 0 ? 32 * (32 - 2 * R) : 0) + 24;
+    return (raw + 127) / 128 * 128;
+}
+constexpr int best_block(int R, int NB, int warps) {   // largest block that fits (at most 16 lines)
+    int b = 1;
+    while (b < 16 && (int)MR_COARSE_SIZE + warps * warp_bytes(R, NB, b + 1) <= 227 * 1024) ++b;
+    return b;
+}
 template <int R, int NB> struct Cfg {
     static constexpr int NBP = R > 0 ? NB : 0;
     static constexpr int WARPS = (R > 0 && NB >= 6) ? 12 : 16;
-    static constexpr int B = R == 0 ? 8 : ((NB <= 5) ? (R == 3 ? 4 : 6) : 4);   // lines voted per block
+    static constexpr int B = R == 0 ? 8 : best_block(R, NB, WARPS);            // lines voted per block
     static constexpr int RL = B + 2 * R;                                       // plane ring, lines
     static constexpr int N_W2 = B * 32;                                        // list capacity
     // per-warp slice (byte offsets)
@@ -72,7 +81,7 @@ template <int R, int NB> struct Cfg {
     static constexpr int W_BYTES = (W_MBAR + 8 + 127) / 128 * 128;
     static constexpr int SLICES = (int)MR_COARSE_SIZE;                 // CTA layout: coarse | slices
     static constexpr int TOTAL = SLICES + WARPS * W_BYTES;
-    static_assert(TOTAL <= 227 * 1024, "shared memory budget");
+    static_assert(TOTAL <= 227 * 1024 && B >= 2, "shared memory budget");
 };
 
 struct FastParams {
@@ -175,17 +184,14 @@ __device__ __forceinline__ CopyPlan copy_plan(const FastParams& P, const Item& i
 // further down into L2 (the next copy then completes at L2 latency instead of DRAM latency).
 // Returns false if the line needs no load (outside the sheet).  ylo / yhi: loadable lines.
 constexpr int PF_LINES = 3;
-__device__ __forceinline__ bool issue_line_copy(const FastParams& P, const CopyPlan& c, int y, int ylo, int yhi,
-                                                uint32_t bar, int lane) {
+__device__ __forceinline__ bool issue_line_copy(const CopyPlan& c, const uint8_t* src, long long pf_off, int y,
+                                                int ylo, int yhi, uint32_t bar, int lane) {
     if (y < ylo || y >= yhi) return false;
     if (lane == 0) {
-        const uint8_t* src = c.src0 + (long long)y * P.job.stride2;
         mbar_expect_tx(bar, c.bytes);
         tma_load_1d(c.dst, src, c.bytes, bar);
-        if (y + PF_LINES < yhi) {
-            const uint8_t* pf = src + (long long)PF_LINES * P.job.stride2;
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf), "r"(c.bytes) : "memory");
-        }
+        if (y + PF_LINES < yhi)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + pf_off), "r"(c.bytes) : "memory");
     }
     return true;
 }
@@ -872,7 +878,10 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
         // loadable lines of this item (none if the strip window has no bytes inside the sheet)
         const int ylo = max(ycat, -P.job.halo_lo);
         const int yhi = plan.bytes ? min(cat_last, (int)P.job.n2 + P.job.halo_hi) : ylo;
-        bool pend = issue_line_copy(P, plan, ycat, ylo, yhi, bar, lane);
+        const long long pf_off = (long long)PF_LINES * P.job.stride2;
+        const uint8_t* srcn = plan.src0 + (long long)ycat * P.job.stride2;   // source of the next line to copy
+        bool pend = issue_line_copy(plan, srcn, pf_off, ycat, ylo, yhi, bar, lane);
+        srcn += P.job.stride2;
         // bytes of one output line of the strip (whole 16-byte chunks, see mr_fast_supported)
         uint32_t obytes = 0;
         if (R > 0) {
@@ -895,7 +904,8 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
                     P, coarse, ws, it, ycat, lane, M, pend ? stage : nullptr,
                     [&]() {
                         __syncwarp();   // every lane is done with the staging buffer
-                        nxt = issue_line_copy(P, plan, ycat + 1, ylo, yhi, bar, lane);
+                        nxt = issue_line_copy(plan, srcn, pf_off, ycat + 1, ylo, yhi, bar, lane);
+                        srcn += P.job.stride2;
                     },
                     c_fine, c_nomatch);
                 pend = nxt;
