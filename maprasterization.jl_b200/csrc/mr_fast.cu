@@ -33,7 +33,10 @@
 
 namespace {
 
-constexpr int STAGE_BYTES = 32 * 96;   // one line of the strip window, packed RGB
+// staging line: the AW aligned words of the strip window, packed RGB (lanes >= AW read past it into
+// the lists; their labels are never used)
+constexpr int stage_bytes(int R) { return ((R > 0 ? 34 - 2 * R : 32) * 96 + 127) / 128 * 128; }
+constexpr int LIST_CAP = 96;           // round-2 word list entries; a block that would overflow is cut short
 
 // Strip geometry for window radius R: U = 32-2R useful pixels per vote word, 32 vote words per
 // warp -> SW = 32*U output pixels per strip = U aligned 32-pixel words, plus one aligned halo word
@@ -55,7 +58,7 @@ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 // (coarse table + per-warp slices) fits the 227 KiB of shared memory of an SM.
 // All work lists hold one entry per 32-pixel WORD (code + pixel mask), so they cannot overflow.
 constexpr int warp_bytes(int R, int NB, int B) {   // per-warp slice for B lines per block
-    const int raw = (B + 2 * R) * (R > 0 ? NB : 0) * 128 + STAGE_BYTES + B * 32 * 6 + (R > 0 ? 32 * (32 - 2 * R) : 0) + 24;
+    const int raw = (B + 2 * R) * (R > 0 ? NB : 0) * 128 + stage_bytes(R) + LIST_CAP * 6 + (R > 0 ? 32 * (32 - 2 * R) : 0) + 24;
     return (raw + 127) / 128 * 128;
 }
 constexpr int best_block(int R, int NB, int warps) {   // largest block that fits (at most 16 lines)
@@ -68,11 +71,11 @@ template <int R, int NB> struct Cfg {
     static constexpr int WARPS = (R > 0 && NB >= 6) ? 12 : 16;
     static constexpr int B = R == 0 ? 8 : best_block(R, NB, WARPS);            // lines voted per block
     static constexpr int RL = B + 2 * R;                                       // plane ring, lines
-    static constexpr int N_W2 = B * 32;                                        // list capacity
+    static constexpr int N_W2 = LIST_CAP;                                      // list capacity
     // per-warp slice (byte offsets)
     static constexpr int W_PLANES = 0;                                 // uint32 [RL][NB][32]
-    static constexpr int W_STAGE = W_PLANES + RL * NBP * 128;          // uint8  [STAGE_BYTES]
-    static constexpr int W_LISTS = W_STAGE + STAGE_BYTES;              // round-2 word list; the exact-vote list
+    static constexpr int W_STAGE = W_PLANES + RL * NBP * 128;          // uint8  [stage_bytes(R)]
+    static constexpr int W_LISTS = W_STAGE + stage_bytes(R);              // round-2 word list; the exact-vote list
     static constexpr int W_W2MASK = W_LISTS;                           // uint32 [N_W2]   overwrites it in place
     static constexpr int W_W2CODE = W_W2MASK + N_W2 * 4;               // uint16 [N_W2]
     static constexpr int W_OUT = W_W2CODE + N_W2 * 2;                  // uint8 [32 * U]: final labels of one line
@@ -650,8 +653,10 @@ __device__ __forceinline__ void vote_word(const FastParams& P, uint8_t* ws, cons
 // Output: the labels of every output line are final here except for the undecided pixels (which get
 // a guess that round 2 / the exact vote overwrite): each vote word writes its U bytes into the warp's
 // line buffer and one TMA bulk store (shared -> global, 32*U contiguous bytes) sends the line out.
+// Returns the number of lines completed: the block is cut short if the round-2 list could overflow
+// (the caller votes the rest after emptying the list).
 template <int R, int NB, bool COUNT>
-__device__ __forceinline__ void block_vote(const FastParams& P, uint8_t* ws, const Item& it, int a, int nl, int vl,
+__device__ __forceinline__ int block_vote(const FastParams& P, uint8_t* ws, const Item& it, int a, int nl, int vl,
                                            uint32_t mask, uint32_t obytes, unsigned& c_nomatch,
                                            unsigned& c_changed) {
     using G = Geo<R>;
@@ -724,6 +729,7 @@ __device__ __forceinline__ void block_vote(const FastParams& P, uint8_t* ws, con
 #pragma unroll
     for (int d = 0; d < SIDE; ++d) hA[d] = hB[d] = 0u;
     int off = ((a - it.y0) % C::RL) * LINE;   // slot of line a - R
+    int n_listed = 0;   // entries this call has put on the round-2 list (warp-uniform)
     uint8_t* gline = it.out + (long long)a * P.job.out_stride2 + it.xw0 + 32 * G::HW;   // strip start, line a
     uint8_t* obuf = ws + C::W_OUT + vl * G::U;
     const uint32_t obuf0 = smem_u32(ws + C::W_OUT);
@@ -762,13 +768,15 @@ __device__ __forceinline__ void block_vote(const FastParams& P, uint8_t* ws, con
             const uint32_t decided = bs_gt_const<WC + 2>(u, (unsigned)N);
             const uint32_t now = decided & mask;
             const uint32_t undec = ~decided & mask;
+            // ---- the line buffer is free once the previous line's bulk store has read it
+            if (vl == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+            if (n_listed > LIST_CAP - 32) return i - 2 * R;   // warp-uniform
+            n_listed += __popc(__ballot_sync(0xffffffffu, undec != 0u));
             if (COUNT) {
                 c_changed += __popc(now & ~((selA & hA[R]) | (~selA & hB[R])));   // centre label != winner
                 c_nomatch += __popc(now & ((a_lab == 0 ? selA : 0u) | (b_lab == 0 ? ~selA : 0u)));
             }
-            // ---- the line buffer is free once the previous line's bulk store has read it
-            if (vl == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            __syncwarp();
             {   // labels of the U output pixels: B ^ (selA ? A ^ B : 0), GP pixels (bytes) per step
                 const uint32_t sel = selA >> R;
                 constexpr int GP = (G::U % 4 == 0) ? 4 : 2;
@@ -799,6 +807,7 @@ __device__ __forceinline__ void block_vote(const FastParams& P, uint8_t* ws, con
             SB = bs_sub<WC, WH>(SB, bs_hsum1<R>(hB[0]));
         }
     }
+    return nl;
 }
 
 // exact vote of one still undecided pixel.  code = line-in-block << 5 | vote word, q = bit
@@ -913,7 +922,9 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
             if constexpr (R > 0) {
                 // ---- votes: round 1 per block (lane = vote word), then round 2 over the word list
                 // round 1 produced, densely over the lanes
-                block_vote<R, NB, COUNT>(P, ws, it, a, vend - a, lane, M.vvalid, obytes, c_nomatch, c_changed);
+#pragma unroll 1
+                for (int va = a; va < vend;) {
+                const int done = block_vote<R, NB, COUNT>(P, ws, it, va, vend - va, lane, M.vvalid, obytes, c_nomatch, c_changed);
                 __syncwarp();
                 const int n2 = cnt[1];
                 if (n2) {   // byte patches follow: the bulk stores of this block must have landed
@@ -930,19 +941,21 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
                         mask = reinterpret_cast<const uint32_t*>(ws + C::W_W2MASK)[base + lane];
                     }
                     __syncwarp();   // entries are in registers: the exact-vote list may overwrite them
-                    if (have) vote_word<R, NB, COUNT>(P, ws, it, a + (code >> 5), a, code & 31, mask, c_nomatch, c_changed);
+                    if (have) vote_word<R, NB, COUNT>(P, ws, it, va + (code >> 5), va, code & 31, mask, c_nomatch, c_changed);
                 }
                 __syncwarp();
                 {   // ---- exact votes of what is still undecided, spread evenly over the lanes
                     const int n = cnt[2];
                     for_each_pixel(reinterpret_cast<const uint16_t*>(ws + C::W_W2CODE),
                                    reinterpret_cast<const uint32_t*>(ws + C::W_W2MASK), n, lane, [&](int code, int q) {
-                                       exact_pixel<R, NB, COUNT>(P, ws, it, a, code, q, c_nomatch, c_changed);
+                                       exact_pixel<R, NB, COUNT>(P, ws, it, va, code, q, c_nomatch, c_changed);
                                    });
                 }
                 __syncwarp();
                 if (lane == 0) { cnt[1] = 0; cnt[2] = 0; }
                 __syncwarp();
+                va += done;
+                }
             }
         }
     }
@@ -986,10 +999,20 @@ cudaError_t launch_t(FastParams& P, int sm_count, cudaStream_t s) {
     // gets several items (dynamic queue), but not so small that the 2R halo lines dominate
     const long long warps = (long long)sm_count * C::WARPS;
     P.n_strips = (int)((P.job.n1 + Geo<R>::SW - 1) / Geo<R>::SW);
-    long long chunk = (P.job.n2 * (long long)P.n_strips * P.job.n_sheets) / (warps * 6);
-    chunk = (chunk / C::B) * C::B;
-    if (chunk < 2 * C::B) chunk = 2 * C::B;
-    if (chunk > 256) chunk = 256;
+    // chunk height: a multiple of the block, chosen so that the items fill whole "waves" of warps
+    // (an item count just above a multiple of the warp count leaves most of the GPU idle in the last
+    // wave) while the 2R extra lines categorised per item stay a small fraction of the chunk.
+    long long chunk = 2 * C::B;
+    double best = -1.0;
+    for (long long c = 2 * C::B; c <= 256; c += C::B) {
+        const long long items = (long long)P.n_strips * P.job.n_sheets * ((P.job.n2 + c - 1) / c);
+        const long long waves = (items + warps - 1) / warps;
+        const double fill = (double)items / (double)(waves * warps);              // last-wave efficiency
+        const double halo = (double)c / ((double)c + 2 * R * 0.45);               // categorise-only halo lines
+        const double gran = waves >= 4 ? 1.0 : 0.85 + 0.05 * (double)(waves - 1); // few waves: no smoothing
+        const double score = fill * halo * gran;
+        if (score > best) { best = score; chunk = c; }
+    }
     P.chunk = (int)chunk;
     P.n_chunks = (int)((P.job.n2 + chunk - 1) / chunk);
     P.n_items = (long long)P.n_strips * P.n_chunks * P.job.n_sheets;
