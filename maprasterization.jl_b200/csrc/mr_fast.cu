@@ -28,6 +28,8 @@
 //
 // Reference semantics: src/categories.jl:76-133 (via the table built in mr_generic.cu) and the
 // north_star-defined majority filter, SURVEY.md Appendix A.3.
+#include <cstdlib>
+
 #include "mr_bitslice.h"
 #include "mr_internal.h"
 
@@ -878,8 +880,6 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
 #pragma unroll 1
     while (next < (unsigned)P.n_items) {
         const Item it = decode_item<R, NB>(P, next);
-        if (lane == 0) next = atomicAdd(P.work_counter, 1u);   // fetch the following item early
-        next = __shfl_sync(0xffffffffu, next, 0);
         const LaneMasks M = lane_masks<R>(P, it.xw0, lane);
         const int cat_last = it.y1 + R;                       // lines [y0-R, y1+R) are categorised
         int ycat = it.y0 - R;                                 // next line to categorise
@@ -901,6 +901,11 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
 #pragma unroll 1
         for (int a = it.y0; a < it.y1; a += C::B) {
             const int vend = min(a + C::B, it.y1);
+            if (vend == it.y1) {   // last block: fetch the following item now (earlier would hoard an item
+                                   // that an idle warp could already be working on)
+                if (lane == 0) next = atomicAdd(P.work_counter, 1u);
+                next = __shfl_sync(0xffffffffu, next, 0);
+            }
             // ---- categorise lines [ycat, vend + R); each arrives by TMA, issued one line ahead
 #pragma unroll 1
             for (; ycat < vend + R; ++ycat) {
@@ -1013,6 +1018,7 @@ cudaError_t launch_t(FastParams& P, int sm_count, cudaStream_t s) {
         const double score = fill * halo * gran;
         if (score > best) { best = score; chunk = c; }
     }
+    if (const char* ov = getenv("MR_CHUNK")) chunk = atoll(ov);   // experiment hook
     P.chunk = (int)chunk;
     P.n_chunks = (int)((P.job.n2 + chunk - 1) / chunk);
     P.n_items = (long long)P.n_strips * P.n_chunks * P.job.n_sheets;
