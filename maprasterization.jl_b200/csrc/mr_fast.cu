@@ -28,8 +28,6 @@
 //
 // Reference semantics: src/categories.jl:76-133 (via the table built in mr_generic.cu) and the
 // north_star-defined majority filter, SURVEY.md Appendix A.3.
-#include <cstdlib>
-
 #include "mr_bitslice.h"
 #include "mr_internal.h"
 
@@ -89,11 +87,20 @@ template <int R, int NB> struct Cfg {
     static_assert(TOTAL <= 227 * 1024 && B >= 2, "shared memory budget");
 };
 
+// Work items = (column, line chunk); column = (sheet, strip).  The lines of a sheet are split into
+// up to four classes with their own chunk height, handed out tallest first (guided scheduling: big
+// items keep the 2R categorise-only halo lines cheap, small items at the end level the finish).
+struct SchedClass {
+    int line0, line1;      // lines [line0, line1) of every column
+    int chunk;             // lines per work item
+    unsigned first_item;   // index of the class's first item
+};
 struct FastParams {
     MrJob job;
     int n_strips;
-    int n_chunks;
-    int chunk;    // lines per work item
+    int cols;              // n_strips * n_sheets
+    int n_classes;
+    SchedClass cls[4];
     long long n_items;
     unsigned int* work_counter;
     int padded;   // lines are readable / writable up to the next multiple of 16 bytes
@@ -836,15 +843,19 @@ template <int R, int NB>
 __device__ __forceinline__ Item decode_item(const FastParams& P, unsigned item) {
     using G = Geo<R>;
     Item it;
-    const unsigned per_sheet = (unsigned)(P.n_strips * P.n_chunks);
-    const int sheet = (int)(item / per_sheet);
-    const int rem = (int)(item - (unsigned)sheet * per_sheet);
-    const int chunk = rem / P.n_strips, strip = rem - chunk * P.n_strips;   // neighbouring strips first
+    int c = 0;
+#pragma unroll
+    for (int k = 1; k < 4; ++k)
+        if (k < P.n_classes && item >= P.cls[k].first_item) c = k;
+    const SchedClass cl = P.cls[c];
+    const unsigned rem = item - cl.first_item;
+    const int chunk = (int)(rem / (unsigned)P.cols), col = (int)(rem - (unsigned)chunk * (unsigned)P.cols);   // neighbouring strips first
+    const int sheet = col / P.n_strips, strip = col - sheet * P.n_strips;
     it.px = P.job.px + (long long)sheet * P.job.sheet_stride;
     it.out = P.job.out + (long long)sheet * P.job.out_sheet_stride;
     it.xw0 = (long long)strip * G::SW - 32 * G::HW;
-    it.y0 = chunk * P.chunk;
-    it.y1 = min(it.y0 + P.chunk, (int)P.job.n2);
+    it.y0 = cl.line0 + chunk * cl.chunk;
+    it.y1 = min(it.y0 + cl.chunk, cl.line1);
     it.edge = (strip == 0) || (it.xw0 + 32 * G::AW > P.job.n1);
     return it;
 }
@@ -986,6 +997,52 @@ unsigned int* g_work[16] = {nullptr};
 int g_work_next[16] = {0};
 constexpr int WORK_SLOTS = 1024;
 
+// ---- host: the item schedule.  Class 0 hands out most of the lines (f0) in tall chunks whose item
+// count fills whole "waves" of warps (an item count just above a multiple of the warp count would
+// leave most of the GPU idle at the end of the class); the rest goes out in small chunks that level
+// the finish.  Chunks are multiples of the block height B.  Small jobs: one class of small chunks.
+void plan_schedule(FastParams& P, int warps, int B, int R) {
+    const long long n2 = P.job.n2;
+    const int cols = P.cols;
+    const double f0 = 0.92;         // measured on B200: 0.86 .. 0.94 within 2 %
+    const long long tail = 2 * B;
+    const double share = (double)n2 * cols / warps;   // lines per warp
+    long long H0 = 0, n0 = 0;
+    if (share >= 6.0 * B) {
+        double best = 0.0;
+        long long hmax = (long long)(f0 * share) / B * B;
+        if (hmax > 512) hmax = 512 / B * B;
+        for (long long h = hmax; h >= 4 * B; h -= B) {
+            const long long n = (long long)(f0 * n2) / h;
+            if (n < 1) continue;
+            const long long items = n * cols, waves = (items + warps - 1) / warps;
+            const double fill = (double)items / (double)(waves * warps);
+            const double halo = (double)h / ((double)h + 2 * R * 0.45);
+            if (fill * halo > best) { best = fill * halo; H0 = h; n0 = n; }
+        }
+    }
+    int k = 0;
+    long long y = 0, items = 0;
+    if (n0 > 0) {
+        P.cls[k] = SchedClass{0, (int)(n0 * H0), (int)H0, 0u};
+        y = n0 * H0;
+        items = n0 * cols;
+        ++k;
+    }
+    if (y < n2) {
+        long long h = tail;
+        if (n0 == 0) {   // small job: about four items per warp, at least one block
+            h = (long long)(share / 4.0) / B * B;
+            if (h < B) h = B;
+        }
+        P.cls[k] = SchedClass{(int)y, (int)n2, (int)h, (unsigned)items};
+        items += ((n2 - y + h - 1) / h) * cols;
+        ++k;
+    }
+    P.n_classes = k;
+    P.n_items = items;
+}
+
 template <int R, int NB, bool COUNT>
 cudaError_t launch_t(FastParams& P, int sm_count, cudaStream_t s) {
     using C = Cfg<R, NB>;
@@ -1004,24 +1061,8 @@ cudaError_t launch_t(FastParams& P, int sm_count, cudaStream_t s) {
     // gets several items (dynamic queue), but not so small that the 2R halo lines dominate
     const long long warps = (long long)sm_count * C::WARPS;
     P.n_strips = (int)((P.job.n1 + Geo<R>::SW - 1) / Geo<R>::SW);
-    // chunk height: a multiple of the block, chosen so that the items fill whole "waves" of warps
-    // (an item count just above a multiple of the warp count leaves most of the GPU idle in the last
-    // wave) while the 2R extra lines categorised per item stay a small fraction of the chunk.
-    long long chunk = 2 * C::B;
-    double best = -1.0;
-    for (long long c = 2 * C::B; c <= 256; c += C::B) {
-        const long long items = (long long)P.n_strips * P.job.n_sheets * ((P.job.n2 + c - 1) / c);
-        const long long waves = (items + warps - 1) / warps;
-        const double fill = (double)items / (double)(waves * warps);              // last-wave efficiency
-        const double halo = (double)c / ((double)c + 2 * R * 0.45);               // categorise-only halo lines
-        const double gran = waves >= 4 ? 1.0 : 0.85 + 0.05 * (double)(waves - 1); // few waves: no smoothing
-        const double score = fill * halo * gran;
-        if (score > best) { best = score; chunk = c; }
-    }
-    if (const char* ov = getenv("MR_CHUNK")) chunk = atoll(ov);   // experiment hook
-    P.chunk = (int)chunk;
-    P.n_chunks = (int)((P.job.n2 + chunk - 1) / chunk);
-    P.n_items = (long long)P.n_strips * P.n_chunks * P.job.n_sheets;
+    P.cols = P.n_strips * P.job.n_sheets;
+    plan_schedule(P, (int)warps, C::B, R);
     if (P.n_items >= (1ll << 31) - (1 << 20)) return cudaErrorNotSupported;
     long long grid = sm_count;
     const long long need = (P.n_items + C::WARPS - 1) / C::WARPS;
