@@ -137,6 +137,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
 
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));   // the table is read-only once the CTA runs
+    return v;
+}
+
 // per-lane validity masks of a strip
 struct LaneMasks {
     unsigned vmask;    // aligned word `lane`: pixels inside [0, n1)
@@ -276,7 +282,7 @@ __device__ __forceinline__ void categorize_line(const FastParams& P, const uint8
     // Cell index r5 | g5<<5 | b5<<10 of a pixel = byte dot product (IDP.4A, off the ALU pipe) of the
     // quantised words with the weights (1, 32, 128): r and g bytes are quantised to x>>3, b bytes to
     // x & 0xF8 (= 8*b5), the byte masks depend only on the position of the word in its 12-byte group.
-    extern __shared__ __align__(128) uint8_t sm_coarse[];   // the coarse table sits at offset 0
+    const uint32_t tab = smem_u32(coarse);   // the coarse table (offset 0 of the dynamic shared memory)
     uint32_t Wp[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) Wp[j] = 0u;
@@ -295,16 +301,17 @@ __device__ __forceinline__ void categorize_line(const FastParams& P, const uint8
             const uint32_t q0 = ((w0 >> 3) & 0x1F001F1Fu) | (w0 & 0x00F80000u);
             const uint32_t q1 = ((w1 >> 3) & 0x1F1F001Fu) | (w1 & 0x0000F800u);
             const uint32_t q2 = ((w2 >> 3) & 0x001F1F00u) | (w2 & 0xF80000F8u);
-            const uint32_t i0 = __dp4a(q0, 0x00802001u, 0u);
-            const uint32_t i1 = __dp4a(q1, 0x00008020u, __dp4a(q0, 0x01000000u, 0u));
-            const uint32_t i2 = __dp4a(q2, 0x00000080u, __dp4a(q1, 0x20010000u, 0u));
-            const uint32_t i3 = __dp4a(q2, 0x80200100u, 0u);
+            // the dot products start from the table's shared-memory address: no separate address add
+            const uint32_t i0 = __dp4a(q0, 0x00802001u, tab);
+            const uint32_t i1 = __dp4a(q1, 0x00008020u, __dp4a(q0, 0x01000000u, tab));
+            const uint32_t i2 = __dp4a(q2, 0x00000080u, __dp4a(q1, 0x20010000u, tab));
+            const uint32_t i3 = __dp4a(q2, 0x80200100u, tab);
             // pixel 16h + 4g + t -> register (4g + t) & 7, byte order by descending pixel index
             const int j = (4 * g) & 7;
-            Wp[j + 0] = Wp[j + 0] * 256u + sm_coarse[i0];
-            Wp[j + 1] = Wp[j + 1] * 256u + sm_coarse[i1];
-            Wp[j + 2] = Wp[j + 2] * 256u + sm_coarse[i2];
-            Wp[j + 3] = Wp[j + 3] * 256u + sm_coarse[i3];
+            Wp[j + 0] = Wp[j + 0] * 256u + lds_u8(i0);
+            Wp[j + 1] = Wp[j + 1] * 256u + lds_u8(i1);
+            Wp[j + 2] = Wp[j + 2] * 256u + lds_u8(i2);
+            Wp[j + 3] = Wp[j + 3] * 256u + lds_u8(i3);
         }
     }
     if (it.edge) {   // warp-uniform: force VOID outside [0, n1)
