@@ -30,6 +30,7 @@ extern "C" {
 #define MR_ERR_CUDA   (-2)   /* CUDA runtime failure */
 #define MR_ERR_STATE  (-3)   /* call order (e.g. no palette set) */
 #define MR_ERR_NOMEM  (-4)
+#define MR_ERR_UNSUPPORTED (-5) /* input the reference handles in a scan-order dependent way */
 
 #define MR_COLOURSPACE_RGB 0 /* match on RGB{Float64}: src/balance.jl:13-15 + src/blur.jl:8 */
 #define MR_COLOURSPACE_LAB 1 /* extension */
@@ -115,6 +116,27 @@ int mr_clean_host(mr_ctx* ctx, const uint8_t* labels, int64_t n1, int64_t n2, in
 int mr_clean_dev(mr_ctx* ctx, const uint8_t* labels_dev, int64_t n1, int64_t n2, int64_t stride2,
                  int R, int halo_lo, int halo_hi, uint8_t* out_dev, int64_t out_stride2,
                  void* stream);
+
+/* Segment prune = the reference's "clean" button: _clean(A, known_categories; categories,
+ * line_threshold, prune_threshold), src/clean.jl:59-93 (call site src/selectcolors.jl:479-489),
+ * over the segmentation fast_scanning!(..., 1e-9; match = (:color,)), src/scan.jl:56-157:
+ * 4-connected segments of equal labels; a segment whose label is not kept becomes 0; a segment
+ * with fewer than prune_threshold pixels, or count / (max(h, w)^2 / 2) < line_threshold, becomes
+ * 0 -- or its known category, if one was clicked inside it (clean.jl:79-85).
+ * keep256[c] != 0 <=> category c is in `categories`.  The known-category plane is the one set by
+ * mr_set_known.  If one segment holds two DIFFERENT known categories the reference result depends
+ * on its scan order (scan.jl:140-146): the call then fails with MR_ERR_UNSUPPORTED.
+ * n1 * n2 < 2^31.  Labels are uint8 (the reference returns the Float64 segment colour; the Julia
+ * wrapper converts).  The device variant synchronises `stream` (the number of segments sizes a
+ * scratch buffer). */
+int mr_clean_segments_dev(mr_ctx* ctx, const uint8_t* labels_dev, int64_t n1, int64_t n2,
+                          int64_t stride2, const uint8_t* keep256, double line_threshold,
+                          double prune_threshold, uint8_t* out_dev, int64_t out_stride2,
+                          int64_t* n_segments, void* stream);
+int mr_clean_segments_host(mr_ctx* ctx, const uint8_t* labels, int64_t n1, int64_t n2,
+                           int64_t stride2, const uint8_t* keep256, double line_threshold,
+                           double prune_threshold, uint8_t* out, int64_t out_stride2,
+                           int64_t* n_segments);
 
 /* Pinned host staging (optional; pageable caller buffers also work, slower). */
 void* mr_host_alloc(size_t bytes);

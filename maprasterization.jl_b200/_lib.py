@@ -21,7 +21,8 @@ SYMBOLS = [
     "mr_version", "mr_create", "mr_destroy", "mr_last_error", "mr_set_palette", "mr_set_known",
     "mr_get_lut", "mr_palette_build_ms", "mr_enable_counters", "mr_read_counters", "mr_launch_count",
     "mr_categorize_clean_host", "mr_categorize_clean_host_band", "mr_categorize_clean_dev", "mr_batch_categorize_clean_dev",
-    "mr_clean_host", "mr_clean_dev", "mr_host_alloc", "mr_host_free", "mr_synth_scan_dev",
+    "mr_clean_host", "mr_clean_dev", "mr_clean_segments_dev", "mr_clean_segments_host",
+    "mr_host_alloc", "mr_host_free", "mr_synth_scan_dev",
 ]
 
 
@@ -75,6 +76,10 @@ def load():
     L.mr_batch_categorize_clean_dev.argtypes = [vp, i32, u8p, i64, i64, i64, i64, i32, i32, u8p, i64, i64, vp]
     L.mr_clean_host.argtypes = [vp, u8p, i64, i64, i64, i32, i32, u8p, i64]
     L.mr_clean_dev.argtypes = [vp, u8p, i64, i64, i64, i32, i32, i32, u8p, i64, vp]
+    L.mr_clean_segments_dev.argtypes = [vp, u8p, i64, i64, i64, u8p, C.c_double, C.c_double, u8p, i64,
+                                        C.POINTER(i64), vp]
+    L.mr_clean_segments_host.argtypes = [vp, u8p, i64, i64, i64, u8p, C.c_double, C.c_double, u8p, i64,
+                                         C.POINTER(i64)]
     L.mr_host_alloc.argtypes = [C.c_size_t]
     L.mr_host_alloc.restype = vp
     L.mr_host_free.argtypes = [vp]
@@ -83,7 +88,8 @@ def load():
     for name in ("mr_set_palette", "mr_set_known", "mr_get_lut", "mr_palette_build_ms", "mr_enable_counters",
                  "mr_read_counters", "mr_categorize_clean_host", "mr_categorize_clean_host_band",
                  "mr_categorize_clean_dev",
-                 "mr_batch_categorize_clean_dev", "mr_clean_host", "mr_clean_dev", "mr_synth_scan_dev"):
+                 "mr_batch_categorize_clean_dev", "mr_clean_host", "mr_clean_dev", "mr_clean_segments_dev",
+                 "mr_clean_segments_host", "mr_synth_scan_dev"):
         getattr(L, name).restype = i32
     _lib = L
     return L
@@ -195,7 +201,32 @@ class Context:
         self._ck(self._L.mr_clean_host(self._h, _ptr(labels), n1, n2, n1, int(R), int(repeat), _ptr(out), n1))
         return out
 
+    def clean_segments_host(self, labels, keep256, line_threshold, prune_threshold):
+        """`_clean` (src/clean.jl:59-93) on host labels; the known plane is the one of set_known.
+        Returns (labels, n_segments)."""
+        labels = np.ascontiguousarray(labels, dtype=np.uint8)
+        keep = np.ascontiguousarray(keep256, dtype=np.uint8)
+        if keep.size != 256:
+            raise ValueError("keep256 must have 256 entries")
+        n2, n1 = labels.shape
+        out = np.empty((n2, n1), dtype=np.uint8)
+        nseg = C.c_int64(0)
+        self._ck(self._L.mr_clean_segments_host(self._h, _ptr(labels), n1, n2, n1, _ptr(keep), float(line_threshold),
+                                                float(prune_threshold), _ptr(out), n1, C.byref(nseg)))
+        return out, int(nseg.value)
+
     # -- device buffers (raw pointers / torch tensors) -------------------------------------
+    def clean_segments_dev(self, labels, n1, n2, stride2, keep256, line_threshold, prune_threshold, out,
+                           out_stride2, stream=0):
+        keep = np.ascontiguousarray(keep256, dtype=np.uint8)
+        if keep.size != 256:
+            raise ValueError("keep256 must have 256 entries")
+        nseg = C.c_int64(0)
+        self._ck(self._L.mr_clean_segments_dev(self._h, _ptr(labels), n1, n2, stride2, _ptr(keep),
+                                               float(line_threshold), float(prune_threshold), _ptr(out),
+                                               out_stride2, C.byref(nseg), stream or None))
+        return int(nseg.value)
+
     def categorize_clean_dev(self, px, n1, n2, stride2, bpp, R, out, out_stride2, halo_lo=0, halo_hi=0, stream=0):
         self._ck(self._L.mr_categorize_clean_dev(self._h, _ptr(px), n1, n2, stride2, bpp, int(R), int(halo_lo),
                                                  int(halo_hi), _ptr(out), out_stride2, stream or None))

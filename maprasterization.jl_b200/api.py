@@ -245,3 +245,44 @@ def clean_u8(labels, *, hood=Window(1), repeat=1, ctx=None):
 def clean(labels, *, hood=Window(1), repeat=1, ctx=None):
     """`clean(labels; hood=Window{1}(), repeat=1)`: Window majority filter, SURVEY Appendix A.3."""
     return clean_u8(labels, hood=hood, repeat=repeat, ctx=ctx).astype(np.int64)
+
+
+def clean_segments_u8(labels, known_categories=None, *, categories, line_threshold=0.01, prune_threshold=20,
+                      ctx=None):
+    """`_clean(A, known_categories; categories, line_threshold, prune_threshold)`
+    (src/clean.jl:59-93; the reference's "clean" button, call site src/selectcolors.jl:479-489):
+    4-connected segments of equal labels (fast_scanning!, src/scan.jl:56-157); segments of a category
+    that is not kept, segments smaller than `prune_threshold` pixels and line-like segments
+    (count / (max(h, w)^2 / 2) < line_threshold) become 0 -- or the known category clicked inside them.
+    labels / known_categories: (n2, n1) integer arrays.  Returns uint8 labels.
+    (The un-underscored name `clean` is taken by the north_star's Window majority filter.)"""
+    labels = np.asarray(labels)
+    if labels.ndim != 2 or not np.issubdtype(labels.dtype, np.integer):
+        raise ValueError("labels must be a 2-D integer array")
+    if labels.size and (labels.min() < 0 or labels.max() > 254):
+        raise ValueError("labels must be in 0..254")
+    keep = np.zeros(256, dtype=np.uint8)
+    cats = np.asarray(list(categories), dtype=np.int64)
+    if cats.size and (cats.min() < 0 or cats.max() > 254):
+        raise ValueError("categories must be in 0..254")
+    keep[cats] = 1
+    ctx = ctx or default_context()
+    if known_categories is None:
+        ctx.set_known(None)
+    else:
+        kn = np.asarray(known_categories)
+        if kn.shape != labels.shape:
+            raise ValueError("known_categories must have the shape of labels")
+        idx = np.flatnonzero(kn)   # lin_idx = i + j*n1 of the (n2, n1) line-major view
+        ctx.set_known(idx, kn.reshape(-1)[idx].astype(np.uint8))
+    try:
+        out, _ = ctx.clean_segments_host(labels.astype(np.uint8), keep, line_threshold, prune_threshold)
+    finally:
+        if known_categories is not None:
+            ctx.set_known(None)
+    return out
+
+
+def clean_segments(labels, known_categories=None, **kw):
+    """Same, eltype Int."""
+    return clean_segments_u8(labels, known_categories, **kw).astype(np.int64)

@@ -35,6 +35,10 @@ struct mr_ctx {
     uint8_t* d_in = nullptr;  size_t d_in_cap = 0;
     uint8_t* d_out = nullptr; size_t d_out_cap = 0;
     uint8_t* d_tmp = nullptr; size_t d_tmp_cap = 0;
+    // segment prune scratch: parent array, component records, keep table + two counters
+    uint8_t* d_parent = nullptr; size_t d_parent_cap = 0;
+    uint8_t* d_rec = nullptr; size_t d_rec_cap = 0;
+    uint8_t* d_small = nullptr;     // 256-byte keep table | n_roots | conflict
     std::vector<cudaEvent_t> ev_up, ev_done;
     std::string err;
 };
@@ -108,6 +112,7 @@ extern "C" void mr_destroy(mr_ctx* ctx) {
     cudaFree(ctx->d_pal); cudaFree(ctx->d_lut); cudaFree(ctx->d_coarse);
     cudaFree(ctx->d_known_idx); cudaFree(ctx->d_known_cat); cudaFree(ctx->d_counters);
     cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_tmp);
+    cudaFree(ctx->d_parent); cudaFree(ctx->d_rec); cudaFree(ctx->d_small);
     if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
@@ -520,6 +525,78 @@ extern "C" int mr_clean_host(mr_ctx* ctx, const uint8_t* labels, int64_t n1, int
 }
 
 // ------------------------------------------------------------------ bench/test utility
+// ------------------------------------------------------------------ segment prune (_clean)
+static int prune_dev(mr_ctx* ctx, const char* fn, const uint8_t* labels_dev, int64_t n1, int64_t n2,
+                     int64_t stride2, const uint8_t* keep256, double line_threshold, double prune_threshold,
+                     uint8_t* out_dev, int64_t out_stride2, int64_t* n_segments, cudaStream_t s) {
+    std::string f(fn);
+    if (!keep256) return fail(ctx, MR_ERR_ARG, f + ": null keep table");
+    if (isnan(line_threshold) || isnan(prune_threshold)) return fail(ctx, MR_ERR_ARG, f + ": NaN threshold");
+    if (n_segments) *n_segments = 0;
+    if (n1 == 0 || n2 == 0) return MR_OK;
+    if ((double)n1 * (double)n2 >= 2147483648.0) return fail(ctx, MR_ERR_ARG, f + ": n1 * n2 must be below 2^31");
+    int rc;
+    if ((rc = grow(ctx, &ctx->d_parent, &ctx->d_parent_cap, mr_prune_parent_bytes(n1, n2)))) return rc;
+    if (!ctx->d_small) CK(cudaMalloc(&ctx->d_small, 512));
+    unsigned int* d_n_roots = reinterpret_cast<unsigned int*>(ctx->d_small + 256);
+    unsigned int* d_conflict = reinterpret_cast<unsigned int*>(ctx->d_small + 260);
+    CK(cudaMemcpyAsync(ctx->d_small, keep256, 256, cudaMemcpyHostToDevice, s));
+    int nl = 0;
+    cudaError_t e = mr_launch_prune_components(labels_dev, n1, n2, stride2, reinterpret_cast<uint32_t*>(ctx->d_parent),
+                                               d_n_roots, s, &nl);
+    ctx->launches += nl;
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "segment prune (components)");
+    unsigned int n_roots = 0;
+    CK(cudaMemcpyAsync(&n_roots, d_n_roots, sizeof n_roots, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if ((rc = grow(ctx, &ctx->d_rec, &ctx->d_rec_cap, mr_prune_rec_bytes(n_roots)))) return rc;
+    nl = 0;
+    e = mr_launch_prune_apply(labels_dev, n1, n2, stride2, reinterpret_cast<const uint32_t*>(ctx->d_parent), ctx->d_rec,
+                              n_roots, ctx->n_known, ctx->d_known_idx, ctx->d_known_cat, ctx->d_small, line_threshold,
+                              prune_threshold, out_dev, out_stride2, d_conflict, s, &nl);
+    ctx->launches += nl;
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "segment prune (apply)");
+    unsigned int conflict = 0;
+    CK(cudaMemcpyAsync(&conflict, d_conflict, sizeof conflict, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (n_segments) *n_segments = n_roots;
+    if (conflict)
+        return fail(ctx, MR_ERR_UNSUPPORTED,
+                    f + ": a segment holds two different known categories; the reference splits it in scan order "
+                        "(src/scan.jl:140-146), which this implementation does not reproduce");
+    return MR_OK;
+}
+
+extern "C" int mr_clean_segments_dev(mr_ctx* ctx, const uint8_t* labels_dev, int64_t n1, int64_t n2, int64_t stride2,
+                                     const uint8_t* keep256, double line_threshold, double prune_threshold,
+                                     uint8_t* out_dev, int64_t out_stride2, int64_t* n_segments, void* stream) {
+    int rc = check_image_args(ctx, "mr_clean_segments_dev", labels_dev, out_dev, n1, n2, stride2, 1, out_stride2, 0, 0, 0);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    return prune_dev(ctx, "mr_clean_segments_dev", labels_dev, n1, n2, stride2, keep256, line_threshold,
+                     prune_threshold, out_dev, out_stride2, n_segments, stream ? (cudaStream_t)stream : ctx->s_main);
+}
+
+extern "C" int mr_clean_segments_host(mr_ctx* ctx, const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2,
+                                      const uint8_t* keep256, double line_threshold, double prune_threshold,
+                                      uint8_t* out, int64_t out_stride2, int64_t* n_segments) {
+    int rc = check_image_args(ctx, "mr_clean_segments_host", labels, out, n1, n2, stride2, 1, out_stride2, 0, 0, 0);
+    if (rc) return rc;
+    if (n_segments) *n_segments = 0;
+    if (n1 == 0 || n2 == 0) return MR_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)n1 * n2;
+    if ((rc = grow(ctx, &ctx->d_out, &ctx->d_out_cap, bytes))) return rc;
+    if ((rc = grow(ctx, &ctx->d_tmp, &ctx->d_tmp_cap, bytes))) return rc;
+    CK(cudaMemcpy2DAsync(ctx->d_out, n1, labels, stride2, n1, n2, cudaMemcpyHostToDevice, ctx->s_main));
+    rc = prune_dev(ctx, "mr_clean_segments_host", ctx->d_out, n1, n2, n1, keep256, line_threshold, prune_threshold,
+                   ctx->d_tmp, n1, n_segments, ctx->s_main);
+    if (rc) return rc;
+    CK(cudaMemcpy2DAsync(out, out_stride2, ctx->d_tmp, n1, n1, n2, cudaMemcpyDeviceToHost, ctx->s_main));
+    CK(cudaStreamSynchronize(ctx->s_main));
+    return MR_OK;
+}
+
 extern "C" int mr_synth_scan_dev(mr_ctx* ctx, uint32_t seed, uint32_t sheet_id, int K,
                                  const uint8_t* palette_rgb_host, int64_t n1, int64_t n2, int64_t line0,
                                  int64_t nlines, int mode, uint8_t* out_dev, int64_t out_stride2, void* stream) {

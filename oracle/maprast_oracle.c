@@ -346,3 +346,156 @@ void mro_synth_scan(uint32_t seed, uint32_t sheet_id, int K, const uint8_t* pale
             synth_pixel(seed, sheet_id, K, palette_rgb, i, line0 + jj, mode, o + 3 * i);
     }
 }
+
+/* ====================================================================================
+ * Segment prune: the reference's real "clean" button, `_clean` (src/clean.jl:59-93), on an
+ * Int label image, through the sequential union-find segmentation `fast_scanning!`
+ * (src/scan.jl:56-157) with threshold 1e-9 and match = (:color,) (src/clean.jl:62-64).
+ * The "colour" of a pixel is its label; PixelProp.category is the known-category plane.
+ *
+ * Restated literally, in the reference's pixel order (CartesianIndices of a column-major
+ * matrix: first index fastest) and neighbour order (x - e1, then x - e2; scan.jl:61-63):
+ *   - a backward neighbour is valid when (mean.color - label)^2 < 1e-9 (scan.jl:81);
+ *     the running mean of equal labels stays exactly the label (scan.jl:106,118,124);
+ *   - no valid neighbour -> new segment (:95-101); all valid roots equal and categories
+ *     mergeable -> join (:104-108); all categories mergeable -> union (:110-133); otherwise
+ *     a new segment starts at this pixel (:140-146).  _canmerge: scan.jl:169.
+ *   - per segment (clean.jl:65-88): size, bounding box, rectangle_area = max(h, w)^2 / 2,
+ *     ratio = count / rectangle_area; label not kept -> 0; count < prune_threshold or
+ *     ratio < line_threshold: no known category -> 0, label not in (0, category) -> category.
+ * Returns the number of segments.  Output: the segment's (new) colour per pixel (clean.jl:91-93).
+ * ==================================================================================== */
+static int64_t ds_find(int64_t* parent, int64_t x) {
+    while (parent[x] != x) {
+        parent[x] = parent[parent[x]];
+        x = parent[x];
+    }
+    return x;
+}
+
+static int canmerge(int a, int b) { return (a == 0) | (b == 0) | (a == b); }
+static int mergecat(int a, int b) { return a == 0 ? b : a; }   /* scan.jl:22-31 (conflicts are guarded) */
+
+int64_t mro_clean_segments(const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2,
+                           const uint8_t* known, int64_t known_stride2, const uint8_t* keep256,
+                           double line_threshold, double prune_threshold,
+                           uint8_t* out, int64_t out_stride2) {
+    const int64_t n = n1 * n2;
+    if (n == 0) return 0;
+    int64_t* result = (int64_t*)malloc(sizeof(int64_t) * (size_t)n);   /* label per pixel */
+    int64_t* parent = (int64_t*)malloc(sizeof(int64_t) * (size_t)n);   /* temp_labels (at most n) */
+    double* mean = (double*)malloc(sizeof(double) * (size_t)n);        /* region_means[...].color */
+    int* cat = (int*)malloc(sizeof(int) * (size_t)n);                  /* region_means[...].category */
+    int64_t* cnt = (int64_t*)malloc(sizeof(int64_t) * (size_t)n);      /* region_pix_count (0 = deleted) */
+    int64_t* bb = (int64_t*)malloc(sizeof(int64_t) * 4 * (size_t)n);   /* region_bbox: i0, j0, i1, j1 */
+    int64_t n_labels = 0;
+    for (int64_t j = 0; j < n2; ++j)
+        for (int64_t i = 0; i < n1; ++i) {
+            const double x = (double)labels[j * stride2 + i];
+            const int ctg = known ? known[j * known_stride2 + i] : 0;
+            int sz = 0, same_label = 1;
+            int64_t prev_label = -1, v_neigh[2];
+            int ctg_neigh[2];
+            for (int d = 0; d < 2; ++d) {   /* neighbourhood(point) = (point - e1, point - e2) */
+                const int64_t pi = d == 0 ? i - 1 : i, pj = d == 0 ? j : j - 1;
+                if (pi < 0 || pj < 0) continue;
+                const int64_t root_p = ds_find(parent, result[pj * n1 + pi]);
+                const double diff = mean[root_p] - x;
+                if (diff * diff < 0.000000001) {
+                    if (prev_label < 0) prev_label = root_p;
+                    else if (prev_label != root_p) same_label = 0;
+                    v_neigh[sz] = root_p;
+                    ctg_neigh[sz] = cat[root_p];
+                    ++sz;
+                }
+            }
+            int64_t lab;
+            int fresh = 0;
+            if (sz == 0) {
+                fresh = 1;
+            } else if (same_label && canmerge(ctg, cat[prev_label])) {
+                lab = prev_label;
+                cnt[lab] += 1;
+                mean[lab] += (x - mean[lab]) / (double)cnt[lab];
+                cat[lab] = mergecat(cat[lab], ctg);
+                if (i < bb[4 * lab + 0]) bb[4 * lab + 0] = i;
+                if (j < bb[4 * lab + 1]) bb[4 * lab + 1] = j;
+                if (i > bb[4 * lab + 2]) bb[4 * lab + 2] = i;
+                if (j > bb[4 * lab + 3]) bb[4 * lab + 3] = j;
+            } else {
+                int ok = 1;
+                for (int k = 0; k < sz; ++k) ok = ok && canmerge(ctg, ctg_neigh[k]);
+                ok = ok && (sz < 2 || canmerge(ctg_neigh[0], ctg_neigh[1]));
+                if (ok) {
+                    int64_t u = v_neigh[0];
+                    for (int k = 0; k < sz; ++k) {   /* union!: the smaller index becomes the root here;
+                                                        which root survives does not change any statistic */
+                        const int64_t a = ds_find(parent, u), b = ds_find(parent, v_neigh[k]);
+                        if (a != b) {
+                            if (a < b) { parent[b] = a; u = a; } else { parent[a] = b; u = b; }
+                        } else u = a;
+                    }
+                    lab = u;
+                    /* scan.jl:117-119: the pixel joins the union label first ... */
+                    cnt[u] += 1;
+                    mean[u] += (x - mean[u]) / (double)cnt[u];
+                    cat[u] = mergecat(cat[u], ctg);
+                    if (i < bb[4 * u + 0]) bb[4 * u + 0] = i;
+                    if (j < bb[4 * u + 1]) bb[4 * u + 1] = j;
+                    if (i > bb[4 * u + 2]) bb[4 * u + 2] = i;
+                    if (j > bb[4 * u + 3]) bb[4 * u + 3] = j;
+                    /* ... then the other segments are folded in (:121-132) */
+                    for (int k = 0; k < sz; ++k) {
+                        const int64_t v = v_neigh[k];
+                        if (v != u && cnt[v] > 0) {
+                            cnt[u] += cnt[v];
+                            mean[u] += (mean[v] - mean[u]) * (double)cnt[v] / (double)cnt[u];
+                            cat[u] = mergecat(cat[u], cat[v]);
+                            if (bb[4 * v + 0] < bb[4 * u + 0]) bb[4 * u + 0] = bb[4 * v + 0];
+                            if (bb[4 * v + 1] < bb[4 * u + 1]) bb[4 * u + 1] = bb[4 * v + 1];
+                            if (bb[4 * v + 2] > bb[4 * u + 2]) bb[4 * u + 2] = bb[4 * v + 2];
+                            if (bb[4 * v + 3] > bb[4 * u + 3]) bb[4 * u + 3] = bb[4 * v + 3];
+                            cnt[v] = 0;   /* delete!(region_pix_count, v) */
+                        }
+                    }
+                } else {
+                    fresh = 1;
+                }
+            }
+            if (fresh) {
+                lab = n_labels++;
+                parent[lab] = lab;
+                mean[lab] = x;
+                cat[lab] = ctg;
+                cnt[lab] = 1;
+                bb[4 * lab + 0] = bb[4 * lab + 2] = i;
+                bb[4 * lab + 1] = bb[4 * lab + 3] = j;
+            }
+            result[j * n1 + i] = lab;
+        }
+    /* clean.jl:65-88 on the surviving segments */
+    int64_t n_seg = 0;
+    for (int64_t l = 0; l < n_labels; ++l) {
+        if (cnt[l] == 0 || parent[l] != l) continue;
+        ++n_seg;
+        const int64_t h = bb[4 * l + 2] - bb[4 * l + 0] + 1, w = bb[4 * l + 3] - bb[4 * l + 1] + 1;
+        const int64_t m = h > w ? h : w;
+        const double rectangle_area = (double)(m * m) / 2.0;
+        const double ratio = (double)cnt[l] / rectangle_area;
+        const double colour = mean[l];
+        int kept = 0;
+        for (int c = 0; c < 256; ++c)
+            if (keep256[c] && colour == (double)c) kept = 1;
+        if (!kept) {
+            mean[l] = 0.0;
+        } else if (((double)cnt[l] < prune_threshold) || (ratio < line_threshold)) {
+            if (cat[l] == 0) mean[l] = 0.0;
+            else if (!(colour == 0.0 || colour == (double)cat[l])) mean[l] = (double)cat[l];
+        }
+    }
+    for (int64_t j = 0; j < n2; ++j)
+        for (int64_t i = 0; i < n1; ++i)
+            out[j * out_stride2 + i] = (uint8_t)mean[ds_find(parent, result[j * n1 + i])];
+    free(result); free(parent); free(mean); free(cat); free(cnt); free(bb);
+    return n_seg;
+}

@@ -87,6 +87,15 @@ void mro_synth_scan(uint32_t seed, uint32_t sheet_id, int K, const uint8_t* pale
                     int64_t n1, int64_t n2, int64_t line0, int64_t nlines,
                     int mode, uint8_t* out, int64_t out_stride2, int nthreads);
 
+/* `_clean` (src/clean.jl:59-93) over `fast_scanning!` (src/scan.jl:56-157) on a label image:
+ * sequential, literal restatement (scan order and neighbour order of the reference).
+ * known: known-category plane (NULL = all 0); keep256[c] != 0: category c is kept
+ * (`categories`); returns the number of segments. */
+int64_t mro_clean_segments(const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2,
+                           const uint8_t* known, int64_t known_stride2, const uint8_t* keep256,
+                           double line_threshold, double prune_threshold,
+                           uint8_t* out, int64_t out_stride2);
+
 int mro_max_threads(void);
 
 #ifdef __cplusplus

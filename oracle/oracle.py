@@ -58,6 +58,9 @@ def lib():
         L.mro_philox4x32.argtypes = [C.c_uint32] * 6 + [C.c_void_p]
         L.mro_synth_scan.argtypes = [C.c_uint32, C.c_uint32, C.c_int, _u8p, _i64, _i64, _i64, _i64,
                                      C.c_int, _u8p, _i64, C.c_int]
+        L.mro_clean_segments.argtypes = [_u8p, _i64, _i64, _i64, C.c_void_p, _i64, _u8p, C.c_double,
+                                         C.c_double, _u8p, _i64]
+        L.mro_clean_segments.restype = _i64
         L.mro_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -151,6 +154,30 @@ def categorize_clean(px, mean, lo, hi, R, colourspace=RGB, channels=3, tie_rule=
     lib().mro_categorize_clean(px.ctypes.data, n1, n2, n1 * bpp, bpp, channels, colourspace,
                                mean.shape[0], mean, lo, hi, R, tie_rule, out.ctypes.data, n1, nthreads)
     return out
+
+
+def keep_table(categories):
+    """256-entry table: 1 where the category is kept (`categories` of _clean, src/clean.jl:59)."""
+    t = np.zeros(256, dtype=np.uint8)
+    t[np.asarray(list(categories), dtype=np.int64)] = 1
+    return t
+
+
+def clean_segments(labels, known=None, categories=(), line_threshold=0.01, prune_threshold=20):
+    """`_clean(A, known; categories, line_threshold, prune_threshold)` (src/clean.jl:59-93),
+    labels / known: (n2, n1) uint8 (line-major view).  Returns (out, n_segments)."""
+    labels = np.ascontiguousarray(labels, dtype=np.uint8)
+    n2, n1 = labels.shape
+    out = np.empty_like(labels)
+    kn = None
+    if known is not None:
+        kn = np.ascontiguousarray(known, dtype=np.uint8)
+        assert kn.shape == labels.shape
+    keep = keep_table(categories)
+    n = lib().mro_clean_segments(labels.ctypes.data, n1, n2, n1, kn.ctypes.data if kn is not None else None, n1,
+                                 keep.ctypes.data, float(line_threshold), float(prune_threshold),
+                                 out.ctypes.data, n1)
+    return out, int(n)
 
 
 def philox4x32(c, k):
