@@ -318,6 +318,43 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": int(launches), "gpu_launches_per_step": launches_per_step,
         "clocks": clocks,
     }
+    if world == 1 and not batch and n1 * nb < (1 << 31):
+        # ---- SURVEY 8(f) "next" row, measured beside the hot path: the reference's segment prune
+        # (_clean, src/clean.jl:59-93) on the labels the fused kernel just produced (device resident)
+        keep = np.zeros(256, dtype=np.uint8)
+        keep[1:K + 1] = 1
+        seg_out = torch.empty_like(out)
+        nseg = ctx.clean_segments_dev(out, n1, nb, n1, keep, 0.01, 20, seg_out, n1)
+        l0 = ctx.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            ctx.clean_segments_dev(out, n1, nb, n1, keep, 0.01, 20, seg_out, n1)
+        e1.record()
+        torch.cuda.synchronize()
+        seg_ms = e0.elapsed_time(e1) / reps
+        res["next_rows"] = {"clean_segments": {
+            "what": "_clean(labels; categories=1..K, line_threshold=0.01, prune_threshold=20), device resident",
+            "value": my_px / (seg_ms * 1e-3) / 1e6, "unit": UNIT, "ms": seg_ms, "segments": nseg,
+            "gpu_launches_per_call": (ctx.launch_count() - l0) / reps,
+            "roofline": {"bound": "hbm", "algorithmic_bytes_per_px": 2,
+                         "achieved": 2 * my_px / (seg_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": 2 * my_px / (seg_ms * 1e-3) / 1e9 / peak}}}
+        if not args.no_cpu_baseline:
+            from oracle import oracle as O
+            lines = max(64, min(nb, (1 << 24) // n1))
+            crop = out[:lines].cpu().numpy()
+            t0 = time.perf_counter()
+            want_seg, _ = O.clean_segments(crop, None, range(1, K + 1), 0.01, 20)
+            dt = time.perf_counter() - t0
+            got_seg = torch.empty((lines, n1), dtype=torch.uint8, device=dev)
+            ctx.clean_segments_dev(out[:lines], n1, lines, n1, keep, 0.01, 20, got_seg, n1)
+            res["next_rows"]["clean_segments"]["cpu_baseline"] = {
+                "value": n1 * lines / dt / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": f"first {lines} lines of the label sheet, sequential C oracle (the reference algorithm is sequential)",
+                "label_mismatches_vs_gpu": int((got_seg.cpu().numpy() != want_seg).sum())}
     if not args.no_cpu_baseline and world == 1:
         from oracle import oracle as O
         cs = O.LAB if stats.colourspace == "lab" else O.RGB
