@@ -5,6 +5,8 @@
 #   _categorize(pixels, points; tolerances, match, segmented, scan_threshold)   src/categories.jl:49-74
 #   _component_stats(A, pointvecs)                                              src/categories.jl:2-30
 #   blur(A; hood=Window{1}(), repeat=1)  (kwarg shape donor for `clean`)        src/blur.jl:6
+#   _clean(A, known_categories; categories, line_threshold, prune_threshold)    src/clean.jl:59-93
+#     (exposed as `clean_segments`: the name `clean` is the north_star's Window majority filter)
 # Every label is computed by libmaprast.so (CUDA, sm_100a) through `ccall`; there is NO CPU
 # fallback: unsupported options throw ArgumentError, a missing GPU makes `Context()` throw.
 #
@@ -16,7 +18,8 @@ module MapRasterizationB200
 using ColorTypes, FixedPointNumbers, Statistics
 import Neighborhoods: Window
 
-export categorize, clean, categorize_clean, categorize_u8, clean_u8, categorize_clean_u8, Context, Palette
+export categorize, clean, categorize_clean, categorize_u8, clean_u8, categorize_clean_u8, clean_segments,
+       clean_segments_u8, Context, Palette
 
 const libmaprast = get(ENV, "LIBMAPRAST", joinpath(@__DIR__, "..", "libmaprast.so"))
 const DEFAULT_CATEGORY_TOLERANCE = 2.0            # src/selectcolors.jl:1
@@ -46,7 +49,7 @@ default_context() = something(_default_ctx[], (_default_ctx[] = Context(); _defa
 function _check(ctx::Context, rc::Cint)
     rc == 0 && return nothing
     msg = unsafe_string(ccall((:mr_last_error, libmaprast), Cstring, (Ptr{Cvoid},), ctx.ptr))
-    rc == -1 ? throw(ArgumentError(msg)) : error("libmaprast ($rc): $msg")
+    (rc == -1 || rc == -5) ? throw(ArgumentError(msg)) : error("libmaprast ($rc): $msg")
 end
 
 # ---- palette = `category_stats` of src/categories.jl:52 ----------------------------------------
@@ -146,5 +149,41 @@ function clean_u8(labels::AbstractMatrix{<:Integer}; hood=Window{1}(), repeat::I
     return out
 end
 clean(labels; kw...) = _rewrap(labels, clean_u8(labels; kw...))
+
+"""
+`_clean(A, known_categories; categories, line_threshold=0.01, prune_threshold=20)` (src/clean.jl:59-93):
+4-connected segments of equal labels (`fast_scanning!`, src/scan.jl:56-157); segments of a category that
+is not in `categories`, with fewer than `prune_threshold` pixels, or with
+`count / (max(h, w)^2 / 2) < line_threshold` become 0 -- or the known category clicked inside them.
+Throws if one segment holds two different known categories (the reference result then depends on
+its scan order).  UInt8 labels out (the reference returns the Float64 segment colour).
+"""
+function clean_segments_u8(A::AbstractMatrix{<:Integer}, known_categories=nothing; categories,
+        line_threshold=0.01, prune_threshold=20, ctx::Context=default_context())
+    (isempty(A) || (0 <= minimum(A) && maximum(A) <= 254)) || throw(ArgumentError("labels must be in 0..254"))
+    L = Matrix{UInt8}(A)
+    n1, n2 = size(L)
+    keep = zeros(UInt8, 256)
+    for c in categories
+        keep[c + 1] = 1
+    end
+    if known_categories === nothing
+        _check(ctx, ccall((:mr_set_known, libmaprast), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{UInt8}), ctx.ptr, 0, C_NULL, C_NULL))
+    else
+        size(known_categories) == size(A) || throw(ArgumentError("known_categories must have the size of A"))
+        idx = Int64[i - 1 for i in eachindex(known_categories) if known_categories[i] != 0]   # i + j*n1, 0-based
+        cat = UInt8[known_categories[i + 1] for i in idx]
+        _check(ctx, ccall((:mr_set_known, libmaprast), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{UInt8}), ctx.ptr, length(idx), idx, cat))
+    end
+    out = similar(L)
+    nseg = Ref{Int64}(0)
+    GC.@preserve L out keep begin
+        _check(ctx, ccall((:mr_clean_segments_host, libmaprast), Cint,
+            (Ptr{Cvoid}, Ptr{UInt8}, Int64, Int64, Int64, Ptr{UInt8}, Float64, Float64, Ptr{UInt8}, Int64, Ref{Int64}),
+            ctx.ptr, pointer(L), n1, n2, n1, pointer(keep), line_threshold, prune_threshold, pointer(out), n1, nseg))
+    end
+    return out
+end
+clean_segments(A, known=nothing; kw...) = _rewrap(A, clean_segments_u8(A, known; kw...))
 
 end # module
