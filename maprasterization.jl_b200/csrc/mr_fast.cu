@@ -289,7 +289,7 @@ __device__ __forceinline__ void categorize_line(const FastParams& P, const uint8
     const uint8_t* mine = staged + lane * 96;
     // rounds run from the last 16 pixels to the first so that "Wp = Wp * 256 + label" (one IMAD on
     // the FMA pipe) leaves pixels 8k+j in byte k of register j.
-#pragma unroll 1
+#pragma unroll
     for (int h = 1; h >= 0; --h) {
         const uint4 v0 = *reinterpret_cast<const uint4*>(mine + 48 * h);
         const uint4 v1 = *reinterpret_cast<const uint4*>(mine + 48 * h + 16);
