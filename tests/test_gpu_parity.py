@@ -121,6 +121,24 @@ def test_uniform_random_colours_and_lattice(ctx, mr, oracle):
                       oracle.categorize_clean(scan, st.mean, st.lo, st.hi, 1)) == 0
 
 
+@pytest.mark.parametrize("R", [1, 2, 3])
+def test_random_labels_every_word_undecided(ctx, mr, oracle, R):
+    """Uniform random colours under a palette whose boxes accept everything: the label of every
+    pixel is random, no window has a clear majority, every vote word overflows into the round-2 /
+    exact-vote lists (the capped list cuts the blocks short) and every MIXED cell is hit."""
+    from maprast_b200 import synth
+    seed, palrgb, _, _ = _workload(mr, 2)
+    st = synth.make_stats(seed, palrgb, tol=60.0)
+    _set(ctx, mr, st)
+    scan = oracle.synth_scan(seed, 3, palrgb, 1936, 200, mode=1)
+    pre = oracle.categorize_u8(scan, st.mean, st.lo, st.hi)
+    assert (pre == 0).mean() < 0.05 and len(np.unique(pre)) >= 16
+    got, cnt = ctx.categorize_clean_host(scan, R, counters=True)
+    want = oracle.categorize_clean(scan, st.mean, st.lo, st.hi, R)
+    assert mismatches(got, want) == 0
+    assert cnt["n_changed"] == int((want != pre).sum()) and cnt["n_nomatch"] == int((want == 0).sum())
+
+
 def test_strided_and_unaligned_views(ctx, mr, oracle):
     seed, palrgb, stats, _ = _workload(mr, 1)
     _set(ctx, mr, stats)
