@@ -7,8 +7,10 @@
 A "step" is one pass of the hot path over the whole synthetic sheet (SURVEY.md 8(d) generator).
   N = 1 : BASELINE config 2 -- 20000 x 20000 RGB{N0f8}, 16-colour palette, clean window 5 (R = 2).
   N > 1 : the same sheet shape per GPU (weak scaling): one 20000 x (20000*N) sheet split into N
-          row bands; every step does the RGB halo exchange (NCCL send/recv of R lines) and one
-          fused launch per rank.  --workload cfg3 / cfg5 select BASELINE configs 3 and 5 instead.
+          row bands, one fused launch per rank and step.  The R halo lines of a band are read in
+          place from the neighbour band's HBM (CUDA IPC peer memory over NVLink, --halo peer, the
+          default) or exchanged with NCCL send/recv before every launch (--halo nccl).
+          --workload cfg3 / cfg5 select BASELINE configs 3 and 5 instead.
 `value` times device-resident inputs; `e2e` times the public host-buffer API (pinned host
 memory -> H2D -> kernel -> D2H) for the same sheet.  Prints ONE JSON line on rank 0.
 The CPU oracle (oracle/) is only used for the cpu_baseline leg and for --impl reference.
@@ -38,6 +40,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto", "cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
+    ap.add_argument("--halo", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N > 1 bands: read the halo lines in place from the neighbour's HBM (CUDA IPC peer "
+                         "memory) or exchange them with NCCL send/recv before every launch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
@@ -127,12 +132,12 @@ def workload_spec(args, world):
     if args.workload == "auto" and world > 1:
         spec["n2"] = spec["n2"] * world          # weak scaling: one config-2 sheet per GPU
         name = (f"weak: {spec['n1']}x{spec['n2']} sheet = {world} row bands of BASELINE config 2 "
-                f"(20000x20000, K=16, window 5), RGB halo exchange of R=2 lines per step")
+                f"(20000x20000, K=16, window 5), R=2 halo lines per band edge (see config.halo)")
         scaling = "weak"
     else:
         names = {1: "BASELINE config 1: 2000x2000, K=8, window 3",
                  2: "BASELINE config 2: 20000x20000 sheet, K=16, clean window 5",
-                 3: "BASELINE config 3: 60000x40000 sheet (2.4 Gpx), K=16, window 5, row bands + halo exchange",
+                 3: "BASELINE config 3: 60000x40000 sheet (2.4 Gpx), K=16, window 5, row bands + halo lines (see config.halo)",
                  4: "BASELINE config 4: 20000x20000, K=64 Lab distance + box, window 7",
                  5: "BASELINE config 5: batch of 256 sheets 4096x4096, K=16, window 5, whole sheets per GPU"}
         name = names[cfg]
@@ -218,10 +223,33 @@ def run_ours(args, rank, world, local_rank):
         my_px = nb * n1
         total_px = n1 * n2
     torch.cuda.synchronize()
+    peer = None
+    halo_mode = "none"
+    if world > 1 and not batch:
+        halo_mode = "nccl send/recv of R lines per neighbour before every launch"
+        if args.halo in ("auto", "peer"):
+            try:
+                peer = D.PeerHalos(ctx, buf, R, rank, world)
+                halo_mode = "in place: TMA line copies read the neighbour band's HBM over NVLink (CUDA IPC peer memory)"
+            except Exception as e:   # noqa: BLE001
+                if args.halo == "peer":
+                    raise
+                peer = None
+                halo_mode += f" (peer mapping unavailable: {type(e).__name__})"
+        # all ranks must take the same path
+        flag = torch.tensor([1 if peer is not None else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0 and peer is not None:
+            peer.close()
+            peer = None
+            halo_mode = "nccl send/recv of R lines per neighbour before every launch"
+        D.exchange_halos(buf, R, rank, world)   # halo slots valid for the host-buffer (e2e) leg either way
 
     def step():
         if batch:
             ctx.batch_categorize_clean_dev(ns, px, n1 * n2 * 3, n1, n2, n1 * 3, 3, R, out, n1 * n2, n1)
+        elif peer is not None:
+            peer.categorize_clean(buf, out)
         elif world > 1:
             D.categorize_clean_band(ctx, buf, R, out, rank, world)
         else:
@@ -307,7 +335,7 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": name, "K": K, "R": R, "colourspace": stats.colourspace,
                    "pixels_total": total_px, "pixels_per_gpu": my_px,
                    "cache": "inputs larger than L2 (%.2f GB per GPU per step)" % (my_px * 4 / 1e9),
-                   "palette_table_build_ms": build_ms},
+                   "palette_table_build_ms": build_ms, "halo": halo_mode},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0,
                      "peak_source": peak_src, "kernel": "fused categorise+clean", "kernel_ms": kern_ms,

@@ -102,6 +102,28 @@ int mr_categorize_clean_dev(mr_ctx* ctx, const uint8_t* px_dev, int64_t n1, int6
                             int halo_lo, int halo_hi,
                             uint8_t* labels_dev, int64_t out_stride2, void* stream);
 
+/* Same, but the halo lines are read IN PLACE from another buffer -- the neighbour band on a peer
+ * GPU of the same box (NVLink / NVSwitch peer memory; mr_ipc_* below maps it into this process).
+ * The kernel's TMA line copies fetch the 2R halo lines straight from the neighbour's HBM, so a
+ * band-sharded sheet needs no halo exchange step at all.  halo_lo_px = first of the halo_lo lines
+ * that precede line 0 (stride2_bytes apart), halo_hi_px = first of the halo_hi lines that follow
+ * line n2-1.  The caller guarantees that the neighbour's lines are complete before the launch
+ * (e.g. a barrier after upload).  Fast path only: packed RGB, 16-byte aligned pointers and
+ * strides, n1 % 16 == 0, R <= 3, K <= 126; no known-category plane.  Replaces nothing in the
+ * reference (which is single-process); SURVEY 8(e). */
+int mr_categorize_clean_dev_peer(mr_ctx* ctx, const uint8_t* px_dev, int64_t n1, int64_t n2,
+                                 int64_t stride2_bytes, int bytes_per_px, int R,
+                                 const uint8_t* halo_lo_px, int halo_lo,
+                                 const uint8_t* halo_hi_px, int halo_hi,
+                                 uint8_t* labels_dev, int64_t out_stride2, void* stream);
+
+/* CUDA IPC plumbing for one-process-per-GPU jobs: export a device allocation (64-byte handle of
+ * the allocation that contains dev_ptr + byte offset of dev_ptr in it), map a neighbour's
+ * allocation into this process with peer access enabled, unmap it. */
+int mr_ipc_export(const void* dev_ptr, void* handle64, int64_t* offset);
+int mr_ipc_open(mr_ctx* ctx, const void* handle64, void** base_out);
+int mr_ipc_close(mr_ctx* ctx, void* base);
+
 /* Batch of independent sheets of identical shape (BASELINE config 5): one launch. */
 int mr_batch_categorize_clean_dev(mr_ctx* ctx, int n_sheets, const uint8_t* px_dev,
                                   int64_t sheet_stride_bytes, int64_t n1, int64_t n2,

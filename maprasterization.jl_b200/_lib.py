@@ -21,6 +21,7 @@ SYMBOLS = [
     "mr_version", "mr_create", "mr_destroy", "mr_last_error", "mr_set_palette", "mr_set_known",
     "mr_get_lut", "mr_palette_build_ms", "mr_enable_counters", "mr_read_counters", "mr_launch_count",
     "mr_categorize_clean_host", "mr_categorize_clean_host_band", "mr_categorize_clean_dev", "mr_batch_categorize_clean_dev",
+    "mr_categorize_clean_dev_peer", "mr_ipc_export", "mr_ipc_open", "mr_ipc_close",
     "mr_clean_host", "mr_clean_dev", "mr_clean_segments_dev", "mr_clean_segments_host",
     "mr_host_alloc", "mr_host_free", "mr_synth_scan_dev",
 ]
@@ -74,6 +75,10 @@ def load():
                                                 C.POINTER(Counters)]
     L.mr_categorize_clean_dev.argtypes = [vp, u8p, i64, i64, i64, i32, i32, i32, i32, u8p, i64, vp]
     L.mr_batch_categorize_clean_dev.argtypes = [vp, i32, u8p, i64, i64, i64, i64, i32, i32, u8p, i64, i64, vp]
+    L.mr_categorize_clean_dev_peer.argtypes = [vp, u8p, i64, i64, i64, i32, i32, u8p, i32, u8p, i32, u8p, i64, vp]
+    L.mr_ipc_export.argtypes = [vp, vp, C.POINTER(i64)]
+    L.mr_ipc_open.argtypes = [vp, vp, C.POINTER(vp)]
+    L.mr_ipc_close.argtypes = [vp, vp]
     L.mr_clean_host.argtypes = [vp, u8p, i64, i64, i64, i32, i32, u8p, i64]
     L.mr_clean_dev.argtypes = [vp, u8p, i64, i64, i64, i32, i32, i32, u8p, i64, vp]
     L.mr_clean_segments_dev.argtypes = [vp, u8p, i64, i64, i64, u8p, C.c_double, C.c_double, u8p, i64,
@@ -88,11 +93,23 @@ def load():
     for name in ("mr_set_palette", "mr_set_known", "mr_get_lut", "mr_palette_build_ms", "mr_enable_counters",
                  "mr_read_counters", "mr_categorize_clean_host", "mr_categorize_clean_host_band",
                  "mr_categorize_clean_dev",
+                 "mr_categorize_clean_dev_peer", "mr_ipc_export", "mr_ipc_open", "mr_ipc_close",
                  "mr_batch_categorize_clean_dev", "mr_clean_host", "mr_clean_dev", "mr_clean_segments_dev",
                  "mr_clean_segments_host", "mr_synth_scan_dev"):
         getattr(L, name).restype = i32
     _lib = L
     return L
+
+
+def ipc_export(dev_ptr):
+    """(64-byte CUDA IPC handle of the allocation holding dev_ptr, byte offset of dev_ptr in it)."""
+    L = load()
+    hb = C.create_string_buffer(64)
+    off = C.c_int64(0)
+    rc = L.mr_ipc_export(C.c_void_p(_ptr(dev_ptr)), hb, C.byref(off))
+    if rc != 0:
+        raise MapRastError(rc, L.mr_last_error(None).decode())
+    return hb.raw, int(off.value)
 
 
 def _ptr(a):
@@ -230,6 +247,23 @@ class Context:
     def categorize_clean_dev(self, px, n1, n2, stride2, bpp, R, out, out_stride2, halo_lo=0, halo_hi=0, stream=0):
         self._ck(self._L.mr_categorize_clean_dev(self._h, _ptr(px), n1, n2, stride2, bpp, int(R), int(halo_lo),
                                                  int(halo_hi), _ptr(out), out_stride2, stream or None))
+
+    def categorize_clean_dev_peer(self, px, n1, n2, stride2, bpp, R, halo_lo_px, halo_lo, halo_hi_px, halo_hi,
+                                  out, out_stride2, stream=0):
+        """Band whose halo lines are read in place from other buffers (peer GPU memory)."""
+        self._ck(self._L.mr_categorize_clean_dev_peer(self._h, _ptr(px), n1, n2, stride2, bpp, int(R),
+                                                      _ptr(halo_lo_px), int(halo_lo), _ptr(halo_hi_px),
+                                                      int(halo_hi), _ptr(out), out_stride2, stream or None))
+
+    def ipc_open(self, handle):
+        """Map another process's device allocation (64-byte CUDA IPC handle); returns its base address."""
+        base = C.c_void_p(0)
+        hb = C.create_string_buffer(bytes(handle), 64)
+        self._ck(self._L.mr_ipc_open(self._h, hb, C.byref(base)))
+        return int(base.value)
+
+    def ipc_close(self, base):
+        self._ck(self._L.mr_ipc_close(self._h, C.c_void_p(base)))
 
     def batch_categorize_clean_dev(self, n_sheets, px, sheet_stride, n1, n2, stride2, bpp, R, out,
                                    out_sheet_stride, out_stride2, stream=0):

@@ -525,6 +525,75 @@ extern "C" int mr_clean_host(mr_ctx* ctx, const uint8_t* labels, int64_t n1, int
 }
 
 // ------------------------------------------------------------------ bench/test utility
+// ------------------------------------------------------------------ bands with remote halo lines
+extern "C" int mr_categorize_clean_dev_peer(mr_ctx* ctx, const uint8_t* px_dev, int64_t n1, int64_t n2,
+                                            int64_t stride2_bytes, int bytes_per_px, int R,
+                                            const uint8_t* halo_lo_px, int halo_lo, const uint8_t* halo_hi_px,
+                                            int halo_hi, uint8_t* labels_dev, int64_t out_stride2, void* stream) {
+    int rc = check_image_args(ctx, "mr_categorize_clean_dev_peer", px_dev, labels_dev, n1, n2, stride2_bytes,
+                              bytes_per_px, out_stride2, R, halo_lo, halo_hi);
+    if (rc) return rc;
+    if ((rc = check_palette(ctx, "mr_categorize_clean_dev_peer", bytes_per_px))) return rc;
+    if ((halo_lo > 0 && !halo_lo_px) || (halo_hi > 0 && !halo_hi_px))
+        return fail(ctx, MR_ERR_ARG, "mr_categorize_clean_dev_peer: null halo pointer with a non-zero halo");
+    if (ctx->n_known > 0)
+        return fail(ctx, MR_ERR_ARG, "mr_categorize_clean_dev_peer: known categories are not supported on this entry point");
+    CK(cudaSetDevice(ctx->device));
+    MrJob job = make_job(ctx, px_dev, labels_dev, n1, n2, stride2_bytes, bytes_per_px, R, halo_lo, halo_hi, out_stride2);
+    job.halo_lo_px = halo_lo > 0 ? halo_lo_px : nullptr;
+    job.halo_hi_px = halo_hi > 0 ? halo_hi_px : nullptr;
+    if (n1 == 0 || n2 == 0) return MR_OK;
+    if (!mr_fast_supported(job))
+        return fail(ctx, MR_ERR_ARG,
+                    "mr_categorize_clean_dev_peer: remote halo lines need the fast path (packed RGB, 16-byte aligned "
+                    "lines and pointers, n1 % 16 == 0, R <= 3, K <= 126)");
+    int nl = 0;
+    cudaError_t e = mr_launch_fast(job, ctx->sm_count, (cudaStream_t)stream, &nl);
+    ctx->launches += nl;
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "fused kernel (remote halos)");
+    return MR_OK;
+}
+
+extern "C" int mr_ipc_export(const void* dev_ptr, void* handle64, int64_t* offset) {
+    if (!dev_ptr || !handle64 || !offset) return fail(nullptr, MR_ERR_ARG, "mr_ipc_export: null argument");
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, const_cast<void*>(dev_ptr));   // handle of the whole allocation
+    if (e != cudaSuccess) return fail_cuda(nullptr, e, "cudaIpcGetMemHandle");
+    // base of the allocation: driver entry point fetched through the runtime (no link-time libcuda)
+    typedef int (*range_fn)(unsigned long long*, size_t*, unsigned long long);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    e = cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || !fn) return fail_cuda(nullptr, e, "cudaGetDriverEntryPoint(cuMemGetAddressRange)");
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (reinterpret_cast<range_fn>(fn)(&base, &size, (unsigned long long)(uintptr_t)dev_ptr) != 0)
+        return fail(nullptr, MR_ERR_CUDA, "mr_ipc_export: cuMemGetAddressRange failed");
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &h, 64);
+    *offset = (int64_t)((unsigned long long)(uintptr_t)dev_ptr - base);
+    return MR_OK;
+}
+
+extern "C" int mr_ipc_open(mr_ctx* ctx, const void* handle64, void** base_out) {
+    if (!ctx || !handle64 || !base_out) return fail(ctx, MR_ERR_ARG, "mr_ipc_open: null argument");
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *base_out = p;
+    return MR_OK;
+}
+
+extern "C" int mr_ipc_close(mr_ctx* ctx, void* base) {
+    if (!ctx) return fail(nullptr, MR_ERR_ARG, "mr_ipc_close: null ctx");
+    if (!base) return MR_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaIpcCloseMemHandle(base));
+    return MR_OK;
+}
+
 // ------------------------------------------------------------------ segment prune (_clean)
 static int prune_dev(mr_ctx* ctx, const char* fn, const uint8_t* labels_dev, int64_t n1, int64_t n2,
                      int64_t stride2, const uint8_t* keep256, double line_threshold, double prune_threshold,

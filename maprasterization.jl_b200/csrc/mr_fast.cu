@@ -180,6 +180,7 @@ struct CopyPlan {
     const uint8_t* src0;   // sheet base + first byte of the window part that is loaded
     uint32_t dst;          // shared address the first loaded byte goes to
     uint32_t bytes;        // 0: nothing to load
+    long long col_off;     // byte offset of the first loaded byte in its line
 };
 
 template <int R>
@@ -193,6 +194,7 @@ __device__ __forceinline__ CopyPlan copy_plan(const FastParams& P, const Item& i
     hi = hi > limit ? limit : hi;
     CopyPlan c;
     c.src0 = it.px + lo;
+    c.col_off = lo;
     c.dst = stage + (uint32_t)(lo - w0);
     c.bytes = hi > lo ? (uint32_t)(hi - lo) : 0u;
     return c;
@@ -202,14 +204,24 @@ __device__ __forceinline__ CopyPlan copy_plan(const FastParams& P, const Item& i
 // further down into L2 (the next copy then completes at L2 latency instead of DRAM latency).
 // Returns false if the line needs no load (outside the sheet).  ylo / yhi: loadable lines.
 constexpr int PF_LINES = 3;
-__device__ __forceinline__ bool issue_line_copy(const CopyPlan& c, const uint8_t* src, long long pf_off, int y,
-                                                int ylo, int yhi, uint32_t bar, int lane) {
+__device__ __forceinline__ bool issue_line_copy(const FastParams& P, const CopyPlan& c, const uint8_t* src,
+                                                long long pf_off, int y, int ylo, int yhi, uint32_t bar, int lane) {
     if (y < ylo || y >= yhi) return false;
     if (lane == 0) {
+        bool pf = y + PF_LINES < yhi;
+        // halo lines that live in the neighbour band's buffer (peer GPU memory): read in place
+        if (y < 0 && P.job.halo_lo_px) {
+            src = P.job.halo_lo_px + (long long)(y + P.job.halo_lo) * P.job.stride2 + c.col_off;
+            pf = false;
+        } else if (y >= P.job.n2 && P.job.halo_hi_px) {
+            src = P.job.halo_hi_px + (long long)(y - P.job.n2) * P.job.stride2 + c.col_off;
+            pf = false;
+        } else if (y + PF_LINES >= P.job.n2 && P.job.halo_hi_px) {
+            pf = false;
+        }
         mbar_expect_tx(bar, c.bytes);
         tma_load_1d(c.dst, src, c.bytes, bar);
-        if (y + PF_LINES < yhi)
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + pf_off), "r"(c.bytes) : "memory");
+        if (pf) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + pf_off), "r"(c.bytes) : "memory");
     }
     return true;
 }
@@ -907,7 +919,7 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
         const int yhi = plan.bytes ? min(cat_last, (int)P.job.n2 + P.job.halo_hi) : ylo;
         const long long pf_off = (long long)PF_LINES * P.job.stride2;
         const uint8_t* srcn = plan.src0 + (long long)ycat * P.job.stride2;   // source of the next line to copy
-        bool pend = issue_line_copy(plan, srcn, pf_off, ycat, ylo, yhi, bar, lane);
+        bool pend = issue_line_copy(P, plan, srcn, pf_off, ycat, ylo, yhi, bar, lane);
         srcn += P.job.stride2;
         // bytes of one output line of the strip (whole 16-byte chunks, see mr_fast_supported)
         uint32_t obytes = 0;
@@ -936,7 +948,7 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
                     P, coarse, ws, it, ycat, lane, M, pend ? stage : nullptr,
                     [&]() {
                         __syncwarp();   // every lane is done with the staging buffer
-                        nxt = issue_line_copy(plan, srcn, pf_off, ycat + 1, ylo, yhi, bar, lane);
+                        nxt = issue_line_copy(P, plan, srcn, pf_off, ycat + 1, ylo, yhi, bar, lane);
                         srcn += P.job.stride2;
                     },
                     c_fine, c_nomatch);
@@ -1103,6 +1115,8 @@ bool mr_fast_supported(const MrJob& job) {
                      (job.out_stride2 % 16 == 0) && (job.sheet_stride % 16 == 0) && (job.out_sheet_stride % 16 == 0);
     if (!a16) return false;
     if (!job.padded && (job.n1 % 16 != 0)) return false;
+    if ((job.halo_lo_px || job.halo_hi_px) &&
+        (job.n_sheets != 1 || (uintptr_t)job.halo_lo_px % 16 != 0 || (uintptr_t)job.halo_hi_px % 16 != 0)) return false;
     return true;
 }
 

@@ -35,6 +35,11 @@ struct MrJob {
     int bpp;                  // 3 | 4 (fused) ; 1 for label input (clean only)
     int R;
     int halo_lo, halo_hi;     // real lines available outside [0, n2)
+    // optional: the halo lines live elsewhere (the neighbour band's buffer, e.g. peer GPU memory over
+    // NVLink): line -k (k = 1..halo_lo) is halo_lo_px + (halo_lo - k) * stride2, line n2 + k is
+    // halo_hi_px + k * stride2.  nullptr: the lines are in place around px (fast path only).
+    const uint8_t* halo_lo_px;
+    const uint8_t* halo_hi_px;
     int padded;               // in/out lines are readable/writable up to the next multiple of 16 bytes
     const uint8_t* lut;       // 2^24 exact table (nullptr when direct evaluation is used)
     const uint8_t* coarse;    // 2^15 coarse table

@@ -60,3 +60,49 @@ def categorize_clean_band(ctx, buf, R, out, rank=None, world=None, group=None, s
     own = buf[R:R + nb]
     ctx.categorize_clean_dev(own, n1, nb, n1 * bpp, bpp, R, out, n1, halo_lo, halo_hi, stream)
     return halo_lo, halo_hi
+
+
+class PeerHalos:
+    """Band neighbours' edge lines mapped into this process (CUDA IPC over NVLink peer memory), so
+    that the fused kernel reads the 2R halo lines in place from the neighbours' HBM and a band-
+    sharded sheet needs no exchange step at all.  One instance per band buffer; collective over
+    `group` (handles are all-gathered once).  The band buffers must stay allocated while in use."""
+
+    def __init__(self, ctx, buf, R, rank=None, world=None, group=None):
+        from . import _lib
+        self.ctx, self.R = ctx, R
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        nb = buf.shape[0] - 2 * R
+        stride = buf.stride(0) * buf.element_size()
+        handle, off = _lib.ipc_export(buf)
+        mine = (handle, off, nb, stride)
+        infos = [None] * self.world
+        dist.all_gather_object(infos, mine, group=group)
+        self._bases = []
+        self.lo_ptr = self.hi_ptr = 0
+        self.halo_lo = self.halo_hi = 0
+        if R > 0 and self.rank > 0:                       # lower neighbour's last R own lines
+            h, o, nbp, st = infos[self.rank - 1]
+            base = ctx.ipc_open(h)
+            self._bases.append(base)
+            self.lo_ptr, self.halo_lo = base + o + nbp * st, R      # own lines start at slot R: last R = slots nb .. nb+R-1
+        if R > 0 and self.rank < self.world - 1:          # upper neighbour's first R own lines
+            h, o, nbp, st = infos[self.rank + 1]
+            base = ctx.ipc_open(h)
+            self._bases.append(base)
+            self.hi_ptr, self.halo_hi = base + o + R * st, R
+        dist.barrier(group=group)
+
+    def categorize_clean(self, buf, out, stream=0):
+        """ONE fused launch on this rank's band; no exchange.  The neighbours' lines must be in place."""
+        R = self.R
+        nb = buf.shape[0] - 2 * R
+        n1, bpp = buf.shape[1], buf.shape[2]
+        self.ctx.categorize_clean_dev_peer(buf[R:R + nb], n1, nb, n1 * bpp, bpp, R, self.lo_ptr or None, self.halo_lo,
+                                           self.hi_ptr or None, self.halo_hi, out, n1, stream)
+
+    def close(self):
+        for b in self._bases:
+            self.ctx.ipc_close(b)
+        self._bases = []

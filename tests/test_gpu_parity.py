@@ -237,6 +237,33 @@ def test_device_bands_equal_whole(ctx, mr, oracle):
     assert torch.equal(whole, banded)
 
 
+def test_bands_with_remote_halo_lines(ctx, mr, oracle):
+    """mr_categorize_clean_dev_peer: the halo lines of a band live in OTHER buffers (on the GPU box
+    with several GPUs: the neighbour's HBM over NVLink; here: separate allocations on one GPU)."""
+    seed, palrgb, stats, spec = _workload(mr, 2)
+    _set(ctx, mr, stats)
+    n1, n2, R = 1936, 300, 2
+    scan = oracle.synth_scan(seed, 1, palrgb, n1, n2)
+    want = oracle.categorize_clean(scan, stats.mean, stats.lo, stats.hi, R)
+    d = torch.from_numpy(scan).cuda()
+    got = torch.empty((n2, n1), dtype=torch.uint8, device="cuda")
+    cuts = [0, 77, 150, 151 + R, n2]
+    for k in range(len(cuts) - 1):
+        a, b = cuts[k], cuts[k + 1]
+        band = d[a:b].clone()                                   # own lines only
+        lo = d[a - R:a].clone() if a > 0 else None              # "neighbour" lines, separate allocations
+        hi = d[b:b + R].clone() if b < n2 else None
+        ctx.categorize_clean_dev_peer(band, n1, b - a, n1 * 3, 3, R, lo, R if a > 0 else 0, hi, R if b < n2 else 0,
+                                      got[a:b], n1)
+        torch.cuda.synchronize()
+    assert mismatches(got.cpu().numpy(), want) == 0
+    with pytest.raises(mr.MapRastError):
+        ctx.categorize_clean_dev_peer(d[10:20], n1, 10, n1 * 3, 3, R, None, R, None, 0, got[10:20], n1)
+    # IPC export of a device pointer (open needs a second process; exercised by bench.py --gpus N)
+    h, off = mr._lib.ipc_export(d[5:])
+    assert len(h) == 64 and off >= 5 * n1 * 3
+
+
 def test_batch_of_sheets(ctx, mr, oracle):
     seed, palrgb, stats, spec = _workload(mr, 5)
     _set(ctx, mr, stats)
