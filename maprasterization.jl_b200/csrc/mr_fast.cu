@@ -311,13 +311,13 @@ __device__ __forceinline__ void categorize_line(const FastParams& P, const uint8
         for (int g = 3; g >= 0; --g) {   // 4 pixels = 12 bytes: [r0 g0 b0 r1] [g1 b1 r2 g2] [b2 r3 g3 b3]
             const uint32_t w0 = w[3 * g], w1 = w[3 * g + 1], w2 = w[3 * g + 2];
             // every byte quantised to x >> 3 (two ALU operations per word); the r / g part of the
-            // index is one byte dot product starting at the table address, the b part (weight 128,
-            // the largest a byte weight can carry) a second one that an IMAD scales by 8
+            // index is one byte dot product starting at the table address, the b part (weight 129)
+            // a second one that an IMAD scales by 8: cell = r5 + 32 g5 + 1032 b5 (MR_COARSE_IDX)
             const uint32_t q0 = (w0 >> 3) & 0x1F1F1F1Fu, q1 = (w1 >> 3) & 0x1F1F1F1Fu, q2 = (w2 >> 3) & 0x1F1F1F1Fu;
-            const uint32_t i0 = __dp4a(q0, 0x00800000u, 0u) * 8u + __dp4a(q0, 0x00002001u, tab);
-            const uint32_t i1 = __dp4a(q1, 0x00008000u, 0u) * 8u + __dp4a(q1, 0x00000020u, __dp4a(q0, 0x01000000u, tab));
-            const uint32_t i2 = __dp4a(q2, 0x00000080u, 0u) * 8u + __dp4a(q1, 0x20010000u, tab);
-            const uint32_t i3 = __dp4a(q2, 0x80000000u, 0u) * 8u + __dp4a(q2, 0x00200100u, tab);
+            const uint32_t i0 = __dp4a(q0, 0x00810000u, 0u) * 8u + __dp4a(q0, 0x00002001u, tab);
+            const uint32_t i1 = __dp4a(q1, 0x00008100u, 0u) * 8u + __dp4a(q1, 0x00000020u, __dp4a(q0, 0x01000000u, tab));
+            const uint32_t i2 = __dp4a(q2, 0x00000081u, 0u) * 8u + __dp4a(q1, 0x20010000u, tab);
+            const uint32_t i3 = __dp4a(q2, 0x81000000u, 0u) * 8u + __dp4a(q2, 0x00200100u, tab);
             // pixel 16h + 4g + t -> register (4g + t) & 7, byte order by descending pixel index
             const int j = (4 * g) & 7;
             Wp[j + 0] = Wp[j + 0] * 256u + lds_u8(i0);

@@ -18,11 +18,11 @@ __global__ void __launch_bounds__(256) k_build_lut(MrPalette pal, uint8_t* __res
     lut[idx] = (uint8_t)mr_eval_px(pal, r, g, b, 255, false, 0);
 }
 
-// One thread per coarse cell c = (r>>3) | (g>>3)<<5 | (b>>3)<<10: uniform label or MIXED.
+// One thread per coarse cell (r>>3, g>>3, b>>3): uniform label or MIXED (layout: MR_COARSE_IDX).
 __global__ void __launch_bounds__(128) k_build_coarse(const uint8_t* __restrict__ lut,
                                                       uint8_t* __restrict__ coarse) {
     unsigned c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= MR_COARSE_SIZE) return;
+    if (c >= (1u << 15)) return;
     unsigned r0 = (c & 31u) << 3, g0 = ((c >> 5) & 31u) << 3, b0 = ((c >> 10) & 31u) << 3;
     unsigned first = lut[r0 | (g0 << 8) | (b0 << 16)];
     unsigned long long want = 0x0101010101010101ull * first;
@@ -33,13 +33,14 @@ __global__ void __launch_bounds__(128) k_build_coarse(const uint8_t* __restrict_
                 lut + (r0 | ((g0 + g) << 8) | ((b0 + b) << 16)));
             uniform = uniform && (v == want);
         }
-    coarse[c] = (uniform && first != MR_MIXED) ? (uint8_t)first : (uint8_t)MR_MIXED;
+    coarse[MR_COARSE_IDX(c & 31u, (c >> 5) & 31u, c >> 10)] =
+        (uniform && first != MR_MIXED) ? (uint8_t)first : (uint8_t)MR_MIXED;
 }
 
 cudaError_t mr_launch_build_lut(const MrPalette& pal, uint8_t* lut, uint8_t* coarse, cudaStream_t s,
                                 int* n_launches) {
     k_build_lut<<<MR_LUT_SIZE / 256, 256, 0, s>>>(pal, lut);
-    k_build_coarse<<<MR_COARSE_SIZE / 128, 128, 0, s>>>(lut, coarse);
+    k_build_coarse<<<(1u << 15) / 128, 128, 0, s>>>(lut, coarse);
     *n_launches += 2;
     return cudaGetLastError();
 }
@@ -58,7 +59,7 @@ __device__ __forceinline__ unsigned g_label(const MrJob& job, const uint8_t* __r
     if (direct) return (unsigned)mr_eval_px(job.pal, p[0], p[1], p[2], job.bpp == 4 ? p[3] : 255,
                                             job.bpp == 4, 0);
     unsigned r = p[0], g = p[1], b = p[2];
-    unsigned v = s_coarse[(r >> 3) | ((g >> 3) << 5) | ((b >> 3) << 10)];
+    unsigned v = s_coarse[MR_COARSE_IDX(r >> 3, g >> 3, b >> 3)];
     if (v == MR_MIXED) {
         v = __ldg(job.lut + (r | (g << 8) | (b << 16)));
         ++fine;

@@ -4,7 +4,13 @@
 #include <stdint.h>
 
 #define MR_LUT_SIZE (1u << 24)      // exact per-colour label table, index r | g<<8 | b<<16
-#define MR_COARSE_SIZE (1u << 15)   // 32^3 cells of 8^3 colours; 0xFF = mixed cell
+// Coarse table: 32^3 cells of 8^3 colours, 0xFF = mixed cell.  Cell (r5, g5, b5) sits at
+// r5 + 32*g5 + 1032*b5: the b stride is 1024 + 8 so that neighbouring b5 values fall into different
+// shared-memory banks (with a stride of 1024 the colours of one map region -- b5 +- 1 -- would all
+// hit the same bank with different words).  Size rounded up to a multiple of 128.
+#define MR_COARSE_BSTRIDE 1032u
+#define MR_COARSE_SIZE 33152u
+#define MR_COARSE_IDX(r5, g5, b5) ((r5) + 32u * (g5) + MR_COARSE_BSTRIDE * (b5))
 #define MR_MIXED 0xFFu
 
 // Device-resident palette (global memory; read uniformly -> broadcast loads).
