@@ -36,7 +36,8 @@ struct mr_ctx {
     uint8_t* d_out = nullptr; size_t d_out_cap = 0;
     uint8_t* d_tmp = nullptr; size_t d_tmp_cap = 0;
     // segment prune scratch: parent array, component records, keep table + two counters
-    uint8_t* d_parent = nullptr; size_t d_parent_cap = 0;
+    uint8_t* d_parent = nullptr; size_t d_parent_cap = 0;   // first run of every (line, chunk)
+    uint8_t* d_runs = nullptr; size_t d_runs_cap = 0;       // run arrays
     uint8_t* d_rec = nullptr; size_t d_rec_cap = 0;
     uint8_t* d_small = nullptr;     // 256-byte keep table | n_roots | conflict
     std::vector<cudaEvent_t> ev_up, ev_done;
@@ -112,7 +113,7 @@ extern "C" void mr_destroy(mr_ctx* ctx) {
     cudaFree(ctx->d_pal); cudaFree(ctx->d_lut); cudaFree(ctx->d_coarse);
     cudaFree(ctx->d_known_idx); cudaFree(ctx->d_known_cat); cudaFree(ctx->d_counters);
     cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_tmp);
-    cudaFree(ctx->d_parent); cudaFree(ctx->d_rec); cudaFree(ctx->d_small);
+    cudaFree(ctx->d_parent); cudaFree(ctx->d_runs); cudaFree(ctx->d_rec); cudaFree(ctx->d_small);
     if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
@@ -604,15 +605,26 @@ static int prune_dev(mr_ctx* ctx, const char* fn, const uint8_t* labels_dev, int
     if (n_segments) *n_segments = 0;
     if (n1 == 0 || n2 == 0) return MR_OK;
     if ((double)n1 * (double)n2 >= 2147483648.0) return fail(ctx, MR_ERR_ARG, f + ": n1 * n2 must be below 2^31");
+    if (labels_dev == out_dev) return fail(ctx, MR_ERR_ARG, f + ": in-place operation is not supported");
     int rc;
-    if ((rc = grow(ctx, &ctx->d_parent, &ctx->d_parent_cap, mr_prune_parent_bytes(n1, n2)))) return rc;
+    const size_t cb_bytes = mr_prune_cbase_bytes(n1, n2);
+    if ((rc = grow(ctx, &ctx->d_parent, &ctx->d_parent_cap, cb_bytes))) return rc;   // chunk bases
+    uint32_t* cbase = reinterpret_cast<uint32_t*>(ctx->d_parent);
     if (!ctx->d_small) CK(cudaMalloc(&ctx->d_small, 512));
     unsigned int* d_n_roots = reinterpret_cast<unsigned int*>(ctx->d_small + 256);
     unsigned int* d_conflict = reinterpret_cast<unsigned int*>(ctx->d_small + 260);
     CK(cudaMemcpyAsync(ctx->d_small, keep256, 256, cudaMemcpyHostToDevice, s));
     int nl = 0;
-    cudaError_t e = mr_launch_prune_components(labels_dev, n1, n2, stride2, reinterpret_cast<uint32_t*>(ctx->d_parent),
-                                               d_n_roots, s, &nl);
+    cudaError_t e = mr_launch_prune_count(labels_dev, n1, n2, stride2, cbase, s, &nl);
+    ctx->launches += nl;
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "segment prune (run count)");
+    unsigned int n_runs = 0;
+    CK(cudaMemcpyAsync(&n_runs, reinterpret_cast<const uint8_t*>(cbase) + cb_bytes - sizeof(uint32_t), sizeof n_runs,
+                       cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if ((rc = grow(ctx, &ctx->d_runs, &ctx->d_runs_cap, mr_prune_run_bytes(n_runs)))) return rc;
+    nl = 0;
+    e = mr_launch_prune_components(labels_dev, n1, n2, stride2, cbase, ctx->d_runs, n_runs, d_n_roots, s, &nl);
     ctx->launches += nl;
     if (e != cudaSuccess) return fail_cuda(ctx, e, "segment prune (components)");
     unsigned int n_roots = 0;
@@ -620,9 +632,9 @@ static int prune_dev(mr_ctx* ctx, const char* fn, const uint8_t* labels_dev, int
     CK(cudaStreamSynchronize(s));
     if ((rc = grow(ctx, &ctx->d_rec, &ctx->d_rec_cap, mr_prune_rec_bytes(n_roots)))) return rc;
     nl = 0;
-    e = mr_launch_prune_apply(labels_dev, n1, n2, stride2, reinterpret_cast<const uint32_t*>(ctx->d_parent), ctx->d_rec,
-                              n_roots, ctx->n_known, ctx->d_known_idx, ctx->d_known_cat, ctx->d_small, line_threshold,
-                              prune_threshold, out_dev, out_stride2, d_conflict, s, &nl);
+    e = mr_launch_prune_apply(labels_dev, n1, n2, stride2, cbase, ctx->d_runs, n_runs, ctx->d_rec, n_roots, ctx->n_known,
+                              ctx->d_known_idx, ctx->d_known_cat, ctx->d_small, line_threshold, prune_threshold, out_dev,
+                              out_stride2, d_conflict, s, &nl);
     ctx->launches += nl;
     if (e != cudaSuccess) return fail_cuda(ctx, e, "segment prune (apply)");
     unsigned int conflict = 0;

@@ -7,32 +7,50 @@
 // different known categories (then the reference splits it at the pixel where the merge is
 // refused, scan.jl:140-146, which depends on the scan order; that case is detected here and
 // reported as MR_ERR_UNSUPPORTED instead of being guessed).  So this is connected-component
-// labelling + per-component statistics + a per-component rule:
+// labelling + per-component statistics + a per-component rule.
 //
-//   k_runs      lane = pixel of a line: parent = start of its horizontal run of equal labels
-//               (warp ballot; a run that began in an earlier 32-pixel group links to that group)
-//   k_vmerge    union of vertically adjacent runs (lock-free union-find, atomicMin linking towards
-//               the smaller index); only the first pixel of every horizontal overlap does the union
-//   k_flatten   parent = root
-//   k_number    roots take a compact id (warp-aggregated atomic counter); id tagged into the root
-//   k_stats     per (run x 32-pixel group): count, bounding box -> atomics on the component's record
-//   k_known     known-category plane (sparse list) -> per-component min / max known category
-//   k_relabel   out = rule(component record)  (clean.jl:65-88, Float64 arithmetic as written there)
+// RUN based: a cleaned map has long horizontal runs of equal labels (~30 pixels on the synthetic
+// sheets), so everything after the first two passes works on runs, not pixels:
 //
-// Pixel index p = y * n1 + x fits 31 bits (n1 * n2 < 2^31; bit 31 tags a numbered root).
-// Bound: HBM; algorithmic traffic 2 B/pixel (label in, label out); this first version moves
-// ~30 B/pixel (4-byte parent array, five passes) -- see DESIGN.md.
+//   k_count    (line, 4096-pixel chunk): number of run starts            } 16 pixels per thread,
+//   k_scan     exclusive scan of the chunk counts -> first run of every chunk / line
+//   k_fill     run start x, label, parent = self                         } 16-byte loads
+//   k_merge    one block per line: every run finds the runs of the previous line that overlap it
+//              (binary search in the sorted run starts) and unites with those of equal label
+//              (lock-free union-find, atomicMin links towards the smaller run index)
+//   k_flatnum  parent = root; roots take a compact component id (tagged into the root's entry)
+//   k_stats    per run: count, bounding box, label -> atomics on the component's record
+//   k_known    known-category plane (sparse list): pixel -> run (binary search) -> component
+//   k_decide   per component: the rule of clean.jl:65-88 (Float64 arithmetic as written there)
+//   k_runout   per run: the label it will be painted with
+//   k_paint    (line, chunk) again: pixel -> run -> label, 16-byte stores
+//
+// Run / pixel indices fit 31 bits (n1 * n2 < 2^31; bit 31 tags a numbered root).
+// Bound: HBM; algorithmic traffic 2 B/pixel (label in, label out); this version reads the labels
+// three times and writes them once (4 B/pixel) plus ~10 B per run.
 #include "mr_internal.h"
 
 namespace {
 
 constexpr uint32_t TAG = 0x80000000u;
+constexpr int PT = 16;            // pixels per thread
+constexpr int BT = 256;           // threads per block
+constexpr int CH = PT * BT;       // pixels per chunk
 
 struct SegRec {                 // one per component
     unsigned int count;
     unsigned int xmin, xmax, ymin, ymax;
     unsigned int cmin, cmax;    // known categories present: min / max of the non-zero ones
-    unsigned int label;
+    unsigned int label;         // input label, later (k_decide) the output label
+};
+
+struct Runs {
+    uint32_t* start;            // x of the first pixel
+    uint32_t* parent;           // union-find over run indices; after k_flatnum: root index, or TAG | id in a root
+    uint8_t* label;
+    uint8_t* out;               // label the run is painted with
+    const uint32_t* cbase;      // first run of every (line, chunk); cbase[n2 * chunks] = number of runs
+    uint32_t chunks;            // chunks per line
 };
 
 __device__ __forceinline__ uint32_t find_root(uint32_t* parent, uint32_t x) {
@@ -58,56 +76,149 @@ __device__ __forceinline__ void unite(uint32_t* parent, uint32_t a, uint32_t b) 
     }
 }
 
-// grid: x = 32-pixel groups of a line, y = lines
-__global__ void k_runs(const uint8_t* __restrict__ lab, int64_t stride2, uint32_t n1, uint32_t n2,
-                       uint32_t* __restrict__ parent) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t groups = (n1 + 31) / 32;
-    const uint64_t gw = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (gw >= (uint64_t)groups * n2) return;
-    const uint32_t y = (uint32_t)(gw / groups), x0 = (uint32_t)(gw % groups) * 32, x = x0 + lane;
-    const bool in = x < n1;
-    const uint8_t* line = lab + (int64_t)y * stride2;
-    const int me = in ? line[x] : -1;
-    int left = __shfl_up_sync(0xffffffffu, me, 1);
-    if (lane == 0) left = x0 > 0 ? line[x0 - 1] : -1;
-    const bool start = in && (left != me);
-    const uint32_t starts = __ballot_sync(0xffffffffu, start);
-    if (!in) return;
-    const uint32_t below = starts & (0xffffffffu >> (31 - lane));   // starts at or before this lane
-    const uint32_t base = y * n1;
-    parent[base + x] = below ? base + x0 + (31 - __clz(below)) : base + x0 - 1;   // previous group continues
-}
-
-__global__ void k_vmerge(const uint8_t* __restrict__ lab, int64_t stride2, uint32_t n1, uint32_t n2,
-                         uint32_t* __restrict__ parent) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (uint64_t)n1 * (n2 - 1)) return;
-    const uint32_t y = (uint32_t)(i / n1) + 1, x = (uint32_t)(i % n1);
-    const uint8_t* line = lab + (int64_t)y * stride2;
-    const uint8_t* up = line - stride2;
-    const uint8_t me = line[x];
-    if (up[x] != me) return;
-    if (x > 0 && line[x - 1] == me && up[x - 1] == me) return;   // the pixel to the left did this union
-    unite(parent, y * n1 + x, (y - 1) * n1 + x);
-}
-
-__global__ void k_flatten(uint32_t* __restrict__ parent, uint64_t n) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    // read-only walk: a path-halving write by another thread could land AFTER the owner stored the
-    // root and leave a non-root in the entry.  Every entry is only ever written by its owner here.
-    uint32_t r = (uint32_t)i, p = parent[r];
-    while (p != r) {
-        r = p;
-        p = parent[r];
+// 16 pixels of a line starting at x (thread t of chunk c: x = c * CH + t * PT); px[k] valid for k < nv.
+// Returns the run-start mask: bit k <=> pixel x + k starts a run (x + k == 0 or label differs from x + k - 1).
+__device__ __forceinline__ uint32_t load_starts(const uint8_t* __restrict__ line, uint32_t x, uint32_t n1, bool al16,
+                                                uint8_t (&px)[PT], int& nv) {
+    nv = x >= n1 ? 0 : (n1 - x < (uint32_t)PT ? (int)(n1 - x) : PT);
+    if (nv == PT && al16) {
+        const uint4 v = *reinterpret_cast<const uint4*>(line + x);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < PT; ++k) px[k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+    } else {
+#pragma unroll
+        for (int k = 0; k < PT; ++k) px[k] = k < nv ? line[x + k] : (uint8_t)0;
     }
-    parent[i] = r;
+    // label of the pixel before this thread's first one: the previous thread's last pixel
+    int prev = __shfl_up_sync(0xffffffffu, (int)px[PT - 1], 1);
+    if ((threadIdx.x & 31) == 0) prev = (x > 0 && nv > 0) ? (int)line[x - 1] : -1;
+    if (x == 0) prev = -1;
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < PT; ++k) {
+        const int cur = px[k];
+        if (k < nv && cur != prev) m |= 1u << k;
+        prev = cur;
+    }
+    return m;
 }
 
-__global__ void k_number(uint32_t* __restrict__ parent, uint64_t n, unsigned int* n_roots) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool root = i < n && parent[i] == (uint32_t)i;
+// exclusive prefix of v over the block (BT = 256 threads); total in *tot
+__device__ __forceinline__ uint32_t block_exclusive(uint32_t v, uint32_t* tot) {
+    __shared__ uint32_t wsum[BT / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t s = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, s, o);
+        if (lane >= o) s += t;
+    }
+    if (lane == 31) wsum[warp] = s;
+    __syncthreads();
+    uint32_t base = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < BT / 32; ++w) {
+        const uint32_t t = wsum[w];
+        if (w < warp) base += t;
+        all += t;
+    }
+    __syncthreads();
+    *tot = all;
+    return base + s - v;
+}
+
+// grid: chunks * n2 blocks, block = (line y, chunk c)
+__global__ void __launch_bounds__(BT) k_count(const uint8_t* __restrict__ lab, int64_t stride2, uint32_t n1, bool al16,
+                                              uint32_t chunks, uint32_t* __restrict__ cnt) {
+    const uint32_t y = blockIdx.x / chunks, c = blockIdx.x - y * chunks, x = c * CH + threadIdx.x * PT;
+    uint8_t px[PT];
+    int nv;
+    const uint32_t m = load_starts(lab + (int64_t)y * stride2, x, n1, al16, px, nv);
+    uint32_t tot;
+    block_exclusive(__popc(m), &tot);
+    if (threadIdx.x == 0) cnt[blockIdx.x] = tot;
+}
+
+// in-place exclusive scan of n counts, total appended at a[n]; one block
+__global__ void __launch_bounds__(1024) k_scan(uint32_t* __restrict__ a, uint64_t n) {
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint64_t i0 = 0; i0 < n; i0 += 1024) {
+        const uint64_t i = i0 + threadIdx.x;
+        const uint32_t v = i < n ? a[i] : 0u;
+        uint32_t s = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += t;
+        }
+        if (lane == 31) wsum[warp] = s;
+        __syncthreads();
+        uint32_t base = carry;
+        for (int w = 0; w < warp; ++w) base += wsum[w];
+        if (i < n) a[i] = base + s - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = base + s;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) a[n] = carry;
+}
+
+__global__ void __launch_bounds__(BT) k_fill(const uint8_t* __restrict__ lab, int64_t stride2, uint32_t n1, bool al16,
+                                             Runs R) {
+    const uint32_t y = blockIdx.x / R.chunks, c = blockIdx.x - y * R.chunks, x = c * CH + threadIdx.x * PT;
+    uint8_t px[PT];
+    int nv;
+    uint32_t m = load_starts(lab + (int64_t)y * stride2, x, n1, al16, px, nv);
+    uint32_t tot;
+    uint32_t idx = R.cbase[blockIdx.x] + block_exclusive(__popc(m), &tot);
+    while (m) {
+        const int k = __ffs(m) - 1;
+        m &= m - 1;
+        R.start[idx] = x + k;
+        R.label[idx] = px[k];
+        R.parent[idx] = idx;
+        ++idx;
+    }
+}
+
+// one block per line y >= 1 (blockIdx.x = y - 1)
+__global__ void __launch_bounds__(128) k_merge(uint32_t n1, Runs R) {
+    const uint32_t y = blockIdx.x + 1;
+    const uint32_t p0 = R.cbase[(uint64_t)(y - 1) * R.chunks], c0 = R.cbase[(uint64_t)y * R.chunks],
+                   c1 = R.cbase[(uint64_t)(y + 1) * R.chunks];
+    for (uint32_t i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
+        const uint32_t s = R.start[i], e = (i + 1 < c1) ? R.start[i + 1] : n1;   // [s, e)
+        const uint8_t L = R.label[i];
+        // last run of the previous line that starts at or before s
+        uint32_t lo = p0, hi = c0;            // invariant: start[lo] <= s (start[p0] = 0), start[hi] > s or hi == c0
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (R.start[mid] <= s) lo = mid; else hi = mid;
+        }
+        for (uint32_t j = lo; j < c0 && R.start[j] < e; ++j)
+            if (R.label[j] == L) unite(R.parent, i, j);
+    }
+}
+
+__global__ void k_flatnum(uint32_t* __restrict__ parent, uint32_t n, unsigned int* n_roots) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool root = false;
+    if (i < n) {
+        // read-only walk (see the note in DESIGN.md: a path-halving write could land after the owner's store);
+        // a root may already carry its tag
+        uint32_t r = i, p = parent[r];
+        root = (p == i);
+        while (!(p & TAG) && p != r) {
+            r = p;
+            p = parent[r];
+        }
+        if (!root) parent[i] = r;
+    }
     const uint32_t m = __ballot_sync(0xffffffffu, root);
     if (!m) return;
     const uint32_t lane = threadIdx.x & 31;
@@ -115,6 +226,11 @@ __global__ void k_number(uint32_t* __restrict__ parent, uint64_t n, unsigned int
     if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(n_roots, (unsigned)__popc(m));
     base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
     if (root) parent[i] = TAG | (base + __popc(m & ((1u << lane) - 1u)));
+}
+
+__device__ __forceinline__ uint32_t comp_id(const uint32_t* parent, uint32_t run) {
+    const uint32_t v = parent[run];
+    return (v & TAG) ? (v & ~TAG) : (parent[v] & ~TAG);
 }
 
 __global__ void k_init_recs(SegRec* rec, unsigned int n) {
@@ -130,135 +246,170 @@ __global__ void k_init_recs(SegRec* rec, unsigned int n) {
     rec[i] = r;
 }
 
-__device__ __forceinline__ uint32_t comp_id(const uint32_t* parent, uint32_t p) {
-    const uint32_t v = parent[p];
-    return (v & TAG) ? (v & ~TAG) : (parent[v] & ~TAG);
+// one block per line
+__global__ void __launch_bounds__(128) k_stats(uint32_t n1, Runs R, SegRec* __restrict__ rec) {
+    const uint32_t y = blockIdx.x;
+    const uint32_t c0 = R.cbase[(uint64_t)y * R.chunks], c1 = R.cbase[(uint64_t)(y + 1) * R.chunks];
+    for (uint32_t i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
+        const uint32_t s = R.start[i], e = (i + 1 < c1) ? R.start[i + 1] : n1;
+        SegRec* r = rec + comp_id(R.parent, i);
+        atomicAdd(&r->count, e - s);
+        if (r->xmin > s) atomicMin(&r->xmin, s);
+        if (r->xmax < e - 1) atomicMax(&r->xmax, e - 1);
+        if (r->ymin > y) atomicMin(&r->ymin, y);
+        if (r->ymax < y) atomicMax(&r->ymax, y);
+        if (R.parent[i] & TAG) r->label = R.label[i];   // the root run writes the component's label
+    }
 }
 
-// same geometry as k_runs: one record update per (run x 32-pixel group)
-__global__ void k_stats(const uint8_t* __restrict__ lab, int64_t stride2, uint32_t n1, uint32_t n2,
-                        const uint32_t* __restrict__ parent, SegRec* __restrict__ rec) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t groups = (n1 + 31) / 32;
-    const uint64_t gw = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (gw >= (uint64_t)groups * n2) return;
-    const uint32_t y = (uint32_t)(gw / groups), x0 = (uint32_t)(gw % groups) * 32, x = x0 + lane;
-    const bool in = x < n1;
-    const uint8_t* line = lab + (int64_t)y * stride2;
-    const int me = in ? line[x] : -1;
-    const int left = __shfl_up_sync(0xffffffffu, me, 1);
-    const bool lead = in && (lane == 0 || left != me);
-    const uint32_t leads = __ballot_sync(0xffffffffu, lead);
-    const uint32_t valid = __ballot_sync(0xffffffffu, in);
-    if (!lead) return;
-    const uint32_t above = leads & ~((2u << lane) - 1u);            // next leader after this lane
-    const uint32_t end = above ? (uint32_t)(__ffs(above) - 1) : (uint32_t)__popc(valid);   // one past the group's last lane
-    const uint32_t len = end - lane;
-    const bool true_start = (x == 0) || (line[x - 1] != me);
-    const bool true_end = (x + len == n1) || (line[x + len] != me);
-    SegRec* r = rec + comp_id(parent, y * n1 + x);
-    atomicAdd(&r->count, len);
-    if (true_start) atomicMin(&r->xmin, x);
-    if (true_end) atomicMax(&r->xmax, x + len - 1);
-    if (r->ymin > y) atomicMin(&r->ymin, y);
-    if (r->ymax < y) atomicMax(&r->ymax, y);
-    if (true_start && r->label != (unsigned)me) r->label = (unsigned)me;   // same value from every writer
-}
-
-__global__ void k_known(const int64_t* __restrict__ idx, const uint8_t* __restrict__ cat, int64_t n_known,
-                        uint64_t npx, const uint32_t* __restrict__ parent, SegRec* __restrict__ rec) {
+__global__ void k_known(const int64_t* __restrict__ idx, const uint8_t* __restrict__ cat, int64_t n_known, uint32_t n1,
+                        uint32_t n2, Runs R, SegRec* __restrict__ rec) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_known) return;
     const int64_t p = idx[i];
     const unsigned c = cat[i];
-    if (p < 0 || (uint64_t)p >= npx || c == 0) return;
-    SegRec* r = rec + comp_id(parent, (uint32_t)p);
+    if (p < 0 || p >= (int64_t)n1 * n2 || c == 0) return;
+    const uint32_t y = (uint32_t)(p / n1), x = (uint32_t)(p % n1);
+    uint32_t lo = R.cbase[(uint64_t)y * R.chunks], hi = R.cbase[(uint64_t)(y + 1) * R.chunks];
+    while (hi - lo > 1) {   // last run of line y that starts at or before x
+        const uint32_t mid = (lo + hi) >> 1;
+        if (R.start[mid] <= x) lo = mid; else hi = mid;
+    }
+    SegRec* r = rec + comp_id(R.parent, lo);
     atomicMin(&r->cmin, c);
     atomicMax(&r->cmax, c);
 }
 
 // clean.jl:65-88 for one component; Float64 operations as written in the reference
-__device__ __forceinline__ unsigned rule(const SegRec& r, const uint8_t* keep, double line_threshold,
-                                         double prune_threshold, unsigned int* conflict) {
+__global__ void k_decide(SegRec* __restrict__ rec, unsigned int n, const uint8_t* __restrict__ keep,
+                         double line_threshold, double prune_threshold, unsigned int* conflict) {
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const SegRec r = rec[i];
     const unsigned L = r.label;
     if (r.cmax != 0 && r.cmin != r.cmax) *conflict = 1u;   // two known categories in one segment
-    if (!keep[L]) return 0u;
-    const unsigned h = r.xmax - r.xmin + 1, w = r.ymax - r.ymin + 1;
-    const unsigned long long m = h > w ? h : w;
-    const double rectangle_area = __ddiv_rn((double)(m * m), 2.0);
-    const double ratio = __ddiv_rn((double)r.count, rectangle_area);
-    if (((double)r.count < prune_threshold) || (ratio < line_threshold)) {
-        const unsigned c = r.cmax;
-        if (c == 0) return 0u;
-        if (!(L == 0 || L == c)) return c;
+    unsigned out = L;
+    if (!keep[L]) {
+        out = 0u;
+    } else {
+        const unsigned h = r.xmax - r.xmin + 1, w = r.ymax - r.ymin + 1;
+        const unsigned long long m = h > w ? h : w;
+        const double rectangle_area = __ddiv_rn((double)(m * m), 2.0);
+        const double ratio = __ddiv_rn((double)r.count, rectangle_area);
+        if (((double)r.count < prune_threshold) || (ratio < line_threshold)) {
+            const unsigned c = r.cmax;
+            if (c == 0) out = 0u;
+            else if (!(L == 0 || L == c)) out = c;
+        }
     }
-    return L;
+    rec[i].label = out;
 }
 
-__global__ void k_relabel(const uint32_t* __restrict__ parent, const SegRec* __restrict__ rec, uint32_t n1,
-                          uint32_t n2, const uint8_t* __restrict__ keep, double line_threshold,
-                          double prune_threshold, uint8_t* __restrict__ out, int64_t out_stride2,
-                          unsigned int* conflict) {
-    __shared__ uint8_t skeep[256];
-    if (threadIdx.x < 256) skeep[threadIdx.x] = keep[threadIdx.x];
-    __syncthreads();
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (uint64_t)n1 * n2) return;
-    const uint32_t y = (uint32_t)(i / n1), x = (uint32_t)(i % n1);
-    const SegRec r = rec[comp_id(parent, (uint32_t)i)];
-    out[(int64_t)y * out_stride2 + x] = (uint8_t)rule(r, skeep, line_threshold, prune_threshold, conflict);
+__global__ void k_runout(Runs R, uint32_t n, const SegRec* __restrict__ rec) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) R.out[i] = (uint8_t)rec[comp_id(R.parent, i)].label;
 }
+
+__global__ void __launch_bounds__(BT) k_paint(const uint8_t* __restrict__ lab, int64_t stride2, uint32_t n1, bool al16,
+                                              Runs R, uint8_t* __restrict__ out, int64_t out_stride2, bool out_al16) {
+    const uint32_t y = blockIdx.x / R.chunks, c = blockIdx.x - y * R.chunks, x = c * CH + threadIdx.x * PT;
+    uint8_t px[PT];
+    int nv;
+    const uint32_t m = load_starts(lab + (int64_t)y * stride2, x, n1, al16, px, nv);
+    uint32_t tot;
+    uint32_t run = R.cbase[blockIdx.x] + block_exclusive(__popc(m), &tot);   // next run to start
+    if (nv == 0) return;
+    uint8_t cur = (m & 1u) ? (uint8_t)0 : R.out[run - 1];   // the run that continues into this thread
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int k = 0; k < PT; ++k) {
+        if ((m >> k) & 1u) cur = R.out[run++];
+        w[k >> 2] |= (uint32_t)cur << (8 * (k & 3));
+    }
+    uint8_t* dst = out + (int64_t)y * out_stride2 + x;
+    if (nv == PT && out_al16) {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+        for (int k = 0; k < nv; ++k) dst[k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+    }
+}
+
+Runs make_runs(void* run_mem, unsigned int n_runs, const uint32_t* cbase, int64_t n1) {
+    Runs R;
+    uint8_t* p = reinterpret_cast<uint8_t*>(run_mem);
+    const size_t n4 = ((size_t)n_runs + 3) / 4 * 4;   // keep the arrays 16-byte aligned
+    R.start = reinterpret_cast<uint32_t*>(p);
+    R.parent = reinterpret_cast<uint32_t*>(p + n4 * 4);
+    R.label = p + n4 * 8;
+    R.out = p + n4 * 9;
+    R.cbase = cbase;
+    R.chunks = (uint32_t)((n1 + CH - 1) / CH);
+    return R;
+}
+
+bool aligned16(const void* p, int64_t stride) { return ((uintptr_t)p % 16 == 0) && (stride % 16 == 0); }
 
 }  // namespace
 
-size_t mr_prune_parent_bytes(int64_t n1, int64_t n2) { return (size_t)n1 * (size_t)n2 * sizeof(uint32_t); }
-size_t mr_prune_rec_bytes(unsigned int n_segments) { return (size_t)n_segments * sizeof(SegRec); }
+size_t mr_prune_cbase_bytes(int64_t n1, int64_t n2) {
+    return ((size_t)((n1 + CH - 1) / CH) * (size_t)n2 + 1) * sizeof(uint32_t);
+}
+size_t mr_prune_run_bytes(unsigned int n_runs) { return (((size_t)n_runs + 3) / 4 * 4) * 10 + 16; }
+size_t mr_prune_rec_bytes(unsigned int n_segments) { return ((size_t)n_segments + 1) * sizeof(SegRec); }
 
-// phase 1: components; leaves the number of components in *d_n_roots (device)
-cudaError_t mr_launch_prune_components(const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2,
-                                       uint32_t* parent, unsigned int* d_n_roots, cudaStream_t s,
-                                       int* n_launches) {
-    const uint64_t npx = (uint64_t)n1 * (uint64_t)n2;
-    const uint64_t groups = (uint64_t)((n1 + 31) / 32) * (uint64_t)n2;
-    const unsigned gb = (unsigned)((groups + 7) / 8);            // 8 warps per block
-    const unsigned pb = (unsigned)((npx + 255) / 256);
-    cudaError_t e = cudaMemsetAsync(d_n_roots, 0, sizeof(unsigned int), s);
-    if (e != cudaSuccess) return e;
-    k_runs<<<gb, 256, 0, s>>>(labels, stride2, (uint32_t)n1, (uint32_t)n2, parent);
-    if (n2 > 1) {
-        const uint64_t nv = (uint64_t)n1 * (uint64_t)(n2 - 1);
-        k_vmerge<<<(unsigned)((nv + 255) / 256), 256, 0, s>>>(labels, stride2, (uint32_t)n1, (uint32_t)n2, parent);
-        *n_launches += 1;
-    }
-    k_flatten<<<pb, 256, 0, s>>>(parent, npx);
-    k_number<<<pb, 256, 0, s>>>(parent, npx, d_n_roots);
-    *n_launches += 3;
+// phase 1: run starts per (line, chunk) and their exclusive scan; the number of runs ends up in
+// cbase[chunks * n2] (device)
+cudaError_t mr_launch_prune_count(const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2, uint32_t* cbase,
+                                  cudaStream_t s, int* n_launches) {
+    const uint32_t chunks = (uint32_t)((n1 + CH - 1) / CH);
+    k_count<<<chunks * (unsigned)n2, BT, 0, s>>>(labels, stride2, (uint32_t)n1, aligned16(labels, stride2), chunks, cbase);
+    k_scan<<<1, 1024, 0, s>>>(cbase, (uint64_t)chunks * (uint64_t)n2);
+    *n_launches += 2;
     return cudaGetLastError();
 }
 
-// phase 2: statistics, rule, output.  *d_conflict (device) becomes non-zero when a segment holds
+// phase 2: runs, vertical merges, component numbering; the number of components ends up in *d_n_roots
+cudaError_t mr_launch_prune_components(const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2,
+                                       const uint32_t* cbase, void* run_mem, unsigned int n_runs,
+                                       unsigned int* d_n_roots, cudaStream_t s, int* n_launches) {
+    const Runs R = make_runs(run_mem, n_runs, cbase, n1);
+    cudaError_t e = cudaMemsetAsync(d_n_roots, 0, sizeof(unsigned int), s);
+    if (e != cudaSuccess) return e;
+    k_fill<<<R.chunks * (unsigned)n2, BT, 0, s>>>(labels, stride2, (uint32_t)n1, aligned16(labels, stride2), R);
+    *n_launches += 1;
+    if (n2 > 1) {
+        k_merge<<<(unsigned)(n2 - 1), 128, 0, s>>>((uint32_t)n1, R);
+        *n_launches += 1;
+    }
+    k_flatnum<<<(n_runs + 255) / 256, 256, 0, s>>>(R.parent, n_runs, d_n_roots);
+    *n_launches += 1;
+    return cudaGetLastError();
+}
+
+// phase 3: statistics, rule, output.  *d_conflict (device) becomes non-zero when a segment holds
 // two different known categories.
 cudaError_t mr_launch_prune_apply(const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2,
-                                  const uint32_t* parent, void* rec, unsigned int n_segments,
-                                  int64_t n_known, const int64_t* known_idx, const uint8_t* known_cat,
-                                  const uint8_t* keep_dev, double line_threshold, double prune_threshold,
-                                  uint8_t* out, int64_t out_stride2, unsigned int* d_conflict, cudaStream_t s,
-                                  int* n_launches) {
-    const uint64_t npx = (uint64_t)n1 * (uint64_t)n2;
-    const uint64_t groups = (uint64_t)((n1 + 31) / 32) * (uint64_t)n2;
+                                  const uint32_t* cbase, void* run_mem, unsigned int n_runs, void* rec,
+                                  unsigned int n_segments, int64_t n_known, const int64_t* known_idx,
+                                  const uint8_t* known_cat, const uint8_t* keep_dev, double line_threshold,
+                                  double prune_threshold, uint8_t* out, int64_t out_stride2,
+                                  unsigned int* d_conflict, cudaStream_t s, int* n_launches) {
+    const Runs R = make_runs(run_mem, n_runs, cbase, n1);
     SegRec* r = reinterpret_cast<SegRec*>(rec);
     cudaError_t e = cudaMemsetAsync(d_conflict, 0, sizeof(unsigned int), s);
     if (e != cudaSuccess) return e;
     k_init_recs<<<(n_segments + 255) / 256, 256, 0, s>>>(r, n_segments);
-    k_stats<<<(unsigned)((groups + 7) / 8), 256, 0, s>>>(labels, stride2, (uint32_t)n1, (uint32_t)n2, parent, r);
+    k_stats<<<(unsigned)n2, 128, 0, s>>>((uint32_t)n1, R, r);
     *n_launches += 2;
     if (n_known > 0) {
-        k_known<<<(unsigned)((n_known + 255) / 256), 256, 0, s>>>(known_idx, known_cat, n_known, npx, parent, r);
+        k_known<<<(unsigned)((n_known + 255) / 256), 256, 0, s>>>(known_idx, known_cat, n_known, (uint32_t)n1,
+                                                                  (uint32_t)n2, R, r);
         *n_launches += 1;
     }
-    k_relabel<<<(unsigned)((npx + 255) / 256), 256, 0, s>>>(parent, r, (uint32_t)n1, (uint32_t)n2, keep_dev,
-                                                            line_threshold, prune_threshold, out, out_stride2,
-                                                            d_conflict);
-    *n_launches += 1;
+    k_decide<<<(n_segments + 255) / 256, 256, 0, s>>>(r, n_segments, keep_dev, line_threshold, prune_threshold, d_conflict);
+    k_runout<<<(n_runs + 255) / 256, 256, 0, s>>>(R, n_runs, r);
+    k_paint<<<R.chunks * (unsigned)n2, BT, 0, s>>>(labels, stride2, (uint32_t)n1, aligned16(labels, stride2), R, out,
+                                                       out_stride2, aligned16(out, out_stride2));
+    *n_launches += 3;
     return cudaGetLastError();
 }
