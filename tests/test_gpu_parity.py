@@ -139,6 +139,24 @@ def test_random_labels_every_word_undecided(ctx, mr, oracle, R):
     assert cnt["n_changed"] == int((want != pre).sum()) and cnt["n_nomatch"] == int((want == 0).sum())
 
 
+@pytest.mark.parametrize("K", [2, 14, 15, 30, 31, 62, 63, 126, 127, 200])
+def test_palette_sizes_cover_every_plane_count(ctx, mr, oracle, K):
+    """K decides the number of label bit planes of the fast kernel (4: K <= 14, 5: <= 30, 6: <= 62,
+    7: <= 126) and K > 126 takes the generic kernel: both sides of every boundary, windows 3 / 5 / 7."""
+    from maprast_b200 import synth
+    seed = 0x5EED0000 + K
+    pal = synth.make_palette(seed, K)
+    st = synth.make_stats(seed, pal)
+    _set(ctx, mr, st)
+    n1, n2 = 1936, 96
+    scan = oracle.synth_scan(seed, 0, pal, n1, n2)
+    pre = oracle.categorize_u8(scan, st.mean, st.lo, st.hi)
+    assert pre.max() >= min(K, 100)
+    for R in (1, 2, 3):
+        got = ctx.categorize_clean_host(scan, R)
+        assert mismatches(got, oracle.majority(pre, R)) == 0
+
+
 def test_strided_and_unaligned_views(ctx, mr, oracle):
     seed, palrgb, stats, _ = _workload(mr, 1)
     _set(ctx, mr, stats)
