@@ -439,12 +439,27 @@ __device__ __forceinline__ void categorize_line(const FastParams& P, const uint8
         };
         if (more) {
 #pragma unroll 1
+            // big palettes (K > 30) have many MIXED cells (5.7 % of the pixels on config 4): four pixels
+            // per lane and pass, their table loads in flight together; small palettes keep the code short
+            constexpr int WIDE = NB >= 6 ? 4 : 1;
             while (__any_sync(0xffffffffu, s != 0u)) {
-                if (s) {
-                    const int q = __ffs(s) - 1;
-                    s &= s - 1;
-                    apply(q, __ldg(P.job.lut + colour(q)));
+                int qq[WIDE];
+                unsigned ll[WIDE];
+                bool hh[WIDE];
+#pragma unroll
+                for (int t = 0; t < WIDE; ++t) {
+                    hh[t] = s != 0u;
+                    qq[t] = 0;
+                    ll[t] = 0;
+                    if (hh[t]) {
+                        qq[t] = __ffs(s) - 1;
+                        s &= s - 1;
+                        ll[t] = __ldg(P.job.lut + colour(qq[t]));
+                    }
                 }
+#pragma unroll
+                for (int t = 0; t < WIDE; ++t)
+                    if (hh[t]) apply(qq[t], ll[t]);
             }
             after_read();
         }
