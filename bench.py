@@ -386,6 +386,28 @@ def run_ours(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "algorithmic_bytes_per_px": 2,
                          "achieved": 2 * my_px / (seg_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": 2 * my_px / (seg_ms * 1e-3) / 1e9 / peak}}}
+        # the standalone Window majority filter, clean(labels; hood): categorise-only labels in, device resident
+        pre = torch.empty_like(out)
+        ctx.categorize_clean_dev(own, n1, nb, n1 * 3, 3, 0, pre, n1)
+        two = torch.empty_like(out)
+        ctx.clean_dev(pre, n1, nb, n1, R, two, n1)
+        torch.cuda.synchronize()
+        l0 = ctx.launch_count()
+        e0.record()
+        for _ in range(reps):
+            ctx.clean_dev(pre, n1, nb, n1, R, two, n1)
+        e1.record()
+        torch.cuda.synchronize()
+        cl_ms = e0.elapsed_time(e1) / reps
+        res["next_rows"]["clean_standalone"] = {
+            "what": "clean(labels; hood=Window{R}) on categorise-only labels, device resident (label-maximum pass + vote kernel)",
+            "value": my_px / (cl_ms * 1e-3) / 1e6, "unit": UNIT, "ms": cl_ms,
+            "gpu_launches_per_call": (ctx.launch_count() - l0) / reps,
+            "equal_to_fused": bool(torch.equal(two, out)),
+            "roofline": {"bound": "hbm", "algorithmic_bytes_per_px": 2,
+                         "achieved": 2 * my_px / (cl_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": 2 * my_px / (cl_ms * 1e-3) / 1e9 / peak}}
+        del pre, two
         if not args.no_cpu_baseline:
             from oracle import oracle as O
             lines = max(64, min(nb, (1 << 24) // n1))

@@ -132,7 +132,10 @@ int mr_batch_categorize_clean_dev(mr_ctx* ctx, int n_sheets, const uint8_t* px_d
                                   int64_t out_stride2, void* stream);
 
 /* clean(labels; hood = Window{R}(), repeat): labels in -> labels out (Appendix A.3).
- * Kwarg shape follows blur(A; hood, repeat), src/blur.jl:6-14. */
+ * Kwarg shape follows blur(A; hood, repeat), src/blur.jl:6-14.  Not in place.  16-byte aligned
+ * lines with n1 % 16 == 0, R <= 3 and labels <= 126 take the bit-sliced fast kernel (the device
+ * variant then synchronises `stream` once: the largest label picks the number of bit planes);
+ * anything else takes the generic kernel. */
 int mr_clean_host(mr_ctx* ctx, const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2,
                   int R, int repeat, uint8_t* out, int64_t out_stride2);
 int mr_clean_dev(mr_ctx* ctx, const uint8_t* labels_dev, int64_t n1, int64_t n2, int64_t stride2,

@@ -308,16 +308,37 @@ static int run_fused(mr_ctx* ctx, const MrJob& job, cudaStream_t s) {
     return MR_OK;
 }
 
-static int run_clean(mr_ctx* ctx, const MrJob& job, cudaStream_t s) {
+// standalone clean (labels in -> labels out).  max_label < 0: not known yet (one reduction pass +
+// read-back picks the plane count of the fast kernel); *max_label_out returns it for the next pass.
+static int run_clean(mr_ctx* ctx, const MrJob& job, cudaStream_t s, int max_label = -1, int* max_label_out = nullptr) {
     if (job.n1 == 0 || job.n2 == 0) return MR_OK;
     int nl = 0;
-    cudaError_t e = mr_launch_generic(job, true, ctx->sm_count, s, &nl);
+    MrJob j = job;
+    j.bpp = 1;
+    j.lut = nullptr;
+    j.pal.K = 0;
+    cudaError_t e = cudaErrorNotSupported;
+    if (mr_fast_supported(j)) {   // geometry qualifies: the plane count needs the largest label
+        if (max_label < 0) {
+            if (!ctx->d_small) CK(cudaMalloc(&ctx->d_small, 512));
+            unsigned int* d_max = reinterpret_cast<unsigned int*>(ctx->d_small + 264);
+            e = mr_launch_max_label(job.px - (int64_t)job.halo_lo * job.stride2, job.n1, job.n2 + job.halo_lo + job.halo_hi,
+                                    job.stride2, d_max, ctx->sm_count, s, &nl);
+            if (e != cudaSuccess) return fail_cuda(ctx, e, "label maximum");
+            unsigned int m = 0;
+            CK(cudaMemcpyAsync(&m, d_max, sizeof m, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            max_label = (int)m;
+        }
+        j.pal.K = max_label;
+        e = mr_fast_supported(j) ? mr_launch_fast(j, ctx->sm_count, s, &nl) : cudaErrorNotSupported;
+    }
+    if (max_label_out) *max_label_out = max_label;
+    if (e == cudaErrorNotSupported) e = mr_launch_generic(job, true, ctx->sm_count, s, &nl);
     ctx->launches += nl;
     if (e != cudaSuccess) return fail_cuda(ctx, e, "clean kernel launch");
     return MR_OK;
 }
-
-// whole-image path with the sparse known-category plane: categorise -> fix-up -> clean
 static int run_with_known(mr_ctx* ctx, MrJob job, cudaStream_t s) {
     const int R = job.R;
     uint8_t* final_out = job.out;
@@ -342,7 +363,7 @@ static int run_with_known(mr_ctx* ctx, MrJob job, cudaStream_t s) {
         MrJob c = job;
         c.px = ctx->d_tmp; c.stride2 = job.n1; c.bpp = 1; c.R = R; c.out = final_out;
         c.out_stride2 = final_stride; c.counters = cnt;
-        return run_clean(ctx, c, s);
+        return run_clean(ctx, c, s, ctx->pal.K);
     }
     return MR_OK;
 }
@@ -390,6 +411,8 @@ extern "C" int mr_clean_dev(mr_ctx* ctx, const uint8_t* labels_dev, int64_t n1, 
     int rc = check_image_args(ctx, "mr_clean_dev", labels_dev, out_dev, n1, n2, stride2, 1, out_stride2, R,
                               halo_lo, halo_hi);
     if (rc) return rc;
+    if (labels_dev == out_dev && n1 > 0 && n2 > 0 && R > 0)
+        return fail(ctx, MR_ERR_ARG, "mr_clean_dev: in-place operation is not supported");
     CK(cudaSetDevice(ctx->device));
     MrJob job = make_job(ctx, labels_dev, out_dev, n1, n2, stride2, 1, R, halo_lo, halo_hi, out_stride2);
     job.lut = nullptr;
@@ -514,10 +537,11 @@ extern "C" int mr_clean_host(mr_ctx* ctx, const uint8_t* labels, int64_t n1, int
     uint8_t* b = ctx->d_tmp;
     CK(cudaMemcpy2DAsync(a, n1, labels, stride2, n1, n2, cudaMemcpyHostToDevice, ctx->s_main));
     const int passes = (R == 0) ? 0 : repeat;
+    int max_label = -1;   // the filter never creates a label: one reduction serves every pass
     for (int p = 0; p < passes; ++p) {
         MrJob job = make_job(ctx, a, b, n1, n2, n1, 1, R, 0, 0, n1);
         job.lut = nullptr;
-        if ((rc = run_clean(ctx, job, ctx->s_main))) return rc;
+        if ((rc = run_clean(ctx, job, ctx->s_main, max_label, &max_label))) return rc;
         uint8_t* t = a; a = b; b = t;
     }
     CK(cudaMemcpy2DAsync(out, out_stride2, a, n1, n1, n2, cudaMemcpyDeviceToHost, ctx->s_main));

@@ -183,13 +183,14 @@ struct CopyPlan {
     long long col_off;     // byte offset of the first loaded byte in its line
 };
 
-template <int R>
+template <int R, int BPP>
 __device__ __forceinline__ CopyPlan copy_plan(const FastParams& P, const Item& it, uint32_t stage) {
     using G = Geo<R>;
-    const long long limit = P.padded ? ((P.job.n1 * 3 + 15) / 16) * 16 : P.job.n1 * 3;
-    const long long w0 = it.xw0 * 3;                      // byte offset of the window in the line
-    long long lo = w0 + (R > 0 ? 80 : 0);                 // halo words: only the chunk next to the interior
-    long long hi = w0 + (long long)G::AW * 96 - (R > 0 ? 80 : 0);
+    constexpr int WB = 32 * BPP;                          // bytes of an aligned 32-pixel word
+    const long long limit = P.padded ? ((P.job.n1 * BPP + 15) / 16) * 16 : P.job.n1 * BPP;
+    const long long w0 = it.xw0 * BPP;                    // byte offset of the window in the line
+    long long lo = w0 + (R > 0 ? WB - 16 : 0);            // halo words: only the chunk next to the interior
+    long long hi = w0 + (long long)G::AW * WB - (R > 0 ? WB - 16 : 0);
     lo = lo < 0 ? 0 : lo;
     hi = hi > limit ? limit : hi;
     CopyPlan c;
@@ -264,6 +265,62 @@ __device__ __forceinline__ void for_each_pixel(const uint16_t* codes, const uint
                 f(code, __ffs(m) - 1);
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Labels in (standalone clean, `clean(labels; hood)`): the staging line holds label bytes instead of
+// packed RGB; lane = one aligned 32-pixel word = 32 bytes.  The bytes are brought into the layout
+// of the bit transpose (pixel 8k+j in byte k of register j), transposed into NB planes and stored
+// to the ring exactly like the categorised labels of the fused path.
+template <int R, int NB, typename F>
+__device__ __forceinline__ void labels_line(uint8_t* ws, const Item& it, int y, int lane, const LaneMasks& M,
+                                            const uint8_t* staged, F after_read) {
+    using G = Geo<R>;
+    using C = Cfg<R, NB>;
+    const int slot = (y - (it.y0 - R)) % C::RL;
+    uint32_t* pl = reinterpret_cast<uint32_t*>(ws + C::W_PLANES) + slot * NB * 32;
+    if (!staged) {   // outside the sheet: VOID everywhere (warp-uniform)
+        after_read();
+#pragma unroll
+        for (int b = 0; b < NB; ++b) pl[b * 32 + lane] = ~0u;
+        return;
+    }
+    const uint4 v0 = *reinterpret_cast<const uint4*>(staged + lane * 32);
+    const uint4 v1 = *reinterpret_cast<const uint4*>(staged + lane * 32 + 16);
+    after_read();
+    const uint32_t nat[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};   // pixel 4n+k in byte k of nat[n]
+    uint32_t T[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {   // pixel 8k+j = byte (j & 3) of nat[2k + (j >> 2)]
+        const uint32_t sel = (uint32_t)(j & 3) | ((uint32_t)(4 + (j & 3)) << 4);
+        const uint32_t lo = __byte_perm(nat[j >> 2], nat[2 + (j >> 2)], sel);
+        const uint32_t hi = __byte_perm(nat[4 + (j >> 2)], nat[6 + (j >> 2)], sel);
+        T[j] = __byte_perm(lo, hi, 0x5410);
+    }
+    if (it.edge) {   // warp-uniform: force VOID outside [0, n1)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) T[j] |= ((~M.vmask >> j) & 0x01010101u) * 0xFFu;
+    }
+#pragma unroll
+    for (int st = 0; st < 3; ++st) {   // bit transpose, see categorize_line
+        const int d = 1 << st;
+        const uint32_t m = st == 0 ? 0x55555555u : (st == 1 ? 0x33333333u : 0x0F0F0F0Fu);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j & d) continue;
+            const uint32_t x = T[j], y2 = T[j + d];
+            T[j] = (x & m) | ((y2 << d) & ~m);
+            T[j + d] = ((x >> d) & m) | (y2 & ~m);
+        }
+    }
+    const int o = G::O0 + lane * G::U;
+    const int k = o >> 5, sh = o & 31;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const uint32_t lo = __shfl_sync(0xffffffffu, T[b], k);
+        const uint32_t hi = __shfl_sync(0xffffffffu, T[b], (k + 1) & 31);
+        pl[b * 32 + lane] = __funnelshift_r(lo, hi, sh);
     }
 }
 
@@ -894,7 +951,8 @@ __device__ __forceinline__ Item decode_item(const FastParams& P, unsigned item) 
     return it;
 }
 
-template <int R, int NB, bool COUNT>
+// LIN: the input is a label image (bpp = 1) instead of packed RGB: standalone clean
+template <int R, int NB, bool COUNT, bool LIN>
 __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastParams P) {
     using C = Cfg<R, NB>;
     extern __shared__ __align__(128) uint8_t sm[];
@@ -905,7 +963,7 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
     const uint32_t bar = smem_u32(ws + C::W_MBAR);
     uint8_t* stage = ws + C::W_STAGE;
     const uint32_t stage_u32 = smem_u32(stage);
-    {
+    if (!LIN) {
         const uint4* src = reinterpret_cast<const uint4*>(P.job.coarse);
         uint4* dst = reinterpret_cast<uint4*>(sm);
         for (int i = tid; i < (int)(MR_COARSE_SIZE / 16); i += C::WARPS * 32) dst[i] = __ldg(src + i);
@@ -928,7 +986,7 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
         const LaneMasks M = lane_masks<R>(P, it.xw0, lane);
         const int cat_last = it.y1 + R;                       // lines [y0-R, y1+R) are categorised
         int ycat = it.y0 - R;                                 // next line to categorise
-        const CopyPlan plan = copy_plan<R>(P, it, stage_u32);
+        const CopyPlan plan = copy_plan<R, (LIN ? 1 : 3)>(P, it, stage_u32);
         // loadable lines of this item (none if the strip window has no bytes inside the sheet)
         const int ylo = max(ycat, -P.job.halo_lo);
         const int yhi = plan.bytes ? min(cat_last, (int)P.job.n2 + P.job.halo_hi) : ylo;
@@ -959,14 +1017,16 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
                     parity ^= 1u;
                 }
                 bool nxt = false;
-                categorize_line<R, NB, COUNT>(
-                    P, coarse, ws, it, ycat, lane, M, pend ? stage : nullptr,
-                    [&]() {
-                        __syncwarp();   // every lane is done with the staging buffer
-                        nxt = issue_line_copy(P, plan, srcn, pf_off, ycat + 1, ylo, yhi, bar, lane);
-                        srcn += P.job.stride2;
-                    },
-                    c_fine, c_nomatch);
+                auto release = [&]() {
+                    __syncwarp();   // every lane is done with the staging buffer
+                    nxt = issue_line_copy(P, plan, srcn, pf_off, ycat + 1, ylo, yhi, bar, lane);
+                    srcn += P.job.stride2;
+                };
+                if constexpr (LIN)
+                    labels_line<R, NB>(ws, it, ycat, lane, M, pend ? stage : nullptr, release);
+                else
+                    categorize_line<R, NB, COUNT>(P, coarse, ws, it, ycat, lane, M, pend ? stage : nullptr, release,
+                                                  c_fine, c_nomatch);
                 pend = nxt;
             }
             if constexpr (R > 0) {
@@ -1077,10 +1137,10 @@ void plan_schedule(FastParams& P, int warps, int B, int R) {
     P.n_items = items;
 }
 
-template <int R, int NB, bool COUNT>
+template <int R, int NB, bool COUNT, bool LIN>
 cudaError_t launch_t(FastParams& P, int sm_count, cudaStream_t s) {
     using C = Cfg<R, NB>;
-    auto kern = k_fast<R, NB, COUNT>;
+    auto kern = k_fast<R, NB, COUNT, LIN>;
     constexpr size_t smem = C::TOTAL;
     static bool configured[16] = {false};
     int dev = 0;
@@ -1107,7 +1167,11 @@ cudaError_t launch_t(FastParams& P, int sm_count, cudaStream_t s) {
 
 template <int R, int NB>
 cudaError_t launch_c(FastParams& P, int sm_count, cudaStream_t s) {
-    return P.job.counters ? launch_t<R, NB, true>(P, sm_count, s) : launch_t<R, NB, false>(P, sm_count, s);
+    if constexpr (R > 0) {
+        if (P.job.bpp == 1)
+            return P.job.counters ? launch_t<R, NB, true, true>(P, sm_count, s) : launch_t<R, NB, false, true>(P, sm_count, s);
+    }
+    return P.job.counters ? launch_t<R, NB, true, false>(P, sm_count, s) : launch_t<R, NB, false, false>(P, sm_count, s);
 }
 
 template <int NB>
@@ -1122,8 +1186,13 @@ cudaError_t launch_r(FastParams& P, int sm_count, cudaStream_t s) {
 
 }  // namespace
 
+// bpp == 1: label image in (standalone clean); job.pal.K then holds the largest label value
 bool mr_fast_supported(const MrJob& job) {
-    if (job.bpp != 3 || job.lut == nullptr || job.coarse == nullptr) return false;
+    if (job.bpp == 1) {
+        if (job.R < 1) return false;
+    } else if (job.bpp != 3 || job.lut == nullptr || job.coarse == nullptr) {
+        return false;
+    }
     if (job.pal.K > 126 || job.R < 0 || job.R > 3) return false;
     if (job.n1 <= 0 || job.n2 <= 0 || job.n2 > (1 << 30) || job.n_sheets <= 0) return false;
     const bool a16 = ((uintptr_t)job.px % 16 == 0) && ((uintptr_t)job.out % 16 == 0) && (job.stride2 % 16 == 0) &&

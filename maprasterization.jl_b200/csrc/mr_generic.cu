@@ -192,3 +192,40 @@ cudaError_t mr_launch_known_fixup(const MrJob& job, int64_t n_known, const int64
     *n_launches += 1;
     return cudaGetLastError();
 }
+
+
+// largest label of a label image (picks the plane count of the fast standalone clean).
+// 16 bytes per thread and step when the lines are 16-byte aligned.
+__global__ void k_max_label(const uint8_t* __restrict__ lab, int64_t n1, int64_t n2, int64_t stride2, bool al16,
+                            unsigned int* __restrict__ out) {
+    unsigned m4 = 0;   // four byte-wise maxima
+    const int64_t per_line = (n1 + 15) / 16;
+    const int64_t n = per_line * n2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t y = i / per_line, x = (i - y * per_line) * 16;
+        const uint8_t* p = lab + y * stride2 + x;
+        if (al16 && x + 16 <= n1) {
+            const uint4 v = *reinterpret_cast<const uint4*>(p);
+            m4 = __vmaxu4(m4, __vmaxu4(__vmaxu4(v.x, v.y), __vmaxu4(v.z, v.w)));
+        } else {
+            for (int k = 0; k < 16 && x + k < n1; ++k) m4 = __vmaxu4(m4, (unsigned)p[k]);
+        }
+    }
+    unsigned m = __vmaxu4(m4, m4 >> 16);
+    m = __vmaxu4(m, m >> 8) & 0xFFu;
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned t = __shfl_xor_sync(0xffffffffu, m, o);
+        m = t > m ? t : m;
+    }
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+
+cudaError_t mr_launch_max_label(const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2, unsigned int* d_out,
+                                int sm_count, cudaStream_t s, int* n_launches) {
+    cudaError_t e = cudaMemsetAsync(d_out, 0, sizeof(unsigned int), s);
+    if (e != cudaSuccess) return e;
+    const bool al16 = ((uintptr_t)labels % 16 == 0) && (stride2 % 16 == 0);
+    k_max_label<<<sm_count * 8, 256, 0, s>>>(labels, n1, n2, stride2, al16, d_out);
+    *n_launches += 1;
+    return cudaGetLastError();
+}

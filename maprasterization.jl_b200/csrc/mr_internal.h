@@ -61,6 +61,8 @@ cudaError_t mr_launch_generic(const MrJob& job, bool labels_in, int sm_count, cu
 // when the job does not qualify (caller then uses the generic kernel).
 cudaError_t mr_launch_fast(const MrJob& job, int sm_count, cudaStream_t s, int* n_launches);
 bool mr_fast_supported(const MrJob& job);
+cudaError_t mr_launch_max_label(const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2, unsigned int* d_out,
+                                int sm_count, cudaStream_t s, int* n_launches);
 cudaError_t mr_launch_known_fixup(const MrJob& job, int64_t n_known, const int64_t* idx,
                                   const uint8_t* cat, uint8_t* labels, int64_t labels_stride2,
                                   cudaStream_t s, int* n_launches);

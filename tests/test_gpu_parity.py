@@ -212,6 +212,28 @@ def test_clean_standalone_and_repeat(ctx, mr, oracle, R, repeat):
     assert mr.clean(L, hood=mr.Window(R), repeat=repeat, ctx=ctx).dtype == np.int64
 
 
+@pytest.mark.parametrize("maxlab", [1, 14, 15, 30, 31, 62, 63, 126, 127, 254])
+def test_clean_standalone_label_ranges(ctx, mr, oracle, maxlab):
+    """standalone clean: the largest label picks the plane count of the fast kernel (labels <= 126);
+    larger labels take the generic kernel.  Blobby label fields with speckle, windows 3 / 5 / 7."""
+    rng = np.random.default_rng(maxlab)
+    n2, n1 = 120, 1936
+    f = rng.integers(0, maxlab + 1, size=(n2 // 8 + 1, n1 // 8 + 1)).astype(np.uint8)
+    lab = np.kron(f, np.ones((8, 8), dtype=np.uint8))[:n2, :n1].copy()
+    lab[0, 0] = maxlab
+    sp = rng.random((n2, n1)) < 0.05
+    lab[sp] = rng.integers(0, maxlab + 1, size=int(sp.sum()))
+    d = torch.from_numpy(lab).cuda()
+    out = torch.empty_like(d)
+    for R in (1, 2, 3):
+        ctx.clean_dev(d, n1, n2, n1, R, out, n1)
+        torch.cuda.synchronize()
+        assert mismatches(out.cpu().numpy(), oracle.majority(lab, R)) == 0
+    assert mismatches(ctx.clean_host(lab, 2, repeat=3), oracle.majority(oracle.majority(oracle.majority(lab, 2), 2), 2)) == 0
+    with pytest.raises(mr.MapRastError):
+        ctx.clean_dev(d, n1, n2, n1, 2, d, n1)       # in place
+
+
 def test_reference_shaped_api(ctx, mr, oracle):
     """categorize(img, points; tolerances, match) -> Int labels, like _categorize (categories.jl:49-74)."""
     seed, palrgb, _, _ = _workload(mr, 1)
