@@ -96,7 +96,9 @@ int mr_categorize_clean_host_band(mr_ctx* ctx, const uint8_t* px, int64_t n1, in
  * px_dev points at line 0 of this band.  halo_lo / halo_hi (0..R) say how many REAL image
  * lines are readable before line 0 / after line n2-1 (the neighbour band's lines after a
  * halo exchange); where they are 0 the window is clipped as at the image border.
- * stream is a cudaStream_t (NULL = default stream).  Asynchronous. */
+ * stream is a cudaStream_t (NULL = default stream).  Asynchronous.  Lines that are not 16-byte
+ * aligned are repacked into aligned pitches (scratch owned by ctx) so that they still take the
+ * fast kernel. */
 int mr_categorize_clean_dev(mr_ctx* ctx, const uint8_t* px_dev, int64_t n1, int64_t n2,
                             int64_t stride2_bytes, int bytes_per_px, int R,
                             int halo_lo, int halo_hi,

@@ -35,6 +35,10 @@ struct mr_ctx {
     uint8_t* d_in = nullptr;  size_t d_in_cap = 0;
     uint8_t* d_out = nullptr; size_t d_out_cap = 0;
     uint8_t* d_tmp = nullptr; size_t d_tmp_cap = 0;
+    // repacking scratch of the device entry points: lines that are not 16-byte aligned are copied
+    // into aligned pitches so that they can take the fast kernel
+    uint8_t* d_rp_in = nullptr;  size_t d_rp_in_cap = 0;
+    uint8_t* d_rp_out = nullptr; size_t d_rp_out_cap = 0;
     // segment prune scratch: parent array, component records, keep table + two counters
     uint8_t* d_parent = nullptr; size_t d_parent_cap = 0;   // first run of every (line, chunk)
     uint8_t* d_runs = nullptr; size_t d_runs_cap = 0;       // run arrays
@@ -112,7 +116,7 @@ extern "C" void mr_destroy(mr_ctx* ctx) {
     for (auto e : ctx->ev_done) cudaEventDestroy(e);
     cudaFree(ctx->d_pal); cudaFree(ctx->d_lut); cudaFree(ctx->d_coarse);
     cudaFree(ctx->d_known_idx); cudaFree(ctx->d_known_cat); cudaFree(ctx->d_counters);
-    cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_tmp);
+    cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_tmp); cudaFree(ctx->d_rp_in); cudaFree(ctx->d_rp_out);
     cudaFree(ctx->d_parent); cudaFree(ctx->d_runs); cudaFree(ctx->d_rec); cudaFree(ctx->d_small);
     if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
@@ -297,11 +301,52 @@ static int grow(mr_ctx* ctx, uint8_t** p, size_t* cap, size_t need) {
 }
 
 // fused (or categorise-only) on device-resident data
+// A job that would take the fast kernel if only its lines were 16-byte aligned (arbitrary n1, tight
+// or odd strides, unaligned base pointers): copy it into aligned pitches (device to device, ~2x the
+// algorithmic traffic) and run the fast kernel there -- still an order of magnitude faster than the
+// generic kernel.
+static bool repack_pays(const MrJob& job) {
+    if (job.n_sheets != 1 || job.halo_lo_px || job.halo_hi_px || job.R > 3) return false;
+    if (mr_fast_supported(job)) return false;
+    MrJob a = job;   // the same job with aligned geometry
+    a.px = a.out = reinterpret_cast<uint8_t*>(uintptr_t(256));
+    a.stride2 = (job.n1 * job.bpp + 15) / 16 * 16;
+    a.out_stride2 = (job.n1 + 15) / 16 * 16;
+    a.padded = 1;
+    return mr_fast_supported(a);
+}
+
+static int run_repacked(mr_ctx* ctx, const MrJob& job, cudaStream_t s, int* nl) {
+    const int64_t T = job.n2 + job.halo_lo + job.halo_hi;
+    const int64_t line_in = (job.n1 * job.bpp + 15) / 16 * 16, line_out = (job.n1 + 15) / 16 * 16;
+    int rc;
+    if ((rc = grow(ctx, &ctx->d_rp_in, &ctx->d_rp_in_cap, (size_t)line_in * T))) return rc;
+    if ((rc = grow(ctx, &ctx->d_rp_out, &ctx->d_rp_out_cap, (size_t)line_out * job.n2))) return rc;
+    CK(cudaMemcpy2DAsync(ctx->d_rp_in, line_in, job.px - (int64_t)job.halo_lo * job.stride2, job.stride2,
+                         job.n1 * job.bpp, T, cudaMemcpyDeviceToDevice, s));
+    MrJob a = job;
+    a.px = ctx->d_rp_in + (int64_t)job.halo_lo * line_in;
+    a.stride2 = line_in;
+    a.out = ctx->d_rp_out;
+    a.out_stride2 = line_out;
+    a.padded = 1;
+    cudaError_t e = mr_launch_fast(a, ctx->sm_count, s, nl);
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "fused kernel launch (repacked lines)");
+    CK(cudaMemcpy2DAsync(job.out, job.out_stride2, ctx->d_rp_out, line_out, job.n1, job.n2, cudaMemcpyDeviceToDevice, s));
+    return MR_OK;
+}
+
 static int run_fused(mr_ctx* ctx, const MrJob& job, cudaStream_t s) {
     if (job.n1 == 0 || job.n2 == 0 || job.n_sheets == 0) return MR_OK;
     int nl = 0;
     cudaError_t e = cudaErrorNotSupported;
-    if (mr_fast_supported(job)) e = mr_launch_fast(job, ctx->sm_count, s, &nl);
+    if (mr_fast_supported(job)) {
+        e = mr_launch_fast(job, ctx->sm_count, s, &nl);
+    } else if (repack_pays(job)) {
+        const int rc = run_repacked(ctx, job, s, &nl);
+        ctx->launches += nl;
+        return rc;
+    }
     if (e == cudaErrorNotSupported) e = mr_launch_generic(job, false, ctx->sm_count, s, &nl);
     ctx->launches += nl;
     if (e != cudaSuccess) return fail_cuda(ctx, e, "fused kernel launch");
@@ -318,7 +363,8 @@ static int run_clean(mr_ctx* ctx, const MrJob& job, cudaStream_t s, int max_labe
     j.lut = nullptr;
     j.pal.K = 0;
     cudaError_t e = cudaErrorNotSupported;
-    if (mr_fast_supported(j)) {   // geometry qualifies: the plane count needs the largest label
+    const bool direct = mr_fast_supported(j), repack = !direct && repack_pays(j);
+    if (direct || repack) {   // geometry qualifies (possibly after repacking): the plane count needs the largest label
         if (max_label < 0) {
             if (!ctx->d_small) CK(cudaMalloc(&ctx->d_small, 512));
             unsigned int* d_max = reinterpret_cast<unsigned int*>(ctx->d_small + 264);
@@ -331,7 +377,17 @@ static int run_clean(mr_ctx* ctx, const MrJob& job, cudaStream_t s, int max_labe
             max_label = (int)m;
         }
         j.pal.K = max_label;
-        e = mr_fast_supported(j) ? mr_launch_fast(j, ctx->sm_count, s, &nl) : cudaErrorNotSupported;
+        e = cudaErrorNotSupported;
+        if (max_label <= 126) {
+            if (direct) {
+                e = mr_launch_fast(j, ctx->sm_count, s, &nl);
+            } else {
+                const int rc = run_repacked(ctx, j, s, &nl);
+                ctx->launches += nl;
+                if (max_label_out) *max_label_out = max_label;
+                return rc;
+            }
+        }
     }
     if (max_label_out) *max_label_out = max_label;
     if (e == cudaErrorNotSupported) e = mr_launch_generic(job, true, ctx->sm_count, s, &nl);
@@ -343,11 +399,12 @@ static int run_with_known(mr_ctx* ctx, MrJob job, cudaStream_t s) {
     const int R = job.R;
     uint8_t* final_out = job.out;
     const int64_t final_stride = job.out_stride2;
+    const int64_t line_tmp = (job.n1 + 15) / 16 * 16;   // aligned intermediate labels: both passes can take the fast kernel
     if (R > 0) {
-        int rc = grow(ctx, &ctx->d_tmp, &ctx->d_tmp_cap, (size_t)job.n1 * job.n2);
+        int rc = grow(ctx, &ctx->d_tmp, &ctx->d_tmp_cap, (size_t)line_tmp * job.n2);
         if (rc) return rc;
         job.out = ctx->d_tmp;
-        job.out_stride2 = job.n1;
+        job.out_stride2 = line_tmp;
     }
     job.R = 0;
     MrCountersDev* cnt = job.counters;
@@ -361,7 +418,7 @@ static int run_with_known(mr_ctx* ctx, MrJob job, cudaStream_t s) {
     if (e != cudaSuccess) return fail_cuda(ctx, e, "known-category fix-up");
     if (R > 0) {
         MrJob c = job;
-        c.px = ctx->d_tmp; c.stride2 = job.n1; c.bpp = 1; c.R = R; c.out = final_out;
+        c.px = ctx->d_tmp; c.stride2 = line_tmp; c.bpp = 1; c.R = R; c.out = final_out;
         c.out_stride2 = final_stride; c.counters = cnt;
         return run_clean(ctx, c, s, ctx->pal.K);
     }
@@ -530,21 +587,23 @@ extern "C" int mr_clean_host(mr_ctx* ctx, const uint8_t* labels, int64_t n1, int
     if (repeat < 0) return fail(ctx, MR_ERR_ARG, "mr_clean_host: repeat must be >= 0");
     if (n1 == 0 || n2 == 0) return MR_OK;
     CK(cudaSetDevice(ctx->device));
-    const size_t bytes = (size_t)n1 * n2;
+    const int64_t line = (n1 + 15) / 16 * 16;   // 16-byte aligned device lines: any n1 takes the fast kernel
+    const size_t bytes = (size_t)line * n2;
     if ((rc = grow(ctx, &ctx->d_out, &ctx->d_out_cap, bytes))) return rc;
     if ((rc = grow(ctx, &ctx->d_tmp, &ctx->d_tmp_cap, bytes))) return rc;
     uint8_t* a = ctx->d_out;
     uint8_t* b = ctx->d_tmp;
-    CK(cudaMemcpy2DAsync(a, n1, labels, stride2, n1, n2, cudaMemcpyHostToDevice, ctx->s_main));
+    CK(cudaMemcpy2DAsync(a, line, labels, stride2, n1, n2, cudaMemcpyHostToDevice, ctx->s_main));
     const int passes = (R == 0) ? 0 : repeat;
     int max_label = -1;   // the filter never creates a label: one reduction serves every pass
     for (int p = 0; p < passes; ++p) {
-        MrJob job = make_job(ctx, a, b, n1, n2, n1, 1, R, 0, 0, n1);
+        MrJob job = make_job(ctx, a, b, n1, n2, line, 1, R, 0, 0, line);
         job.lut = nullptr;
+        job.padded = 1;
         if ((rc = run_clean(ctx, job, ctx->s_main, max_label, &max_label))) return rc;
         uint8_t* t = a; a = b; b = t;
     }
-    CK(cudaMemcpy2DAsync(out, out_stride2, a, n1, n1, n2, cudaMemcpyDeviceToHost, ctx->s_main));
+    CK(cudaMemcpy2DAsync(out, out_stride2, a, line, n1, n2, cudaMemcpyDeviceToHost, ctx->s_main));
     CK(cudaStreamSynchronize(ctx->s_main));
     return MR_OK;
 }

@@ -167,6 +167,41 @@ def test_strided_and_unaligned_views(ctx, mr, oracle):
     assert mismatches(got, want) == 0
 
 
+@pytest.mark.parametrize("n1,pitch_px", [(1001, 1001), (1937, 2000), (333, 340)])
+def test_device_entry_points_with_unaligned_lines(ctx, mr, oracle, n1, pitch_px):
+    """Device pointers whose lines are not 16-byte aligned (odd n1, odd pitches, offset bases): the
+    library repacks them into aligned pitches and still runs the fast kernel; bands with halos too."""
+    seed, palrgb, stats, spec = _workload(mr, 2)
+    _set(ctx, mr, stats)
+    n2, R = 150, 2
+    scan = oracle.synth_scan(seed, 5, palrgb, n1, n2)
+    want = oracle.categorize_clean(scan, stats.mean, stats.lo, stats.hi, R)
+    pre = oracle.categorize_u8(scan, stats.mean, stats.lo, stats.hi)
+    buf = torch.zeros((n2, pitch_px, 3), dtype=torch.uint8, device="cuda")
+    buf[:, :n1] = torch.from_numpy(scan).cuda()
+    out = torch.full((n2, pitch_px + 3), 77, dtype=torch.uint8, device="cuda")
+    l0 = ctx.launch_count()
+    ctx.categorize_clean_dev(buf, n1, n2, pitch_px * 3, 3, R, out, pitch_px + 3)
+    torch.cuda.synchronize()
+    assert mismatches(out[:, :n1].cpu().numpy(), want) == 0
+    assert bool((out[:, n1:] == 77).all())                      # nothing written outside the image
+    assert ctx.launch_count() - l0 == 1
+    # a band with halos out of the same buffer
+    a, b = 40, 110
+    band = torch.full((b - a, n1), 9, dtype=torch.uint8, device="cuda")
+    ctx.categorize_clean_dev(buf[a:], n1, b - a, pitch_px * 3, 3, R, band, n1, halo_lo=R, halo_hi=R)
+    torch.cuda.synchronize()
+    assert mismatches(band.cpu().numpy(), want[a:b]) == 0
+    # standalone clean on unaligned label lines
+    lab = torch.zeros((n2, pitch_px), dtype=torch.uint8, device="cuda")
+    lab[:, :n1] = torch.from_numpy(pre).cuda()
+    out2 = torch.full((n2, pitch_px + 1), 55, dtype=torch.uint8, device="cuda")
+    ctx.clean_dev(lab, n1, n2, pitch_px, R, out2, pitch_px + 1)
+    torch.cuda.synchronize()
+    assert mismatches(out2[:, :n1].cpu().numpy(), want) == 0 and bool((out2[:, n1:] == 55).all())
+    assert mismatches(ctx.clean_host(pre, R), want) == 0
+
+
 def test_rgba_direct_path(ctx, mr, oracle):
     rng = np.random.default_rng(8)
     mean, mn, mx, sd, tol = random_palette(rng, 5, C=4, spread=0.4)
