@@ -23,7 +23,7 @@ def _crop_check(ctx, oracle, stats, d_scan, d_out, n1, n2, R, boxes, cs):
         assert mismatches(got[ys, xs], want[ys, xs]) == 0
 
 
-@pytest.mark.parametrize("cfg", [2, 4])
+@pytest.mark.parametrize("cfg", [2, 3, 4])
 def test_full_size_sheet(ctx, mr, oracle, cfg):
     from maprast_b200 import synth
     seed, palrgb, stats, spec = synth.config_workload(cfg)
@@ -63,6 +63,7 @@ def test_full_size_sheet(ctx, mr, oracle, cfg):
     seam = mr.distributed.band_range(n2, 8, 3)[1]
     boxes = [(0, s, 0, s), (n1 - s, n1, 0, s), (0, s, n2 - s, n2), (n1 - s, n1, n2 - s, n2),
              (n1 // 2, n1 // 2 + s, seam - s // 2, seam + s // 2), (7777, 7777 + s, 9999, 9999 + s),
+             (n1 - 3 * s, n1 - 2 * s, n2 - 3 * s, n2 - 2 * s),
              (n1 - s, n1, seam - 40, seam + 40)]
     _crop_check(ctx, oracle, stats, d, out, n1, n2, R, boxes, cs)
     # (4) clean is idempotent on constant regions and label histogram is plausible
