@@ -39,6 +39,7 @@ struct mr_ctx {
     // into aligned pitches so that they can take the fast kernel
     uint8_t* d_rp_in = nullptr;  size_t d_rp_in_cap = 0;
     uint8_t* d_rp_out = nullptr; size_t d_rp_out_cap = 0;
+    uint8_t* d_lab = nullptr;    size_t d_lab_cap = 0;     // categorise-only labels of the RGBA path
     // segment prune scratch: parent array, component records, keep table + two counters
     uint8_t* d_parent = nullptr; size_t d_parent_cap = 0;   // first run of every (line, chunk)
     uint8_t* d_runs = nullptr; size_t d_runs_cap = 0;       // run arrays
@@ -116,7 +117,7 @@ extern "C" void mr_destroy(mr_ctx* ctx) {
     for (auto e : ctx->ev_done) cudaEventDestroy(e);
     cudaFree(ctx->d_pal); cudaFree(ctx->d_lut); cudaFree(ctx->d_coarse);
     cudaFree(ctx->d_known_idx); cudaFree(ctx->d_known_cat); cudaFree(ctx->d_counters);
-    cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_tmp); cudaFree(ctx->d_rp_in); cudaFree(ctx->d_rp_out);
+    cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_tmp); cudaFree(ctx->d_rp_in); cudaFree(ctx->d_rp_out); cudaFree(ctx->d_lab);
     cudaFree(ctx->d_parent); cudaFree(ctx->d_runs); cudaFree(ctx->d_rec); cudaFree(ctx->d_small);
     if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
@@ -175,7 +176,7 @@ extern "C" int mr_set_palette(mr_ctx* ctx, int K, const double* mean, const doub
     ctx->palette_set = true;
     ctx->lut_valid = false;
     ctx->build_ms = 0.f;
-    if (channels == 3) {
+    {   // exact label table over the 2^24 colours (4-channel statistics: alpha = 255 in the distance)
         cudaEvent_t a, b;
         CK(cudaEventCreate(&a));
         CK(cudaEventCreate(&b));
@@ -336,8 +337,13 @@ static int run_repacked(mr_ctx* ctx, const MrJob& job, cudaStream_t s, int* nl) 
     return MR_OK;
 }
 
+static int run_rgba(mr_ctx* ctx, const MrJob& job, cudaStream_t s);
+
 static int run_fused(mr_ctx* ctx, const MrJob& job, cudaStream_t s) {
     if (job.n1 == 0 || job.n2 == 0 || job.n_sheets == 0) return MR_OK;
+    if (job.bpp == 4 && ctx->lut_valid && job.n_sheets == 1 && job.R <= 3 && job.pal.K <= 126 && !job.counters &&
+        !job.halo_lo_px && !job.halo_hi_px)
+        return run_rgba(ctx, job, s);
     int nl = 0;
     cudaError_t e = cudaErrorNotSupported;
     if (mr_fast_supported(job)) {
@@ -395,6 +401,41 @@ static int run_clean(mr_ctx* ctx, const MrJob& job, cudaStream_t s, int max_labe
     if (e != cudaSuccess) return fail_cuda(ctx, e, "clean kernel launch");
     return MR_OK;
 }
+// RGBA{N0f8} sheets on the fast kernels: strip the alpha byte into packed RGB (aligned pitch),
+// categorise every line (own + halo) with the label table (alpha = 255), re-evaluate the pixels
+// that are not opaque directly, then run the standalone majority filter on the labels.
+// (Known-category points: run_with_known calls this with R = 0 and does its fix-up in between.)
+static int run_rgba(mr_ctx* ctx, const MrJob& job, cudaStream_t s) {
+    const int64_t T = job.n2 + job.halo_lo + job.halo_hi;
+    const int64_t line_rgb = (job.n1 * 3 + 15) / 16 * 16, line_lab = (job.n1 + 15) / 16 * 16;
+    int rc;
+    if ((rc = grow(ctx, &ctx->d_rp_in, &ctx->d_rp_in_cap, (size_t)line_rgb * T))) return rc;
+    if ((rc = grow(ctx, &ctx->d_lab, &ctx->d_lab_cap, (size_t)line_lab * T))) return rc;
+    if (!ctx->d_small) CK(cudaMalloc(&ctx->d_small, 512));
+    unsigned int* d_special = reinterpret_cast<unsigned int*>(ctx->d_small + 268);
+    const uint8_t* px0 = job.px - (int64_t)job.halo_lo * job.stride2;
+    int nl = 0;
+    cudaError_t e = mr_launch_rgba_strip(px0, job.stride2, job.n1, T, ctx->d_rp_in, line_rgb, d_special, s, &nl);
+    if (e == cudaSuccess) {
+        MrJob c = job;   // categorise only, all T lines as one sheet
+        c.px = ctx->d_rp_in; c.stride2 = line_rgb; c.bpp = 3; c.R = 0; c.n2 = T; c.halo_lo = c.halo_hi = 0;
+        c.out = ctx->d_lab; c.out_stride2 = line_lab; c.padded = 1; c.lut = ctx->d_lut; c.counters = nullptr;
+        e = mr_launch_fast(c, ctx->sm_count, s, &nl);
+    }
+    if (e == cudaSuccess)
+        e = mr_launch_alpha_fix(job.pal, px0, job.stride2, job.n1, T, ctx->d_lab, line_lab, d_special, s, &nl);
+    ctx->launches += nl;
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "RGBA front end");
+    uint8_t* own = ctx->d_lab + (int64_t)job.halo_lo * line_lab;
+    if (job.R == 0) {
+        CK(cudaMemcpy2DAsync(job.out, job.out_stride2, own, line_lab, job.n1, job.n2, cudaMemcpyDeviceToDevice, s));
+        return MR_OK;
+    }
+    MrJob c = job;
+    c.px = own; c.stride2 = line_lab; c.bpp = 1; c.lut = nullptr;
+    return run_clean(ctx, c, s, ctx->pal.K);
+}
+
 static int run_with_known(mr_ctx* ctx, MrJob job, cudaStream_t s) {
     const int R = job.R;
     uint8_t* final_out = job.out;

@@ -229,3 +229,67 @@ cudaError_t mr_launch_max_label(const uint8_t* labels, int64_t n1, int64_t n2, i
     *n_launches += 1;
     return cudaGetLastError();
 }
+
+
+// ------------------------------------------------------------------ RGBA{N0f8} front end
+// RGBA sheets take the fast kernels through packed RGB: k_rgba_strip drops the alpha byte (and notes
+// whether any pixel is not opaque), the label table -- built with alpha = 255 in the distance
+// (src/categories.jl:92) -- serves every opaque pixel, and k_alpha_fix re-evaluates the others
+// directly (alpha term, alpha == 0 rule of src/categories.jl:115-118) before the majority filter.
+__global__ void k_rgba_strip(const uint8_t* __restrict__ px, int64_t stride2, int64_t n1, int64_t lines,
+                             uint8_t* __restrict__ rgb, int64_t rgb_stride2, unsigned int* __restrict__ any_special) {
+    const int64_t groups = (n1 + 3) / 4;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool special = false;
+    if (i < groups * lines) {
+        const int64_t y = i / groups, x = (i - y * groups) * 4;
+        const uint8_t* p = px + y * stride2 + x * 4;
+        uint8_t* q = rgb + y * rgb_stride2 + x * 3;
+        if (x + 4 <= n1 && ((uintptr_t)p % 4 == 0)) {
+            const uint32_t a = *reinterpret_cast<const uint32_t*>(p), b = *reinterpret_cast<const uint32_t*>(p + 4),
+                           c = *reinterpret_cast<const uint32_t*>(p + 8), d = *reinterpret_cast<const uint32_t*>(p + 12);
+            special = ((a & b & c & d) >> 24) != 0xFFu;
+            uint32_t* o = reinterpret_cast<uint32_t*>(q);   // rgb lines are 16-byte aligned, x * 3 is a multiple of 4
+            o[0] = (a & 0x00FFFFFFu) | (b << 24);
+            o[1] = ((b >> 8) & 0x0000FFFFu) | (c << 16);
+            o[2] = ((c >> 16) & 0x000000FFu) | (d << 8);
+        } else {
+            for (int k = 0; k < 4 && x + k < n1; ++k) {
+                q[3 * k] = p[4 * k]; q[3 * k + 1] = p[4 * k + 1]; q[3 * k + 2] = p[4 * k + 2];
+                special = special || p[4 * k + 3] != 0xFFu;
+            }
+        }
+    }
+    if (__any_sync(0xffffffffu, special) && (threadIdx.x & 31) == 0) *any_special = 1u;
+}
+
+__global__ void k_alpha_fix(MrPalette pal, const uint8_t* __restrict__ px, int64_t stride2, int64_t n1, int64_t lines,
+                            uint8_t* __restrict__ labels, int64_t labels_stride2,
+                            const unsigned int* __restrict__ any_special) {
+    if (*any_special == 0u) return;   // every pixel is opaque: nothing to do
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n1 * lines) return;
+    const int64_t y = i / n1, x = i - y * n1;
+    const uint8_t* p = px + y * stride2 + x * 4;
+    if (p[3] != 0xFFu) labels[y * labels_stride2 + x] = (uint8_t)mr_eval_px(pal, p[0], p[1], p[2], p[3], true, 0);
+}
+
+cudaError_t mr_launch_rgba_strip(const uint8_t* px, int64_t stride2, int64_t n1, int64_t lines, uint8_t* rgb,
+                                 int64_t rgb_stride2, unsigned int* d_any_special, cudaStream_t s, int* n_launches) {
+    cudaError_t e = cudaMemsetAsync(d_any_special, 0, sizeof(unsigned int), s);
+    if (e != cudaSuccess) return e;
+    const int64_t n = (n1 + 3) / 4 * lines;
+    k_rgba_strip<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(px, stride2, n1, lines, rgb, rgb_stride2, d_any_special);
+    *n_launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t mr_launch_alpha_fix(const MrPalette& pal, const uint8_t* px, int64_t stride2, int64_t n1, int64_t lines,
+                                uint8_t* labels, int64_t labels_stride2, const unsigned int* d_any_special,
+                                cudaStream_t s, int* n_launches) {
+    const int64_t n = n1 * lines;
+    k_alpha_fix<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(pal, px, stride2, n1, lines, labels, labels_stride2,
+                                                            d_any_special);
+    *n_launches += 1;
+    return cudaGetLastError();
+}

@@ -61,6 +61,11 @@ cudaError_t mr_launch_generic(const MrJob& job, bool labels_in, int sm_count, cu
 // when the job does not qualify (caller then uses the generic kernel).
 cudaError_t mr_launch_fast(const MrJob& job, int sm_count, cudaStream_t s, int* n_launches);
 bool mr_fast_supported(const MrJob& job);
+cudaError_t mr_launch_rgba_strip(const uint8_t* px, int64_t stride2, int64_t n1, int64_t lines, uint8_t* rgb,
+                                 int64_t rgb_stride2, unsigned int* d_any_special, cudaStream_t s, int* n_launches);
+cudaError_t mr_launch_alpha_fix(const MrPalette& pal, const uint8_t* px, int64_t stride2, int64_t n1, int64_t lines,
+                                uint8_t* labels, int64_t labels_stride2, const unsigned int* d_any_special,
+                                cudaStream_t s, int* n_launches);
 cudaError_t mr_launch_max_label(const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2, unsigned int* d_out,
                                 int sm_count, cudaStream_t s, int* n_launches);
 cudaError_t mr_launch_known_fixup(const MrJob& job, int64_t n_known, const int64_t* idx,

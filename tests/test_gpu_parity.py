@@ -218,6 +218,46 @@ def test_rgba_direct_path(ctx, mr, oracle):
         ctx.categorize_clean_host(px[..., :3].copy(), 1)
 
 
+@pytest.mark.parametrize("transparent", [0.0, 0.02, 0.6])
+def test_rgba_sheets_take_the_fast_kernels(ctx, mr, oracle, transparent):
+    """RGBA{N0f8} with 4-channel statistics (alpha joins the distance, src/categories.jl:92; alpha == 0
+    never matches, :115-118): alpha byte stripped, label table for opaque pixels, direct re-evaluation
+    of the others, standalone majority filter.  Opaque, sprinkled and mostly transparent sheets."""
+    from maprast_b200 import synth
+    seed, palrgb, stats3, spec = _workload(mr, 2)
+    rng = np.random.default_rng(11)
+    K = spec["K"]
+    mean = np.concatenate([stats3.mean, 1.0 - rng.random((K, 1)) * 0.05], axis=1)
+    mn = np.concatenate([stats3.min, np.full((K, 1), 0.9)], axis=1)
+    mx = np.concatenate([stats3.max, np.full((K, 1), 1.0)], axis=1)
+    sd = np.concatenate([stats3.sd, np.full((K, 1), 0.01)], axis=1)
+    pal = mr.Palette(mean, mn, mx, sd, np.full(K, 2.0))
+    ctx.set_known(None)
+    ctx.set_palette(pal.mean, pal.lo, pal.hi, mr._lib.RGB, 4)
+    ctx.palette = None
+    n1, n2, R = 1001, 140, 2
+    rgb = oracle.synth_scan(seed, 2, palrgb, n1, n2)
+    alpha = np.full((n2, n1, 1), 255, dtype=np.uint8)
+    sp = rng.random((n2, n1)) < transparent
+    alpha[sp, 0] = rng.choice(np.array([0, 0, 7, 128, 254], dtype=np.uint8), size=int(sp.sum()))
+    scan = np.ascontiguousarray(np.concatenate([rgb, alpha], axis=2))
+    want = oracle.categorize_clean(scan, pal.mean, pal.lo, pal.hi, R, channels=4)
+    l0 = ctx.launch_count()
+    got = ctx.categorize_clean_host(scan, R)
+    assert mismatches(got, want) == 0
+    assert ctx.launch_count() - l0 <= 6        # strip, categorise, alpha fix, label maximum, vote -- not the generic kernel
+    pre = oracle.categorize_u8(scan, pal.mean, pal.lo, pal.hi, channels=4)
+    assert mismatches(ctx.categorize_clean_host(scan, 0), pre) == 0
+    if transparent > 0:
+        assert (pre[sp & (alpha[..., 0] == 0)] == 0).all()
+    # device entry point, band with halos
+    d = torch.from_numpy(scan).cuda()
+    band = torch.empty((60, n1), dtype=torch.uint8, device="cuda")
+    ctx.categorize_clean_dev(d[40:], n1, 60, n1 * 4, 4, R, band, n1, halo_lo=R, halo_hi=R)
+    torch.cuda.synchronize()
+    assert mismatches(band.cpu().numpy(), want[40:100]) == 0
+
+
 def test_known_category_override(ctx, mr, oracle):
     seed, palrgb, stats, _ = _workload(mr, 1)
     _set(ctx, mr, stats)
