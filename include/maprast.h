@@ -151,8 +151,9 @@ int mr_clean_dev(mr_ctx* ctx, const uint8_t* labels_dev, int64_t n1, int64_t n2,
  * with fewer than prune_threshold pixels, or count / (max(h, w)^2 / 2) < line_threshold, becomes
  * 0 -- or its known category, if one was clicked inside it (clean.jl:79-85).
  * keep256[c] != 0 <=> category c is in `categories`.  The known-category plane is the one set by
- * mr_set_known.  If one segment holds two DIFFERENT known categories the reference result depends
- * on its scan order (scan.jl:140-146): the call then fails with MR_ERR_UNSUPPORTED.
+ * mr_set_known.  If one segment with a KEPT label holds two DIFFERENT known categories the
+ * reference result depends on its scan order (scan.jl:140-146): the call then fails with
+ * MR_ERR_UNSUPPORTED (segments whose label is not kept become 0 however they are split).
  * n1 * n2 < 2^31.  Labels are uint8 (the reference returns the Float64 segment colour; the Julia
  * wrapper converts).  The device variant synchronises `stream` (the number of segments sizes a
  * scratch buffer). */

@@ -286,3 +286,57 @@ def clean_segments_u8(labels, known_categories=None, *, categories, line_thresho
 def clean_segments(labels, known_categories=None, **kw):
     """Same, eltype Int."""
     return clean_segments_u8(labels, known_categories, **kw).astype(np.int64)
+
+
+@dataclass
+class MapSelection:
+    """`MapSelection` (src/selectcolors.jl:3-8): what `selectcolors` returns -- the clicked points per
+    category and the widget settings (src/selectcolors.jl:111-127: `category_tolerances`,
+    `category_keep`, `prune_threshold`, `line_threshold`, `match`, `segment`, ...)."""
+    settings: dict
+    removals: list = field(default_factory=list)
+    points: list = field(default_factory=list)
+    output: object = None
+
+    def tolerances(self):
+        t = self.settings.get("category_tolerances")
+        return None if t is None else np.asarray(t, dtype=np.float64)
+
+    def kept_categories(self):
+        """`_kept_categories` (src/selectcolors.jl:189): 1-based indices of the keep toggles that are on."""
+        keep = self.settings.get("category_keep")
+        if keep is None:
+            return tuple(range(1, len(self.points) + 1))
+        return tuple(i + 1 for i, k in enumerate(keep) if k)
+
+
+def rasterize(img, sel, *, hood=None, colourspace="rgb", ctx=None):
+    """The button sequence of `selectcolors` without the GUI, on the GPU path:
+    "categorize" (src/selectcolors.jl:466-478: `_categorize(pixels, points; tolerances, match,
+    segmented)`, known-category points from `_set_categories!`, :670-681) -> optional Window
+    majority filter (`hood`; north_star's `clean`) -> "clean" (:479-489: `_clean(A, known;
+    categories = kept, line_threshold, prune_threshold)`).
+    Returns a dict with the uint8 label images `categorized` and `cleaned`.
+    Settings that select unsupported stages raise ValueError (no CPU fallback): `segment=True`,
+    a `match` other than ("color",), `blur_repeat > 0`."""
+    if not isinstance(sel, MapSelection):
+        raise ValueError("sel must be a MapSelection")
+    st = sel.settings
+    match = tuple(st.get("match", ("color",)))
+    _check_match(match, bool(st.get("segment", False)))
+    if int(st.get("blur_repeat", 0)) != 0:
+        raise ValueError("blur_repeat > 0 (colour pre-smoothing, src/blur.jl) is not supported by the B200 hot path")
+    _check_img(img)
+    ctx = ctx or default_context()
+    n2, n1 = img.shape[:2]
+    tol = sel.tolerances()
+    R = 0 if hood is None else (hood.R if isinstance(hood, Window) else int(hood))
+    categorized = categorize_clean_u8(img, sel.points, tolerances=tol, hood=Window(R), colourspace=colourspace,
+                                      use_known=True, ctx=ctx)
+    idx, cat = _known_from_points(sel.points, n1)
+    known = np.zeros((n2, n1), dtype=np.uint8)
+    known.reshape(-1)[idx] = cat
+    cleaned = clean_segments_u8(categorized, known, categories=sel.kept_categories(),
+                                line_threshold=float(st.get("line_threshold", 0.01)),
+                                prune_threshold=float(st.get("prune_threshold", 20)), ctx=ctx)
+    return {"categorized": categorized, "cleaned": cleaned}

@@ -5,8 +5,10 @@
 // (`fast_scanning!`, src/scan.jl:56-157, threshold 1e-9, match = (:color,)): two pixels end up in
 // one segment iff they are 4-connected through equal labels -- provided no segment holds two
 // different known categories (then the reference splits it at the pixel where the merge is
-// refused, scan.jl:140-146, which depends on the scan order; that case is detected here and
-// reported as MR_ERR_UNSUPPORTED instead of being guessed).  So this is connected-component
+// refused, scan.jl:140-146, which depends on the scan order; for a segment whose label is kept
+// that case is detected here and reported as MR_ERR_UNSUPPORTED instead of being guessed; a
+// segment whose label is not kept -- e.g. the no-match background with clicked points that did
+// not match -- becomes 0 whichever way it is split).  So this is connected-component
 // labelling + per-component statistics + a per-component rule.
 //
 // RUN based: a cleaned map has long horizontal runs of equal labels (~30 pixels on the synthetic
@@ -287,11 +289,11 @@ __global__ void k_decide(SegRec* __restrict__ rec, unsigned int n, const uint8_t
     if (i >= n) return;
     const SegRec r = rec[i];
     const unsigned L = r.label;
-    if (r.cmax != 0 && r.cmin != r.cmax) *conflict = 1u;   // two known categories in one segment
     unsigned out = L;
     if (!keep[L]) {
-        out = 0u;
+        out = 0u;   // however the reference would split this segment, every part has a label that is not kept
     } else {
+        if (r.cmax != 0 && r.cmin != r.cmax) *conflict = 1u;   // two known categories in one kept segment
         const unsigned h = r.xmax - r.xmin + 1, w = r.ymax - r.ymin + 1;
         const unsigned long long m = h > w ? h : w;
         const double rectangle_area = __ddiv_rn((double)(m * m), 2.0);

@@ -19,7 +19,7 @@ using ColorTypes, FixedPointNumbers, Statistics
 import Neighborhoods: Window
 
 export categorize, clean, categorize_clean, categorize_u8, clean_u8, categorize_clean_u8, clean_segments,
-       clean_segments_u8, Context, Palette
+       clean_segments_u8, rasterize, MapSelection, Context, Palette
 
 const libmaprast = get(ENV, "LIBMAPRAST", joinpath(@__DIR__, "..", "libmaprast.so"))
 const DEFAULT_CATEGORY_TOLERANCE = 2.0            # src/selectcolors.jl:1
@@ -185,5 +185,49 @@ function clean_segments_u8(A::AbstractMatrix{<:Integer}, known_categories=nothin
     return out
 end
 clean_segments(A, known=nothing; kw...) = _rewrap(A, clean_segments_u8(A, known; kw...))
+
+# ---- MapSelection: the non-interactive entry (src/selectcolors.jl:3-8, 21-24, 111-127) ------------
+"Same fields as the reference's `MapSelection`; `settings` is the NamedTuple built at src/selectcolors.jl:111-125."
+struct MapSelection{S<:NamedTuple,O}
+    settings::S
+    removals::Vector{Vector{NTuple{2,Float32}}}
+    points::Vector{Vector{NTuple{2,Float32}}}
+    output::O
+end
+
+_kept_categories(bitindex::AbstractVector{Bool}) = (1:length(bitindex))[bitindex]     # src/selectcolors.jl:189
+
+"`_set_categories!` (src/selectcolors.jl:670-681): later categories overwrite earlier ones."
+function _known_plane(sz, points)
+    A = zeros(UInt8, sz)
+    for (i, pv) in enumerate(points), p in pv
+        A[round(Int, p[1]), round(Int, p[2])] = i
+    end
+    return A
+end
+
+categorize_u8(img, sel::MapSelection; kw...) =
+    categorize_clean_u8(img, sel.points; tolerances=collect(Float64, sel.settings.category_tolerances),
+                        hood=Window{0}(), match=get(sel.settings, :match, (:color,)),
+                        segmented=get(sel.settings, :segment, false), kw...)
+categorize(img, sel::MapSelection; kw...) = _rewrap(img, categorize_u8(img, sel; kw...))
+
+"""
+The button sequence of `selectcolors` without the GUI: "categorize" (src/selectcolors.jl:466-478),
+optional Window majority filter (`hood`), "clean" (:479-489).  Returns `(; categorized, cleaned)`.
+"""
+function rasterize(img, sel::MapSelection; hood=Window{0}(), ctx::Context=default_context())
+    get(sel.settings, :blur_repeat, 0) == 0 ||
+        throw(ArgumentError("blur_repeat > 0 is not supported by the B200 hot path"))
+    categorized = categorize_clean_u8(img, sel.points;
+        tolerances=collect(Float64, sel.settings.category_tolerances), hood,
+        match=get(sel.settings, :match, (:color,)), segmented=get(sel.settings, :segment, false), ctx)
+    known = _known_plane(size(categorized), sel.points)
+    keep = get(sel.settings, :category_keep, fill(true, length(sel.points)))
+    cleaned = clean_segments_u8(categorized, known; categories=_kept_categories(collect(Bool, keep)),
+        line_threshold=get(sel.settings, :line_threshold, 0.01),
+        prune_threshold=get(sel.settings, :prune_threshold, 20), ctx)
+    return (; categorized=_rewrap(img, categorized), cleaned=_rewrap(img, cleaned))
+end
 
 end # module

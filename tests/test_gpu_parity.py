@@ -332,6 +332,46 @@ def test_reference_shaped_api(ctx, mr, oracle):
 
 
 # ---------------------------------------------------------------- device API: bands, batch, synth
+def test_map_selection_pipeline(ctx, mr, oracle):
+    """MapSelection (src/selectcolors.jl:3-8) -> categorize -> majority clean -> segment prune, the
+    button sequence of selectcolors (:466-489) without the GUI, against the oracle stage by stage."""
+    from maprast_b200 import synth
+    seed, palrgb, stats, spec = _workload(mr, 1)
+    n1, n2, K = 640, 400, spec["K"]
+    scan = oracle.synth_scan(seed, 0, palrgb, n1, n2)
+    rng = np.random.default_rng(3)
+    # clicked points: pixels whose colour is close to each palette colour (1-based (i, j))
+    points = []
+    for c in range(K):
+        d = np.abs(scan.astype(np.int32) - palrgb[c].astype(np.int32)).sum(axis=2)
+        js, is_ = np.nonzero(d < 12)
+        pick = rng.choice(len(js), size=12, replace=False)
+        points.append([(float(is_[p] + 1), float(js[p] + 1)) for p in pick])
+    tol = np.full(K, 2.5)
+    keep = [True] * K
+    keep[2] = False
+    sel = mr.MapSelection(settings=dict(category_tolerances=tol, category_keep=keep, prune_threshold=30,
+                                        line_threshold=0.02, match=("color",), segment=False, blur_repeat=0),
+                          points=points)
+    # no majority filter: a clicked point then carries its own category or 0 (src/categories.jl:110-112),
+    # so two different known categories can only meet in the no-match background
+    res = mr.rasterize(scan, sel, hood=None, ctx=ctx)
+    pal = mr.Palette.from_points(scan, points, tol)
+    idx, cat = mr.api._known_from_points(points, n1)
+    pre = oracle.categorize_u8(scan, pal.mean, pal.lo, pal.hi, known_idx=idx, known_cat=cat)
+    want_cat = pre
+    assert mismatches(res["categorized"], want_cat) == 0
+    known = np.zeros((n2, n1), dtype=np.uint8)
+    known.reshape(-1)[idx] = cat
+    want_clean, _ = oracle.clean_segments(want_cat, known, sel.kept_categories(), 0.02, 30)
+    assert mismatches(res["cleaned"], want_clean) == 0
+    assert not (res["cleaned"] == 3).any() and (res["categorized"] == 3).any()
+    with pytest.raises(ValueError):
+        mr.rasterize(scan, mr.MapSelection(settings=dict(segment=True), points=points), ctx=ctx)
+    with pytest.raises(ValueError):
+        mr.rasterize(scan, mr.MapSelection(settings=dict(blur_repeat=1), points=points), ctx=ctx)
+
+
 def test_device_bands_equal_whole(ctx, mr, oracle):
     """band-sharded launches (with halos) are byte-identical to one launch."""
     seed, palrgb, stats, spec = _workload(mr, 2)

@@ -83,6 +83,11 @@ def test_known_categories_and_conflict(ctx, mr, oracle):
     with pytest.raises(mr.MapRastError) as ei:
         ctx.clean_segments_host(lab2, oracle.keep_table((1, 2, 4)), 0.0, 100)
     assert ei.value.code == -5
+    # ... but not when the segment's label is not kept (e.g. the no-match background holding clicked
+    # points that did not match): every part of it becomes 0 however the reference splits it
+    got2, _ = ctx.clean_segments_host(lab2, oracle.keep_table((1, 2)), 0.0, 100)
+    want2, _ = oracle.clean_segments(lab2, kn2, (1, 2), 0.0, 100)
+    assert mismatches(got2, want2) == 0 and not got2.any()
     ctx.set_known(None)
 
 
