@@ -1,26 +1,31 @@
-// mr_fast.cu -- the tuned fused categorise + clean kernel for packed RGB{N0f8} sheets (sm_100a).
+// mr_fast.cu -- the tuned fused categorise + clean kernel for packed RGB{N0f8} sheets (sm_100a),
+// and, with a labels-in front end, the standalone Window majority filter.
 //
 // WARP-AUTONOMOUS design: one persistent CTA per SM, every warp is an independent worker that
 // pulls  strip x line-chunk  items from a global queue and owns a private slice of shared memory
-// (plane ring, TMA staging line, work lists).  Only the 32 KiB coarse colour table is shared.
-// There is no block barrier after start-up: a warp that waits (TMA, exact-table gathers) is hidden
-// by the other 15 warps, not by a barrier-synchronised phase structure.
+// (plane ring, TMA staging line, output line, round-2 list).  Only the coarse colour table is
+// shared.  There is no block barrier after start-up: a warp that waits (TMA, exact-table gathers)
+// is hidden by the other 15 warps, not by a barrier-synchronised phase structure.
 //
-// Per warp, for an item of lines [y0, y1) of a strip of 32*U output pixels (U = 32-2R):
-//   categorise  lane = one aligned 32-pixel word of the line.  The packed RGB of the line arrives
-//               by a 1-D TMA bulk copy (cp.async.bulk + mbarrier) issued one line ahead.  Colours ->
-//               labels through the coarse table; labels go (a) straight to global memory as the
-//               provisional output (16-byte stores) and (b) as NB bit planes into the warp's ring.
-//               Plane words are stored OVERLAPPED: vote lane l owns the 32 pixels starting R before
-//               its U output pixels, so a vote window never leaves the lane's own words.
-//   fix         colours that fall into a MIXED coarse cell (~1 %) are resolved from the exact
-//               2^24-entry table (L2 resident), densely over the lanes, per block of B lines.
-//   vote        Window{R} majority, bit-sliced: per word two candidate labels (A, B); their
-//               (2R+1)^2 box counts come from plane-wise match masks, a vertical carry-save sum and
-//               a horizontal shift-and-add sum.  A pixel is decided when max(cA,cB) > N - cA - cB
-//               (no other label can reach or tie it); the winner of {A, B} is the larger count,
-//               ties -> lower label (Appendix A.3).  Only changed pixels are written (byte stores
-//               into the L2-hot line).
+// Per warp, for an item of lines [y0, y1) of a strip of 32*U output pixels (U = 32-2R), in blocks
+// of B output lines (B = the largest block whose ring fits the shared memory):
+//   load        the packed RGB of a line arrives by a 1-D TMA bulk copy (cp.async.bulk + mbarrier)
+//               issued one line ahead (halo lines of a band possibly from a peer GPU's memory);
+//               the line three further down is prefetched into L2.
+//   categorise  lane = one aligned 32-pixel word.  Bytes quantised to x>>3, cell address by byte dot
+//               products (IDP.4A), one LDS.U8 gather per pixel from the coarse table, labels
+//               transposed into NB bit planes (delta-swap network) and stored to the warp's ring as
+//               OVERLAPPED vote words: vote lane l owns the 32 pixels starting R before its U output
+//               pixels, so a vote window never leaves the lane's own words.
+//   MIXED       colours in a MIXED coarse cell (~1 %) take the exact 2^24-entry table (L2 resident):
+//               colours captured from the staging line, loads in flight during the transpose, bits
+//               patched in registers before the planes are stored.
+//   vote        Window{R} majority, bit-sliced, two candidate labels (A, B) per (vote word, block):
+//               per line match masks and their horizontal window sums once, box counts sliding down
+//               the block.  A pixel is decided when max(cA,cB) > N - cA - cB (no other label can
+//               reach or tie it); winner = larger count, ties -> lower label (Appendix A.3).
+//   store       every vote word writes its U label bytes into the warp's line buffer; one TMA bulk
+//               store per line.  Undecided pixels get a guess that the next stage overwrites.
 //   round 2     words with undecided pixels are re-voted, densely over the lanes, with candidates
 //               taken from those pixels; what is still undecided (3-label junctions, clipped
 //               corners) gets an exact popcount vote, again densely.
@@ -52,11 +57,9 @@ template <int R> struct Geo {
     static constexpr int WC = R == 1 ? 4 : (R == 2 ? 5 : 6);   // bits of a box count (<= (2R+1)^2)
 };
 
-constexpr int cmax(int a, int b) { return a > b ? a : b; }
-
 // kernel configuration per (R, NB): warps per CTA and lines per block, sized so that one CTA
 // (coarse table + per-warp slices) fits the 227 KiB of shared memory of an SM.
-// All work lists hold one entry per 32-pixel WORD (code + pixel mask), so they cannot overflow.
+// The round-2 list holds one entry per 32-pixel WORD (code + pixel mask) and is capped (LIST_CAP).
 constexpr int warp_bytes(int R, int NB, int B) {   // per-warp slice for B lines per block
     const int raw = (B + 2 * R) * (R > 0 ? NB : 0) * 128 + stage_bytes(R) + LIST_CAP * 6 + (R > 0 ? 32 * (32 - 2 * R) : 0) + 24;
     return (raw + 127) / 128 * 128;
