@@ -362,6 +362,20 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": int(launches), "gpu_launches_per_step": launches_per_step,
         "clocks": clocks,
     }
+    # ---- diagnostics SURVEY 8(d) asks for: one counted launch outside the timed region (MIXED-cell =
+    # "near-tie" pixels resolved through the exact table, no-match labels, labels the filter changed)
+    # and the throughput with the per-palette table build NOT amortised over many sheets
+    ctx.enable_counters(True)
+    ctx.read_counters(reset=True)
+    step()
+    torch.cuda.synchronize()
+    cnt = ctx.read_counters(reset=True)
+    ctx.enable_counters(False)
+    res["diagnostics"] = {
+        "counted_pixels": cnt["n_pixels"], "exact_table_pixels": cnt["n_fine"], "nomatch_pixels": cnt["n_nomatch"],
+        "changed_by_clean_pixels": cnt["n_changed"],
+        "value_unamortised_table_build": my_px / ((kern_ms + build_ms) * 1e-3) / 1e6,
+        "note": "counters of rank 0's share; table build = 2^24 exact Float64 evaluations per palette, once per mr_set_palette"}
     if world == 1 and not batch and n1 * nb < (1 << 31):
         # ---- SURVEY 8(f) "next" row, measured beside the hot path: the reference's segment prune
         # (_clean, src/clean.jl:59-93) on the labels the fused kernel just produced (device resident)
