@@ -37,9 +37,49 @@ __global__ void __launch_bounds__(128) k_build_coarse(const uint8_t* __restrict_
         (uniform && first != MR_MIXED) ? (uint8_t)first : (uint8_t)MR_MIXED;
 }
 
+// RGB colour space: one block per (g, b) pair, thread = r.  The squared g / b (and alpha = 255)
+// differences of every category are computed once per block; per colour and category the
+// reference's left fold ((q_r + q_g) + q_b) [+ q_a] is then two additions -- the same individually
+// rounded operations as mr_eval_px, in the same order (src/categories.jl:91-95), first minimum,
+// box test on the winner (:119-121, :131-133).
+__global__ void __launch_bounds__(256) k_build_lut_rgb(MrPalette pal, uint8_t* __restrict__ lut) {
+    __shared__ double s_mr[254], s_qg[254], s_qb[254], s_qa[254];
+    const int g = blockIdx.x & 255, b = blockIdx.x >> 8, r = threadIdx.x;
+    const int C = pal.C, K = pal.K;
+    const double xg = __ddiv_rn((double)g, 255.0), xb = __ddiv_rn((double)b, 255.0), xr = __ddiv_rn((double)r, 255.0);
+    for (int c = threadIdx.x; c < K; c += blockDim.x) {
+        const double* m = pal.mean + (size_t)c * C;
+        s_mr[c] = __ldg(m + 0);
+        const double dg = __dsub_rn(xg, __ldg(m + 1)), db = __dsub_rn(xb, __ldg(m + 2));
+        s_qg[c] = __dmul_rn(dg, dg);
+        s_qb[c] = __dmul_rn(db, db);
+        if (C == 4) {
+            const double da = __dsub_rn(1.0, __ldg(m + 3));   // Float64(N0f8(255)) = 1.0
+            s_qa[c] = __dmul_rn(da, da);
+        }
+    }
+    __syncthreads();
+    int best = 0;
+    double beste = 0.0;
+    for (int c = 0; c < K; ++c) {
+        const double dr = __dsub_rn(xr, s_mr[c]);
+        double e = __dadd_rn(__dadd_rn(__dmul_rn(dr, dr), s_qg[c]), s_qb[c]);
+        if (C == 4) e = __dadd_rn(e, s_qa[c]);
+        if (c == 0 || e < beste) { beste = e; best = c; }   // first minimum
+    }
+    const double* l = pal.lo + (size_t)best * C;
+    const double* h = pal.hi + (size_t)best * C;
+    const bool ok = (xr >= __ldg(l + 0)) && (xr <= __ldg(h + 0)) && (xg >= __ldg(l + 1)) && (xg <= __ldg(h + 1)) &&
+                    (xb >= __ldg(l + 2)) && (xb <= __ldg(h + 2));
+    lut[(unsigned)r | ((unsigned)g << 8) | ((unsigned)b << 16)] = ok ? (uint8_t)(best + 1) : (uint8_t)0;
+}
+
 cudaError_t mr_launch_build_lut(const MrPalette& pal, uint8_t* lut, uint8_t* coarse, cudaStream_t s,
                                 int* n_launches) {
-    k_build_lut<<<MR_LUT_SIZE / 256, 256, 0, s>>>(pal, lut);
+    if (pal.colourspace == 0 && pal.K <= 254)
+        k_build_lut_rgb<<<65536, 256, 0, s>>>(pal, lut);
+    else
+        k_build_lut<<<MR_LUT_SIZE / 256, 256, 0, s>>>(pal, lut);
     k_build_coarse<<<(1u << 15) / 128, 128, 0, s>>>(lut, coarse);
     *n_launches += 2;
     return cudaGetLastError();
