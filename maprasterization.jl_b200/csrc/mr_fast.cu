@@ -760,7 +760,7 @@ __device__ __forceinline__ void vote_word(const FastParams& P, uint8_t* ws, cons
 // (the caller votes the rest after emptying the list).
 template <int R, int NB, bool COUNT>
 __device__ __forceinline__ int block_vote(const FastParams& P, uint8_t* ws, const Item& it, int a, int nl, int vl,
-                                           uint32_t mask, uint32_t obytes, unsigned& c_nomatch,
+                                           uint32_t mask, uint32_t obytes, unsigned& hint, unsigned& c_nomatch,
                                            unsigned& c_changed) {
     using G = Geo<R>;
     using C = Cfg<R, NB>;
@@ -771,49 +771,46 @@ __device__ __forceinline__ int block_vote(const FastParams& P, uint8_t* ws, cons
     constexpr int LINE = NB * 128, RING = C::RL * LINE;
     const uint8_t* base = ws + C::W_PLANES + vl * 4;
     // ---- candidates (heuristic only): A = label at the centre of the block, B = the label farthest
-    // from the centre among the pixels of the centre / first / last line that differ from A.  Labels
-    // are read through a vertical bitwise majority of three lines, which hides isolated speckle.
+    // from the centre among the pixels of the centre line that differ from A; if the centre line
+    // shows only A, the other label this vote word saw in the blocks above (`hint`: the previous B,
+    // or the previous A when A changed).  Labels are read through a vertical bitwise majority of
+    // three lines, which hides isolated speckle.
     unsigned a_lab = 0, b_lab = 0;
     {
-        bool found = false;
-#pragma unroll 1
-        for (int t = 0; t < 3 && !found; ++t) {
-            const int yy = t == 0 ? a + (nl >> 1) : (t == 1 ? a : a + nl - 1);
-            int off = ((yy - 1 - (it.y0 - R)) % C::RL) * LINE;
-            uint32_t Q[NB];
-            {
-                uint32_t X[3][NB];
+        const int yy = a + (nl >> 1);
+        int off = ((yy - 1 - (it.y0 - R)) % C::RL) * LINE;
+        uint32_t Q[NB];
+        {
+            uint32_t X[3][NB];
 #pragma unroll
-                for (int d = 0; d < 3; ++d) {
+            for (int d = 0; d < 3; ++d) {
 #pragma unroll
-                    for (int b = 0; b < NB; ++b) X[d][b] = *reinterpret_cast<const uint32_t*>(base + off + b * 128);
-                    off += LINE;
-                    if (off == RING) off = 0;
-                }
-#pragma unroll
-                for (int b = 0; b < NB; ++b) Q[b] = mr_maj(X[0][b], X[1][b], X[2][b]);
+                for (int b = 0; b < NB; ++b) X[d][b] = *reinterpret_cast<const uint32_t*>(base + off + b * 128);
+                off += LINE;
+                if (off == RING) off = 0;
             }
-            if (t == 0) {
 #pragma unroll
-                for (int b = 0; b < NB; ++b) a_lab |= ((Q[b] >> 16) & 1u) << b;
-                b_lab = a_lab;
-            }
-            uint32_t nota = 0u, isvoid = ~0u;
-#pragma unroll
-            for (int b = 0; b < NB; ++b) {
-                nota |= Q[b] ^ (0u - ((a_lab >> b) & 1u));
-                isvoid &= Q[b];
-            }
-            nota &= mask & ~isvoid;
-            if (nota) {
-                const int pf = __ffs(nota) - 1, pl = 31 - __clz(nota);
-                const int pos = (pl - 16 > 16 - pf) ? pl : pf;
-                b_lab = 0;
-#pragma unroll
-                for (int b = 0; b < NB; ++b) b_lab |= ((Q[b] >> pos) & 1u) << b;
-                found = true;
-            }
+            for (int b = 0; b < NB; ++b) Q[b] = mr_maj(X[0][b], X[1][b], X[2][b]);
         }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) a_lab |= ((Q[b] >> 16) & 1u) << b;
+        uint32_t nota = 0u, isvoid = ~0u;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            nota |= Q[b] ^ (0u - ((a_lab >> b) & 1u));
+            isvoid &= Q[b];
+        }
+        nota &= mask & ~isvoid;
+        const unsigned prev_a = hint >> 8, prev_b = hint & 0xFFu;
+        b_lab = (prev_a != a_lab) ? prev_a : prev_b;     // no second label on the centre line: the one from above
+        if (nota) {
+            const int pf = __ffs(nota) - 1, pl = 31 - __clz(nota);
+            const int pos = (pl - 16 > 16 - pf) ? pl : pf;
+            b_lab = 0;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) b_lab |= ((Q[b] >> pos) & 1u) << b;
+        }
+        hint = (a_lab << 8) | b_lab;
     }
     const uint32_t nbm = (b_lab != a_lab && b_lab != VOIDL) ? ~0u : 0u;   // B == A -> B's masks are empty
     const uint32_t avm = (a_lab != VOIDL) ? ~0u : 0u;
@@ -987,6 +984,7 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
     while (next < (unsigned)P.n_items) {
         const Item it = decode_item<R, NB>(P, next);
         const LaneMasks M = lane_masks<R>(P, it.xw0, lane);
+        unsigned hint = ((1u << NB) - 1u) * 0x101u;          // candidate memory of this vote word: none yet (VOID, VOID)
         const int cat_last = it.y1 + R;                       // lines [y0-R, y1+R) are categorised
         int ycat = it.y0 - R;                                 // next line to categorise
         const CopyPlan plan = copy_plan<R, (LIN ? 1 : 3)>(P, it, stage_u32);
@@ -1037,7 +1035,8 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
                 // round 1 produced, densely over the lanes
 #pragma unroll 1
                 for (int va = a; va < vend;) {
-                const int done = block_vote<R, NB, COUNT>(P, ws, it, va, vend - va, lane, M.vvalid, obytes, c_nomatch, c_changed);
+                const int done = block_vote<R, NB, COUNT>(P, ws, it, va, vend - va, lane, M.vvalid, obytes, hint, c_nomatch,
+                                                          c_changed);
                 __syncwarp();
                 const int n2 = cnt[1];
                 if (n2) {   // byte patches follow: the bulk stores of this block must have landed
