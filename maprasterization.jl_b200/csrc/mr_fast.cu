@@ -821,13 +821,21 @@ __device__ __forceinline__ int block_vote(const FastParams& P, uint8_t* ws, cons
         LA[b] = 0u - ((a_lab >> b) & 1u);
         LB[b] = 0u - ((b_lab >> b) & 1u);
     }
-    // ---- slide down the block.  hA / hB: match masks of the last 2R+1 lines (oldest first)
+    // ---- slide down the block
     Bs<WC> SA, SB;
 #pragma unroll
     for (int k = 0; k < WC; ++k) SA.b[k] = SB.b[k] = 0u;
-    uint32_t hA[SIDE], hB[SIDE];
+    Bs<WH> HA[SIDE], HB[SIDE];        // horizontal window sums of the last 2R+1 lines (oldest first)
+    uint32_t cA = 0u, cB = 0u;        // COUNT: match masks of the last R+1 lines packed away below
+    uint32_t hA[R + 1], hB[R + 1];
 #pragma unroll
-    for (int d = 0; d < SIDE; ++d) hA[d] = hB[d] = 0u;
+    for (int d = 0; d < SIDE; ++d) {
+#pragma unroll
+        for (int k = 0; k < WH; ++k) HA[d].b[k] = HB[d].b[k] = 0u;
+    }
+#pragma unroll
+    for (int d = 0; d <= R; ++d) hA[d] = hB[d] = 0u;
+    (void)cA; (void)cB;
     int off = ((a - it.y0) % C::RL) * LINE;   // slot of line a - R
     int n_listed = 0;   // entries this call has put on the round-2 list (warp-uniform)
     uint8_t* gline = it.out + (long long)a * P.job.out_stride2 + it.xw0 + 32 * G::HW;   // strip start, line a
@@ -845,15 +853,24 @@ __device__ __forceinline__ int block_vote(const FastParams& P, uint8_t* ws, cons
         }
         off += LINE;
         if (off == RING) off = 0;
-        SA = bs_add<WC, WH, WC>(SA, bs_hsum1<R>(ma));
-        SB = bs_add<WC, WH, WC>(SB, bs_hsum1<R>(mb));
 #pragma unroll
         for (int d = 0; d < SIDE - 1; ++d) {
-            hA[d] = hA[d + 1];
-            hB[d] = hB[d + 1];
+            HA[d] = HA[d + 1];
+            HB[d] = HB[d + 1];
         }
-        hA[SIDE - 1] = ma;
-        hB[SIDE - 1] = mb;
+        HA[SIDE - 1] = bs_hsum1<R>(ma);
+        HB[SIDE - 1] = bs_hsum1<R>(mb);
+        SA = bs_add<WC, WH, WC>(SA, HA[SIDE - 1]);
+        SB = bs_add<WC, WH, WC>(SB, HB[SIDE - 1]);
+        if (COUNT) {   // the centre line's own match masks (line i - R) tell whether its label changed
+#pragma unroll
+            for (int d = 0; d < R; ++d) {
+                hA[d] = hA[d + 1];
+                hB[d] = hB[d + 1];
+            }
+            hA[R] = ma;
+            hB[R] = mb;
+        }
         if (i >= 2 * R) {
             // ---- decide output line a + i - 2R: winner of {A, B} is the mode iff max > N - cA - cB
             uint32_t eq;
@@ -874,7 +891,7 @@ __device__ __forceinline__ int block_vote(const FastParams& P, uint8_t* ws, cons
             if (n_listed > LIST_CAP - 32) return i - 2 * R;   // warp-uniform
             n_listed += __popc(__ballot_sync(0xffffffffu, undec != 0u));
             if (COUNT) {
-                c_changed += __popc(now & ~((selA & hA[R]) | (~selA & hB[R])));   // centre label != winner
+                c_changed += __popc(now & ~((selA & hA[0]) | (~selA & hB[0])));   // centre label != winner
                 c_nomatch += __popc(now & ((a_lab == 0 ? selA : 0u) | (b_lab == 0 ? ~selA : 0u)));
             }
             {   // labels of the U output pixels: B ^ (selA ? A ^ B : 0), GP pixels (bytes) per step
@@ -903,8 +920,8 @@ __device__ __forceinline__ int block_vote(const FastParams& P, uint8_t* ws, cons
                 reinterpret_cast<uint16_t*>(ws + C::W_W2CODE)[e] = (uint16_t)(((i - 2 * R) << 5) | vl);
                 reinterpret_cast<uint32_t*>(ws + C::W_W2MASK)[e] = undec;
             }
-            SA = bs_sub<WC, WH>(SA, bs_hsum1<R>(hA[0]));
-            SB = bs_sub<WC, WH>(SB, bs_hsum1<R>(hB[0]));
+            SA = bs_sub<WC, WH>(SA, HA[0]);
+            SB = bs_sub<WC, WH>(SB, HB[0]);
         }
     }
     return nl;
