@@ -142,17 +142,23 @@ __global__ void __launch_bounds__(BT) k_count(const uint8_t* __restrict__ lab, i
     if (threadIdx.x == 0) cnt[blockIdx.x] = tot;
 }
 
-// in-place exclusive scan of n counts, total appended at a[n]; one block
+// in-place exclusive scan of n counts, total appended at a[n]; one block, 8 entries per thread and step
 __global__ void __launch_bounds__(1024) k_scan(uint32_t* __restrict__ a, uint64_t n) {
+    constexpr int E = 8;
     __shared__ uint32_t wsum[32];
     __shared__ uint32_t carry;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (uint64_t i0 = 0; i0 < n; i0 += 1024) {
-        const uint64_t i = i0 + threadIdx.x;
-        const uint32_t v = i < n ? a[i] : 0u;
-        uint32_t s = v;
+    for (uint64_t i0 = 0; i0 < n; i0 += 1024 * E) {
+        const uint64_t i = i0 + (uint64_t)threadIdx.x * E;
+        uint32_t v[E], mine = 0;
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+            v[k] = i + k < n ? a[i + k] : 0u;
+            mine += v[k];
+        }
+        uint32_t s = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t t = __shfl_up_sync(0xffffffffu, s, o);
@@ -162,7 +168,12 @@ __global__ void __launch_bounds__(1024) k_scan(uint32_t* __restrict__ a, uint64_
         __syncthreads();
         uint32_t base = carry;
         for (int w = 0; w < warp; ++w) base += wsum[w];
-        if (i < n) a[i] = base + s - v;
+        uint32_t run = base + s - mine;
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+            if (i + k < n) a[i + k] = run;
+            run += v[k];
+        }
         __syncthreads();
         if (threadIdx.x == 1023) carry = base + s;
         __syncthreads();
