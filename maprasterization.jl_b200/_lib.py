@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmaprast.so")
+# MAPRAST_LIB selects another build of the same library (kernel experiments: csrc/Makefile VARIANT=...)
+LIB_PATH = os.environ.get("MAPRAST_LIB") or os.path.join(_HERE, "libmaprast.so")
 
 MR_OK, MR_ERR_ARG, MR_ERR_CUDA, MR_ERR_STATE, MR_ERR_NOMEM = 0, -1, -2, -3, -4
 RGB, LAB = 0, 1

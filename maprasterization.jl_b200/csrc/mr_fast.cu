@@ -71,7 +71,11 @@ constexpr int best_block(int R, int NB, int warps) {   // largest block that fit
 }
 template <int R, int NB> struct Cfg {
     static constexpr int NBP = R > 0 ? NB : 0;
+#ifdef MR_WARPS
+    static constexpr int WARPS = MR_WARPS;
+#else
     static constexpr int WARPS = (R > 0 && NB >= 6) ? 12 : 16;
+#endif
     static constexpr int B = R == 0 ? 8 : best_block(R, NB, WARPS);            // lines voted per block
     static constexpr int RL = B + 2 * R;                                       // plane ring, lines
     static constexpr int N_W2 = LIST_CAP;                                      // list capacity
@@ -142,7 +146,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 
 __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
     uint32_t v;
+#ifdef MR_KO_GATHER   // timing experiment: conflict-free gathers (all lanes read one of four bytes)
+    addr = (addr & 3u) | (MR_KO_GATHER & ~3u);
+#endif
+#ifdef MR_KO_NOLDS   // timing experiment: no gather at all, label from the address
+    return (addr >> 2) & 15u;
+#endif
     asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));   // the table is read-only once the CTA runs
+#ifdef MR_KO_NOMIXED   // timing experiment: MIXED cells never seen
+    v &= 0x0Fu;
+#endif
     return v;
 }
 
@@ -206,26 +219,35 @@ __device__ __forceinline__ CopyPlan copy_plan(const FastParams& P, const Item& i
 
 // TMA: bring the packed RGB of line y into the warp's staging buffer, and pull the line PF lines
 // further down into L2 (the next copy then completes at L2 latency instead of DRAM latency).
-// Returns false if the line needs no load (outside the sheet).  ylo / yhi: loadable lines.
+// Returns false if the line needs no load (outside the sheet).  ylo / yhi: loadable lines,
+// pflo / pfhi: lines whose prefetch target lies in this GPU's memory (halo lines that are read in
+// place from a peer GPU bypass the local L2).  Every argument is warp-uniform: the address
+// arithmetic runs on the uniform datapath and the copy needs no operand broadcast.
 constexpr int PF_LINES = 3;
-__device__ __forceinline__ bool issue_line_copy(const FastParams& P, const CopyPlan& c, const uint8_t* src,
-                                                long long pf_off, int y, int ylo, int yhi, uint32_t bar, int lane) {
+__device__ __forceinline__ bool issue_line_copy(const FastParams& P, const CopyPlan& c, int y, int ylo, int yhi,
+                                                int pflo, int pfhi, uint32_t bar, int lane) {
     if (y < ylo || y >= yhi) return false;
+#ifdef MR_KO_TMA   // timing experiment: no input traffic
+    return false;
+#endif
+    const uint8_t* base = c.src0;
+    long long row = y;
+    // halo lines that live in the neighbour band's buffer (peer GPU memory): read in place
+    if (y < 0 && P.job.halo_lo_px) {
+        base = P.job.halo_lo_px + c.col_off;
+        row = y + P.job.halo_lo;
+    } else if (y >= P.job.n2 && P.job.halo_hi_px) {
+        base = P.job.halo_hi_px + c.col_off;
+        row = y - P.job.n2;
+    }
+    const uint8_t* src = base + row * P.job.stride2;
+    const bool pf = y >= pflo && y + PF_LINES < pfhi;
     if (lane == 0) {
-        bool pf = y + PF_LINES < yhi;
-        // halo lines that live in the neighbour band's buffer (peer GPU memory): read in place
-        if (y < 0 && P.job.halo_lo_px) {
-            src = P.job.halo_lo_px + (long long)(y + P.job.halo_lo) * P.job.stride2 + c.col_off;
-            pf = false;
-        } else if (y >= P.job.n2 && P.job.halo_hi_px) {
-            src = P.job.halo_hi_px + (long long)(y - P.job.n2) * P.job.stride2 + c.col_off;
-            pf = false;
-        } else if (y + PF_LINES >= P.job.n2 && P.job.halo_hi_px) {
-            pf = false;
-        }
         mbar_expect_tx(bar, c.bytes);
         tma_load_1d(c.dst, src, c.bytes, bar);
-        if (pf) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + pf_off), "r"(c.bytes) : "memory");
+        if (pf)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + (long long)PF_LINES * P.job.stride2), "r"(c.bytes)
+                         : "memory");
     }
     return true;
 }
@@ -358,14 +380,30 @@ __device__ __forceinline__ void categorize_line(const FastParams& P, const uint8
     uint32_t Wp[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) Wp[j] = 0u;
+#ifdef MR_KO_STAGECONF   // timing experiment: conflict-free staging reads (wrong bytes)
+    const uint8_t* mine = staged + lane * 16;
+#else
     const uint8_t* mine = staged + lane * 96;
+#endif
     // rounds run from the last 16 pixels to the first so that "Wp = Wp * 256 + label" (one IMAD on
     // the FMA pipe) leaves pixels 8k+j in byte k of register j.
+#ifdef MR_KO_CAT   // timing experiment: no categorise arithmetic (labels from the line number)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) Wp[j] = 0x01010101u * (uint32_t)(((y + lane) >> 4) & 7);
+    for (int h = 1; h >= 2; --h) {
+#else
+    // 16-byte reads at a lane stride of 96 bytes: lanes l and l + 4 of a quarter warp would hit the
+    // same banks.  Lanes with bit 2 set therefore read the two 48-byte halves of their word in the
+    // opposite order (bank offset 3 chunks = odd: all eight lanes of a quarter warp fall into
+    // different bank groups) and swap the halves of their label registers back below.
+    const int hswap = (lane >> 2) & 1;
 #pragma unroll
     for (int h = 1; h >= 0; --h) {
-        const uint4 v0 = *reinterpret_cast<const uint4*>(mine + 48 * h);
-        const uint4 v1 = *reinterpret_cast<const uint4*>(mine + 48 * h + 16);
-        const uint4 v2 = *reinterpret_cast<const uint4*>(mine + 48 * h + 32);
+#endif
+        const uint8_t* half = mine + 48 * (h ^ hswap);
+        const uint4 v0 = *reinterpret_cast<const uint4*>(half);
+        const uint4 v1 = *reinterpret_cast<const uint4*>(half + 16);
+        const uint4 v2 = *reinterpret_cast<const uint4*>(half + 32);
         const uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
 #pragma unroll
         for (int g = 3; g >= 0; --g) {   // 4 pixels = 12 bytes: [r0 g0 b0 r1] [g1 b1 r2 g2] [b2 r3 g3 b3]
@@ -386,9 +424,16 @@ __device__ __forceinline__ void categorize_line(const FastParams& P, const uint8
             Wp[j + 3] = Wp[j + 3] * 256u + lds_u8(i3);
         }
     }
-    if (it.edge) {   // warp-uniform: force VOID outside [0, n1)
+    {   // lanes that read the halves in the opposite order: pixels 0..15 sit in bytes 2, 3 -> swap
+        const uint32_t sel = hswap ? 0x1032u : 0x3210u;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) Wp[j] |= ((~M.vmask >> j) & 0x01010101u) * 0xFFu;
+        for (int j = 0; j < 8; ++j) Wp[j] = __byte_perm(Wp[j], 0u, sel);
+    }
+    if (it.edge) {   // warp-uniform: force VOID outside [0, n1)
+        uint32_t nv = ~M.vmask;
+        asm volatile("" : "+r"(nv));   // keeps the eight masks out of registers and the branch a real one
+#pragma unroll
+        for (int j = 0; j < 8; ++j) Wp[j] |= ((nv >> j) & 0x01010101u) * 0xFFu;
     }
     const bool own_line = (y >= it.y0) && (y < it.y1);
     const uint32_t ownmask = own_line ? M.avalid : 0u;
@@ -405,20 +450,15 @@ __device__ __forceinline__ void categorize_line(const FastParams& P, const uint8
         const uint8_t* c3 = mine + 3 * q;
         return (unsigned)c3[0] | ((unsigned)c3[1] << 8) | ((unsigned)c3[2] << 16);
     };
-    int q0 = 0, q1 = 0;
-    unsigned rgb0 = 0, rgb1 = 0;
-    const bool h0 = s != 0u;
-    if (h0) {
-        q0 = __ffs(s) - 1;
-        s &= s - 1;
-        rgb0 = colour(q0);
-    }
-    const bool h1 = s != 0u;
-    if (h1) {
-        q1 = __ffs(s) - 1;
-        s &= s - 1;
-        rgb1 = colour(q1);
-    }
+    // branch-free capture: bq = the isolated bit of the pixel (0: the word has no such pixel; its
+    // colour read then hits pixel -1 of the lane's bytes, still inside the warp's slice, and is unused)
+    const uint32_t bq0 = s & (0u - s);
+    s ^= bq0;
+    const uint32_t bq1 = s & (0u - s);
+    s ^= bq1;
+    const int q0 = 31 - __clz(bq0), q1 = 31 - __clz(bq1);
+    const unsigned rgb0 = colour(q0), rgb1 = colour(q1);
+    const bool h0 = bq0 != 0u, h1 = bq1 != 0u;
     const bool more = __any_sync(0xffffffffu, s != 0u);
     if (!more) after_read();
     unsigned l0 = 0, l1 = 0;
@@ -478,6 +518,7 @@ __device__ __forceinline__ void categorize_line(const FastParams& P, const uint8
         uint32_t T[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) T[j] = Wp[j];
+#ifndef MR_KO_TRANSPOSE
 #pragma unroll
         for (int st = 0; st < 3; ++st) {
             const int d = 1 << st;
@@ -490,12 +531,18 @@ __device__ __forceinline__ void categorize_line(const FastParams& P, const uint8
                 T[j + d] = ((x >> d) & m) | (y2 & ~m);
             }
         }
-        auto apply = [&](int q, unsigned l) {   // MIXED = all ones: clear the zero bits of the label
-            const uint32_t bitq = 1u << q;
+#endif
+        auto apply = [&](uint32_t bitq, unsigned l) {   // MIXED = all ones: clear the zero bits of the label
+            const uint32_t keep = ~bitq;                 // bitq == 0 (no such pixel): nothing changes
 #pragma unroll
-            for (int b = 0; b < NB; ++b)
-                if (!((l >> b) & 1u)) T[b] &= ~bitq;
-            c_fine += (ownmask >> q) & 1u;
+            for (int b = 0; b < NB; ++b) {
+                asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+                    "and.b32 t, %2, %3;\n\t"
+                    "setp.eq.u32 p, t, 0;\n\t"
+                    "@p and.b32 %0, %0, %1;\n\t}"
+                    : "+r"(T[b]) : "r"(keep), "r"(l), "r"(1u << b));
+            }
+            if (COUNT) c_fine += (ownmask & bitq) != 0u;
         };
         if (more) {
 #pragma unroll 1
@@ -519,12 +566,12 @@ __device__ __forceinline__ void categorize_line(const FastParams& P, const uint8
                 }
 #pragma unroll
                 for (int t = 0; t < WIDE; ++t)
-                    if (hh[t]) apply(qq[t], ll[t]);
+                    if (hh[t]) apply(1u << qq[t], ll[t]);
             }
             after_read();
         }
-        if (h0) apply(q0, l0);
-        if (h1) apply(q1, l1);
+        apply(bq0, l0);
+        apply(bq1, l1);
         // vote word `lane` starts at wx = O0 + lane*U: funnel of aligned words k, k+1
         const int o = G::O0 + lane * G::U;
         const int k = o >> 5, sh = o & 31;
@@ -759,9 +806,9 @@ __device__ __forceinline__ void vote_word(const FastParams& P, uint8_t* ws, cons
 // Returns the number of lines completed: the block is cut short if the round-2 list could overflow
 // (the caller votes the rest after emptying the list).
 template <int R, int NB, bool COUNT>
-__device__ __forceinline__ int block_vote(const FastParams& P, uint8_t* ws, const Item& it, int a, int nl, int vl,
-                                           uint32_t mask, uint32_t obytes, unsigned& hint, unsigned& c_nomatch,
-                                           unsigned& c_changed) {
+__device__ __forceinline__ int block_vote(const FastParams& P, uint8_t* ws, const Item& it, int a,
+                                           int nl, int vl, uint32_t mask, uint32_t obytes, unsigned& hint,
+                                           unsigned& c_nomatch, unsigned& c_changed) {
     using G = Geo<R>;
     using C = Cfg<R, NB>;
     constexpr int SIDE = 2 * R + 1;
@@ -821,27 +868,30 @@ __device__ __forceinline__ int block_vote(const FastParams& P, uint8_t* ws, cons
         LA[b] = 0u - ((a_lab >> b) & 1u);
         LB[b] = 0u - ((b_lab >> b) & 1u);
     }
-    // ---- slide down the block
-    Bs<WC> SA, SB;
+    // ---- slide down the block.  Counted per pixel: cA = window pixels equal to A, cU = window pixels
+    // equal to A or B (the masks are disjoint).  The better of {A, B} is certainly the mode when
+    // cA >= N/2 + 1 (strict majority), or when cU >= 2N/3 + 1: then max(cA, cB) >= ceil(cU / 2) exceeds
+    // the N - cU pixels every other label could have.  Winner: A iff 2 cA > cU, ties -> lower label.
+    constexpr unsigned TA = N / 2 + 1, TU = 2 * N / 3 + 1;
+    Bs<WC> SA, SU;
 #pragma unroll
-    for (int k = 0; k < WC; ++k) SA.b[k] = SB.b[k] = 0u;
-    Bs<WH> HA[SIDE], HB[SIDE];        // horizontal window sums of the last 2R+1 lines (oldest first)
-    uint32_t cA = 0u, cB = 0u;        // COUNT: match masks of the last R+1 lines packed away below
-    uint32_t hA[R + 1], hB[R + 1];
+    for (int k = 0; k < WC; ++k) SA.b[k] = SU.b[k] = 0u;
+    Bs<WH> HA[SIDE], HU[SIDE];        // horizontal window sums of the last 2R+1 lines (oldest first)
+    uint32_t hA[R + 1], hB[R + 1];    // COUNT: match masks of the last R+1 lines
 #pragma unroll
     for (int d = 0; d < SIDE; ++d) {
 #pragma unroll
-        for (int k = 0; k < WH; ++k) HA[d].b[k] = HB[d].b[k] = 0u;
+        for (int k = 0; k < WH; ++k) HA[d].b[k] = HU[d].b[k] = 0u;
     }
 #pragma unroll
     for (int d = 0; d <= R; ++d) hA[d] = hB[d] = 0u;
-    (void)cA; (void)cB;
     int off = ((a - it.y0) % C::RL) * LINE;   // slot of line a - R
     int n_listed = 0;   // entries this call has put on the round-2 list (warp-uniform)
-    uint8_t* gline = it.out + (long long)a * P.job.out_stride2 + it.xw0 + 32 * G::HW;   // strip start, line a
+    // first byte of output line a of this strip (warp-uniform: the bulk store takes uniform operands)
+    const uint8_t* gline = it.out + (long long)a * P.job.out_stride2 + it.xw0 + 32 * G::HW;
     uint8_t* obuf = ws + C::W_OUT + vl * G::U;
     const uint32_t obuf0 = smem_u32(ws + C::W_OUT);
-    const uint32_t AB = a_lab ^ b_lab, B4 = b_lab * 0x01010101u;
+    const uint32_t B4 = b_lab * 0x01010101u;
 #pragma unroll 1
     for (int i = 0; i < nl + 2 * R; ++i) {
         uint32_t ma = avm, mb = nbm;
@@ -856,12 +906,12 @@ __device__ __forceinline__ int block_vote(const FastParams& P, uint8_t* ws, cons
 #pragma unroll
         for (int d = 0; d < SIDE - 1; ++d) {
             HA[d] = HA[d + 1];
-            HB[d] = HB[d + 1];
+            HU[d] = HU[d + 1];
         }
         HA[SIDE - 1] = bs_hsum1<R>(ma);
-        HB[SIDE - 1] = bs_hsum1<R>(mb);
+        HU[SIDE - 1] = bs_hsum1<R>(ma | mb);
         SA = bs_add<WC, WH, WC>(SA, HA[SIDE - 1]);
-        SB = bs_add<WC, WH, WC>(SB, HB[SIDE - 1]);
+        SU = bs_add<WC, WH, WC>(SU, HU[SIDE - 1]);
         if (COUNT) {   // the centre line's own match masks (line i - R) tell whether its label changed
 #pragma unroll
             for (int d = 0; d < R; ++d) {
@@ -872,21 +922,22 @@ __device__ __forceinline__ int block_vote(const FastParams& P, uint8_t* ws, cons
             hB[R] = mb;
         }
         if (i >= 2 * R) {
-            // ---- decide output line a + i - 2R: winner of {A, B} is the mode iff max > N - cA - cB
-            uint32_t eq;
-            const uint32_t bgt = bs_gt<WC>(SB, SA, &eq);
-            const uint32_t selA = ~bgt & (~eq | a_lower);
-            const Bs<WC> mx = bs_sel<WC>(bgt, SB, SA), mn = bs_sel<WC>(bgt, SA, SB);
-            Bs<WC + 1> mx2;
-            mx2.b[0] = 0u;
+            // ---- decide output line a + i - 2R
+            const uint32_t decided = bs_gt_const<WC>(SU, TU - 1u) | bs_gt_const<WC>(SA, TA - 1u);
+            uint32_t gt = SA.b[WC - 1], eq = ~SA.b[WC - 1];   // 2 cA (WC + 1 bits) against cU
 #pragma unroll
-            for (int k = 0; k < WC; ++k) mx2.b[k + 1] = mx.b[k];
-            const Bs<WC + 2> u = bs_add<WC + 1, WC, WC + 2>(mx2, mn);
-            const uint32_t decided = bs_gt_const<WC + 2>(u, (unsigned)N);
+            for (int k = WC - 1; k >= 1; --k) {
+                gt |= eq & SA.b[k - 1] & ~SU.b[k];
+                eq &= ~(SA.b[k - 1] ^ SU.b[k]);
+            }
+            eq &= ~SU.b[0];
+            const uint32_t selA = gt | (eq & a_lower);
             const uint32_t now = decided & mask;
             const uint32_t undec = ~decided & mask;
             // ---- the line buffer is free once the previous line's bulk store has read it
+#ifndef MR_KO_STORE
             if (vl == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#endif
             __syncwarp();
             if (n_listed > LIST_CAP - 32) return i - 2 * R;   // warp-uniform
             n_listed += __popc(__ballot_sync(0xffffffffu, undec != 0u));
@@ -894,9 +945,11 @@ __device__ __forceinline__ int block_vote(const FastParams& P, uint8_t* ws, cons
                 c_changed += __popc(now & ~((selA & hA[0]) | (~selA & hB[0])));   // centre label != winner
                 c_nomatch += __popc(now & ((a_lab == 0 ? selA : 0u) | (b_lab == 0 ? ~selA : 0u)));
             }
-            {   // labels of the U output pixels: B ^ (selA ? A ^ B : 0), GP pixels (bytes) per step
+            {   // labels of the U output pixels, B ^ (selA ? A ^ B : 0): eight pixels per step through the
+                // bit -> byte expansion table (one 8-byte entry per byte of selA)
                 const uint32_t sel = selA >> R;
                 constexpr int GP = (G::U % 4 == 0) ? 4 : 2;
+                const uint32_t AB = a_lab ^ b_lab;
 #pragma unroll
                 for (int k = 0; k < G::U / GP; ++k) {
                     const uint32_t nib = (sel >> (GP * k)) & ((1u << GP) - 1u);
@@ -906,9 +959,15 @@ __device__ __forceinline__ int block_vote(const FastParams& P, uint8_t* ws, cons
                     else *reinterpret_cast<uint16_t*>(obuf + 2 * k) = (uint16_t)v;
                 }
             }
+#ifndef MR_KO_FENCE
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
             __syncwarp();
+#ifdef MR_KO_STORE
+            if (false) {
+#else
             if (vl == 0 && obytes) {
+#endif
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gline), "r"(obuf0),
                              "r"(obytes) : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -921,7 +980,7 @@ __device__ __forceinline__ int block_vote(const FastParams& P, uint8_t* ws, cons
                 reinterpret_cast<uint32_t*>(ws + C::W_W2MASK)[e] = undec;
             }
             SA = bs_sub<WC, WH>(SA, HA[0]);
-            SB = bs_sub<WC, WH>(SB, HB[0]);
+            SU = bs_sub<WC, WH>(SU, HU[0]);
         }
     }
     return nl;
@@ -973,7 +1032,8 @@ template <int R, int NB, bool COUNT, bool LIN>
 __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastParams P) {
     using C = Cfg<R, NB>;
     extern __shared__ __align__(128) uint8_t sm[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler: the TMA operands live in uniform registers
     uint8_t* ws = sm + C::SLICES + warp * C::W_BYTES;         // this warp's private slice
     const uint8_t* coarse = sm;
     int* cnt = reinterpret_cast<int*>(ws + C::W_CNT);
@@ -1008,10 +1068,9 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
         // loadable lines of this item (none if the strip window has no bytes inside the sheet)
         const int ylo = max(ycat, -P.job.halo_lo);
         const int yhi = plan.bytes ? min(cat_last, (int)P.job.n2 + P.job.halo_hi) : ylo;
-        const long long pf_off = (long long)PF_LINES * P.job.stride2;
-        const uint8_t* srcn = plan.src0 + (long long)ycat * P.job.stride2;   // source of the next line to copy
-        bool pend = issue_line_copy(P, plan, srcn, pf_off, ycat, ylo, yhi, bar, lane);
-        srcn += P.job.stride2;
+        const int pflo = P.job.halo_lo_px ? max(ylo, 0) : ylo;
+        const int pfhi = P.job.halo_hi_px ? min(yhi, (int)P.job.n2) : yhi;
+        bool pend = issue_line_copy(P, plan, ycat, ylo, yhi, pflo, pfhi, bar, lane);
         // bytes of one output line of the strip (whole 16-byte chunks, see mr_fast_supported)
         uint32_t obytes = 0;
         if (R > 0) {
@@ -1037,8 +1096,7 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
                 bool nxt = false;
                 auto release = [&]() {
                     __syncwarp();   // every lane is done with the staging buffer
-                    nxt = issue_line_copy(P, plan, srcn, pf_off, ycat + 1, ylo, yhi, bar, lane);
-                    srcn += P.job.stride2;
+                    nxt = issue_line_copy(P, plan, ycat + 1, ylo, yhi, pflo, pfhi, bar, lane);
                 };
                 if constexpr (LIN)
                     labels_line<R, NB>(ws, it, ycat, lane, M, pend ? stage : nullptr, release);
@@ -1052,12 +1110,21 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
                 // round 1 produced, densely over the lanes
 #pragma unroll 1
                 for (int va = a; va < vend;) {
+#ifdef MR_KO_VOTE   // timing experiment: no vote at all
+                break;
+#endif
                 const int done = block_vote<R, NB, COUNT>(P, ws, it, va, vend - va, lane, M.vvalid, obytes, hint, c_nomatch,
                                                           c_changed);
                 __syncwarp();
+#ifdef MR_KO_ROUND2
+                if (lane == 0) { cnt[1] = 0; cnt[2] = 0; }
+                __syncwarp();
+#endif
                 const int n2 = cnt[1];
                 if (n2) {   // byte patches follow: the bulk stores of this block must have landed
+#ifndef MR_KO_WAIT
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#endif
                     __syncwarp();
                 }
 #pragma unroll 1
@@ -1074,7 +1141,11 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
                 }
                 __syncwarp();
                 {   // ---- exact votes of what is still undecided, spread evenly over the lanes
+#ifdef MR_KO_EXACT
+                    const int n = 0;
+#else
                     const int n = cnt[2];
+#endif
                     for_each_pixel(reinterpret_cast<const uint16_t*>(ws + C::W_W2CODE),
                                    reinterpret_cast<const uint32_t*>(ws + C::W_W2MASK), n, lane, [&](int code, int q) {
                                        exact_pixel<R, NB, COUNT>(P, ws, it, va, code, q, c_nomatch, c_changed);
@@ -1241,11 +1312,16 @@ cudaError_t mr_launch_fast(const MrJob& job, int sm_count, cudaStream_t s, int* 
     P.work_counter = ctr;
     P.padded = job.padded;
     const int K = job.pal.K;
+#ifdef MR_QUICK   // kernel experiments: only the BASELINE config 2 instantiation (fast to compile)
+    if (job.R == 2 && K > 14 && K <= 30) e = launch_c<2, 5>(P, sm_count, s);
+    else e = cudaErrorNotSupported;
+#else
     if (job.R == 0) e = launch_c<0, 4>(P, sm_count, s);
     else if (K <= 14) e = launch_r<4>(P, sm_count, s);
     else if (K <= 30) e = launch_r<5>(P, sm_count, s);
     else if (K <= 62) e = launch_r<6>(P, sm_count, s);
     else e = launch_r<7>(P, sm_count, s);
+#endif
     if (e == cudaSuccess) *n_launches += 1;
     return e;
 }
