@@ -5,12 +5,14 @@
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one pass of the hot path over the whole synthetic sheet (SURVEY.md 8(d) generator).
-  N = 1 : BASELINE config 2 -- 20000 x 20000 RGB{N0f8}, 16-colour palette, clean window 5 (R = 2).
-  N > 1 : the same sheet shape per GPU (weak scaling): one 20000 x (20000*N) sheet split into N
-          row bands, one fused launch per rank and step.  The R halo lines of a band are read in
+  N = 1 : BASELINE config 2 -- 20000 x 20000 RGB{N0f8}, 16-colour palette, clean window 5 (R = 2);
+          configs 1, 3, 4 and 5 are measured beside it (`next_rows.cfg*`, each with its roofline).
+  N > 1 : BASELINE config 3 -- the 60000 x 40000 (2.4 Gpx) sheet split into N row bands (STRONG
+          scaling), one fused launch per rank and step.  The R halo lines of a band are read in
           place from the neighbour band's HBM (CUDA IPC peer memory over NVLink, --halo peer, the
-          default) or exchanged with NCCL send/recv before every launch (--halo nccl).
-          --workload cfg3 / cfg5 select BASELINE configs 3 and 5 instead.
+          default) or exchanged with NCCL send/recv before every launch (--halo nccl).  Config 5
+          (256 sheets of 4096 x 4096, whole sheets per rank) is measured beside it.
+          --workload weak2 = one config-2 sheet per GPU (weak scaling); cfgN = that config.
 `value` times device-resident inputs; `e2e` times the public host-buffer API (pinned host
 memory -> H2D -> kernel -> D2H) for the same sheet.  Prints ONE JSON line on rank 0.
 The CPU oracle (oracle/) is only used for the cpu_baseline leg and for --impl reference.
@@ -38,7 +40,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "weak2", "cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
     ap.add_argument("--halo", default="auto", choices=["auto", "peer", "nccl"],
                     help="N > 1 bands: read the halo lines in place from the neighbour's HBM (CUDA IPC peer "
@@ -46,6 +48,14 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
+
+
+def host_cores():
+    """Cores this process may run on (affinity mask), not what OMP_NUM_THREADS says."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
 
 
 def measured_peak():
@@ -124,12 +134,12 @@ class ClockSampler:
 def workload_spec(args, world):
     from maprast_b200 import synth
     wl = args.workload
-    if wl == "auto":
-        wl = "cfg2"
-    cfg = int(wl[3])
+    if wl == "auto":                 # the sheet north_star names for this GPU count
+        wl = "cfg2" if world == 1 else "cfg3"
+    cfg = 2 if wl == "weak2" else int(wl[3])
     seed, palrgb, stats, spec = synth.config_workload(cfg)
     spec = dict(spec)
-    if args.workload == "auto" and world > 1:
+    if wl == "weak2" and world > 1:
         spec["n2"] = spec["n2"] * world          # weak scaling: one config-2 sheet per GPU
         name = (f"weak: {spec['n1']}x{spec['n2']} sheet = {world} row bands of BASELINE config 2 "
                 f"(20000x20000, K=16, window 5), R=2 halo lines per band edge (see config.halo)")
@@ -141,7 +151,7 @@ def workload_spec(args, world):
                  4: "BASELINE config 4: 20000x20000, K=64 Lab distance + box, window 7",
                  5: "BASELINE config 5: batch of 256 sheets 4096x4096, K=16, window 5, whole sheets per GPU"}
         name = names[cfg]
-        scaling = "weak" if world == 1 else "strong"
+        scaling = "strong"    # total work fixed: the driver's N = 1 point is config 2, N > 1 is config 3 (same Mpx/s metric)
     return cfg, seed, palrgb, stats, spec, name, scaling
 
 
@@ -153,26 +163,31 @@ def run_reference(args, rank, world):
     same workload."""
     if rank != 0:
         return
+    # every host core, whatever the launcher exported: torch.distributed.run sets OMP_NUM_THREADS=1
+    # for its workers, which would time one thread against N GPUs
+    cores = host_cores()
+    os.environ["OMP_NUM_THREADS"] = str(cores)
     import numpy as np
     from oracle import oracle as O
     cfg, seed, palrgb, stats, spec, name, scaling = workload_spec(args, max(args.gpus, 1))
-    cores = O.max_threads()
     cs = O.LAB if stats.colourspace == "lab" else O.RGB
     n1 = spec["n1"]
-    # size the per-step sample so that warmup+steps stay within ~2 minutes
+    run = lambda sc: O.categorize_clean(sc, stats.mean, stats.lo, stats.hi, spec["R"], cs, nthreads=cores)  # noqa: E731
+    # size the per-step sample so that warmup+steps stay within ~2 minutes (same rule at every N)
     probe_lines = max(8, min(spec["n2"], (1 << 21) // n1))
-    scan = O.synth_scan(seed, 0, palrgb, n1, spec["n2"], 0, probe_lines)
+    scan = O.synth_scan(seed, 0, palrgb, n1, spec["n2"], 0, probe_lines, nthreads=cores)
+    run(scan)
     t0 = time.perf_counter()
-    O.categorize_clean(scan, stats.mean, stats.lo, stats.hi, spec["R"], cs)
+    run(scan)
     rate = n1 * probe_lines / (time.perf_counter() - t0)        # px/s
     budget = 90.0 / max(1, args.steps + args.warmup)
     lines = int(min(spec["n2"], max(probe_lines, rate * min(budget, 10.0) / n1)))
-    scan = O.synth_scan(seed, 0, palrgb, n1, spec["n2"], 0, lines)
+    scan = O.synth_scan(seed, 0, palrgb, n1, spec["n2"], 0, lines, nthreads=cores)
     for _ in range(args.warmup):
-        O.categorize_clean(scan, stats.mean, stats.lo, stats.hi, spec["R"], cs)
+        run(scan)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.categorize_clean(scan, stats.mean, stats.lo, stats.hi, spec["R"], cs)
+        run(scan)
     dt = (time.perf_counter() - t0) / args.steps
     mpx = n1 * lines / dt / 1e6
     sample = f"first {lines} lines ({n1 * lines / 1e6:.1f} Mpx) of the sheet per step, {cores} OpenMP threads"
@@ -188,6 +203,76 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------ our arm
+def measure_config(mr, cfg, dev, peak, reps=5, sheets=None):
+    """Fused kernel on BASELINE config `cfg`, one GPU, device-resident input: dict with value + roofline.
+    Its own context (own palette); buffers are freed on return.  sheets: config-5 share of this GPU."""
+    import torch
+    from maprast_b200 import synth
+    seed, palrgb, stats, spec = synth.config_workload(cfg)
+    n1, n2, R, K = spec["n1"], spec["n2"], spec["R"], spec["K"]
+    s0, s1 = sheets if sheets else (0, spec["n_sheets"])
+    ns = s1 - s0
+    ctx = mr.Context(dev.index)
+    try:
+        ctx.set_palette(stats.mean, stats.lo, stats.hi, mr._lib.LAB if stats.colourspace == "lab" else mr._lib.RGB)
+        px = torch.empty((ns, n2, n1, 3), dtype=torch.uint8, device=dev)
+        for s in range(ns):
+            ctx.synth_scan_dev(seed, s0 + s, palrgb, n1, n2, 0, n2, px[s], n1 * 3)
+        out = torch.empty((ns, n2, n1), dtype=torch.uint8, device=dev)
+
+        def step():
+            if ns > 1:
+                ctx.batch_categorize_clean_dev(ns, px, n1 * n2 * 3, n1, n2, n1 * 3, 3, R, out, n1 * n2, n1)
+            else:
+                ctx.categorize_clean_dev(px[0], n1, n2, n1 * 3, 3, R, out[0], n1)
+        npx = ns * n1 * n2
+        small = npx * ALGO_BYTES_PER_PX < (512 << 20)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if small else None
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(reps):
+            if small:
+                flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step()
+            b.record()
+            torch.cuda.synchronize()
+            ms.append(a.elapsed_time(b))
+        med = statistics.median(ms)
+        ach = ALGO_BYTES_PER_PX * npx / (med * 1e-3) / 1e9
+        return {"what": f"BASELINE config {cfg}: {ns} x {n1}x{n2}, K={K}, window {2 * R + 1}, {stats.colourspace}, device resident, one launch per step",
+                "value": npx / (med * 1e-3) / 1e6, "unit": UNIT, "ms_median": med, "ms_min": min(ms), "pixels": npx,
+                "palette_table_build_ms": ctx.palette_build_ms(),
+                "cache": "L2 flushed before every step" if small else "input larger than L2",
+                "roofline": {"bound": "hbm", "algorithmic_bytes_per_px": ALGO_BYTES_PER_PX, "achieved": ach, "peak": peak,
+                             "unit": "GB/s", "frac": ach / peak}}
+    finally:
+        ctx.close()
+
+
+def copy_ceiling(host_in, host_out, dev, reps=3):
+    """Pure pinned H2D || D2H of the e2e step's bytes on two streams of this rank (no kernel): seconds per step."""
+    import torch
+    d_in = torch.empty_like(host_in, device=dev)
+    d_out = torch.empty_like(host_out, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    best = None
+    for _ in range(reps + 1):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s1):
+            d_in.copy_(host_in, non_blocking=True)
+        with torch.cuda.stream(s2):
+            host_out.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return best
+
+
 def run_ours(args, rank, world, local_rank):
     import numpy as np
     import torch
@@ -335,17 +420,41 @@ def run_ours(args, rank, world, local_rank):
     e2e_value = total_px / float(t.item()) / 1e6
     # e2e labels must equal the device-resident labels (same code path, same bytes)
     same = bool(torch.equal(host_out.to(dev).view(-1), out.view(-1)))
+    # what the host side alone allows: the same bytes over the same kind of streams, no kernel
+    barrier()
+    t = torch.tensor([copy_ceiling(host_in, host_out, dev)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ceiling = total_px / float(t.item()) / 1e6
+    del host_in, host_out, hin, hout
+    peak, peak_src = measured_peak()
+    # ---- the other BASELINE configs beside the headline one (same kernel, same call)
+    extra = {}
+    if world == 1:
+        for c in (1, 3, 4, 5):
+            if c != cfg:
+                extra[f"cfg{c}"] = measure_config(mr, c, dev, peak)
+    elif cfg != 5:   # batch of 256 sheets, whole sheets per rank, no halo (every rank takes part)
+        sh = D.sheet_range(256, world, rank)
+        r5 = measure_config(mr, 5, dev, peak, sheets=sh)
+        t = torch.tensor([r5["ms_median"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        px5 = 256 * 4096 * 4096
+        r5["value"] = px5 / (float(t.item()) * 1e-3) / 1e6
+        r5["what"] = f"BASELINE config 5: 256 sheets 4096x4096 over {world} GPUs ({sh[1] - sh[0]} per GPU), no halo; value = all sheets / slowest rank"
+        r5["roofline"]["note"] = "rank 0's share against one GPU's peak"
+        extra["cfg5"] = r5
 
     if rank != 0:
         return
-    peak, peak_src = measured_peak()
     kern_ms = statistics.mean(step_ms)      # one fused launch per step on this stream
     launches_per_step = launches / args.steps
     achieved = ALGO_BYTES_PER_PX * my_px / (kern_ms * 1e-3) / 1e9
     wl_key = args.workload if args.workload != "auto" else "cfg2"
     res = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "ms_per_step_min": min(step_ms),
+        "ms_per_step_median": statistics.median(step_ms), "higher_is_better": True,
         "scaling": scaling, "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": name, "K": K, "R": R, "colourspace": stats.colourspace,
                    "pixels_total": total_px, "pixels_per_gpu": my_px,
@@ -358,7 +467,11 @@ def run_ours(args, rank, world, local_rank):
                      "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX * my_px,
                      "traffic": ncu_traffic(wl_key) if world == 1 else None},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(total_px * 3),
-                "d2h_bytes_per_step": int(total_px), "steps": e2e_steps, "labels_equal_device_path": same},
+                "d2h_bytes_per_step": int(total_px), "steps": e2e_steps, "labels_equal_device_path": same,
+                "ceiling": {"value": e2e_ceiling, "unit": UNIT,
+                            "what": "pinned H2D || D2H of the same bytes on two streams per rank, no kernel (max over ranks): "
+                                    "the host link, not the kernel, bounds the end-to-end number",
+                            "frac_of_ceiling": e2e_value / e2e_ceiling}},
         "gpu_launches": int(launches), "gpu_launches_per_step": launches_per_step,
         "clocks": clocks,
     }
@@ -376,6 +489,7 @@ def run_ours(args, rank, world, local_rank):
         "changed_by_clean_pixels": cnt["n_changed"],
         "value_unamortised_table_build": my_px / ((kern_ms + build_ms) * 1e-3) / 1e6,
         "note": "counters of rank 0's share; table build = 2^24 exact Float64 evaluations per palette, once per mr_set_palette"}
+    res["next_rows"] = dict(extra)
     if world == 1 and not batch and n1 * nb < (1 << 31):
         # ---- SURVEY 8(f) "next" row, measured beside the hot path: the reference's segment prune
         # (_clean, src/clean.jl:59-93) on the labels the fused kernel just produced (device resident)
@@ -393,13 +507,13 @@ def run_ours(args, rank, world, local_rank):
         e1.record()
         torch.cuda.synchronize()
         seg_ms = e0.elapsed_time(e1) / reps
-        res["next_rows"] = {"clean_segments": {
+        res["next_rows"]["clean_segments"] = {
             "what": "_clean(labels; categories=1..K, line_threshold=0.01, prune_threshold=20), device resident",
             "value": my_px / (seg_ms * 1e-3) / 1e6, "unit": UNIT, "ms": seg_ms, "segments": nseg,
             "gpu_launches_per_call": (ctx.launch_count() - l0) / reps,
             "roofline": {"bound": "hbm", "algorithmic_bytes_per_px": 2,
                          "achieved": 2 * my_px / (seg_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": 2 * my_px / (seg_ms * 1e-3) / 1e9 / peak}}}
+                         "frac": 2 * my_px / (seg_ms * 1e-3) / 1e9 / peak}}
         # the standalone Window majority filter, clean(labels; hood): categorise-only labels in, device resident
         pre = torch.empty_like(out)
         ctx.categorize_clean_dev(own, n1, nb, n1 * 3, 3, 0, pre, n1)

@@ -60,8 +60,13 @@ template <int R> struct Geo {
 // kernel configuration per (R, NB): warps per CTA and lines per block, sized so that one CTA
 // (coarse table + per-warp slices) fits the 227 KiB of shared memory of an SM.
 // The round-2 list holds one entry per 32-pixel WORD (code + pixel mask) and is capped (LIST_CAP).
+// One ring line = NB planes of 32 words, plus one word of skew: the words of one vote word on
+// consecutive lines then sit in consecutive banks (round 2 reads (line, word) pairs that mostly
+// share the word and differ in the line).
+__host__ __device__ constexpr int ring_line(int NB) { return NB * 128 + 4; }
+constexpr int ring_bytes(int R, int NB, int B) { return R > 0 ? ((B + 2 * R) * ring_line(NB) + 127) / 128 * 128 : 0; }
 constexpr int warp_bytes(int R, int NB, int B) {   // per-warp slice for B lines per block
-    const int raw = (B + 2 * R) * (R > 0 ? NB : 0) * 128 + stage_bytes(R) + LIST_CAP * 6 + (R > 0 ? 32 * (32 - 2 * R) : 0) + 24;
+    const int raw = ring_bytes(R, NB, B) + stage_bytes(R) + LIST_CAP * 6 + (R > 0 ? 32 * (32 - 2 * R) : 0) + 24;
     return (raw + 127) / 128 * 128;
 }
 constexpr int best_block(int R, int NB, int warps) {   // largest block that fits (at most 16 lines)
@@ -80,8 +85,8 @@ template <int R, int NB> struct Cfg {
     static constexpr int RL = B + 2 * R;                                       // plane ring, lines
     static constexpr int N_W2 = LIST_CAP;                                      // list capacity
     // per-warp slice (byte offsets)
-    static constexpr int W_PLANES = 0;                                 // uint32 [RL][NB][32]
-    static constexpr int W_STAGE = W_PLANES + RL * NBP * 128;          // uint8  [stage_bytes(R)]
+    static constexpr int W_PLANES = 0;                                 // uint32 [RL][NB * 32 + 1]
+    static constexpr int W_STAGE = W_PLANES + ring_bytes(R, NB, B);    // uint8  [stage_bytes(R)]
     static constexpr int W_LISTS = W_STAGE + stage_bytes(R);              // round-2 word list; the exact-vote list
     static constexpr int W_W2MASK = W_LISTS;                           // uint32 [N_W2]   overwrites it in place
     static constexpr int W_W2CODE = W_W2MASK + N_W2 * 4;               // uint16 [N_W2]
@@ -304,7 +309,7 @@ __device__ __forceinline__ void labels_line(uint8_t* ws, const Item& it, int y, 
     using G = Geo<R>;
     using C = Cfg<R, NB>;
     const int slot = (y - (it.y0 - R)) % C::RL;
-    uint32_t* pl = reinterpret_cast<uint32_t*>(ws + C::W_PLANES) + slot * NB * 32;
+    uint32_t* pl = reinterpret_cast<uint32_t*>(ws + C::W_PLANES) + slot * (ring_line(NB) / 4);
     if (!staged) {   // outside the sheet: VOID everywhere (warp-uniform)
         after_read();
 #pragma unroll
@@ -361,7 +366,7 @@ __device__ __forceinline__ void categorize_line(const FastParams& P, const uint8
     using G = Geo<R>;
     using C = Cfg<R, NB>;
     const int slot = (y - (it.y0 - R)) % C::RL;
-    uint32_t* pl = reinterpret_cast<uint32_t*>(ws + C::W_PLANES) + slot * NB * 32;
+    uint32_t* pl = reinterpret_cast<uint32_t*>(ws + C::W_PLANES) + slot * (ring_line(NB) / 4);
     if (!staged) {   // outside the sheet: VOID everywhere (warp-uniform)
         after_read();
         if (R > 0) {
@@ -450,15 +455,18 @@ __device__ __forceinline__ void categorize_line(const FastParams& P, const uint8
         const uint8_t* c3 = mine + 3 * q;
         return (unsigned)c3[0] | ((unsigned)c3[1] << 8) | ((unsigned)c3[2] << 16);
     };
-    // branch-free capture: bq = the isolated bit of the pixel (0: the word has no such pixel; its
-    // colour read then hits pixel -1 of the lane's bytes, still inside the warp's slice, and is unused)
+    // bq = the isolated bit of the pixel (0: the word has no such pixel).  Only the lanes that have
+    // one read its colour: these byte reads sit 96 bytes apart between lanes, i.e. up to eight lanes
+    // per bank -- issued by all 32 lanes they were a quarter of the kernel's shared-memory wavefronts.
     const uint32_t bq0 = s & (0u - s);
     s ^= bq0;
     const uint32_t bq1 = s & (0u - s);
     s ^= bq1;
     const int q0 = 31 - __clz(bq0), q1 = 31 - __clz(bq1);
-    const unsigned rgb0 = colour(q0), rgb1 = colour(q1);
     const bool h0 = bq0 != 0u, h1 = bq1 != 0u;
+    unsigned rgb0 = 0u, rgb1 = 0u;
+    if (h0) rgb0 = colour(q0);
+    if (h1) rgb1 = colour(q1);
     const bool more = __any_sync(0xffffffffu, s != 0u);
     if (!more) after_read();
     unsigned l0 = 0, l1 = 0;
@@ -659,7 +667,7 @@ template <int R, int NB>
 __device__ __forceinline__ void load_planes(const uint8_t* ws, const Item& it, int y, int vl,
                                             uint32_t (&Pl)[2 * R + 1][NB]) {
     using C = Cfg<R, NB>;
-    constexpr int LINE = NB * 128, RING = C::RL * LINE;
+    constexpr int LINE = ring_line(NB), RING = C::RL * LINE;
     const uint8_t* base = ws + C::W_PLANES + vl * 4;
     int off = ((y - it.y0) % C::RL) * LINE;   // slot of line y - R
 #pragma unroll
@@ -815,7 +823,7 @@ __device__ __forceinline__ int block_vote(const FastParams& P, uint8_t* ws, cons
     constexpr int N = SIDE * SIDE;
     constexpr int WH = R == 1 ? 2 : 3, WC = G::WC;
     constexpr unsigned VOIDL = (1u << NB) - 1u;
-    constexpr int LINE = NB * 128, RING = C::RL * LINE;
+    constexpr int LINE = ring_line(NB), RING = C::RL * LINE;
     const uint8_t* base = ws + C::W_PLANES + vl * 4;
     // ---- candidates (heuristic only): A = label at the centre of the block, B = the label farthest
     // from the centre among the pixels of the centre line that differ from A; if the centre line

@@ -23,9 +23,15 @@ int mro_max_threads(void) {
 #endif
 }
 
+/* nthreads <= 0: the OpenMP default (OMP_NUM_THREADS); an explicit request is honoured up to the
+ * number of processors, even when a launcher exported OMP_NUM_THREADS=1 (torch.distributed.run). */
 static int clamp_threads(int nthreads) {
-    int m = mro_max_threads();
-    if (nthreads <= 0 || nthreads > m) nthreads = m;
+    if (nthreads <= 0) return mro_max_threads();
+#ifdef _OPENMP
+    if (nthreads > omp_get_num_procs()) nthreads = omp_get_num_procs();
+#else
+    nthreads = 1;
+#endif
     return nthreads;
 }
 
