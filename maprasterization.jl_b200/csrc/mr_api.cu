@@ -29,6 +29,7 @@ struct mr_ctx {
     uint8_t* d_known_cat = nullptr;
     // counters
     MrCountersDev* d_counters = nullptr;
+    MrWorkRing work;                // item queues of the fast kernel
     bool count_on = false;
     int64_t launches = 0;
     // grow-only device scratch for the host entry points
@@ -98,6 +99,8 @@ extern "C" mr_ctx* mr_create(int device, int* err) {
     ok = ok && cudaMalloc(&ctx->d_coarse, MR_COARSE_SIZE) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_counters, sizeof(MrCountersDev)) == cudaSuccess;
     ok = ok && cudaMemset(ctx->d_counters, 0, sizeof(MrCountersDev)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->work.slots, MR_WORK_SLOTS * sizeof(unsigned int)) == cudaSuccess;
+    ok = ok && cudaMemset(ctx->work.slots, 0, MR_WORK_SLOTS * sizeof(unsigned int)) == cudaSuccess;
     if (!ok) {
         if (g_err.empty()) fail(nullptr, MR_ERR_CUDA, "mr_create: CUDA initialisation failed");
         if (err) *err = MR_ERR_CUDA;
@@ -116,7 +119,7 @@ extern "C" void mr_destroy(mr_ctx* ctx) {
     for (auto e : ctx->ev_up) cudaEventDestroy(e);
     for (auto e : ctx->ev_done) cudaEventDestroy(e);
     cudaFree(ctx->d_pal); cudaFree(ctx->d_lut); cudaFree(ctx->d_coarse);
-    cudaFree(ctx->d_known_idx); cudaFree(ctx->d_known_cat); cudaFree(ctx->d_counters);
+    cudaFree(ctx->d_known_idx); cudaFree(ctx->d_known_cat); cudaFree(ctx->d_counters); cudaFree(ctx->work.slots);
     cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_tmp); cudaFree(ctx->d_rp_in); cudaFree(ctx->d_rp_out); cudaFree(ctx->d_lab);
     cudaFree(ctx->d_parent); cudaFree(ctx->d_runs); cudaFree(ctx->d_rec); cudaFree(ctx->d_small);
     if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
@@ -331,7 +334,7 @@ static int run_repacked(mr_ctx* ctx, const MrJob& job, cudaStream_t s, int* nl) 
     a.out = ctx->d_rp_out;
     a.out_stride2 = line_out;
     a.padded = 1;
-    cudaError_t e = mr_launch_fast(a, ctx->sm_count, s, nl);
+    cudaError_t e = mr_launch_fast(a, ctx->sm_count, s, nl, &ctx->work);
     if (e != cudaSuccess) return fail_cuda(ctx, e, "fused kernel launch (repacked lines)");
     CK(cudaMemcpy2DAsync(job.out, job.out_stride2, ctx->d_rp_out, line_out, job.n1, job.n2, cudaMemcpyDeviceToDevice, s));
     return MR_OK;
@@ -347,7 +350,7 @@ static int run_fused(mr_ctx* ctx, const MrJob& job, cudaStream_t s) {
     int nl = 0;
     cudaError_t e = cudaErrorNotSupported;
     if (mr_fast_supported(job)) {
-        e = mr_launch_fast(job, ctx->sm_count, s, &nl);
+        e = mr_launch_fast(job, ctx->sm_count, s, &nl, &ctx->work);
     } else if (repack_pays(job)) {
         const int rc = run_repacked(ctx, job, s, &nl);
         ctx->launches += nl;
@@ -386,7 +389,7 @@ static int run_clean(mr_ctx* ctx, const MrJob& job, cudaStream_t s, int max_labe
         e = cudaErrorNotSupported;
         if (max_label <= 126) {
             if (direct) {
-                e = mr_launch_fast(j, ctx->sm_count, s, &nl);
+                e = mr_launch_fast(j, ctx->sm_count, s, &nl, &ctx->work);
             } else {
                 const int rc = run_repacked(ctx, j, s, &nl);
                 ctx->launches += nl;
@@ -420,7 +423,7 @@ static int run_rgba(mr_ctx* ctx, const MrJob& job, cudaStream_t s) {
         MrJob c = job;   // categorise only, all T lines as one sheet
         c.px = ctx->d_rp_in; c.stride2 = line_rgb; c.bpp = 3; c.R = 0; c.n2 = T; c.halo_lo = c.halo_hi = 0;
         c.out = ctx->d_lab; c.out_stride2 = line_lab; c.padded = 1; c.lut = ctx->d_lut; c.counters = nullptr;
-        e = mr_launch_fast(c, ctx->sm_count, s, &nl);
+        e = mr_launch_fast(c, ctx->sm_count, s, &nl, &ctx->work);
     }
     if (e == cudaSuccess)
         e = mr_launch_alpha_fix(job.pal, px0, job.stride2, job.n1, T, ctx->d_lab, line_lab, d_special, s, &nl);
@@ -673,7 +676,7 @@ extern "C" int mr_categorize_clean_dev_peer(mr_ctx* ctx, const uint8_t* px_dev, 
                     "mr_categorize_clean_dev_peer: remote halo lines need the fast path (packed RGB, 16-byte aligned "
                     "lines and pointers, n1 % 16 == 0, R <= 3, K <= 126)");
     int nl = 0;
-    cudaError_t e = mr_launch_fast(job, ctx->sm_count, (cudaStream_t)stream, &nl);
+    cudaError_t e = mr_launch_fast(job, ctx->sm_count, (cudaStream_t)stream, &nl, &ctx->work);
     ctx->launches += nl;
     if (e != cudaSuccess) return fail_cuda(ctx, e, "fused kernel (remote halos)");
     return MR_OK;

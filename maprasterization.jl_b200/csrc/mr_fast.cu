@@ -33,6 +33,8 @@
 //
 // Reference semantics: src/categories.jl:76-133 (via the table built in mr_generic.cu) and the
 // north_star-defined majority filter, SURVEY.md Appendix A.3.
+#include <mutex>
+
 #include "mr_bitslice.h"
 #include "mr_internal.h"
 
@@ -114,7 +116,8 @@ struct FastParams {
     int n_classes;
     SchedClass cls[4];
     long long n_items;
-    unsigned int* work_counter;
+    unsigned int* work_counter;   // this launch's item queue (zero when the launch starts)
+    unsigned int* work_reset;     // a slot far ahead in the ring: zeroed here for a later launch (no memset per launch)
     int padded;   // lines are readable / writable up to the next multiple of 16 bytes
 };
 
@@ -816,7 +819,7 @@ __device__ __forceinline__ void vote_word(const FastParams& P, uint8_t* ws, cons
 template <int R, int NB, bool COUNT>
 __device__ __forceinline__ int block_vote(const FastParams& P, uint8_t* ws, const Item& it, int a,
                                            int nl, int vl, uint32_t mask, uint32_t obytes, unsigned& hint,
-                                           unsigned& c_nomatch, unsigned& c_changed) {
+                                           unsigned& c_nomatch, unsigned& c_changed, int& n_w2) {
     using G = Geo<R>;
     using C = Cfg<R, NB>;
     constexpr int SIDE = 2 * R + 1;
@@ -947,8 +950,14 @@ __device__ __forceinline__ int block_vote(const FastParams& P, uint8_t* ws, cons
             if (vl == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 #endif
             __syncwarp();
-            if (n_listed > LIST_CAP - 32) return i - 2 * R;   // warp-uniform
-            n_listed += __popc(__ballot_sync(0xffffffffu, undec != 0u));
+            if (n_listed > LIST_CAP - 32) {   // warp-uniform
+                n_w2 = n_listed;
+                return i - 2 * R;
+            }
+            // list slot of this word: entries so far + the undecided words of the lanes below (no atomic)
+            const uint32_t bal = __ballot_sync(0xffffffffu, undec != 0u);
+            const int e = n_listed + __popc(bal & ((1u << vl) - 1u));
+            n_listed += __popc(bal);
             if (COUNT) {
                 c_changed += __popc(now & ~((selA & hA[0]) | (~selA & hB[0])));   // centre label != winner
                 c_nomatch += __popc(now & ((a_lab == 0 ? selA : 0u) | (b_lab == 0 ? ~selA : 0u)));
@@ -982,8 +991,6 @@ __device__ __forceinline__ int block_vote(const FastParams& P, uint8_t* ws, cons
             }
             gline += P.job.out_stride2;
             if (undec) {
-                int* cnt = reinterpret_cast<int*>(ws + C::W_CNT);
-                const int e = atomicAdd(cnt + 1, 1);
                 reinterpret_cast<uint16_t*>(ws + C::W_W2CODE)[e] = (uint16_t)(((i - 2 * R) << 5) | vl);
                 reinterpret_cast<uint32_t*>(ws + C::W_W2MASK)[e] = undec;
             }
@@ -991,6 +998,7 @@ __device__ __forceinline__ int block_vote(const FastParams& P, uint8_t* ws, cons
             SU = bs_sub<WC, WH>(SU, HU[0]);
         }
     }
+    n_w2 = n_listed;
     return nl;
 }
 
@@ -1062,6 +1070,7 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
     unsigned c_fine = 0, c_nomatch = 0, c_changed = 0;
     uint32_t parity = 0;
 
+    if (blockIdx.x == 0 && tid == 0) *P.work_reset = 0u;
     unsigned next = 0;
     if (lane == 0) next = atomicAdd(P.work_counter, 1u);
     next = __shfl_sync(0xffffffffu, next, 0);
@@ -1091,8 +1100,8 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
             const int vend = min(a + C::B, it.y1);
             if (vend == it.y1) {   // last block: fetch the following item now (earlier would hoard an item
                                    // that an idle warp could already be working on)
+                // only lane 0 holds the answer until the item ends: nobody waits for the atomic's trip to L2
                 if (lane == 0) next = atomicAdd(P.work_counter, 1u);
-                next = __shfl_sync(0xffffffffu, next, 0);
             }
             // ---- categorise lines [ycat, vend + R); each arrives by TMA, issued one line ahead
 #pragma unroll 1
@@ -1121,14 +1130,13 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
 #ifdef MR_KO_VOTE   // timing experiment: no vote at all
                 break;
 #endif
+                int n2 = 0;   // entries round 1 put on the word list
                 const int done = block_vote<R, NB, COUNT>(P, ws, it, va, vend - va, lane, M.vvalid, obytes, hint, c_nomatch,
-                                                          c_changed);
+                                                          c_changed, n2);
                 __syncwarp();
 #ifdef MR_KO_ROUND2
-                if (lane == 0) { cnt[1] = 0; cnt[2] = 0; }
-                __syncwarp();
+                n2 = 0;
 #endif
-                const int n2 = cnt[1];
                 if (n2) {   // byte patches follow: the bulk stores of this block must have landed
 #ifndef MR_KO_WAIT
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -1166,6 +1174,7 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
                 }
             }
         }
+        next = __shfl_sync(0xffffffffu, next, 0);   // the item fetched in the last block
     }
     if (R > 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // line buffer still in use
     if (COUNT && P.job.counters) {
@@ -1185,9 +1194,7 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
 }
 
 // ---------------------------------------------------------------------------------------------
-unsigned int* g_work[16] = {nullptr};
-int g_work_next[16] = {0};
-constexpr int WORK_SLOTS = 1024;
+std::mutex g_cfg_mutex;   // cudaFuncSetAttribute bookkeeping below (contexts may live on several host threads)
 
 // ---- host: the item schedule.  Class 0 hands out most of the lines (f0) in tall chunks whose item
 // count fills whole "waves" of warps (an item count just above a multiple of the warp count would
@@ -1240,14 +1247,18 @@ cudaError_t launch_t(FastParams& P, int sm_count, cudaStream_t s) {
     using C = Cfg<R, NB>;
     auto kern = k_fast<R, NB, COUNT, LIN>;
     constexpr size_t smem = C::TOTAL;
-    static bool configured[16] = {false};
+    static bool configured[64] = {false};
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (dev < 16 && !configured[dev]) {
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured[dev] = true;
+    if (dev < 0 || dev >= 64) return cudaErrorNotSupported;
+    {
+        std::lock_guard<std::mutex> lock(g_cfg_mutex);
+        if (!configured[dev]) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured[dev] = true;
+        }
     }
     // work items: strips x line chunks; the chunk height is chosen so that every warp of the GPU
     // gets several items (dynamic queue), but not so small that the 2R halo lines dominate
@@ -1302,26 +1313,26 @@ bool mr_fast_supported(const MrJob& job) {
     return true;
 }
 
-cudaError_t mr_launch_fast(const MrJob& job, int sm_count, cudaStream_t s, int* n_launches) {
+cudaError_t mr_launch_fast(const MrJob& job, int sm_count, cudaStream_t s, int* n_launches, MrWorkRing* ring) {
     if (!mr_fast_supported(job)) return cudaErrorNotSupported;
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    if (dev >= 16) return cudaErrorNotSupported;
-    if (!g_work[dev]) {
-        e = cudaMalloc(&g_work[dev], WORK_SLOTS * sizeof(unsigned int));
-        if (e != cudaSuccess) return e;
-    }
-    unsigned int* ctr = g_work[dev] + (g_work_next[dev]++ % WORK_SLOTS);
-    e = cudaMemsetAsync(ctr, 0, sizeof(unsigned int), s);
-    if (e != cudaSuccess) return e;
+    if (!ring || !ring->slots) return cudaErrorInvalidValue;
+    cudaError_t e = cudaSuccess;
+    // item queue of this launch: the next slot of the context's ring.  Every slot is zero when its
+    // turn comes: the ring starts zeroed, and each launch zeroes the slot half a ring ahead (no
+    // launch can still be running when the slot it used comes up for zeroing MR_WORK_SLOTS / 2
+    // launches later).  No memset, no global state: contexts are independent.
+    const unsigned seq = ring->next++;
+    unsigned int* ctr = ring->slots + (seq % MR_WORK_SLOTS);
     FastParams P;
     P.job = job;
     P.work_counter = ctr;
+    P.work_reset = ring->slots + ((seq + MR_WORK_SLOTS / 2) % MR_WORK_SLOTS);
     P.padded = job.padded;
     const int K = job.pal.K;
-#ifdef MR_QUICK   // kernel experiments: only the BASELINE config 2 instantiation (fast to compile)
+#ifdef MR_QUICK   // kernel experiments: only the BASELINE config 1 / 2 / 4 / 5 instantiations (fast to compile)
     if (job.R == 2 && K > 14 && K <= 30) e = launch_c<2, 5>(P, sm_count, s);
+    else if (job.R == 3 && K > 62) e = launch_c<3, 7>(P, sm_count, s);
+    else if (job.R == 1 && K <= 14) e = launch_c<1, 4>(P, sm_count, s);
     else e = cudaErrorNotSupported;
 #else
     if (job.R == 0) e = launch_c<0, 4>(P, sm_count, s);

@@ -59,7 +59,14 @@ cudaError_t mr_launch_generic(const MrJob& job, bool labels_in, int sm_count, cu
                               int* n_launches);
 // Fast path (packed RGB, 16-byte aligned lines, R in 0..3).  Returns cudaErrorNotSupported
 // when the job does not qualify (caller then uses the generic kernel).
-cudaError_t mr_launch_fast(const MrJob& job, int sm_count, cudaStream_t s, int* n_launches);
+// Item-queue counters of the fast kernel, owned by a context (mr_ctx): MR_WORK_SLOTS zero-initialised
+// uint32 on the device, handed out round robin (see mr_launch_fast).
+#define MR_WORK_SLOTS 4096u
+struct MrWorkRing {
+    unsigned int* slots = nullptr;   // device, MR_WORK_SLOTS entries, zeroed at creation
+    unsigned int next = 0;           // launches so far (the context is caller-serialised)
+};
+cudaError_t mr_launch_fast(const MrJob& job, int sm_count, cudaStream_t s, int* n_launches, MrWorkRing* ring);
 bool mr_fast_supported(const MrJob& job);
 cudaError_t mr_launch_rgba_strip(const uint8_t* px, int64_t stride2, int64_t n1, int64_t lines, uint8_t* rgb,
                                  int64_t rgb_stride2, unsigned int* d_any_special, cudaStream_t s, int* n_launches);
