@@ -11,12 +11,14 @@
  *   - image = Julia column-major Matrix, n1 = size(A,1) is the memory-fast axis;
  *     a "line" is n1 consecutive pixels; stride2 = bytes between lines.
  *   - pixels are packed RGB{N0f8} (bpp = 3) or RGBA{N0f8} (bpp = 4).
- *   - labels are uint8: 0 = no match, 1..K = category (K <= 255).
+ *   - labels are uint8: 0 = no match, 1..K = category (K <= 254; 255 is reserved and rejected).
  *   - every function returns 0 (MR_OK) or a negative error code, never throws
  *     or aborts; mr_last_error() gives the message.  There is NO CPU fallback:
  *     without a usable CUDA device mr_create fails.
- *   - one ctx = one GPU; calls on one ctx must be serialised by the caller;
- *     different ctxs are independent.
+ *   - one ctx = one GPU; calls on one ctx must be serialised by the caller, and asynchronous
+ *     (device-pointer) calls on one ctx must all use the same stream (the ctx owns scratch
+ *     buffers that those launches share); different ctxs are independent, also on one device
+ *     and from different host threads (no process-global state).
  */
 #ifndef MAPRAST_H
 #define MAPRAST_H

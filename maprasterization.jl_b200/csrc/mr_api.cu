@@ -200,6 +200,8 @@ extern "C" int mr_set_palette(mr_ctx* ctx, int K, const double* mean, const doub
 extern "C" int mr_set_known(mr_ctx* ctx, int64_t n, const int64_t* lin_idx, const uint8_t* cat) {
     if (!ctx) return fail(nullptr, MR_ERR_ARG, "mr_set_known: null ctx");
     if (n < 0 || (n > 0 && (!lin_idx || !cat))) return fail(ctx, MR_ERR_ARG, "mr_set_known: bad arguments");
+    for (int64_t k = 0; k < n; ++k)
+        if (lin_idx[k] < 0) return fail(ctx, MR_ERR_ARG, "mr_set_known: negative linear index");
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->s_main));
     cudaFree(ctx->d_known_idx); ctx->d_known_idx = nullptr;
@@ -385,6 +387,8 @@ static int run_clean(mr_ctx* ctx, const MrJob& job, cudaStream_t s, int max_labe
             CK(cudaStreamSynchronize(s));
             max_label = (int)m;
         }
+        if (max_label > 254)
+            return fail(ctx, MR_ERR_ARG, "clean: label 255 is reserved (labels are 0 = no match, 1..254 = category)");
         j.pal.K = max_label;
         e = cudaErrorNotSupported;
         if (max_label <= 126) {

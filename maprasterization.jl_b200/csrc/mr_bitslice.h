@@ -4,7 +4,7 @@
 // 32 pixels (bit i of every word belongs to pixel i).  Additions and comparisons then cost a
 // handful of 3-input logic ops (LOP3) per bit for 32 pixels, which is what lets the window
 // majority vote of SURVEY.md Appendix A.3 run inside ~10 instructions per pixel.
-// Host+device so the same code is unit-tested on the CPU (tests/cpu/test_bitslice.cpp).
+// Host+device: plain C++ apart from the funnel shifts, which have a host fallback.
 #pragma once
 #include <stdint.h>
 

@@ -216,8 +216,8 @@ __global__ void k_known_fixup(MrJob job, int64_t n_known, const int64_t* __restr
                               int64_t labels_stride2) {
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k >= n_known) return;
+    if (idx[k] < 0 || idx[k] >= job.n1 * job.n2 || cat[k] == 0) return;   // never write outside the plane
     const int64_t i = idx[k] % job.n1, j = idx[k] / job.n1;
-    if (cat[k] == 0 || j >= job.n2) return;
     const uint8_t* p = job.px + j * job.stride2 + i * job.bpp;
     labels[j * labels_stride2 + i] =
         (uint8_t)mr_eval_px(job.pal, p[0], p[1], p[2], job.bpp == 4 ? p[3] : 255, job.bpp == 4, cat[k]);
