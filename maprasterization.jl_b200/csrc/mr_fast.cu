@@ -232,15 +232,11 @@ __device__ __forceinline__ CopyPlan copy_plan(const FastParams& P, const Item& i
 // place from a peer GPU bypass the local L2).  Every argument is warp-uniform: the address
 // arithmetic runs on the uniform datapath and the copy needs no operand broadcast.
 constexpr int PF_LINES = 3;
-__device__ __forceinline__ bool issue_line_copy(const FastParams& P, const CopyPlan& c, int y, int ylo, int yhi,
-                                                int pflo, int pfhi, uint32_t bar, int lane) {
-    if (y < ylo || y >= yhi) return false;
-#ifdef MR_KO_TMA   // timing experiment: no input traffic
-    return false;
-#endif
+// global address of the loaded part of line y (halo lines of a band may live in the neighbour band's
+// buffer, i.e. in a peer GPU's memory: they are read in place)
+__device__ __forceinline__ const uint8_t* line_address(const FastParams& P, const CopyPlan& c, int y) {
     const uint8_t* base = c.src0;
     long long row = y;
-    // halo lines that live in the neighbour band's buffer (peer GPU memory): read in place
     if (y < 0 && P.job.halo_lo_px) {
         base = P.job.halo_lo_px + c.col_off;
         row = y + P.job.halo_lo;
@@ -248,13 +244,25 @@ __device__ __forceinline__ bool issue_line_copy(const FastParams& P, const CopyP
         base = P.job.halo_hi_px + c.col_off;
         row = y - P.job.n2;
     }
-    const uint8_t* src = base + row * P.job.stride2;
+    return base + row * P.job.stride2;
+}
+// `cur` walks down the lines of the item: the copies are issued for consecutive y, so the address is the
+// previous one plus the line stride except at the first loadable line and where a band meets its halo
+// lines (the full 64-bit address arithmetic once per line was 5 % of the kernel's instructions).
+__device__ __forceinline__ bool issue_line_copy(const FastParams& P, const CopyPlan& c, int y, int ylo, int yhi,
+                                                int pflo, int pfhi, uint32_t bar, int lane, const uint8_t*& cur) {
+    if (y < ylo || y >= yhi) return false;
+#ifdef MR_KO_TMA   // timing experiment: no input traffic
+    return false;
+#endif
+    if (y == ylo || y == 0 || y == (int)P.job.n2) cur = line_address(P, c, y);
+    else cur += P.job.stride2;
     const bool pf = y >= pflo && y + PF_LINES < pfhi;
     if (lane == 0) {
         mbar_expect_tx(bar, c.bytes);
-        tma_load_1d(c.dst, src, c.bytes, bar);
+        tma_load_1d(c.dst, cur, c.bytes, bar);
         if (pf)
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + (long long)PF_LINES * P.job.stride2), "r"(c.bytes)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(cur + (long long)PF_LINES * P.job.stride2), "r"(c.bytes)
                          : "memory");
     }
     return true;
@@ -903,8 +911,18 @@ __device__ __forceinline__ int block_vote(const FastParams& P, uint8_t* ws, cons
     uint8_t* obuf = ws + C::W_OUT + vl * G::U;
     const uint32_t obuf0 = smem_u32(ws + C::W_OUT);
     const uint32_t B4 = b_lab * 0x01010101u;
+    const int n_it = nl + 2 * R;
 #pragma unroll 1
-    for (int i = 0; i < nl + 2 * R; ++i) {
+    for (int i = 0; i < n_it; ++i) {
+        // ring of horizontal sums: line i goes to slot DN, line i - 2R (leaving the window) sits in slot DO.
+        // (Unrolling the loop by SIDE so that the slots become compile-time indices without this rotation
+        // was measured 20 % slower: five copies of the body no longer fit the instruction cache.)
+        constexpr int DN = SIDE - 1, DO = 0;
+#pragma unroll
+        for (int d = 0; d < SIDE - 1; ++d) {
+            HA[d] = HA[d + 1];
+            HU[d] = HU[d + 1];
+        }
         uint32_t ma = avm, mb = nbm;
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
@@ -914,15 +932,10 @@ __device__ __forceinline__ int block_vote(const FastParams& P, uint8_t* ws, cons
         }
         off += LINE;
         if (off == RING) off = 0;
-#pragma unroll
-        for (int d = 0; d < SIDE - 1; ++d) {
-            HA[d] = HA[d + 1];
-            HU[d] = HU[d + 1];
-        }
-        HA[SIDE - 1] = bs_hsum1<R>(ma);
-        HU[SIDE - 1] = bs_hsum1<R>(ma | mb);
-        SA = bs_add<WC, WH, WC>(SA, HA[SIDE - 1]);
-        SU = bs_add<WC, WH, WC>(SU, HU[SIDE - 1]);
+        HA[DN] = bs_hsum1<R>(ma);
+        HU[DN] = bs_hsum1<R>(ma | mb);
+        SA = bs_add<WC, WH, WC>(SA, HA[DN]);
+        SU = bs_add<WC, WH, WC>(SU, HU[DN]);
         if (COUNT) {   // the centre line's own match masks (line i - R) tell whether its label changed
 #pragma unroll
             for (int d = 0; d < R; ++d) {
@@ -966,12 +979,13 @@ __device__ __forceinline__ int block_vote(const FastParams& P, uint8_t* ws, cons
                 // bit -> byte expansion table (one 8-byte entry per byte of selA)
                 const uint32_t sel = selA >> R;
                 constexpr int GP = (G::U % 4 == 0) ? 4 : 2;
-                const uint32_t AB = a_lab ^ b_lab;
 #pragma unroll
                 for (int k = 0; k < G::U / GP; ++k) {
                     const uint32_t nib = (sel >> (GP * k)) & ((1u << GP) - 1u);
                     const uint32_t m = (nib * 0x00204081u) & 0x01010101u;   // bit j -> byte j
-                    const uint32_t v = B4 ^ (m * AB);
+                    // byte j = m_j ? A : B without leaving the multiply-add pipe: (B4 - m B) has 0 or B in
+                    // every byte (no borrow), adding m A then puts A into the zeroed bytes (no carry)
+                    const uint32_t v = m * a_lab + (B4 - m * b_lab);
                     if (GP == 4) *reinterpret_cast<uint32_t*>(obuf + 4 * k) = v;
                     else *reinterpret_cast<uint16_t*>(obuf + 2 * k) = (uint16_t)v;
                 }
@@ -994,8 +1008,8 @@ __device__ __forceinline__ int block_vote(const FastParams& P, uint8_t* ws, cons
                 reinterpret_cast<uint16_t*>(ws + C::W_W2CODE)[e] = (uint16_t)(((i - 2 * R) << 5) | vl);
                 reinterpret_cast<uint32_t*>(ws + C::W_W2MASK)[e] = undec;
             }
-            SA = bs_sub<WC, WH>(SA, HA[0]);
-            SU = bs_sub<WC, WH>(SU, HU[0]);
+            SA = bs_sub<WC, WH>(SA, HA[DO]);
+            SU = bs_sub<WC, WH>(SU, HU[DO]);
         }
     }
     n_w2 = n_listed;
@@ -1087,7 +1101,8 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
         const int yhi = plan.bytes ? min(cat_last, (int)P.job.n2 + P.job.halo_hi) : ylo;
         const int pflo = P.job.halo_lo_px ? max(ylo, 0) : ylo;
         const int pfhi = P.job.halo_hi_px ? min(yhi, (int)P.job.n2) : yhi;
-        bool pend = issue_line_copy(P, plan, ycat, ylo, yhi, pflo, pfhi, bar, lane);
+        const uint8_t* cur_src = nullptr;   // address of the line copied last
+        bool pend = issue_line_copy(P, plan, ycat, ylo, yhi, pflo, pfhi, bar, lane, cur_src);
         // bytes of one output line of the strip (whole 16-byte chunks, see mr_fast_supported)
         uint32_t obytes = 0;
         if (R > 0) {
@@ -1113,7 +1128,7 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
                 bool nxt = false;
                 auto release = [&]() {
                     __syncwarp();   // every lane is done with the staging buffer
-                    nxt = issue_line_copy(P, plan, ycat + 1, ylo, yhi, pflo, pfhi, bar, lane);
+                    nxt = issue_line_copy(P, plan, ycat + 1, ylo, yhi, pflo, pfhi, bar, lane, cur_src);
                 };
                 if constexpr (LIN)
                     labels_line<R, NB>(ws, it, ycat, lane, M, pend ? stage : nullptr, release);
