@@ -168,6 +168,30 @@ int mr_clean_segments_host(mr_ctx* ctx, const uint8_t* labels, int64_t n1, int64
                            double prune_threshold, uint8_t* out, int64_t out_stride2,
                            int64_t* n_segments);
 
+/* fill_gaps(src; categories, neighborhood = VonNeumann{2}(), missingval = 0, stats, match = (:color,),
+ * known, original, mask), src/clean.jl:2-54, applied `repeat` times as _fill does
+ * (src/selectcolors.jl:683-699; call site :490-501).  Per pixel and pass: a masked pixel stays
+ * (clean.jl:13); a clicked point whose category is kept takes it (:14, the plane of mr_set_known);
+ * a kept label stays, a label that is not kept becomes 0 (:16-17, :35-36); a gap (0) whose 12
+ * VonNeumann{2} neighbours are not "mostly missing" (:20) takes the kept category with the largest
+ * inverse-distance weight if that exceeds 1 (:21-23), and when the runner-up also exceeds 1 the one
+ * of the two whose mean colour is closer to the ORIGINAL pixel (:24-31, the colour error of
+ * categories.jl:91-95 against the palette of mr_set_palette; stats[i] = palette row categories[i]-1).
+ * categories: the kept categories, 1..K, in the caller's order (equal weights go to the earlier one,
+ * findmax).  px: the pixels the categoriser saw (packed RGB / RGBA, same geometry as labels).
+ * mask: optional plane, nonzero = masked (NULL: none).  Neighbours outside the image read as 0;
+ * output has the size of the input; not in place.  Asynchronous on `stream` (device variant). */
+int mr_fill_gaps_dev(mr_ctx* ctx, const uint8_t* labels_dev, int64_t n1, int64_t n2, int64_t stride2,
+                     const uint8_t* px_dev, int64_t px_stride2, int bytes_per_px,
+                     const uint8_t* mask_dev, int64_t mask_stride2,
+                     const uint8_t* categories, int n_categories, int repeat,
+                     uint8_t* out_dev, int64_t out_stride2, void* stream);
+int mr_fill_gaps_host(mr_ctx* ctx, const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2,
+                      const uint8_t* px, int64_t px_stride2, int bytes_per_px,
+                      const uint8_t* mask, int64_t mask_stride2,
+                      const uint8_t* categories, int n_categories, int repeat,
+                      uint8_t* out, int64_t out_stride2);
+
 /* Pinned host staging (optional; pageable caller buffers also work, slower). */
 void* mr_host_alloc(size_t bytes);
 void mr_host_free(void* p);

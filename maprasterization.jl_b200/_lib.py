@@ -24,6 +24,7 @@ SYMBOLS = [
     "mr_categorize_clean_host", "mr_categorize_clean_host_band", "mr_categorize_clean_dev", "mr_batch_categorize_clean_dev",
     "mr_categorize_clean_dev_peer", "mr_ipc_export", "mr_ipc_open", "mr_ipc_close",
     "mr_clean_host", "mr_clean_dev", "mr_clean_segments_dev", "mr_clean_segments_host",
+    "mr_fill_gaps_dev", "mr_fill_gaps_host",
     "mr_host_alloc", "mr_host_free", "mr_synth_scan_dev",
 ]
 
@@ -86,6 +87,8 @@ def load():
                                         C.POINTER(i64), vp]
     L.mr_clean_segments_host.argtypes = [vp, u8p, i64, i64, i64, u8p, C.c_double, C.c_double, u8p, i64,
                                          C.POINTER(i64)]
+    L.mr_fill_gaps_dev.argtypes = [vp, u8p, i64, i64, i64, u8p, i64, i32, u8p, i64, u8p, i32, i32, u8p, i64, vp]
+    L.mr_fill_gaps_host.argtypes = [vp, u8p, i64, i64, i64, u8p, i64, i32, u8p, i64, u8p, i32, i32, u8p, i64]
     L.mr_host_alloc.argtypes = [C.c_size_t]
     L.mr_host_alloc.restype = vp
     L.mr_host_free.argtypes = [vp]
@@ -96,7 +99,7 @@ def load():
                  "mr_categorize_clean_dev",
                  "mr_categorize_clean_dev_peer", "mr_ipc_export", "mr_ipc_open", "mr_ipc_close",
                  "mr_batch_categorize_clean_dev", "mr_clean_host", "mr_clean_dev", "mr_clean_segments_dev",
-                 "mr_clean_segments_host", "mr_synth_scan_dev"):
+                 "mr_clean_segments_host", "mr_fill_gaps_dev", "mr_fill_gaps_host", "mr_synth_scan_dev"):
         getattr(L, name).restype = i32
     _lib = L
     return L
@@ -233,7 +236,33 @@ class Context:
                                                 float(prune_threshold), _ptr(out), n1, C.byref(nseg)))
         return out, int(nseg.value)
 
+    def fill_gaps_host(self, labels, px, categories, mask=None, repeat=1):
+        """`fill_gaps` (src/clean.jl:2-54) `repeat` times on host buffers; palette = `stats`, the known plane
+        is the one of set_known.  labels / mask: (n2, n1) uint8, px: (n2, n1, bpp) uint8."""
+        labels = np.ascontiguousarray(labels, dtype=np.uint8)
+        px = np.ascontiguousarray(px, dtype=np.uint8)
+        n2, n1 = labels.shape
+        if px.ndim != 3 or px.shape[:2] != (n2, n1) or px.shape[2] not in (3, 4):
+            raise ValueError("px must be a (n2, n1, 3|4) uint8 array of the shape of labels")
+        cats = np.ascontiguousarray(categories, dtype=np.uint8)
+        mk = None
+        if mask is not None:
+            mk = np.ascontiguousarray(mask, dtype=np.uint8)
+            if mk.shape != labels.shape:
+                raise ValueError("mask must have the shape of labels")
+        out = np.empty((n2, n1), dtype=np.uint8)
+        self._ck(self._L.mr_fill_gaps_host(self._h, _ptr(labels), n1, n2, n1, _ptr(px), n1 * px.shape[2], px.shape[2],
+                                           _ptr(mk), n1, _ptr(cats), cats.size, int(repeat), _ptr(out), n1))
+        return out
+
     # -- device buffers (raw pointers / torch tensors) -------------------------------------
+    def fill_gaps_dev(self, labels, n1, n2, stride2, px, px_stride2, bpp, categories, out, out_stride2, mask=None,
+                      mask_stride2=0, repeat=1, stream=0):
+        cats = np.ascontiguousarray(categories, dtype=np.uint8)
+        self._ck(self._L.mr_fill_gaps_dev(self._h, _ptr(labels), n1, n2, stride2, _ptr(px), px_stride2, int(bpp),
+                                          _ptr(mask), mask_stride2, _ptr(cats), cats.size, int(repeat), _ptr(out),
+                                          out_stride2, stream or None))
+
     def clean_segments_dev(self, labels, n1, n2, stride2, keep256, line_threshold, prune_threshold, out,
                            out_stride2, stream=0):
         keep = np.ascontiguousarray(keep256, dtype=np.uint8)

@@ -288,6 +288,56 @@ def clean_segments(labels, known_categories=None, **kw):
     return clean_segments_u8(labels, known_categories, **kw).astype(np.int64)
 
 
+def fill_gaps_u8(src, *, categories, stats, original, known=None, mask=None, match=("color",), missingval=0,
+                 neighborhood="VonNeumann{2}", repeat=1, ctx=None):
+    """`fill_gaps(src; categories, neighborhood = VonNeumann{2}(), missingval, stats, match, known, original,
+    mask)` (src/clean.jl:2-54), applied `repeat` times as `_fill` does (src/selectcolors.jl:683-699).
+    src / known / mask: (n2, n1) arrays; original: the (n2, n1, 3|4) uint8 image the categoriser saw;
+    stats: the `Palette` (`stats[i]` of clean.jl:29-30 is the row of `categories[i]`); categories: the kept
+    categories in order.  Only `missingval = 0`, `VonNeumann{2}` and `match = ("color",)` exist on the GPU
+    path (what `_fill` passes, minus the texture planes)."""
+    if missingval != 0:
+        raise ValueError("fill_gaps: only missingval = 0 (what _fill passes) is supported")
+    if str(neighborhood).replace(" ", "") not in ("VonNeumann{2}", "VonNeumann{2}()"):
+        raise ValueError("fill_gaps: only the VonNeumann{2} neighbourhood is supported")
+    if tuple(match) != ("color",):
+        raise ValueError("fill_gaps: only match = ('color',) is supported")
+    if not isinstance(stats, Palette):
+        raise ValueError("stats must be a Palette")
+    src = np.asarray(src)
+    if src.ndim != 2 or not np.issubdtype(src.dtype, np.integer):
+        raise ValueError("src must be a 2-D integer array")
+    if src.size and (src.min() < 0 or src.max() > 254):
+        raise ValueError("labels must be in 0..254")
+    _check_img(original)
+    if original.shape[:2] != src.shape:
+        raise ValueError("original must have the shape of src")
+    cats = np.asarray(list(categories), dtype=np.int64)
+    if cats.size and (cats.min() < 1 or cats.max() > stats.K):
+        raise ValueError("categories must be in 1..K")
+    ctx = ctx or default_context()
+    _upload_palette(ctx, stats)
+    if known is None:
+        ctx.set_known(None)
+    else:
+        kn = np.asarray(known)
+        if kn.shape != src.shape:
+            raise ValueError("known must have the shape of src")
+        idx = np.flatnonzero(kn)
+        ctx.set_known(idx, kn.reshape(-1)[idx].astype(np.uint8))
+    try:
+        return ctx.fill_gaps_host(src.astype(np.uint8), original, cats.astype(np.uint8),
+                                  None if mask is None else (np.asarray(mask) != 0).astype(np.uint8), repeat)
+    finally:
+        if known is not None:
+            ctx.set_known(None)
+
+
+def fill_gaps(src, **kw):
+    """Same, eltype Int."""
+    return fill_gaps_u8(src, **kw).astype(np.int64)
+
+
 @dataclass
 class MapSelection:
     """`MapSelection` (src/selectcolors.jl:3-8): what `selectcolors` returns -- the clicked points per
@@ -316,7 +366,8 @@ def rasterize(img, sel, *, hood=None, colourspace="rgb", ctx=None):
     segmented)`, known-category points from `_set_categories!`, :670-681) -> optional Window
     majority filter (`hood`; north_star's `clean`) -> "clean" (:479-489: `_clean(A, known;
     categories = kept, line_threshold, prune_threshold)`).
-    Returns a dict with the uint8 label images `categorized` and `cleaned`.
+    -> "fill" (:490-501: `_fill` = `fill_gaps` `fill_repeat` times, :683-699; the polygon mask is the caller's).
+    Returns a dict with the uint8 label images `categorized`, `cleaned` and `filled`.
     Settings that select unsupported stages raise ValueError (no CPU fallback): `segment=True`,
     a `match` other than ("color",), `blur_repeat > 0`."""
     if not isinstance(sel, MapSelection):
@@ -339,4 +390,8 @@ def rasterize(img, sel, *, hood=None, colourspace="rgb", ctx=None):
     cleaned = clean_segments_u8(categorized, known, categories=sel.kept_categories(),
                                 line_threshold=float(st.get("line_threshold", 0.01)),
                                 prune_threshold=float(st.get("prune_threshold", 20)), ctx=ctx)
-    return {"categorized": categorized, "cleaned": cleaned}
+    # `_component_stats(original, points[categories])` (selectcolors.jl:689): the rows of the kept categories
+    pal = ctx.palette if isinstance(ctx.palette, Palette) else _as_palette(img, sel.points, tol, colourspace)
+    filled = fill_gaps_u8(cleaned, categories=sel.kept_categories(), stats=pal, original=img, known=known,
+                          mask=None, repeat=int(st.get("fill_repeat", 1)), ctx=ctx)
+    return {"categorized": categorized, "cleaned": cleaned, "filled": filled}

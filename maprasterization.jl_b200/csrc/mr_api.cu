@@ -809,6 +809,97 @@ extern "C" int mr_clean_segments_host(mr_ctx* ctx, const uint8_t* labels, int64_
     return MR_OK;
 }
 
+// ------------------------------------------------------------------ fill_gaps (src/clean.jl:2-54)
+static int fill_check(mr_ctx* ctx, const char* fn, const void* labels, const void* px, const void* out, int64_t n1,
+                      int64_t n2, int64_t stride2, int64_t px_stride2, int bpp, const void* mask, int64_t mask_stride2,
+                      const uint8_t* categories, int n_categories, int repeat, int64_t out_stride2) {
+    std::string f(fn);
+    int rc = check_image_args(ctx, fn, labels, out, n1, n2, stride2, 1, out_stride2, 0, 0, 0);
+    if (rc) return rc;
+    if ((rc = check_palette(ctx, fn, bpp))) return rc;
+    if (n1 > 0 && n2 > 0 && !px) return fail(ctx, MR_ERR_ARG, f + ": null pixel buffer (`original`)");
+    if (px_stride2 < n1 * bpp) return fail(ctx, MR_ERR_ARG, f + ": pixel stride smaller than a line");
+    if (mask && mask_stride2 < n1) return fail(ctx, MR_ERR_ARG, f + ": mask stride smaller than a line");
+    if (n_categories < 0 || n_categories > 254 || (n_categories > 0 && !categories))
+        return fail(ctx, MR_ERR_ARG, f + ": bad category list");
+    for (int k = 0; k < n_categories; ++k)
+        if (categories[k] < 1 || categories[k] > ctx->pal.K)
+            return fail(ctx, MR_ERR_ARG, f + ": categories must be in 1..K (stats[i] is the palette row of categories[i])");
+    if (repeat < 0) return fail(ctx, MR_ERR_ARG, f + ": negative repeat");
+    if (labels == out && n1 > 0 && n2 > 0) return fail(ctx, MR_ERR_ARG, f + ": in-place operation is not supported");
+    return MR_OK;
+}
+
+// `repeat` passes (selectcolors.jl:692-696); odd passes write `out`, even passes the scratch plane, arranged
+// so that the last pass lands in `out`
+static int fill_dev(mr_ctx* ctx, const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2, const uint8_t* px,
+                    int64_t px_stride2, int bpp, const uint8_t* mask, int64_t mask_stride2, const uint8_t* categories,
+                    int n_categories, int repeat, uint8_t* out, int64_t out_stride2, cudaStream_t s) {
+    if (n1 == 0 || n2 == 0) return MR_OK;
+    if (repeat == 0) {
+        CK(cudaMemcpy2DAsync(out, out_stride2, labels, stride2, n1, n2, cudaMemcpyDeviceToDevice, s));
+        return MR_OK;
+    }
+    const int64_t pitch = (n1 + 15) / 16 * 16;
+    int rc;
+    if (repeat > 1 && (rc = grow(ctx, &ctx->d_lab, &ctx->d_lab_cap, (size_t)pitch * n2))) return rc;
+    const uint8_t* src = labels;
+    int64_t src_stride = stride2;
+    for (int it = 0; it < repeat; ++it) {
+        const bool to_out = ((repeat - 1 - it) % 2) == 0;
+        uint8_t* dst = to_out ? out : ctx->d_lab;
+        const int64_t dst_stride = to_out ? out_stride2 : pitch;
+        int nl = 0;
+        cudaError_t e = mr_launch_fill_gaps(ctx->pal, src, n1, n2, src_stride, px, px_stride2, bpp, mask, mask_stride2,
+                                            categories, n_categories, ctx->n_known, ctx->d_known_idx, ctx->d_known_cat,
+                                            dst, dst_stride, ctx->sm_count, s, &nl);
+        ctx->launches += nl;
+        if (e != cudaSuccess) return fail_cuda(ctx, e, "fill_gaps launch");
+        src = dst;
+        src_stride = dst_stride;
+    }
+    return MR_OK;
+}
+
+extern "C" int mr_fill_gaps_dev(mr_ctx* ctx, const uint8_t* labels_dev, int64_t n1, int64_t n2, int64_t stride2,
+                                const uint8_t* px_dev, int64_t px_stride2, int bytes_per_px, const uint8_t* mask_dev,
+                                int64_t mask_stride2, const uint8_t* categories, int n_categories, int repeat,
+                                uint8_t* out_dev, int64_t out_stride2, void* stream) {
+    int rc = fill_check(ctx, "mr_fill_gaps_dev", labels_dev, px_dev, out_dev, n1, n2, stride2, px_stride2, bytes_per_px,
+                        mask_dev, mask_stride2, categories, n_categories, repeat, out_stride2);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    return fill_dev(ctx, labels_dev, n1, n2, stride2, px_dev, px_stride2, bytes_per_px, mask_dev, mask_stride2, categories,
+                    n_categories, repeat, out_dev, out_stride2, stream ? (cudaStream_t)stream : ctx->s_main);
+}
+
+extern "C" int mr_fill_gaps_host(mr_ctx* ctx, const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2,
+                                 const uint8_t* px, int64_t px_stride2, int bytes_per_px, const uint8_t* mask,
+                                 int64_t mask_stride2, const uint8_t* categories, int n_categories, int repeat,
+                                 uint8_t* out, int64_t out_stride2) {
+    int rc = fill_check(ctx, "mr_fill_gaps_host", labels, px, out, n1, n2, stride2, px_stride2, bytes_per_px, mask,
+                        mask_stride2, categories, n_categories, repeat, out_stride2);
+    if (rc) return rc;
+    if (n1 == 0 || n2 == 0) return MR_OK;
+    CK(cudaSetDevice(ctx->device));
+    const int64_t pitch = (n1 + 15) / 16 * 16, ppitch = (n1 * bytes_per_px + 15) / 16 * 16;
+    const size_t plane = (size_t)pitch * n2;
+    // d_out: labels in | result ; d_tmp: mask ; d_in: pixels
+    if ((rc = grow(ctx, &ctx->d_out, &ctx->d_out_cap, 2 * plane))) return rc;
+    if ((rc = grow(ctx, &ctx->d_in, &ctx->d_in_cap, (size_t)ppitch * n2))) return rc;
+    if (mask && (rc = grow(ctx, &ctx->d_tmp, &ctx->d_tmp_cap, plane))) return rc;
+    cudaStream_t s = ctx->s_main;
+    CK(cudaMemcpy2DAsync(ctx->d_out, pitch, labels, stride2, n1, n2, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpy2DAsync(ctx->d_in, ppitch, px, px_stride2, n1 * bytes_per_px, n2, cudaMemcpyHostToDevice, s));
+    if (mask) CK(cudaMemcpy2DAsync(ctx->d_tmp, pitch, mask, mask_stride2, n1, n2, cudaMemcpyHostToDevice, s));
+    rc = fill_dev(ctx, ctx->d_out, n1, n2, pitch, ctx->d_in, ppitch, bytes_per_px, mask ? ctx->d_tmp : nullptr, pitch,
+                  categories, n_categories, repeat, ctx->d_out + plane, pitch, s);
+    if (rc) return rc;
+    CK(cudaMemcpy2DAsync(out, out_stride2, ctx->d_out + plane, pitch, n1, n2, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return MR_OK;
+}
+
 extern "C" int mr_synth_scan_dev(mr_ctx* ctx, uint32_t seed, uint32_t sheet_id, int K,
                                  const uint8_t* palette_rgb_host, int64_t n1, int64_t n2, int64_t line0,
                                  int64_t nlines, int mode, uint8_t* out_dev, int64_t out_stride2, void* stream) {

@@ -98,3 +98,11 @@ cudaError_t mr_launch_prune_apply(const uint8_t* labels, int64_t n1, int64_t n2,
                                   const uint8_t* known_cat, const uint8_t* keep_dev, double line_threshold,
                                   double prune_threshold, uint8_t* out, int64_t out_stride2,
                                   unsigned int* d_conflict, cudaStream_t s, int* n_launches);
+
+// fill_gaps (src/clean.jl:2-54), one pass; the known-category override (clean.jl:14) runs as a second,
+// sparse launch (mr_fill.cu)
+cudaError_t mr_launch_fill_gaps(const MrPalette& pal, const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2,
+                                const uint8_t* px, int64_t px_stride2, int bpp, const uint8_t* mask,
+                                int64_t mask_stride2, const uint8_t* categories, int n_categories, int64_t n_known,
+                                const int64_t* known_idx, const uint8_t* known_cat, uint8_t* out, int64_t out_stride2,
+                                int sm_count, cudaStream_t s, int* n_launches);

@@ -505,3 +505,93 @@ int64_t mro_clean_segments(const uint8_t* labels, int64_t n1, int64_t n2, int64_
     free(result); free(parent); free(mean); free(cat); free(cnt); free(bb);
     return n_seg;
 }
+
+/* =====================================================================================
+ * fill_gaps (src/clean.jl:2-54) and its repeat loop `_fill` (src/selectcolors.jl:683-699).
+ * PARITY UNPINNED: the reference has no test or fixture for fill_gaps, and the neighbourhood
+ * type lives in Neighborhoods.jl 0.1, which is not in the reference tree.  Decisions made here
+ * (stated in DESIGN.md section 11):
+ *   - VonNeumann{2} = the 12 offsets with 1 <= |d1| + |d2| <= 2, visited in CartesianIndices
+ *     order (d1, the memory-fast axis, runs fastest).  Whether the centre belongs to the
+ *     neighbourhood does not matter: the stencil only runs for a centre equal to missingval,
+ *     which shifts both sides of the "mostly missing" test (clean.jl:20) by one and never
+ *     matches a category.  The visiting order only matters for the rounding of the Float64 sums.
+ *   - distances = sqrt(d1^2 + d2^2) in Float64: weights 1/1, 1/sqrt(2), 1/2 (clean.jl:44-52).
+ *   - neighbours outside the image read as missingval; the result has the size of the input.
+ *   - missingval = 0 (as _fill passes it); `original` is the pixel the categoriser saw and the
+ *     colour error is the categoriser's own (categories.jl:91-95, match = (:color,)).
+ * categories: the kept categories in the caller's order (findmax / the reduce of clean.jl:24-27
+ * return the FIRST of equal counts, i.e. the one that comes first in this list).
+ * mean: K x C palette means (stats[i] of clean.jl:29-30 = row categories[i]-1).
+ * known / mask may be NULL.  Not in place. */
+static double fill_colour_error(const uint8_t* px, int bpp, int C, int colourspace, const double* m) {
+    double x[4] = {0.0, 0.0, 0.0, 0.0};
+    if (colourspace == MRO_LAB) {
+        mro_rgb8_to_lab(px[0], px[1], px[2], x);
+    } else {
+        x[0] = mro_n0f8(px[0]); x[1] = mro_n0f8(px[1]); x[2] = mro_n0f8(px[2]);
+        if (bpp == 4) x[3] = mro_n0f8(px[3]);
+    }
+    double d0 = x[0] - m[0], d1 = x[1] - m[1], d2 = x[2] - m[2];
+    double e = d0 * d0 + d1 * d1;
+    e = e + d2 * d2;
+    if (C == 4) { double d3 = x[3] - m[3]; e = e + d3 * d3; }
+    return e;
+}
+
+void mro_fill_gaps(const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2,
+                   const uint8_t* px, int64_t px_stride2, int bpp, int C, int colourspace,
+                   const double* mean, const uint8_t* known, int64_t known_stride2,
+                   const uint8_t* mask, int64_t mask_stride2,
+                   const uint8_t* categories, int n_categories, uint8_t* out, int64_t out_stride2) {
+    static const int D1[12] = {0, -1, 0, 1, -2, -1, 1, 2, -1, 0, 1, 0};
+    static const int D2[12] = {-2, -1, -1, -1, 0, 0, 0, 0, 1, 1, 1, 2};
+    double invd[12];
+    for (int k = 0; k < 12; ++k) invd[k] = 1.0 / sqrt((double)(D1[k] * D1[k] + D2[k] * D2[k]));
+    int kept[256];
+    for (int c = 0; c < 256; ++c) kept[c] = 0;
+    for (int i = 0; i < n_categories; ++i) kept[categories[i]] = 1;
+    double* cnt = (double*)malloc(sizeof(double) * (size_t)(n_categories > 0 ? n_categories : 1));
+    for (int64_t j = 0; j < n2; ++j)
+        for (int64_t i = 0; i < n1; ++i) {
+            const int v = labels[j * stride2 + i];
+            uint8_t* o = out + j * out_stride2 + i;
+            if (mask && mask[j * mask_stride2 + i]) { *o = (uint8_t)v; continue; }              /* clean.jl:13 */
+            const int kn = known ? known[j * known_stride2 + i] : 0;
+            if (kn != 0 && kept[kn]) { *o = (uint8_t)kn; continue; }                            /* clean.jl:14 */
+            if (v != 0) { *o = kept[v] ? (uint8_t)v : 0; continue; }                            /* clean.jl:16-17, 35-36 */
+            int hood[12], missing = 0;
+            for (int k = 0; k < 12; ++k) {
+                const int64_t a = i + D1[k], b = j + D2[k];
+                hood[k] = (a >= 0 && a < n1 && b >= 0 && b < n2) ? labels[b * stride2 + a] : 0;
+                missing += hood[k] == 0;                                                        /* clean.jl:15 */
+            }
+            if (missing > 12 - 12 / 4) { *o = 0; continue; }                                    /* clean.jl:20 */
+            for (int c = 0; c < n_categories; ++c) {                                            /* clean.jl:43-54 */
+                double acc = 0.0;
+                for (int k = 0; k < 12; ++k)
+                    if (hood[k] != 0 && hood[k] == categories[c]) acc += invd[k];
+                cnt[c] = acc;
+            }
+            int im = 0;                                                                         /* findmax: first maximum */
+            for (int c = 1; c < n_categories; ++c)
+                if (cnt[c] > cnt[im]) im = c;
+            if (n_categories == 0 || !(cnt[im] > 1.0)) { *o = 0; continue; }                    /* clean.jl:23 */
+            double second = 0.0;                                                                /* clean.jl:24-27 */
+            int is = -1;
+            for (int c = 0; c < n_categories; ++c) {
+                if (c == im) continue;
+                if (cnt[c] > second) { second = cnt[c]; is = c; }
+            }
+            int pick = im;
+            if (second > 1.0) {                                                                 /* clean.jl:28-31 */
+                const uint8_t* p = px + j * px_stride2 + i * bpp;
+                const double ea = fill_colour_error(p, bpp, C, colourspace, mean + (int64_t)(categories[im] - 1) * C);
+                const double eb = fill_colour_error(p, bpp, C, colourspace, mean + (int64_t)(categories[is] - 1) * C);
+                pick = ea <= eb ? im : is;
+            }
+            *o = categories[pick];
+        }
+    free(cnt);
+}
+

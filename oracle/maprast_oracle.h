@@ -15,6 +15,8 @@
  *   - majority ("clean") filter:   parity unpinned (north_star-defined; the
  *     reference has no window-majority body), SURVEY.md Appendix A.3.
  *   - Lab variant:                 parity unpinned (extension, Appendix A.4).
+ *   - segment prune, fill_gaps:    parity unpinned (the reference has no fixtures for
+ *     _clean / fill_gaps; fill_gaps also depends on Neighborhoods.jl 0.1, not in the tree).
  *
  * Conventions: image is column-major n1 x n2, n1 is the memory-fast axis
  * ("line" = n1 contiguous pixels), stride2 = bytes between consecutive lines.
@@ -95,6 +97,15 @@ int64_t mro_clean_segments(const uint8_t* labels, int64_t n1, int64_t n2, int64_
                            const uint8_t* known, int64_t known_stride2, const uint8_t* keep256,
                            double line_threshold, double prune_threshold,
                            uint8_t* out, int64_t out_stride2);
+
+/* fill_gaps (src/clean.jl:2-54), one pass; PARITY UNPINNED (see the .c file for the decisions
+ * about Neighborhoods.jl's VonNeumann{2}).  categories: kept categories in the caller's order;
+ * mean: K x C palette means; known / mask: full planes or NULL.  Not in place. */
+void mro_fill_gaps(const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2,
+                   const uint8_t* px, int64_t px_stride2, int bpp, int C, int colourspace,
+                   const double* mean, const uint8_t* known, int64_t known_stride2,
+                   const uint8_t* mask, int64_t mask_stride2,
+                   const uint8_t* categories, int n_categories, uint8_t* out, int64_t out_stride2);
 
 int mro_max_threads(void);
 

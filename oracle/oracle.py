@@ -61,6 +61,8 @@ def lib():
         L.mro_clean_segments.argtypes = [_u8p, _i64, _i64, _i64, C.c_void_p, _i64, _u8p, C.c_double,
                                          C.c_double, _u8p, _i64]
         L.mro_clean_segments.restype = _i64
+        L.mro_fill_gaps.argtypes = [_u8p, _i64, _i64, _i64, _u8p, _i64, C.c_int, C.c_int, C.c_int, _f64p,
+                                    C.c_void_p, _i64, C.c_void_p, _i64, _u8p, C.c_int, _u8p, _i64]
         L.mro_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -178,6 +180,28 @@ def clean_segments(labels, known=None, categories=(), line_threshold=0.01, prune
                                  keep.ctypes.data, float(line_threshold), float(prune_threshold),
                                  out.ctypes.data, n1)
     return out, int(n)
+
+
+def fill_gaps(labels, px, mean, categories, known=None, mask=None, repeat=1, colourspace=RGB):
+    """`fill_gaps` (src/clean.jl:2-54) applied `repeat` times as `_fill` does (src/selectcolors.jl:692-696).
+    labels / known / mask: (n2, n1) uint8, px: (n2, n1, bpp) uint8, mean: K x C, categories: ordered kept list."""
+    labels = np.ascontiguousarray(labels, dtype=np.uint8)
+    px = _img(px)
+    n2, n1 = labels.shape
+    assert px.shape[:2] == (n2, n1)
+    mean = _f64(mean)
+    cats = np.ascontiguousarray(list(categories), dtype=np.uint8)
+    kn = np.ascontiguousarray(known, dtype=np.uint8) if known is not None else None
+    mk = np.ascontiguousarray(mask, dtype=np.uint8) if mask is not None else None
+    cur = labels
+    for _ in range(repeat):
+        out = np.empty_like(cur)
+        lib().mro_fill_gaps(cur.ctypes.data, n1, n2, n1, px.ctypes.data, n1 * px.shape[2], px.shape[2],
+                            mean.shape[1], colourspace, mean, kn.ctypes.data if kn is not None else None, n1,
+                            mk.ctypes.data if mk is not None else None, n1, cats.ctypes.data, cats.size,
+                            out.ctypes.data, n1)
+        cur = out
+    return cur if repeat > 0 else labels.copy()
 
 
 def philox4x32(c, k):
