@@ -22,6 +22,7 @@
  */
 #ifndef MAPRAST_H
 #define MAPRAST_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -69,6 +70,13 @@ int mr_set_palette(mr_ctx* ctx, int K, const double* mean, const double* lo, con
 /* Known-category plane, replaces _set_categories! (src/selectcolors.jl:670-681) feeding
  * the override at src/categories.jl:110-112.  lin_idx = i + j*n1 (0-based). n = 0 clears. */
 int mr_set_known(mr_ctx* ctx, int64_t n, const int64_t* lin_idx, const uint8_t* cat);
+
+/* Same for one row band of a larger sheet: lin_idx still count from SHEET line 0 and first_line is the
+ * sheet line of line 0 of the px / px_dev passed to the band entry points below.  Points on the band's
+ * halo lines matter too (their labels enter the windows of the band's edge lines); points outside
+ * [first_line - halo_lo, first_line + n2 + halo_hi) are ignored.  mr_set_known resets first_line to 0. */
+int mr_set_known_band(mr_ctx* ctx, int64_t n, const int64_t* lin_idx, const uint8_t* cat,
+                      int64_t first_line);
 
 /* Introspection used by the parity tests (exhaustive 2^24 sweep) and reports. */
 int mr_get_lut(mr_ctx* ctx, uint8_t* lut_host /* 2^24 bytes, index r | g<<8 | b<<16 */);
@@ -191,6 +199,44 @@ int mr_fill_gaps_host(mr_ctx* ctx, const uint8_t* labels, int64_t n1, int64_t n2
                       const uint8_t* mask, int64_t mask_stride2,
                       const uint8_t* categories, int n_categories, int repeat,
                       uint8_t* out, int64_t out_stride2);
+
+/* ---- several GPUs of one box behind one object (mr_create(device_ids, n_dev)) ----------
+ * The reference call site (src/selectcolors.jl:466-478) stays a single call: the library owns one
+ * context and one host thread per device, splits the sheet into contiguous row bands over n2
+ * (mr_multi_band_range; multiples of 16 lines) and runs the fused path on every band at once.
+ * device_ids = NULL: devices 0..n_dev-1; n_dev <= 0: every visible device.  A device may be listed more
+ * than once (one context per entry).  Results are byte-identical to the single-GPU call.
+ * mr_multi_set_known takes WHOLE-SHEET indices; every band receives the points its windows can see. */
+typedef struct mr_multi mr_multi;
+mr_multi* mr_multi_create(const int* device_ids, int n_dev, int* err);
+void mr_multi_destroy(mr_multi* m);
+const char* mr_multi_last_error(const mr_multi* m); /* m may be NULL: last error of this thread */
+int mr_multi_device_count(const mr_multi* m);
+mr_ctx* mr_multi_ctx(mr_multi* m, int i);            /* the context of band i (owned by m) */
+int mr_multi_band_range(const mr_multi* m, int64_t n2, int i, int64_t* line0, int64_t* nlines);
+int mr_multi_set_palette(mr_multi* m, int K, const double* mean, const double* lo, const double* hi,
+                         int colourspace, int channels);
+int mr_multi_set_known(mr_multi* m, int64_t n, const int64_t* lin_idx, const uint8_t* cat);
+/* Host-resident sheet: every band reads its halo lines from the caller's sheet; no exchange between
+ * GPUs.  counters (may be NULL) = sums over the bands. */
+int mr_multi_categorize_clean_host(mr_multi* m, const uint8_t* px, int64_t n1, int64_t n2,
+                                   int64_t stride2_bytes, int bytes_per_px, int R,
+                                   uint8_t* labels_out, int64_t out_stride2, mr_counters* counters);
+/* Batch of independent host-resident sheets (BASELINE config 5): contiguous groups of sheets per device. */
+int mr_multi_batch_categorize_clean_host(mr_multi* m, int n_sheets, const uint8_t* px,
+                                         int64_t sheet_stride_bytes, int64_t n1, int64_t n2,
+                                         int64_t stride2_bytes, int bytes_per_px, int R,
+                                         uint8_t* labels_out, int64_t out_sheet_stride,
+                                         int64_t out_stride2);
+/* Device-resident bands: band_px[i] / band_out[i] point at line 0 of band i in the memory of device i
+ * (lines of mr_multi_band_range(i), stride2_bytes apart; no halo slots).  The fused kernel reads the
+ * 2R halo lines of a band in place from the neighbour bands over NVLink peer access, which
+ * mr_multi_create enabled in-process (MR_ERR_UNSUPPORTED when the devices cannot reach each other).
+ * Fast-path geometry only (packed RGB, 16-byte aligned pointers / strides, n1 % 16 == 0, R <= 3,
+ * K <= 126).  Runs on the default stream of every device and returns when all bands are done. */
+int mr_multi_categorize_clean_dev(mr_multi* m, const uint8_t* const* band_px, int64_t n1, int64_t n2,
+                                  int64_t stride2_bytes, int bytes_per_px, int R,
+                                  uint8_t* const* band_out, int64_t out_stride2);
 
 /* Pinned host staging (optional; pageable caller buffers also work, slower). */
 void* mr_host_alloc(size_t bytes);

@@ -24,7 +24,10 @@ SYMBOLS = [
     "mr_categorize_clean_host", "mr_categorize_clean_host_band", "mr_categorize_clean_dev", "mr_batch_categorize_clean_dev",
     "mr_categorize_clean_dev_peer", "mr_ipc_export", "mr_ipc_open", "mr_ipc_close",
     "mr_clean_host", "mr_clean_dev", "mr_clean_segments_dev", "mr_clean_segments_host",
-    "mr_fill_gaps_dev", "mr_fill_gaps_host",
+    "mr_fill_gaps_dev", "mr_fill_gaps_host", "mr_set_known_band",
+    "mr_multi_create", "mr_multi_destroy", "mr_multi_last_error", "mr_multi_device_count", "mr_multi_ctx",
+    "mr_multi_band_range", "mr_multi_set_palette", "mr_multi_set_known", "mr_multi_categorize_clean_host",
+    "mr_multi_batch_categorize_clean_host", "mr_multi_categorize_clean_dev",
     "mr_host_alloc", "mr_host_free", "mr_synth_scan_dev",
 ]
 
@@ -89,6 +92,22 @@ def load():
                                          C.POINTER(i64)]
     L.mr_fill_gaps_dev.argtypes = [vp, u8p, i64, i64, i64, u8p, i64, i32, u8p, i64, u8p, i32, i32, u8p, i64, vp]
     L.mr_fill_gaps_host.argtypes = [vp, u8p, i64, i64, i64, u8p, i64, i32, u8p, i64, u8p, i32, i32, u8p, i64]
+    L.mr_set_known_band.argtypes = [vp, i64, vp, vp, i64]
+    L.mr_multi_create.argtypes = [vp, i32, C.POINTER(i32)]
+    L.mr_multi_create.restype = vp
+    L.mr_multi_destroy.argtypes = [vp]
+    L.mr_multi_destroy.restype = None
+    L.mr_multi_last_error.argtypes = [vp]
+    L.mr_multi_last_error.restype = C.c_char_p
+    L.mr_multi_device_count.argtypes = [vp]
+    L.mr_multi_ctx.argtypes = [vp, i32]
+    L.mr_multi_ctx.restype = vp
+    L.mr_multi_band_range.argtypes = [vp, i64, i32, C.POINTER(i64), C.POINTER(i64)]
+    L.mr_multi_set_palette.argtypes = [vp, i32, vp, vp, vp, i32, i32]
+    L.mr_multi_set_known.argtypes = [vp, i64, vp, vp]
+    L.mr_multi_categorize_clean_host.argtypes = [vp, u8p, i64, i64, i64, i32, i32, u8p, i64, C.POINTER(Counters)]
+    L.mr_multi_batch_categorize_clean_host.argtypes = [vp, i32, u8p, i64, i64, i64, i64, i32, i32, u8p, i64, i64]
+    L.mr_multi_categorize_clean_dev.argtypes = [vp, vp, i64, i64, i64, i32, i32, vp, i64]
     L.mr_host_alloc.argtypes = [C.c_size_t]
     L.mr_host_alloc.restype = vp
     L.mr_host_free.argtypes = [vp]
@@ -99,7 +118,10 @@ def load():
                  "mr_categorize_clean_dev",
                  "mr_categorize_clean_dev_peer", "mr_ipc_export", "mr_ipc_open", "mr_ipc_close",
                  "mr_batch_categorize_clean_dev", "mr_clean_host", "mr_clean_dev", "mr_clean_segments_dev",
-                 "mr_clean_segments_host", "mr_fill_gaps_dev", "mr_fill_gaps_host", "mr_synth_scan_dev"):
+                 "mr_clean_segments_host", "mr_fill_gaps_dev", "mr_fill_gaps_host", "mr_synth_scan_dev",
+                 "mr_set_known_band", "mr_multi_device_count", "mr_multi_band_range", "mr_multi_set_palette",
+                 "mr_multi_set_known", "mr_multi_categorize_clean_host", "mr_multi_batch_categorize_clean_host",
+                 "mr_multi_categorize_clean_dev"):
         getattr(L, name).restype = i32
     _lib = L
     return L
@@ -174,6 +196,12 @@ class Context:
         idx = np.ascontiguousarray(lin_idx, dtype=np.int64)
         ct = np.ascontiguousarray(cat, dtype=np.uint8)
         self._ck(self._L.mr_set_known(self._h, idx.size, _ptr(idx), _ptr(ct)))
+
+    def set_known_band(self, lin_idx, cat, first_line):
+        """Whole-sheet indices; first_line = sheet line of line 0 of the band passed to the next calls."""
+        idx = np.ascontiguousarray(lin_idx, dtype=np.int64)
+        ct = np.ascontiguousarray(cat, dtype=np.uint8)
+        self._ck(self._L.mr_set_known_band(self._h, idx.size, _ptr(idx), _ptr(ct), int(first_line)))
 
     def get_lut(self):
         lut = np.empty(LUT_SIZE, dtype=np.uint8)
@@ -309,3 +337,89 @@ class Context:
         pal = np.ascontiguousarray(palette_rgb, dtype=np.uint8)
         self._ck(self._L.mr_synth_scan_dev(self._h, seed, sheet_id, pal.shape[0], _ptr(pal), n1, n2, line0, nlines,
                                            mode, _ptr(out), out_stride2, stream or None))
+
+
+class MultiContext:
+    """Several GPUs of one box behind one handle (mr_multi_*): the library owns one context and one host
+    thread per device; a sheet is split into row bands over n2, a batch into groups of sheets."""
+
+    def __init__(self, devices=None):
+        L = load()
+        err = C.c_int(0)
+        if devices is None:
+            self._h = L.mr_multi_create(None, 0, C.byref(err))
+        else:
+            ids = (C.c_int * len(devices))(*[int(d) for d in devices])
+            self._h = L.mr_multi_create(ids, len(devices), C.byref(err))
+        if not self._h:
+            raise MapRastError(err.value, L.mr_multi_last_error(None).decode())
+        self._L = L
+        self.n_dev = int(L.mr_multi_device_count(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.mr_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise MapRastError(rc, self._L.mr_multi_last_error(self._h).decode())
+
+    def band_range(self, n2, i):
+        a, n = C.c_int64(0), C.c_int64(0)
+        self._ck(self._L.mr_multi_band_range(self._h, int(n2), int(i), C.byref(a), C.byref(n)))
+        return int(a.value), int(n.value)
+
+    def set_palette(self, mean, lo, hi, colourspace=RGB, channels=None):
+        mean = np.ascontiguousarray(mean, dtype=np.float64)
+        lo = np.ascontiguousarray(lo, dtype=np.float64)
+        hi = np.ascontiguousarray(hi, dtype=np.float64)
+        K, Cn = mean.shape
+        self._ck(self._L.mr_multi_set_palette(self._h, K, _ptr(mean), _ptr(lo), _ptr(hi), int(colourspace),
+                                              int(channels or Cn)))
+
+    def set_known(self, lin_idx=None, cat=None):
+        if lin_idx is None or len(lin_idx) == 0:
+            self._ck(self._L.mr_multi_set_known(self._h, 0, None, None))
+            return
+        idx = np.ascontiguousarray(lin_idx, dtype=np.int64)
+        ct = np.ascontiguousarray(cat, dtype=np.uint8)
+        self._ck(self._L.mr_multi_set_known(self._h, idx.size, _ptr(idx), _ptr(ct)))
+
+    def categorize_clean_host(self, px, R, out=None, counters=False):
+        """px: (n2, n1, bpp) uint8 numpy (or a raw pinned buffer wrapped as such); labels (n2, n1)."""
+        if px.dtype != np.uint8 or px.ndim != 3 or px.shape[2] not in (3, 4):
+            raise ValueError("px must be a (n2, n1, 3|4) uint8 array")
+        if px.strides[2] != 1 or px.strides[1] != px.shape[2]:
+            px = np.ascontiguousarray(px)
+        n2, n1, bpp = px.shape
+        stride2 = px.strides[0] if n2 > 1 else n1 * bpp
+        if out is None:
+            out = np.empty((n2, n1), dtype=np.uint8)
+        cnt = Counters() if counters else None
+        self._ck(self._L.mr_multi_categorize_clean_host(self._h, _ptr(px), n1, n2, stride2, bpp, int(R), _ptr(out),
+                                                        out.strides[0] if n2 > 1 else n1,
+                                                        C.byref(cnt) if counters else None))
+        return (out, cnt.as_dict()) if counters else out
+
+    def batch_categorize_clean_host(self, px, R, out=None):
+        """px: (n_sheets, n2, n1, bpp) uint8, C-contiguous."""
+        px = np.ascontiguousarray(px, dtype=np.uint8)
+        ns, n2, n1, bpp = px.shape
+        if out is None:
+            out = np.empty((ns, n2, n1), dtype=np.uint8)
+        self._ck(self._L.mr_multi_batch_categorize_clean_host(self._h, ns, _ptr(px), n2 * n1 * bpp, n1, n2, n1 * bpp, bpp,
+                                                              int(R), _ptr(out), n2 * n1, n1))
+        return out
+
+    def categorize_clean_dev(self, band_px, n1, n2, stride2, bpp, R, band_out, out_stride2):
+        """band_px / band_out: one device buffer (torch tensor or address) per band, on that band's device."""
+        pin = (C.c_void_p * self.n_dev)(*[_ptr(b) if b is not None else None for b in band_px])
+        pout = (C.c_void_p * self.n_dev)(*[_ptr(b) if b is not None else None for b in band_out])
+        self._ck(self._L.mr_multi_categorize_clean_dev(self._h, pin, n1, n2, stride2, bpp, int(R), pout, out_stride2))

@@ -25,6 +25,7 @@ struct mr_ctx {
     float build_ms = 0.f;
     // known-category plane (sparse)
     int64_t n_known = 0;
+    int64_t known_origin = 0;       // sheet line of line 0 of the px of the next calls (bands); 0 for whole images
     int64_t* d_known_idx = nullptr;
     uint8_t* d_known_cat = nullptr;
     // counters
@@ -197,6 +198,13 @@ extern "C" int mr_set_palette(mr_ctx* ctx, int K, const double* mean, const doub
     return MR_OK;
 }
 
+extern "C" int mr_set_known_band(mr_ctx* ctx, int64_t n, const int64_t* lin_idx, const uint8_t* cat, int64_t first_line) {
+    if (first_line < 0) return fail(ctx, MR_ERR_ARG, "mr_set_known_band: negative first_line");
+    const int rc = mr_set_known(ctx, n, lin_idx, cat);
+    if (rc == MR_OK) ctx->known_origin = first_line;
+    return rc;
+}
+
 extern "C" int mr_set_known(mr_ctx* ctx, int64_t n, const int64_t* lin_idx, const uint8_t* cat) {
     if (!ctx) return fail(nullptr, MR_ERR_ARG, "mr_set_known: null ctx");
     if (n < 0 || (n > 0 && (!lin_idx || !cat))) return fail(ctx, MR_ERR_ARG, "mr_set_known: bad arguments");
@@ -207,6 +215,7 @@ extern "C" int mr_set_known(mr_ctx* ctx, int64_t n, const int64_t* lin_idx, cons
     cudaFree(ctx->d_known_idx); ctx->d_known_idx = nullptr;
     cudaFree(ctx->d_known_cat); ctx->d_known_cat = nullptr;
     ctx->n_known = 0;
+    ctx->known_origin = 0;
     if (n == 0) return MR_OK;
     CK(cudaMalloc(&ctx->d_known_idx, n * 8));
     CK(cudaMalloc(&ctx->d_known_cat, n));
@@ -443,31 +452,52 @@ static int run_rgba(mr_ctx* ctx, const MrJob& job, cudaStream_t s) {
     return run_clean(ctx, c, s, ctx->pal.K);
 }
 
+// Known-category points (categories.jl:110-112) change single labels BEFORE the majority filter sees
+// them: categorise every line the windows read (the band's own lines and its halo lines, wherever they
+// live) into an aligned label plane, fix the clicked pixels up, then run the standalone filter on it.
 static int run_with_known(mr_ctx* ctx, MrJob job, cudaStream_t s) {
     const int R = job.R;
-    uint8_t* final_out = job.out;
-    const int64_t final_stride = job.out_stride2;
+    const int hl = R > 0 ? job.halo_lo : 0, hh = R > 0 ? job.halo_hi : 0;
+    const int64_t T = job.n2 + hl + hh;
     const int64_t line_tmp = (job.n1 + 15) / 16 * 16;   // aligned intermediate labels: both passes can take the fast kernel
+    uint8_t* plane = job.out;
+    int64_t plane_stride = job.out_stride2;
     if (R > 0) {
-        int rc = grow(ctx, &ctx->d_tmp, &ctx->d_tmp_cap, (size_t)line_tmp * job.n2);
+        int rc = grow(ctx, &ctx->d_tmp, &ctx->d_tmp_cap, (size_t)line_tmp * T);
         if (rc) return rc;
-        job.out = ctx->d_tmp;
-        job.out_stride2 = line_tmp;
+        plane = ctx->d_tmp;
+        plane_stride = line_tmp;
     }
-    job.R = 0;
-    MrCountersDev* cnt = job.counters;
-    if (R > 0) job.counters = nullptr;
-    int rc = run_fused(ctx, job, s);
-    if (rc) return rc;
+    // categorise-only passes: [halo lines before | own lines | halo lines after] -> plane
+    struct Piece { const uint8_t* px; int64_t lines, at; };
+    Piece pieces[3];
+    int np = 0;
+    if (job.halo_lo_px || job.halo_hi_px) {
+        if (hl) pieces[np++] = Piece{job.halo_lo_px ? job.halo_lo_px + (int64_t)(job.halo_lo - hl) * job.stride2
+                                                    : job.px - (int64_t)hl * job.stride2, hl, 0};
+        pieces[np++] = Piece{job.px, job.n2, hl};
+        if (hh) pieces[np++] = Piece{job.halo_hi_px ? job.halo_hi_px : job.px + job.n2 * job.stride2, hh, hl + job.n2};
+    } else {
+        pieces[np++] = Piece{job.px - (int64_t)hl * job.stride2, T, 0};
+    }
+    for (int k = 0; k < np; ++k) {
+        MrJob c = job;
+        c.px = pieces[k].px; c.n2 = pieces[k].lines; c.R = 0; c.halo_lo = c.halo_hi = 0;
+        c.halo_lo_px = c.halo_hi_px = nullptr;
+        c.out = plane + pieces[k].at * plane_stride; c.out_stride2 = plane_stride;
+        if (R > 0) c.counters = nullptr;
+        int rc = run_fused(ctx, c, s);
+        if (rc) return rc;
+    }
     int nl = 0;
-    cudaError_t e = mr_launch_known_fixup(job, ctx->n_known, ctx->d_known_idx, ctx->d_known_cat, job.out,
-                                          job.out_stride2, s, &nl);
+    cudaError_t e = mr_launch_known_fixup(job, ctx->n_known, ctx->d_known_idx, ctx->d_known_cat, plane, plane_stride,
+                                          ctx->known_origin, -(int64_t)hl, T, s, &nl);
     ctx->launches += nl;
     if (e != cudaSuccess) return fail_cuda(ctx, e, "known-category fix-up");
     if (R > 0) {
         MrJob c = job;
-        c.px = ctx->d_tmp; c.stride2 = line_tmp; c.bpp = 1; c.R = R; c.out = final_out;
-        c.out_stride2 = final_stride; c.counters = cnt;
+        c.px = plane + (int64_t)hl * plane_stride; c.stride2 = plane_stride; c.bpp = 1;
+        c.halo_lo = hl; c.halo_hi = hh; c.halo_lo_px = c.halo_hi_px = nullptr;
         return run_clean(ctx, c, s, ctx->pal.K);
     }
     return MR_OK;
@@ -482,11 +512,7 @@ extern "C" int mr_categorize_clean_dev(mr_ctx* ctx, const uint8_t* px_dev, int64
     if ((rc = check_palette(ctx, "mr_categorize_clean_dev", bpp))) return rc;
     CK(cudaSetDevice(ctx->device));
     MrJob job = make_job(ctx, px_dev, labels_dev, n1, n2, stride2, bpp, R, halo_lo, halo_hi, out_stride2);
-    if (ctx->n_known > 0) {
-        if (halo_lo || halo_hi)
-            return fail(ctx, MR_ERR_ARG, "mr_categorize_clean_dev: known-category points need a whole-image call (no halos)");
-        return run_with_known(ctx, job, (cudaStream_t)stream);
-    }
+    if (ctx->n_known > 0) return run_with_known(ctx, job, (cudaStream_t)stream);
     return run_fused(ctx, job, (cudaStream_t)stream);
 }
 
@@ -550,8 +576,6 @@ static int host_impl(mr_ctx* ctx, const char* fn, const uint8_t* px, int64_t n1,
         if (counters) memset(counters, 0, sizeof *counters);
         return MR_OK;
     }
-    if (ctx->n_known > 0 && (halo_lo || halo_hi))
-        return fail(ctx, MR_ERR_ARG, std::string(fn) + ": known-category points need a whole-image call (no halos)");
     CK(cudaSetDevice(ctx->device));
     const int64_t T = n2 + halo_lo + halo_hi;            // lines resident on the device
     const int64_t line_in = (n1 * bpp + 15) / 16 * 16;   // 16-byte aligned device lines
@@ -668,8 +692,6 @@ extern "C" int mr_categorize_clean_dev_peer(mr_ctx* ctx, const uint8_t* px_dev, 
     if ((rc = check_palette(ctx, "mr_categorize_clean_dev_peer", bytes_per_px))) return rc;
     if ((halo_lo > 0 && !halo_lo_px) || (halo_hi > 0 && !halo_hi_px))
         return fail(ctx, MR_ERR_ARG, "mr_categorize_clean_dev_peer: null halo pointer with a non-zero halo");
-    if (ctx->n_known > 0)
-        return fail(ctx, MR_ERR_ARG, "mr_categorize_clean_dev_peer: known categories are not supported on this entry point");
     CK(cudaSetDevice(ctx->device));
     MrJob job = make_job(ctx, px_dev, labels_dev, n1, n2, stride2_bytes, bytes_per_px, R, halo_lo, halo_hi, out_stride2);
     job.halo_lo_px = halo_lo > 0 ? halo_lo_px : nullptr;
@@ -679,6 +701,7 @@ extern "C" int mr_categorize_clean_dev_peer(mr_ctx* ctx, const uint8_t* px_dev, 
         return fail(ctx, MR_ERR_ARG,
                     "mr_categorize_clean_dev_peer: remote halo lines need the fast path (packed RGB, 16-byte aligned "
                     "lines and pointers, n1 % 16 == 0, R <= 3, K <= 126)");
+    if (ctx->n_known > 0) return run_with_known(ctx, job, (cudaStream_t)stream);
     int nl = 0;
     cudaError_t e = mr_launch_fast(job, ctx->sm_count, (cudaStream_t)stream, &nl, &ctx->work);
     ctx->launches += nl;

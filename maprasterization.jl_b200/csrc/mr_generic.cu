@@ -211,24 +211,31 @@ cudaError_t mr_launch_generic(const MrJob& job, bool labels_in, int sm_count, cu
 // src/categories.jl:110-112 + src/selectcolors.jl:670-681: a clicked pixel with known
 // category k is labelled (best == k) ? best : 0, skipping the box test.  Sparse (<= a few
 // hundred pixels), so it runs as its own tiny kernel on the categorised plane.
+// The indices count from sheet line 0; the plane `labels` holds the band-local lines
+// [j_first, j_first + n_lines) of a band whose line 0 is sheet line `origin` (whole image: 0, 0, n2).
+// Points outside the plane are skipped (never a write outside it).
 __global__ void k_known_fixup(MrJob job, int64_t n_known, const int64_t* __restrict__ idx,
                               const uint8_t* __restrict__ cat, uint8_t* __restrict__ labels,
-                              int64_t labels_stride2) {
+                              int64_t labels_stride2, int64_t origin, int64_t j_first, int64_t n_lines) {
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k >= n_known) return;
-    if (idx[k] < 0 || idx[k] >= job.n1 * job.n2 || cat[k] == 0) return;   // never write outside the plane
-    const int64_t i = idx[k] % job.n1, j = idx[k] / job.n1;
-    const uint8_t* p = job.px + j * job.stride2 + i * job.bpp;
-    labels[j * labels_stride2 + i] =
+    if (idx[k] < 0 || cat[k] == 0) return;
+    const int64_t i = idx[k] % job.n1, j = idx[k] / job.n1 - origin;   // band-local line
+    if (j < j_first || j >= j_first + n_lines) return;
+    const uint8_t* line = job.px + j * job.stride2;
+    if (j < 0 && job.halo_lo_px) line = job.halo_lo_px + (j + job.halo_lo) * job.stride2;
+    else if (j >= job.n2 && job.halo_hi_px) line = job.halo_hi_px + (j - job.n2) * job.stride2;
+    const uint8_t* p = line + i * job.bpp;
+    labels[(j - j_first) * labels_stride2 + i] =
         (uint8_t)mr_eval_px(job.pal, p[0], p[1], p[2], job.bpp == 4 ? p[3] : 255, job.bpp == 4, cat[k]);
 }
 
 cudaError_t mr_launch_known_fixup(const MrJob& job, int64_t n_known, const int64_t* idx,
-                                  const uint8_t* cat, uint8_t* labels, int64_t labels_stride2,
-                                  cudaStream_t s, int* n_launches) {
+                                  const uint8_t* cat, uint8_t* labels, int64_t labels_stride2, int64_t origin,
+                                  int64_t j_first, int64_t n_lines, cudaStream_t s, int* n_launches) {
     if (n_known <= 0) return cudaSuccess;
     k_known_fixup<<<(unsigned)((n_known + 127) / 128), 128, 0, s>>>(job, n_known, idx, cat, labels,
-                                                                     labels_stride2);
+                                                                     labels_stride2, origin, j_first, n_lines);
     *n_launches += 1;
     return cudaGetLastError();
 }

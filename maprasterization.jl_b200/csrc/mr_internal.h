@@ -76,8 +76,8 @@ cudaError_t mr_launch_alpha_fix(const MrPalette& pal, const uint8_t* px, int64_t
 cudaError_t mr_launch_max_label(const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2, unsigned int* d_out,
                                 int sm_count, cudaStream_t s, int* n_launches);
 cudaError_t mr_launch_known_fixup(const MrJob& job, int64_t n_known, const int64_t* idx,
-                                  const uint8_t* cat, uint8_t* labels, int64_t labels_stride2,
-                                  cudaStream_t s, int* n_launches);
+                                  const uint8_t* cat, uint8_t* labels, int64_t labels_stride2, int64_t origin,
+                                  int64_t j_first, int64_t n_lines, cudaStream_t s, int* n_launches);
 cudaError_t mr_launch_synth(uint32_t seed, uint32_t sheet, int K, const uint8_t* pal_dev, int64_t n1,
                             int64_t line0, int64_t nlines, int mode, uint8_t* out, int64_t out_stride2,
                             cudaStream_t s, int* n_launches);

@@ -10,16 +10,19 @@
 # Every label is computed by libmaprast.so (CUDA, sm_100a) through `ccall`; there is NO CPU
 # fallback: unsupported options throw ArgumentError, a missing GPU makes `Context()` throw.
 #
-# NOTE: Julia is not installed in the build image, so this file is reviewed but not executed
-# there; the same C ABI is exercised by the Python mirror (maprasterization.jl_b200/api.py) that
-# the test-suite runs.  Keep the two in sync (include/maprast.h is the contract).
+#   fill_gaps(src; categories, stats, known, original, mask, ...)                src/clean.jl:2-54
+#
+# NOTE: Julia is not installed in the build image, so this file has NEVER BEEN EXECUTED; the same C
+# ABI is exercised by the Python mirror (maprasterization.jl_b200/api.py) that the test-suite runs, and
+# tests/test_julia_binding.py checks every `ccall` below (symbol, return type, argument count and
+# widths) against the prototypes of include/maprast.h.  Keep the two in sync (the header is the contract).
 module MapRasterizationB200
 
 using ColorTypes, FixedPointNumbers, Statistics
 import Neighborhoods: Window
 
 export categorize, clean, categorize_clean, categorize_u8, clean_u8, categorize_clean_u8, clean_segments,
-       clean_segments_u8, rasterize, MapSelection, Context, Palette
+       clean_segments_u8, fill_gaps, fill_gaps_u8, rasterize, MapSelection, Context, MultiContext, Palette
 
 const libmaprast = get(ENV, "LIBMAPRAST", joinpath(@__DIR__, "..", "libmaprast.so"))
 const DEFAULT_CATEGORY_TOLERANCE = 2.0            # src/selectcolors.jl:1
@@ -102,10 +105,30 @@ _check_match(match, segmented) = begin
     segmented && throw(ArgumentError("segmented=true is not supported by the B200 hot path"))
 end
 
+# ---- known-category plane (`_set_categories!`, src/selectcolors.jl:670-681) ---------------------------
+# The plane lives in the context until it is replaced: EVERY entry point below sets or clears it before
+# its call and clears it afterwards, so that no call ever sees the points of an earlier one.
+_clear_known(ctx::Context) =
+    _check(ctx, ccall((:mr_set_known, libmaprast), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{UInt8}), ctx.ptr, 0, C_NULL, C_NULL))
+
+function _set_known(ctx::Context, known::Union{Nothing,AbstractMatrix}, sz)
+    known === nothing && return _clear_known(ctx)
+    size(known) == sz || throw(ArgumentError("the known-category plane must have the size of the image"))
+    idx = Int64[i - 1 for i in eachindex(IndexLinear(), known) if known[i] != 0]   # i + j*n1, 0-based
+    cat = UInt8[known[i + 1] for i in idx]
+    GC.@preserve idx cat begin
+        _check(ctx, ccall((:mr_set_known, libmaprast), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{UInt8}),
+            ctx.ptr, length(idx), pointer(idx), pointer(cat)))
+    end
+end
+
 # ---- the hot path ---------------------------------------------------------------------------------
-"Fused clean(categorize(img)): UInt8 labels, 0 = no match."
+"""
+Fused clean(categorize(img)): UInt8 labels, 0 = no match.  `known`: optional plane of known categories
+(0 = none) for the override of src/categories.jl:110-112; `nothing` = no clicked points.
+"""
 function categorize_clean_u8(img::AbstractMatrix{T}, points_or_palette; tolerances=nothing,
-        hood=Window{1}(), match=(:color,), segmented=false, scan_threshold=0.1,
+        hood=Window{1}(), match=(:color,), segmented=false, scan_threshold=0.1, known=nothing,
         ctx::Context=default_context()) where {T<:Union{RGB{N0f8},RGBA{N0f8}}}
     _check_match(match, segmented)
     A = img isa Matrix ? img : Matrix(img)                       # dense, column-major, n1 = size(A, 1)
@@ -115,10 +138,15 @@ function categorize_clean_u8(img::AbstractMatrix{T}, points_or_palette; toleranc
     n1, n2 = size(A)
     R = _radius(hood)
     out = Matrix{UInt8}(undef, n1, n2)
-    GC.@preserve A out begin
-        _check(ctx, ccall((:mr_categorize_clean_host, libmaprast), Cint,
-            (Ptr{Cvoid}, Ptr{UInt8}, Int64, Int64, Int64, Cint, Cint, Ptr{UInt8}, Int64, Ptr{MRCounters}),
-            ctx.ptr, pointer(A), n1, n2, n1 * sizeof(T), sizeof(T), R, pointer(out), n1, C_NULL))
+    _set_known(ctx, known, size(A))
+    try
+        GC.@preserve A out begin
+            _check(ctx, ccall((:mr_categorize_clean_host, libmaprast), Cint,
+                (Ptr{Cvoid}, Ptr{UInt8}, Int64, Int64, Int64, Cint, Cint, Ptr{UInt8}, Int64, Ptr{MRCounters}),
+                ctx.ptr, pointer(A), n1, n2, n1 * sizeof(T), sizeof(T), R, pointer(out), n1, C_NULL))
+        end
+    finally
+        known === nothing || _clear_known(ctx)
     end
     return out
 end
@@ -128,7 +156,12 @@ _radius(::Window{R}) where {R} = R
 # eltype Int and the input's container type, like `map(pixels) do ... end` (src/categories.jl:69-73)
 _rewrap(img, labels::Matrix{UInt8}) = _rebuild(img, Int.(labels))
 _rebuild(img::Matrix, data) = data
-_rebuild(img, data) = applicable(rebuild, img, data) ? rebuild(img, data) : data   # Rasters.Raster in => Raster out
+# Raster / DimArray in => the same wrapper out: `rebuild` is looked up in the module that owns the input's
+# type (Rasters and DimensionalData both bind it), so this file needs no dependency on either package.
+function _rebuild(img, data)
+    m = parentmodule(typeof(img))
+    return isdefined(m, :rebuild) ? getfield(m, :rebuild)(img, data) : data
+end
 
 categorize_clean(img, p; kw...) = _rewrap(img, categorize_clean_u8(img, p; kw...))
 categorize_u8(img, p; kw...) = categorize_clean_u8(img, p; hood=Window{0}(), kw...)
@@ -167,24 +200,61 @@ function clean_segments_u8(A::AbstractMatrix{<:Integer}, known_categories=nothin
     for c in categories
         keep[c + 1] = 1
     end
-    if known_categories === nothing
-        _check(ctx, ccall((:mr_set_known, libmaprast), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{UInt8}), ctx.ptr, 0, C_NULL, C_NULL))
-    else
-        size(known_categories) == size(A) || throw(ArgumentError("known_categories must have the size of A"))
-        idx = Int64[i - 1 for i in eachindex(known_categories) if known_categories[i] != 0]   # i + j*n1, 0-based
-        cat = UInt8[known_categories[i + 1] for i in idx]
-        _check(ctx, ccall((:mr_set_known, libmaprast), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{UInt8}), ctx.ptr, length(idx), idx, cat))
-    end
     out = similar(L)
     nseg = Ref{Int64}(0)
-    GC.@preserve L out keep begin
-        _check(ctx, ccall((:mr_clean_segments_host, libmaprast), Cint,
-            (Ptr{Cvoid}, Ptr{UInt8}, Int64, Int64, Int64, Ptr{UInt8}, Float64, Float64, Ptr{UInt8}, Int64, Ref{Int64}),
-            ctx.ptr, pointer(L), n1, n2, n1, pointer(keep), line_threshold, prune_threshold, pointer(out), n1, nseg))
+    _set_known(ctx, known_categories, size(A))
+    try
+        GC.@preserve L out keep begin
+            _check(ctx, ccall((:mr_clean_segments_host, libmaprast), Cint,
+                (Ptr{Cvoid}, Ptr{UInt8}, Int64, Int64, Int64, Ptr{UInt8}, Float64, Float64, Ptr{UInt8}, Int64, Ref{Int64}),
+                ctx.ptr, pointer(L), n1, n2, n1, pointer(keep), Float64(line_threshold), Float64(prune_threshold),
+                pointer(out), n1, nseg))
+        end
+    finally
+        known_categories === nothing || _clear_known(ctx)
     end
     return out
 end
 clean_segments(A, known=nothing; kw...) = _rewrap(A, clean_segments_u8(A, known; kw...))
+
+"""
+`fill_gaps(src; categories, neighborhood=VonNeumann{2}(), missingval=0, stats, match=(:color,), known, original,
+mask)` (src/clean.jl:2-54), applied `repeat` times as `_fill` does (src/selectcolors.jl:683-699).
+`stats`: the `Palette` of the categoriser (`stats[i]` of clean.jl:29-30 = its column `categories[i]`);
+`original`: the image the categoriser saw; `known` / `mask`: planes of the size of `src` or `nothing`.
+Only `missingval = 0`, the VonNeumann{2} neighbourhood and `match = (:color,)` exist on the GPU path.
+"""
+function fill_gaps_u8(src::AbstractMatrix{<:Integer}; categories, stats::Palette, original::AbstractMatrix{T},
+        known=nothing, mask=nothing, match=(:color,), missingval=0, repeat::Int=1,
+        ctx::Context=default_context()) where {T<:Union{RGB{N0f8},RGBA{N0f8}}}
+    missingval == 0 || throw(ArgumentError("fill_gaps: only missingval = 0 is supported"))
+    _check_match(match, false)
+    size(original) == size(src) || throw(ArgumentError("original must have the size of src"))
+    (isempty(src) || (0 <= minimum(src) && maximum(src) <= 254)) || throw(ArgumentError("labels must be in 0..254"))
+    L = Matrix{UInt8}(src)
+    O = original isa Matrix ? original : Matrix(original)
+    n1, n2 = size(L)
+    cats = UInt8[c for c in categories]
+    M = mask === nothing ? UInt8[] : Matrix{UInt8}(mask .!= 0)
+    mask === nothing || size(mask) == size(src) || throw(ArgumentError("mask must have the size of src"))
+    out = similar(L)
+    _upload(ctx, stats)
+    _set_known(ctx, known, size(src))
+    try
+        GC.@preserve L O M cats out begin
+            _check(ctx, ccall((:mr_fill_gaps_host, libmaprast), Cint,
+                (Ptr{Cvoid}, Ptr{UInt8}, Int64, Int64, Int64, Ptr{UInt8}, Int64, Cint, Ptr{UInt8}, Int64,
+                 Ptr{UInt8}, Cint, Cint, Ptr{UInt8}, Int64),
+                ctx.ptr, pointer(L), n1, n2, n1, pointer(O), n1 * sizeof(T), sizeof(T),
+                mask === nothing ? Ptr{UInt8}(C_NULL) : pointer(M), n1, pointer(cats), length(cats), repeat,
+                pointer(out), n1))
+        end
+    finally
+        known === nothing || _clear_known(ctx)
+    end
+    return out
+end
+fill_gaps(src; kw...) = _rewrap(src, fill_gaps_u8(src; kw...))
 
 # ---- MapSelection: the non-interactive entry (src/selectcolors.jl:3-8, 21-24, 111-127) ------------
 "Same fields as the reference's `MapSelection`; `settings` is the NamedTuple built at src/selectcolors.jl:111-125."
@@ -213,21 +283,72 @@ categorize_u8(img, sel::MapSelection; kw...) =
 categorize(img, sel::MapSelection; kw...) = _rewrap(img, categorize_u8(img, sel; kw...))
 
 """
-The button sequence of `selectcolors` without the GUI: "categorize" (src/selectcolors.jl:466-478),
-optional Window majority filter (`hood`), "clean" (:479-489).  Returns `(; categorized, cleaned)`.
+The button sequence of `selectcolors` without the GUI: "categorize" (src/selectcolors.jl:466-478, with the
+known-category override of the clicked points), optional Window majority filter (`hood`), "clean"
+(:479-489), "fill" (:490-501, `fill_repeat` passes of `fill_gaps`; `mask` = the caller's polygon mask).
+Returns `(; categorized, cleaned, filled)`.
 """
-function rasterize(img, sel::MapSelection; hood=Window{0}(), ctx::Context=default_context())
+function rasterize(img, sel::MapSelection; hood=Window{0}(), mask=nothing, ctx::Context=default_context())
     get(sel.settings, :blur_repeat, 0) == 0 ||
         throw(ArgumentError("blur_repeat > 0 is not supported by the B200 hot path"))
-    categorized = categorize_clean_u8(img, sel.points;
-        tolerances=collect(Float64, sel.settings.category_tolerances), hood,
-        match=get(sel.settings, :match, (:color,)), segmented=get(sel.settings, :segment, false), ctx)
-    known = _known_plane(size(categorized), sel.points)
+    A = img isa Matrix ? img : Matrix(img)
+    pal = Palette(A, sel.points; tolerances=collect(Float64, sel.settings.category_tolerances))
+    known = _known_plane(size(A), sel.points)
+    categorized = categorize_clean_u8(A, pal; hood, match=get(sel.settings, :match, (:color,)),
+        segmented=get(sel.settings, :segment, false), known, ctx)
     keep = get(sel.settings, :category_keep, fill(true, length(sel.points)))
-    cleaned = clean_segments_u8(categorized, known; categories=_kept_categories(collect(Bool, keep)),
+    kept = _kept_categories(collect(Bool, keep))
+    cleaned = clean_segments_u8(categorized, known; categories=kept,
         line_threshold=get(sel.settings, :line_threshold, 0.01),
         prune_threshold=get(sel.settings, :prune_threshold, 20), ctx)
-    return (; categorized=_rewrap(img, categorized), cleaned=_rewrap(img, cleaned))
+    filled = fill_gaps_u8(cleaned; categories=kept, stats=pal, original=A, known, mask,
+        repeat=get(sel.settings, :fill_repeat, 1), ctx)
+    return (; categorized=_rewrap(img, categorized), cleaned=_rewrap(img, cleaned), filled=_rewrap(img, filled))
+end
+
+# ---- several GPUs of one box (mr_multi_*): one call, the library splits the sheet into row bands ------
+mutable struct MultiContext
+    ptr::Ptr{Cvoid}
+    function MultiContext(devices::AbstractVector{<:Integer}=Int[])
+        err = Ref{Cint}(0)
+        ids = Cint[d for d in devices]
+        p = GC.@preserve ids ccall((:mr_multi_create, libmaprast), Ptr{Cvoid}, (Ptr{Cint}, Cint, Ref{Cint}),
+            isempty(ids) ? Ptr{Cint}(C_NULL) : pointer(ids), length(ids), err)
+        p == C_NULL && error(unsafe_string(ccall((:mr_multi_last_error, libmaprast), Cstring, (Ptr{Cvoid},), C_NULL)))
+        m = new(p)
+        finalizer(x -> ccall((:mr_multi_destroy, libmaprast), Cvoid, (Ptr{Cvoid},), x.ptr), m)
+        return m
+    end
+end
+
+function _check(m::MultiContext, rc::Cint)
+    rc == 0 && return nothing
+    msg = unsafe_string(ccall((:mr_multi_last_error, libmaprast), Cstring, (Ptr{Cvoid},), m.ptr))
+    (rc == -1 || rc == -5) ? throw(ArgumentError(msg)) : error("libmaprast ($rc): $msg")
+end
+
+"Fused clean(categorize(img)) over every GPU of the handle: byte-identical to the single-GPU call."
+function categorize_clean_u8(img::AbstractMatrix{T}, pal::Palette, m::MultiContext; hood=Window{1}(),
+        known=nothing) where {T<:Union{RGB{N0f8},RGBA{N0f8}}}
+    A = img isa Matrix ? img : Matrix(img)
+    n1, n2 = size(A)
+    C, K = size(pal.mean)
+    _check(m, ccall((:mr_multi_set_palette, libmaprast), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Cint),
+        m.ptr, K, pal.mean, pal.lo, pal.hi, pal.colourspace, C))
+    idx = known === nothing ? Int64[] : Int64[i - 1 for i in eachindex(IndexLinear(), known) if known[i] != 0]
+    cat = UInt8[known[i + 1] for i in idx]
+    out = Matrix{UInt8}(undef, n1, n2)
+    GC.@preserve A out idx cat begin
+        _check(m, ccall((:mr_multi_set_known, libmaprast), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{UInt8}),
+            m.ptr, length(idx), pointer(idx), pointer(cat)))
+        _check(m, ccall((:mr_multi_categorize_clean_host, libmaprast), Cint,
+            (Ptr{Cvoid}, Ptr{UInt8}, Int64, Int64, Int64, Cint, Cint, Ptr{UInt8}, Int64, Ptr{MRCounters}),
+            m.ptr, pointer(A), n1, n2, n1 * sizeof(T), sizeof(T), _radius(hood), pointer(out), n1, C_NULL))
+        _check(m, ccall((:mr_multi_set_known, libmaprast), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{UInt8}),
+            m.ptr, 0, C_NULL, C_NULL))
+    end
+    return out
 end
 
 end # module
