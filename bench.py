@@ -514,6 +514,41 @@ def run_ours(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "algorithmic_bytes_per_px": 2,
                          "achieved": 2 * my_px / (seg_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": 2 * my_px / (seg_ms * 1e-3) / 1e9 / peak}}
+        # fill_gaps (src/clean.jl:2-54, the "fill" button) on the pruned labels, device resident, one pass
+        cats = list(range(1, K + 1))
+        fill_out = torch.empty_like(out)
+        if not batch and stats.colourspace == "rgb":
+            ctx.fill_gaps_dev(seg_out, n1, nb, n1, own, n1 * 3, 3, cats, fill_out, n1)
+            torch.cuda.synchronize()
+            l0 = ctx.launch_count()
+            e0.record()
+            for _ in range(reps):
+                ctx.fill_gaps_dev(seg_out, n1, nb, n1, own, n1 * 3, 3, cats, fill_out, n1)
+            e1.record()
+            torch.cuda.synchronize()
+            fg_ms = e0.elapsed_time(e1) / reps
+            res["next_rows"]["fill_gaps"] = {
+                "what": "fill_gaps(cleaned; categories=1..K, VonNeumann{2}, original = the scan), one pass, device resident",
+                "value": my_px / (fg_ms * 1e-3) / 1e6, "unit": UNIT, "ms": fg_ms,
+                "gap_pixels_in": int((seg_out == 0).sum().item()), "gap_pixels_out": int((fill_out == 0).sum().item()),
+                "gpu_launches_per_call": (ctx.launch_count() - l0) / reps,
+                "roofline": {"bound": "hbm", "algorithmic_bytes_per_px": 2,
+                             "achieved": 2 * my_px / (fg_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": 2 * my_px / (fg_ms * 1e-3) / 1e9 / peak,
+                             "note": "label in + label out; the original pixel (3 B) is only read where two categories tie"}}
+            if not args.no_cpu_baseline:
+                from oracle import oracle as O
+                lines = max(64, min(nb, (1 << 23) // n1))
+                t0 = time.perf_counter()
+                want_f = O.fill_gaps(seg_out[:lines].cpu().numpy(), own[:lines].cpu().numpy(), stats.mean, cats)
+                dt = time.perf_counter() - t0
+                got_f = torch.empty((lines, n1), dtype=torch.uint8, device=dev)
+                ctx.fill_gaps_dev(seg_out[:lines], n1, lines, n1, own[:lines], n1 * 3, 3, cats, got_f, n1)
+                res["next_rows"]["fill_gaps"]["cpu_baseline"] = {
+                    "value": n1 * lines / dt / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
+                    "sample": f"first {lines} lines, sequential C oracle",
+                    "label_mismatches_vs_gpu": int((got_f.cpu().numpy() != want_f).sum())}
+        del fill_out
         # the standalone Window majority filter, clean(labels; hood): categorise-only labels in, device resident
         pre = torch.empty_like(out)
         ctx.categorize_clean_dev(own, n1, nb, n1 * 3, 3, 0, pre, n1)
@@ -535,6 +570,16 @@ def run_ours(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "algorithmic_bytes_per_px": 2,
                          "achieved": 2 * my_px / (cl_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": 2 * my_px / (cl_ms * 1e-3) / 1e9 / peak}}
+        e0.record()
+        for _ in range(reps):
+            ctx.clean_dev(pre, n1, nb, n1, R, two, n1, max_label=K)
+        e1.record()
+        torch.cuda.synchronize()
+        clb_ms = e0.elapsed_time(e1) / reps
+        res["next_rows"]["clean_standalone"]["bounded"] = {
+            "what": "same through mr_clean_dev_bounded (label bound = K from the caller: one launch, no synchronisation)",
+            "value": my_px / (clb_ms * 1e-3) / 1e6, "ms": clb_ms, "equal_to_fused": bool(torch.equal(two, out)),
+            "roofline_frac": 2 * my_px / (clb_ms * 1e-3) / 1e9 / peak}
         del pre, two
         if not args.no_cpu_baseline:
             from oracle import oracle as O

@@ -154,6 +154,13 @@ int mr_clean_dev(mr_ctx* ctx, const uint8_t* labels_dev, int64_t n1, int64_t n2,
                  int R, int halo_lo, int halo_hi, uint8_t* out_dev, int64_t out_stride2,
                  void* stream);
 
+/* Same as mr_clean_dev with an upper bound of the label values supplied by the caller (typically the K of
+ * the palette that produced them; a label above the bound is undefined behaviour of the vote, not of
+ * memory): skips the label-maximum pass and its stream synchronisation -- fully asynchronous. */
+int mr_clean_dev_bounded(mr_ctx* ctx, const uint8_t* labels_dev, int64_t n1, int64_t n2, int64_t stride2,
+                         int R, int halo_lo, int halo_hi, int max_label, uint8_t* out_dev,
+                         int64_t out_stride2, void* stream);
+
 /* Segment prune = the reference's "clean" button: _clean(A, known_categories; categories,
  * line_threshold, prune_threshold), src/clean.jl:59-93 (call site src/selectcolors.jl:479-489),
  * over the segmentation fast_scanning!(..., 1e-9; match = (:color,)), src/scan.jl:56-157:

@@ -23,7 +23,7 @@ SYMBOLS = [
     "mr_get_lut", "mr_palette_build_ms", "mr_enable_counters", "mr_read_counters", "mr_launch_count",
     "mr_categorize_clean_host", "mr_categorize_clean_host_band", "mr_categorize_clean_dev", "mr_batch_categorize_clean_dev",
     "mr_categorize_clean_dev_peer", "mr_ipc_export", "mr_ipc_open", "mr_ipc_close",
-    "mr_clean_host", "mr_clean_dev", "mr_clean_segments_dev", "mr_clean_segments_host",
+    "mr_clean_host", "mr_clean_dev", "mr_clean_dev_bounded", "mr_clean_segments_dev", "mr_clean_segments_host",
     "mr_fill_gaps_dev", "mr_fill_gaps_host", "mr_set_known_band",
     "mr_multi_create", "mr_multi_destroy", "mr_multi_last_error", "mr_multi_device_count", "mr_multi_ctx",
     "mr_multi_band_range", "mr_multi_set_palette", "mr_multi_set_known", "mr_multi_categorize_clean_host",
@@ -86,6 +86,7 @@ def load():
     L.mr_ipc_close.argtypes = [vp, vp]
     L.mr_clean_host.argtypes = [vp, u8p, i64, i64, i64, i32, i32, u8p, i64]
     L.mr_clean_dev.argtypes = [vp, u8p, i64, i64, i64, i32, i32, i32, u8p, i64, vp]
+    L.mr_clean_dev_bounded.argtypes = [vp, u8p, i64, i64, i64, i32, i32, i32, i32, u8p, i64, vp]
     L.mr_clean_segments_dev.argtypes = [vp, u8p, i64, i64, i64, u8p, C.c_double, C.c_double, u8p, i64,
                                         C.POINTER(i64), vp]
     L.mr_clean_segments_host.argtypes = [vp, u8p, i64, i64, i64, u8p, C.c_double, C.c_double, u8p, i64,
@@ -119,7 +120,7 @@ def load():
                  "mr_categorize_clean_dev_peer", "mr_ipc_export", "mr_ipc_open", "mr_ipc_close",
                  "mr_batch_categorize_clean_dev", "mr_clean_host", "mr_clean_dev", "mr_clean_segments_dev",
                  "mr_clean_segments_host", "mr_fill_gaps_dev", "mr_fill_gaps_host", "mr_synth_scan_dev",
-                 "mr_set_known_band", "mr_multi_device_count", "mr_multi_band_range", "mr_multi_set_palette",
+                 "mr_set_known_band", "mr_clean_dev_bounded", "mr_multi_device_count", "mr_multi_band_range", "mr_multi_set_palette",
                  "mr_multi_set_known", "mr_multi_categorize_clean_host", "mr_multi_batch_categorize_clean_host",
                  "mr_multi_categorize_clean_dev"):
         getattr(L, name).restype = i32
@@ -329,7 +330,12 @@ class Context:
                                                        stride2, bpp, int(R), _ptr(out), out_sheet_stride,
                                                        out_stride2, stream or None))
 
-    def clean_dev(self, labels, n1, n2, stride2, R, out, out_stride2, halo_lo=0, halo_hi=0, stream=0):
+    def clean_dev(self, labels, n1, n2, stride2, R, out, out_stride2, halo_lo=0, halo_hi=0, stream=0, max_label=None):
+        """max_label: upper bound of the labels (e.g. K): no label-maximum pass, no synchronisation."""
+        if max_label is not None:
+            self._ck(self._L.mr_clean_dev_bounded(self._h, _ptr(labels), n1, n2, stride2, int(R), int(halo_lo),
+                                                  int(halo_hi), int(max_label), _ptr(out), out_stride2, stream or None))
+            return
         self._ck(self._L.mr_clean_dev(self._h, _ptr(labels), n1, n2, stride2, int(R), int(halo_lo), int(halo_hi),
                                       _ptr(out), out_stride2, stream or None))
 

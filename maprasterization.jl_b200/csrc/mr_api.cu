@@ -550,6 +550,24 @@ extern "C" int mr_clean_dev(mr_ctx* ctx, const uint8_t* labels_dev, int64_t n1, 
     return run_clean(ctx, job, (cudaStream_t)stream);
 }
 
+// Same with an upper bound of the labels supplied by the caller (e.g. the K of the palette that produced
+// them): no label-maximum pass and no stream synchronisation -- fully asynchronous.
+extern "C" int mr_clean_dev_bounded(mr_ctx* ctx, const uint8_t* labels_dev, int64_t n1, int64_t n2, int64_t stride2,
+                                    int R, int halo_lo, int halo_hi, int max_label, uint8_t* out_dev,
+                                    int64_t out_stride2, void* stream) {
+    int rc = check_image_args(ctx, "mr_clean_dev_bounded", labels_dev, out_dev, n1, n2, stride2, 1, out_stride2, R,
+                              halo_lo, halo_hi);
+    if (rc) return rc;
+    if (max_label < 0 || max_label > 254)
+        return fail(ctx, MR_ERR_ARG, "mr_clean_dev_bounded: max_label must be in 0..254");
+    if (labels_dev == out_dev && n1 > 0 && n2 > 0 && R > 0)
+        return fail(ctx, MR_ERR_ARG, "mr_clean_dev_bounded: in-place operation is not supported");
+    CK(cudaSetDevice(ctx->device));
+    MrJob job = make_job(ctx, labels_dev, out_dev, n1, n2, stride2, 1, R, halo_lo, halo_hi, out_stride2);
+    job.lut = nullptr;
+    return run_clean(ctx, job, (cudaStream_t)stream, max_label);
+}
+
 // ------------------------------------------------------------------ host entry points
 static int ensure_events(mr_ctx* ctx, size_t n) {
     while (ctx->ev_up.size() < n) {
@@ -893,7 +911,7 @@ extern "C" int mr_fill_gaps_dev(mr_ctx* ctx, const uint8_t* labels_dev, int64_t 
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
     return fill_dev(ctx, labels_dev, n1, n2, stride2, px_dev, px_stride2, bytes_per_px, mask_dev, mask_stride2, categories,
-                    n_categories, repeat, out_dev, out_stride2, stream ? (cudaStream_t)stream : ctx->s_main);
+                    n_categories, repeat, out_dev, out_stride2, (cudaStream_t)stream);
 }
 
 extern "C" int mr_fill_gaps_host(mr_ctx* ctx, const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2,

@@ -469,20 +469,32 @@ __device__ __forceinline__ void categorize_line(const FastParams& P, const uint8
     // bq = the isolated bit of the pixel (0: the word has no such pixel).  Only the lanes that have
     // one read its colour: these byte reads sit 96 bytes apart between lanes, i.e. up to eight lanes
     // per bank -- issued by all 32 lanes they were a quarter of the kernel's shared-memory wavefronts.
-    const uint32_t bq0 = s & (0u - s);
-    s ^= bq0;
-    const uint32_t bq1 = s & (0u - s);
-    s ^= bq1;
-    const int q0 = 31 - __clz(bq0), q1 = 31 - __clz(bq1);
-    const bool h0 = bq0 != 0u, h1 = bq1 != 0u;
-    unsigned rgb0 = 0u, rgb1 = 0u;
-    if (h0) rgb0 = colour(q0);
-    if (h1) rgb1 = colour(q1);
+    // MIXED pixels per word that are looked up without holding the line: three for small palettes (a word with
+    // more occurs on 8 % of the lines of config 2, with two it was 37 %); big palettes have so many MIXED
+    // pixels that the wide loop below runs on most lines anyway (three: 4 % slower on config 4)
+#ifdef MR_NQ
+    constexpr int NQ = MR_NQ;
+#else
+    constexpr int NQ = NB >= 6 ? 2 : 3;
+#endif
+    uint32_t bq[NQ];
+    int qi[NQ];
+    unsigned rgbq[NQ], lq[NQ];
+#pragma unroll
+    for (int t = 0; t < NQ; ++t) {
+        bq[t] = s & (0u - s);
+        s ^= bq[t];
+        qi[t] = 31 - __clz(bq[t]);
+        rgbq[t] = 0u;
+        if (bq[t]) rgbq[t] = colour(qi[t]);
+    }
     const bool more = __any_sync(0xffffffffu, s != 0u);
     if (!more) after_read();
-    unsigned l0 = 0, l1 = 0;
-    if (h0) l0 = __ldg(P.job.lut + rgb0);
-    if (h1) l1 = __ldg(P.job.lut + rgb1);
+#pragma unroll
+    for (int t = 0; t < NQ; ++t) {
+        lq[t] = 0u;
+        if (bq[t]) lq[t] = __ldg(P.job.lut + rgbq[t]);
+    }
     if constexpr (R == 0) {
         // ---- no clean: the categorised labels are the output
         uint8_t* orow = it.out + (long long)y * P.job.out_stride2 + it.xw0 + (long long)lane * 32;
@@ -529,8 +541,9 @@ __device__ __forceinline__ void categorize_line(const FastParams& P, const uint8
             }
             after_read();
         }
-        if (h0) patch(q0, l0);
-        if (h1) patch(q1, l1);
+#pragma unroll
+        for (int t = 0; t < NQ; ++t)
+            if (bq[t]) patch(qi[t], lq[t]);
     } else {
         // ---- bit transpose (three delta-swap stages between register pairs): T[b] bit q = bit b of
         // the label of pixel q of aligned word `lane`
@@ -589,8 +602,8 @@ __device__ __forceinline__ void categorize_line(const FastParams& P, const uint8
             }
             after_read();
         }
-        apply(bq0, l0);
-        apply(bq1, l1);
+#pragma unroll
+        for (int t = 0; t < NQ; ++t) apply(bq[t], lq[t]);
         // vote word `lane` starts at wx = O0 + lane*U: funnel of aligned words k, k+1
         const int o = G::O0 + lane * G::U;
         const int k = o >> 5, sh = o & 31;
@@ -792,10 +805,12 @@ __device__ __forceinline__ void vote_word(const FastParams& P, uint8_t* ws, cons
     vote_core<R, NB>(Pl, a_lab, b_lab, decided, selA, diff, zero);
     uint32_t now = decided & mask;
     const uint32_t undec = ~decided & mask;
+#ifndef MR_STATS
     if (COUNT) {
         c_changed += __popc(now & diff);
         c_nomatch += __popc(now & zero);
     }
+#endif
     uint8_t* orow = it.out + (long long)y * P.job.out_stride2 + it.xw0 + G::O0 + vl * G::U;
 #pragma unroll 1
     while (now) {   // round 1 stored a guess for these pixels: overwrite it with the decision
@@ -971,10 +986,17 @@ __device__ __forceinline__ int block_vote(const FastParams& P, uint8_t* ws, cons
             const uint32_t bal = __ballot_sync(0xffffffffu, undec != 0u);
             const int e = n_listed + __popc(bal & ((1u << vl) - 1u));
             n_listed += __popc(bal);
+#ifdef MR_STATS   // experiment: n_nomatch = pixels round 1 leaves undecided, n_changed = listed words, n_fine = exact pixels
+            if (COUNT) {
+                c_nomatch += __popc(undec);
+                c_changed += undec != 0u;
+            }
+#else
             if (COUNT) {
                 c_changed += __popc(now & ~((selA & hA[0]) | (~selA & hB[0])));   // centre label != winner
                 c_nomatch += __popc(now & ((a_lab == 0 ? selA : 0u) | (b_lab == 0 ? ~selA : 0u)));
             }
+#endif
             {   // labels of the U output pixels, B ^ (selA ? A ^ B : 0): eight pixels per step through the
                 // bit -> byte expansion table (one 8-byte entry per byte of selA)
                 const uint32_t sel = selA >> R;
@@ -1029,10 +1051,14 @@ __device__ __forceinline__ void exact_pixel(const FastParams& P, uint8_t* ws, co
 #pragma unroll
     for (int b = 0; b < NB; ++b) centre |= ((Pl[R][b] >> q) & 1u) << b;
     it.out[(long long)y * P.job.out_stride2 + it.xw0 + G::O0 + vl * G::U + q] = (uint8_t)best;   // over round 1's guess
+#ifdef MR_STATS
+    if (COUNT) c_changed += 0x10000u;
+#else
     if (COUNT) {
         c_nomatch += (best == 0);
         c_changed += (best != centre);
     }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1198,6 +1224,10 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
             c_nomatch += __shfl_xor_sync(0xffffffffu, c_nomatch, o);
             c_changed += __shfl_xor_sync(0xffffffffu, c_changed, o);
         }
+#ifdef MR_STATS
+        c_fine = c_changed >> 16;
+        c_changed &= 0xFFFFu;
+#endif
         if (lane == 0) {
             atomicAdd(&P.job.counters->n_fine, (unsigned long long)c_fine);
             atomicAdd(&P.job.counters->n_nomatch, (unsigned long long)c_nomatch);

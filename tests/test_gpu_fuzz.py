@@ -51,6 +51,11 @@ def test_fused_random_geometry(ctx, mr, oracle, seed):
         ctx.clean_dev(lab, n1, n2, n1, R, out2, n1)
         torch.cuda.synchronize()
         assert mismatches(out2.cpu().numpy(), want) == 0, info
+        # the same with the label bound supplied by the caller (no label-maximum pass, no synchronisation)
+        out2.zero_()
+        ctx.clean_dev(lab, n1, n2, n1, R, out2, n1, max_label=st.K)
+        torch.cuda.synchronize()
+        assert mismatches(out2.cpu().numpy(), want) == 0, info
 
 
 @pytest.mark.parametrize("seed", range(12))
