@@ -183,6 +183,31 @@ int mr_clean_segments_host(mr_ctx* ctx, const uint8_t* labels, int64_t n1, int64
                            double prune_threshold, uint8_t* out, int64_t out_stride2,
                            int64_t* n_segments);
 
+/* blur(A; hood = Window{R}(), repeat), src/blur.jl:6-14 (the "blur" button, src/selectcolors.jl:455-465):
+ * every pass replaces a pixel by mean(neighbors(h)) over its Window{R} (centre included) in
+ * RGB{Float64}.  Input: packed RGB{N0f8} (bytes_per_px = 3; Float64(::N0f8) = i/255) or RGB{Float64}
+ * (bytes_per_px = 24, three doubles per pixel); output: RGB{Float64}, 24 bytes per pixel, same geometry.
+ * repeat = 0 is the conversion A .* 1.0.  Sum in neighbourhood order (memory-fast axis fastest), times
+ * 1 / (2R+1)^2; neighbours outside the image are the zero colour (decisions about
+ * Neighborhoods.jl / ColorVectorSpace, parity unpinned).  Strides in bytes, multiples of 8 for Float64. */
+int mr_blur_host(mr_ctx* ctx, const void* px, int64_t n1, int64_t n2, int64_t stride2_bytes,
+                 int bytes_per_px, int R, int repeat, double* out, int64_t out_stride2_bytes);
+int mr_blur_dev(mr_ctx* ctx, const void* px_dev, int64_t n1, int64_t n2, int64_t stride2_bytes,
+                int bytes_per_px, int R, int repeat, double* out_dev, int64_t out_stride2_bytes,
+                void* stream);
+
+/* The categoriser on RGB{Float64} pixels -- what `blur` / `_balance` hand to
+ * _categorize(pixels, points; ...) (src/categories.jl:49-52,68-73; the reference's own known-answer
+ * vectors are Float64 colours) -- followed by the Window{R} majority filter.  Direct Float64
+ * evaluation per pixel (no table).  3-channel RGB statistics only; the known plane of mr_set_known
+ * applies.  px: three doubles per pixel, stride2 in bytes (multiple of 8). */
+int mr_categorize_clean_f64_host(mr_ctx* ctx, const double* px, int64_t n1, int64_t n2,
+                                 int64_t stride2_bytes, int R, uint8_t* labels_out,
+                                 int64_t out_stride2);
+int mr_categorize_clean_f64_dev(mr_ctx* ctx, const double* px_dev, int64_t n1, int64_t n2,
+                                int64_t stride2_bytes, int R, uint8_t* labels_dev,
+                                int64_t out_stride2, void* stream);
+
 /* fill_gaps(src; categories, neighborhood = VonNeumann{2}(), missingval = 0, stats, match = (:color,),
  * known, original, mask), src/clean.jl:2-54, applied `repeat` times as _fill does
  * (src/selectcolors.jl:683-699; call site :490-501).  Per pixel and pass: a masked pixel stays

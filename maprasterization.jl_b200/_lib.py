@@ -25,6 +25,7 @@ SYMBOLS = [
     "mr_categorize_clean_dev_peer", "mr_ipc_export", "mr_ipc_open", "mr_ipc_close",
     "mr_clean_host", "mr_clean_dev", "mr_clean_dev_bounded", "mr_clean_segments_dev", "mr_clean_segments_host",
     "mr_fill_gaps_dev", "mr_fill_gaps_host", "mr_set_known_band",
+    "mr_blur_host", "mr_blur_dev", "mr_categorize_clean_f64_host", "mr_categorize_clean_f64_dev",
     "mr_multi_create", "mr_multi_destroy", "mr_multi_last_error", "mr_multi_device_count", "mr_multi_ctx",
     "mr_multi_band_range", "mr_multi_set_palette", "mr_multi_set_known", "mr_multi_categorize_clean_host",
     "mr_multi_batch_categorize_clean_host", "mr_multi_categorize_clean_dev",
@@ -94,6 +95,10 @@ def load():
     L.mr_fill_gaps_dev.argtypes = [vp, u8p, i64, i64, i64, u8p, i64, i32, u8p, i64, u8p, i32, i32, u8p, i64, vp]
     L.mr_fill_gaps_host.argtypes = [vp, u8p, i64, i64, i64, u8p, i64, i32, u8p, i64, u8p, i32, i32, u8p, i64]
     L.mr_set_known_band.argtypes = [vp, i64, vp, vp, i64]
+    L.mr_blur_host.argtypes = [vp, vp, i64, i64, i64, i32, i32, i32, vp, i64]
+    L.mr_blur_dev.argtypes = [vp, vp, i64, i64, i64, i32, i32, i32, vp, i64, vp]
+    L.mr_categorize_clean_f64_host.argtypes = [vp, vp, i64, i64, i64, i32, u8p, i64]
+    L.mr_categorize_clean_f64_dev.argtypes = [vp, vp, i64, i64, i64, i32, u8p, i64, vp]
     L.mr_multi_create.argtypes = [vp, i32, C.POINTER(i32)]
     L.mr_multi_create.restype = vp
     L.mr_multi_destroy.argtypes = [vp]
@@ -120,6 +125,7 @@ def load():
                  "mr_categorize_clean_dev_peer", "mr_ipc_export", "mr_ipc_open", "mr_ipc_close",
                  "mr_batch_categorize_clean_dev", "mr_clean_host", "mr_clean_dev", "mr_clean_segments_dev",
                  "mr_clean_segments_host", "mr_fill_gaps_dev", "mr_fill_gaps_host", "mr_synth_scan_dev",
+                 "mr_blur_host", "mr_blur_dev", "mr_categorize_clean_f64_host", "mr_categorize_clean_f64_dev",
                  "mr_set_known_band", "mr_clean_dev_bounded", "mr_multi_device_count", "mr_multi_band_range", "mr_multi_set_palette",
                  "mr_multi_set_known", "mr_multi_categorize_clean_host", "mr_multi_batch_categorize_clean_host",
                  "mr_multi_categorize_clean_dev"):
@@ -264,6 +270,27 @@ class Context:
         self._ck(self._L.mr_clean_segments_host(self._h, _ptr(labels), n1, n2, n1, _ptr(keep), float(line_threshold),
                                                 float(prune_threshold), _ptr(out), n1, C.byref(nseg)))
         return out, int(nseg.value)
+
+    def blur_host(self, img, R=1, repeat=1):
+        """`blur(A; hood=Window{R}(), repeat)` (src/blur.jl:6-14): (n2, n1, 3) uint8 or float64 -> float64."""
+        img = np.ascontiguousarray(img)
+        if img.ndim != 3 or img.shape[2] != 3 or img.dtype not in (np.uint8, np.float64):
+            raise ValueError("img must be a (n2, n1, 3) uint8 (RGB{N0f8}) or float64 (RGB{Float64}) array")
+        n2, n1, _ = img.shape
+        bpp = 3 if img.dtype == np.uint8 else 24
+        out = np.empty((n2, n1, 3), dtype=np.float64)
+        self._ck(self._L.mr_blur_host(self._h, _ptr(img), n1, n2, n1 * bpp, bpp, int(R), int(repeat), _ptr(out), n1 * 24))
+        return out
+
+    def categorize_clean_f64_host(self, px, R):
+        """px: (n2, n1, 3) float64 (RGB{Float64}); labels (n2, n1) uint8."""
+        px = np.ascontiguousarray(px, dtype=np.float64)
+        if px.ndim != 3 or px.shape[2] != 3:
+            raise ValueError("px must be a (n2, n1, 3) float64 array")
+        n2, n1, _ = px.shape
+        out = np.empty((n2, n1), dtype=np.uint8)
+        self._ck(self._L.mr_categorize_clean_f64_host(self._h, _ptr(px), n1, n2, n1 * 24, int(R), _ptr(out), n1))
+        return out
 
     def fill_gaps_host(self, labels, px, categories, mask=None, repeat=1):
         """`fill_gaps` (src/clean.jl:2-54) `repeat` times on host buffers; palette = `stats`, the known plane

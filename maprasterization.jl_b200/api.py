@@ -135,7 +135,12 @@ class Palette:
             if (i < 0).any() or (i >= n1).any() or (j < 0).any() or (j >= n2).any():
                 raise IndexError("point outside the image (BoundsError in the reference)")
             samples = img[j, i]
-            vals = rgb8_to_lab(samples[:, :3]) if colourspace == "lab" else samples.astype(np.float64) / 255.0
+            if img.dtype == np.float64:      # RGB{Float64} image (blurred / balanced): the values themselves
+                if colourspace == "lab":
+                    raise ValueError("Lab statistics need an N0f8 image")
+                vals = samples
+            else:
+                vals = rgb8_to_lab(samples[:, :3]) if colourspace == "lab" else samples.astype(np.float64) / 255.0
             st = component_stats(vals)
             mean[c], mn[c], mx[c], sd[c] = st["mean"], st["min"], st["max"], st["sd"]
         return cls(mean, mn, mx, sd, tolerances, colourspace)
@@ -183,10 +188,16 @@ def _known_from_points(points, n1):
     return idx, cat
 
 
-def _check_img(img):
+def _is_f64_img(img):
+    return isinstance(img, np.ndarray) and img.dtype == np.float64 and img.ndim == 3 and img.shape[2] == 3
+
+
+def _check_img(img, f64_ok=False):
+    if f64_ok and _is_f64_img(img):
+        return
     if not isinstance(img, np.ndarray) or img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] not in (3, 4):
-        raise ValueError("img must be a (n2, n1, 3|4) uint8 array (RGB{N0f8} / RGBA{N0f8}); other element "
-                         "types are not supported by the B200 hot path")
+        raise ValueError("img must be a (n2, n1, 3|4) uint8 array (RGB{N0f8} / RGBA{N0f8}) or a (n2, n1, 3) float64 "
+                         "array (RGB{Float64}, e.g. the output of blur); other element types are not supported")
 
 
 def categorize_clean_u8(img, points_or_palette, *, tolerances=None, hood=Window(1), match=("color",),
@@ -195,7 +206,7 @@ def categorize_clean_u8(img, points_or_palette, *, tolerances=None, hood=Window(
     """Fused clean(categorize(img)) returning uint8 labels (n2, n1)."""
     del scan_threshold   # only used by the unsupported segmented branch
     _check_match(match, segmented)
-    _check_img(img)
+    _check_img(img, f64_ok=True)
     ctx = ctx or default_context()
     pal = _as_palette(img, points_or_palette, tolerances, colourspace)
     _upload_palette(ctx, pal)
@@ -204,7 +215,24 @@ def categorize_clean_u8(img, points_or_palette, *, tolerances=None, hood=Window(
     else:
         ctx.set_known(None)
     R = hood.R if isinstance(hood, Window) else int(hood)
+    if _is_f64_img(img):     # RGB{Float64} pixels (blurred / balanced): direct Float64 evaluation
+        if pal.colourspace != "rgb":
+            raise ValueError("RGB{Float64} pixels take RGB statistics")
+        if counters:
+            raise ValueError("counters are not available for RGB{Float64} pixels")
+        return ctx.categorize_clean_f64_host(img, R)
     return ctx.categorize_clean_host(img, R, counters=counters)
+
+
+def blur(A, *, hood=Window(1), repeat=1, ctx=None):
+    """`blur(A; hood=Window{1}(), repeat=1)` (src/blur.jl:6-14): `repeat` passes of the Window mean in
+    RGB{Float64}.  A: (n2, n1, 3) uint8 (RGB{N0f8}) or float64; returns (n2, n1, 3) float64."""
+    _check_img(A, f64_ok=True)
+    if A.shape[2] != 3:
+        raise ValueError("blur takes RGB pixels")
+    ctx = ctx or default_context()
+    R = hood.R if isinstance(hood, Window) else int(hood)
+    return ctx.blur_host(A, R, repeat)
 
 
 def categorize_clean(img, points_or_palette, **kw):
@@ -368,21 +396,29 @@ def rasterize(img, sel, *, hood=None, colourspace="rgb", ctx=None):
     categories = kept, line_threshold, prune_threshold)`).
     -> "fill" (:490-501: `_fill` = `fill_gaps` `fill_repeat` times, :683-699; the polygon mask is the caller's).
     Returns a dict with the uint8 label images `categorized`, `cleaned` and `filled`.
+    `blur_repeat > 0` runs `blur` first and categorises its RGB{Float64} output (statistics from the
+    blurred image, as the reference does); the tie-break of `fill_gaps` then still reads the unblurred pixel.
     Settings that select unsupported stages raise ValueError (no CPU fallback): `segment=True`,
-    a `match` other than ("color",), `blur_repeat > 0`."""
+    a `match` other than ("color",)."""
     if not isinstance(sel, MapSelection):
         raise ValueError("sel must be a MapSelection")
     st = sel.settings
     match = tuple(st.get("match", ("color",)))
     _check_match(match, bool(st.get("segment", False)))
-    if int(st.get("blur_repeat", 0)) != 0:
-        raise ValueError("blur_repeat > 0 (colour pre-smoothing, src/blur.jl) is not supported by the B200 hot path")
     _check_img(img)
     ctx = ctx or default_context()
     n2, n1 = img.shape[:2]
     tol = sel.tolerances()
     R = 0 if hood is None else (hood.R if isinstance(hood, Window) else int(hood))
-    categorized = categorize_clean_u8(img, sel.points, tolerances=tol, hood=Window(R), colourspace=colourspace,
+    # "blur" button (src/selectcolors.jl:455-465): blur(balanced; repeat = blur_repeat); `_balance` with fewer
+    # than 8 points is A .* 1.0 (src/balance.jl:16-18), the fitted detrend itself is outside this path
+    blur_repeat = int(st.get("blur_repeat", 0))
+    pixels = img
+    if blur_repeat > 0:
+        if img.shape[2] != 3 or colourspace != "rgb":
+            raise ValueError("blur_repeat > 0 needs RGB{N0f8} pixels and RGB matching")
+        pixels = blur(img, repeat=blur_repeat, ctx=ctx)
+    categorized = categorize_clean_u8(pixels, sel.points, tolerances=tol, hood=Window(R), colourspace=colourspace,
                                       use_known=True, ctx=ctx)
     idx, cat = _known_from_points(sel.points, n1)
     known = np.zeros((n2, n1), dtype=np.uint8)

@@ -42,6 +42,8 @@ struct mr_ctx {
     uint8_t* d_rp_in = nullptr;  size_t d_rp_in_cap = 0;
     uint8_t* d_rp_out = nullptr; size_t d_rp_out_cap = 0;
     uint8_t* d_lab = nullptr;    size_t d_lab_cap = 0;     // categorise-only labels of the RGBA path
+    uint8_t* d_f64 = nullptr;    size_t d_f64_cap = 0;     // RGB{Float64} scratch images of blur (ping-pong, host staging)
+    uint8_t* d_f64b = nullptr;   size_t d_f64b_cap = 0;
     // segment prune scratch: parent array, component records, keep table + two counters
     uint8_t* d_parent = nullptr; size_t d_parent_cap = 0;   // first run of every (line, chunk)
     uint8_t* d_runs = nullptr; size_t d_runs_cap = 0;       // run arrays
@@ -121,7 +123,7 @@ extern "C" void mr_destroy(mr_ctx* ctx) {
     for (auto e : ctx->ev_done) cudaEventDestroy(e);
     cudaFree(ctx->d_pal); cudaFree(ctx->d_lut); cudaFree(ctx->d_coarse);
     cudaFree(ctx->d_known_idx); cudaFree(ctx->d_known_cat); cudaFree(ctx->d_counters); cudaFree(ctx->work.slots);
-    cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_tmp); cudaFree(ctx->d_rp_in); cudaFree(ctx->d_rp_out); cudaFree(ctx->d_lab);
+    cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_tmp); cudaFree(ctx->d_rp_in); cudaFree(ctx->d_rp_out); cudaFree(ctx->d_lab); cudaFree(ctx->d_f64); cudaFree(ctx->d_f64b);
     cudaFree(ctx->d_parent); cudaFree(ctx->d_runs); cudaFree(ctx->d_rec); cudaFree(ctx->d_small);
     if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
@@ -847,6 +849,142 @@ extern "C" int mr_clean_segments_host(mr_ctx* ctx, const uint8_t* labels, int64_
     if (rc) return rc;
     CK(cudaMemcpy2DAsync(out, out_stride2, ctx->d_tmp, n1, n1, n2, cudaMemcpyDeviceToHost, ctx->s_main));
     CK(cudaStreamSynchronize(ctx->s_main));
+    return MR_OK;
+}
+
+// ------------------------------------------------------------------ blur + categorise on RGB{Float64}
+static int blur_check(mr_ctx* ctx, const char* fn, const void* in, const void* out, int64_t n1, int64_t n2,
+                      int64_t in_stride2, int in_bytes_per_px, int R, int repeat, int64_t out_stride2) {
+    std::string f(fn);
+    if (!ctx) return fail(nullptr, MR_ERR_ARG, f + ": null ctx");
+    if (n1 < 0 || n2 < 0) return fail(ctx, MR_ERR_ARG, f + ": negative size");
+    if (in_bytes_per_px != 3 && in_bytes_per_px != 24)
+        return fail(ctx, MR_ERR_ARG, f + ": pixels must be packed RGB{N0f8} (3 bytes) or RGB{Float64} (24 bytes)");
+    if (n1 > 0 && n2 > 0 && (!in || !out)) return fail(ctx, MR_ERR_ARG, f + ": null buffer");
+    if (in_stride2 < n1 * in_bytes_per_px || out_stride2 < n1 * 24) return fail(ctx, MR_ERR_ARG, f + ": stride smaller than a line");
+    if (in_bytes_per_px == 24 && in_stride2 % 8 != 0) return fail(ctx, MR_ERR_ARG, f + ": Float64 lines must be 8-byte aligned");
+    if (out_stride2 % 8 != 0) return fail(ctx, MR_ERR_ARG, f + ": Float64 lines must be 8-byte aligned");
+    if (R < 0 || R > 7) return fail(ctx, MR_ERR_ARG, f + ": window radius R must be in 0..7");
+    if (repeat < 0) return fail(ctx, MR_ERR_ARG, f + ": negative repeat");
+    if (in == out && n1 > 0 && n2 > 0) return fail(ctx, MR_ERR_ARG, f + ": in-place operation is not supported");
+    return MR_OK;
+}
+
+// `repeat` passes; the first reads the caller's pixels, the last writes `out`, the ones in between ping-pong
+// between `out` and a scratch image.  repeat == 0: the conversion A .* 1.0 (a pass with R = 0).
+static int blur_dev(mr_ctx* ctx, const void* in, int in_bpp, int64_t in_stride2, int64_t n1, int64_t n2, int R, int repeat,
+                    double* out, int64_t out_stride2, cudaStream_t s) {
+    if (n1 == 0 || n2 == 0) return MR_OK;
+    int passes = repeat, radius = R;
+    if (repeat == 0) { passes = 1; radius = 0; }
+    const int64_t pitch = n1 * 24;
+    int rc;
+    if (passes > 1 && (rc = grow(ctx, &ctx->d_f64, &ctx->d_f64_cap, (size_t)pitch * n2))) return rc;
+    const void* src = in;
+    int64_t src_stride = in_stride2;
+    bool src_u8 = in_bpp == 3;
+    for (int it = 0; it < passes; ++it) {
+        const bool to_out = ((passes - 1 - it) % 2) == 0;
+        double* dst = to_out ? out : reinterpret_cast<double*>(ctx->d_f64);
+        const int64_t dst_stride = to_out ? out_stride2 : pitch;
+        int nl = 0;
+        cudaError_t e = mr_launch_blur(src, src_u8, src_stride, n1, n2, radius, dst, dst_stride, ctx->sm_count, s, &nl);
+        ctx->launches += nl;
+        if (e != cudaSuccess) return fail_cuda(ctx, e, "blur launch");
+        src = dst; src_stride = dst_stride; src_u8 = false;
+    }
+    return MR_OK;
+}
+
+extern "C" int mr_blur_dev(mr_ctx* ctx, const void* px_dev, int64_t n1, int64_t n2, int64_t stride2, int bytes_per_px,
+                           int R, int repeat, double* out_dev, int64_t out_stride2, void* stream) {
+    int rc = blur_check(ctx, "mr_blur_dev", px_dev, out_dev, n1, n2, stride2, bytes_per_px, R, repeat, out_stride2);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    return blur_dev(ctx, px_dev, bytes_per_px, stride2, n1, n2, R, repeat, out_dev, out_stride2, (cudaStream_t)stream);
+}
+
+extern "C" int mr_blur_host(mr_ctx* ctx, const void* px, int64_t n1, int64_t n2, int64_t stride2, int bytes_per_px,
+                            int R, int repeat, double* out, int64_t out_stride2) {
+    int rc = blur_check(ctx, "mr_blur_host", px, out, n1, n2, stride2, bytes_per_px, R, repeat, out_stride2);
+    if (rc) return rc;
+    if (n1 == 0 || n2 == 0) return MR_OK;
+    CK(cudaSetDevice(ctx->device));
+    const int64_t in_pitch = (n1 * bytes_per_px + 15) / 16 * 16, out_pitch = n1 * 24;
+    if ((rc = grow(ctx, &ctx->d_in, &ctx->d_in_cap, (size_t)in_pitch * n2))) return rc;
+    if ((rc = grow(ctx, &ctx->d_f64b, &ctx->d_f64b_cap, (size_t)out_pitch * n2))) return rc;
+    cudaStream_t s = ctx->s_main;
+    CK(cudaMemcpy2DAsync(ctx->d_in, in_pitch, px, stride2, n1 * bytes_per_px, n2, cudaMemcpyHostToDevice, s));
+    rc = blur_dev(ctx, ctx->d_in, bytes_per_px, in_pitch, n1, n2, R, repeat, reinterpret_cast<double*>(ctx->d_f64b), out_pitch, s);
+    if (rc) return rc;
+    CK(cudaMemcpy2DAsync(out, out_stride2, ctx->d_f64b, out_pitch, n1 * 24, n2, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return MR_OK;
+}
+
+// categorise (+ known points) on Float64 colours, then the standalone majority filter
+static int cat_f64_dev(mr_ctx* ctx, const double* px, int64_t n1, int64_t n2, int64_t stride2, int R, uint8_t* out,
+                       int64_t out_stride2, cudaStream_t s) {
+    if (n1 == 0 || n2 == 0) return MR_OK;
+    uint8_t* plane = out;
+    int64_t plane_stride = out_stride2;
+    const int64_t line_tmp = (n1 + 15) / 16 * 16;
+    int rc;
+    if (R > 0) {
+        if ((rc = grow(ctx, &ctx->d_tmp, &ctx->d_tmp_cap, (size_t)line_tmp * n2))) return rc;
+        plane = ctx->d_tmp;
+        plane_stride = line_tmp;
+    }
+    int nl = 0;
+    cudaError_t e = mr_launch_categorize_f64(ctx->pal, px, stride2, n1, n2, ctx->n_known, ctx->d_known_idx, ctx->d_known_cat,
+                                             plane, plane_stride, (ctx->count_on && R == 0) ? ctx->d_counters : nullptr,
+                                             ctx->sm_count, s, &nl);
+    ctx->launches += nl;
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "Float64 categorise launch");
+    if (R > 0) {
+        MrJob c = make_job(ctx, plane, out, n1, n2, plane_stride, 1, R, 0, 0, out_stride2);
+        c.lut = nullptr;
+        c.padded = 1;
+        return run_clean(ctx, c, s, ctx->pal.K);
+    }
+    return MR_OK;
+}
+
+static int cat_f64_check(mr_ctx* ctx, const char* fn, const void* px, const void* out, int64_t n1, int64_t n2,
+                         int64_t stride2, int R, int64_t out_stride2) {
+    std::string f(fn);
+    int rc = check_image_args(ctx, fn, px, out, n1, n2, stride2, 24, out_stride2, R, 0, 0);
+    if (rc) return rc;
+    if (!ctx->palette_set) return fail(ctx, MR_ERR_STATE, f + ": mr_set_palette has not been called");
+    if (ctx->pal.C != 3 || ctx->pal.colourspace != MR_COLOURSPACE_RGB)
+        return fail(ctx, MR_ERR_ARG, f + ": RGB{Float64} pixels take 3-channel RGB statistics");
+    if (stride2 % 8 != 0) return fail(ctx, MR_ERR_ARG, f + ": Float64 lines must be 8-byte aligned");
+    return MR_OK;
+}
+
+extern "C" int mr_categorize_clean_f64_dev(mr_ctx* ctx, const double* px_dev, int64_t n1, int64_t n2, int64_t stride2,
+                                           int R, uint8_t* labels_dev, int64_t out_stride2, void* stream) {
+    int rc = cat_f64_check(ctx, "mr_categorize_clean_f64_dev", px_dev, labels_dev, n1, n2, stride2, R, out_stride2);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    return cat_f64_dev(ctx, px_dev, n1, n2, stride2, R, labels_dev, out_stride2, (cudaStream_t)stream);
+}
+
+extern "C" int mr_categorize_clean_f64_host(mr_ctx* ctx, const double* px, int64_t n1, int64_t n2, int64_t stride2,
+                                            int R, uint8_t* labels_out, int64_t out_stride2) {
+    int rc = cat_f64_check(ctx, "mr_categorize_clean_f64_host", px, labels_out, n1, n2, stride2, R, out_stride2);
+    if (rc) return rc;
+    if (n1 == 0 || n2 == 0) return MR_OK;
+    CK(cudaSetDevice(ctx->device));
+    const int64_t pitch = n1 * 24, line_out = (n1 + 15) / 16 * 16;
+    if ((rc = grow(ctx, &ctx->d_f64b, &ctx->d_f64b_cap, (size_t)pitch * n2))) return rc;
+    if ((rc = grow(ctx, &ctx->d_out, &ctx->d_out_cap, (size_t)line_out * n2))) return rc;
+    cudaStream_t s = ctx->s_main;
+    CK(cudaMemcpy2DAsync(ctx->d_f64b, pitch, px, stride2, n1 * 24, n2, cudaMemcpyHostToDevice, s));
+    rc = cat_f64_dev(ctx, reinterpret_cast<const double*>(ctx->d_f64b), n1, n2, pitch, R, ctx->d_out, line_out, s);
+    if (rc) return rc;
+    CK(cudaMemcpy2DAsync(labels_out, out_stride2, ctx->d_out, line_out, n1, n2, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
     return MR_OK;
 }
 

@@ -54,19 +54,12 @@ __device__ __forceinline__ void mr_rgb8_to_lab(const double* __restrict__ lin, i
     B = __dmul_rn(200.0, __dsub_rn(fy, fz));
 }
 
-// known: 0 = ordinary pixel; k != 0 = clicked point of category k (categories.jl:110-112)
-__device__ __forceinline__ int mr_eval_px(const MrPalette& pal, int r8, int g8, int b8, int a8,
-                                          bool has_alpha, int known) {
-    double x0, x1, x2, x3 = 0.0;
+// categorise one colour given as Float64 channels (x3 = alpha, used when pal.C == 4).
+// known: 0 = ordinary pixel; k != 0 = clicked point of category k (categories.jl:110-112);
+// transparent: the alpha == 0 rule of categories.jl:116 applies to this pixel.
+__device__ __forceinline__ int mr_eval_f64(const MrPalette& pal, double x0, double x1, double x2, double x3,
+                                           bool transparent, int known) {
     const int C = pal.C;
-    if (pal.colourspace == 1) {
-        mr_rgb8_to_lab(pal.lin, r8, g8, b8, x0, x1, x2);
-    } else {
-        x0 = __ddiv_rn((double)r8, 255.0);   // Float64(::N0f8) = correctly rounded i/255
-        x1 = __ddiv_rn((double)g8, 255.0);
-        x2 = __ddiv_rn((double)b8, 255.0);
-        if (C == 4) x3 = __ddiv_rn((double)a8, 255.0);
-    }
     int best = 0;
     double beste = 0.0;
     for (int c = 0; c < pal.K; ++c) {
@@ -82,10 +75,25 @@ __device__ __forceinline__ int mr_eval_px(const MrPalette& pal, int r8, int g8, 
         if (c == 0 || e < beste) { beste = e; best = c; }   // first minimum
     }
     if (known != 0) return (best + 1 == known) ? best + 1 : 0;
-    if (has_alpha && a8 == 0) return 0;                      // categories.jl:116
+    if (transparent) return 0;                               // categories.jl:116
     const double* l = pal.lo + (size_t)best * C;
     const double* h = pal.hi + (size_t)best * C;
     bool ok = (x0 >= __ldg(l + 0)) && (x0 <= __ldg(h + 0)) && (x1 >= __ldg(l + 1)) &&
               (x1 <= __ldg(h + 1)) && (x2 >= __ldg(l + 2)) && (x2 <= __ldg(h + 2));
     return ok ? best + 1 : 0;
+}
+
+// the same for a pixel given as N0f8 bytes
+__device__ __forceinline__ int mr_eval_px(const MrPalette& pal, int r8, int g8, int b8, int a8,
+                                          bool has_alpha, int known) {
+    double x0, x1, x2, x3 = 0.0;
+    if (pal.colourspace == 1) {
+        mr_rgb8_to_lab(pal.lin, r8, g8, b8, x0, x1, x2);
+    } else {
+        x0 = __ddiv_rn((double)r8, 255.0);   // Float64(::N0f8) = correctly rounded i/255
+        x1 = __ddiv_rn((double)g8, 255.0);
+        x2 = __ddiv_rn((double)b8, 255.0);
+        if (pal.C == 4) x3 = __ddiv_rn((double)a8, 255.0);
+    }
+    return mr_eval_f64(pal, x0, x1, x2, x3, has_alpha && a8 == 0, known);
 }

@@ -33,6 +33,8 @@
 //
 // Reference semantics: src/categories.jl:76-133 (via the table built in mr_generic.cu) and the
 // north_star-defined majority filter, SURVEY.md Appendix A.3.
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "mr_bitslice.h"
@@ -1248,8 +1250,12 @@ std::mutex g_cfg_mutex;   // cudaFuncSetAttribute bookkeeping below (contexts ma
 void plan_schedule(FastParams& P, int warps, int B, int R) {
     const long long n2 = P.job.n2;
     const int cols = P.cols;
-    const double f0 = 0.92;         // measured on B200: 0.86 .. 0.94 within 2 %
-    const long long tail = 2 * B;
+    double f0 = 0.92;         // measured on B200: 0.86 .. 0.94 within 2 %
+    long long tail = 2 * B;
+#ifdef MR_SCHED_ENV   // schedule experiments: MAPRAST_F0 (share of the tall class), MAPRAST_TAIL (blocks per tail item)
+    if (const char* e = getenv("MAPRAST_F0")) f0 = atof(e);
+    if (const char* e = getenv("MAPRAST_TAIL")) tail = atoll(e) * B;
+#endif
     const double share = (double)n2 * cols / warps;   // lines per warp
     long long H0 = 0, n0 = 0;
     if (share >= 6.0 * B) {

@@ -22,7 +22,7 @@ using ColorTypes, FixedPointNumbers, Statistics
 import Neighborhoods: Window
 
 export categorize, clean, categorize_clean, categorize_u8, clean_u8, categorize_clean_u8, clean_segments,
-       clean_segments_u8, fill_gaps, fill_gaps_u8, rasterize, MapSelection, Context, MultiContext, Palette
+       clean_segments_u8, fill_gaps, fill_gaps_u8, blur, rasterize, MapSelection, Context, MultiContext, Palette
 
 const libmaprast = get(ENV, "LIBMAPRAST", joinpath(@__DIR__, "..", "libmaprast.so"))
 const DEFAULT_CATEGORY_TOLERANCE = 2.0            # src/selectcolors.jl:1
@@ -63,7 +63,7 @@ struct Palette
     colourspace::Cint       # 0 RGB, 1 Lab
 end
 
-_channels(::Type{<:RGB}) = (:r, :g, :b)
+_channels(::Type{<:RGB}) = (:r, :g, :b)      # RGB{N0f8} and RGB{Float64} (the output of `blur`)
 _channels(::Type{<:RGBA}) = (:r, :g, :b, :alpha)
 
 "`_component_stats` for one category (src/categories.jl:5-9, 18-30) on Float64 channels."
@@ -152,6 +152,47 @@ function categorize_clean_u8(img::AbstractMatrix{T}, points_or_palette; toleranc
 end
 
 _radius(::Window{R}) where {R} = R
+
+"""
+`blur(A; hood=Window{1}(), repeat=1)` (src/blur.jl:6-14): `repeat` passes of the Window mean in RGB{Float64}.
+`A`: `Matrix{RGB{N0f8}}` or `Matrix{RGB{Float64}}`; returns `Matrix{RGB{Float64}}` (the input's wrapper type is kept).
+"""
+function blur(img::AbstractMatrix{T}; hood=Window{1}(), repeat::Int=1, ctx::Context=default_context()) where {T<:Union{RGB{N0f8},RGB{Float64}}}
+    A = img isa Matrix ? img : Matrix(img)
+    n1, n2 = size(A)
+    out = Matrix{RGB{Float64}}(undef, n1, n2)
+    GC.@preserve A out begin
+        _check(ctx, ccall((:mr_blur_host, libmaprast), Cint,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Cint, Cint, Cint, Ptr{Float64}, Int64),
+            ctx.ptr, pointer(A), n1, n2, n1 * sizeof(T), sizeof(T), _radius(hood), repeat,
+            Ptr{Float64}(pointer(out)), n1 * 24))
+    end
+    return _rebuild(img, out)
+end
+
+"Fused clean(categorize(img)) on RGB{Float64} pixels (what `blur` / `_balance` hand to `_categorize`): direct Float64 evaluation."
+function categorize_clean_u8(img::AbstractMatrix{RGB{Float64}}, points_or_palette; tolerances=nothing,
+        hood=Window{1}(), match=(:color,), segmented=false, scan_threshold=0.1, known=nothing,
+        ctx::Context=default_context())
+    _check_match(match, segmented)
+    A = img isa Matrix ? img : Matrix(img)
+    pal = points_or_palette isa Palette ? points_or_palette :
+          Palette(A, points_or_palette; tolerances=something(tolerances, fill(DEFAULT_CATEGORY_TOLERANCE, length(points_or_palette))))
+    _upload(ctx, pal)
+    n1, n2 = size(A)
+    out = Matrix{UInt8}(undef, n1, n2)
+    _set_known(ctx, known, size(A))
+    try
+        GC.@preserve A out begin
+            _check(ctx, ccall((:mr_categorize_clean_f64_host, libmaprast), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Cint, Ptr{UInt8}, Int64),
+                ctx.ptr, Ptr{Float64}(pointer(A)), n1, n2, n1 * 24, _radius(hood), pointer(out), n1))
+        end
+    finally
+        known === nothing || _clear_known(ctx)
+    end
+    return out
+end
 
 # eltype Int and the input's container type, like `map(pixels) do ... end` (src/categories.jl:69-73)
 _rewrap(img, labels::Matrix{UInt8}) = _rebuild(img, Int.(labels))
@@ -289,12 +330,13 @@ known-category override of the clicked points), optional Window majority filter 
 Returns `(; categorized, cleaned, filled)`.
 """
 function rasterize(img, sel::MapSelection; hood=Window{0}(), mask=nothing, ctx::Context=default_context())
-    get(sel.settings, :blur_repeat, 0) == 0 ||
-        throw(ArgumentError("blur_repeat > 0 is not supported by the B200 hot path"))
     A = img isa Matrix ? img : Matrix(img)
-    pal = Palette(A, sel.points; tolerances=collect(Float64, sel.settings.category_tolerances))
+    # "blur" button (src/selectcolors.jl:455-465); `_balance` with fewer than 8 points is A .* 1.0 (src/balance.jl:16-18)
+    blur_repeat = get(sel.settings, :blur_repeat, 0)
+    pixels = blur_repeat > 0 ? blur(A; repeat=blur_repeat, ctx) : A
+    pal = Palette(pixels, sel.points; tolerances=collect(Float64, sel.settings.category_tolerances))
     known = _known_plane(size(A), sel.points)
-    categorized = categorize_clean_u8(A, pal; hood, match=get(sel.settings, :match, (:color,)),
+    categorized = categorize_clean_u8(pixels, pal; hood, match=get(sel.settings, :match, (:color,)),
         segmented=get(sel.settings, :segment, false), known, ctx)
     keep = get(sel.settings, :category_keep, fill(true, length(sel.points)))
     kept = _kept_categories(collect(Bool, keep))

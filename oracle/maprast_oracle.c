@@ -595,3 +595,52 @@ void mro_fill_gaps(const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride
     free(cnt);
 }
 
+/* =====================================================================================
+ * blur(A; hood = Window{R}(), repeat) (src/blur.jl:6-14) on RGB{Float64}, and the image-level
+ * categoriser on RGB{Float64} pixels (src/categories.jl:68-73 over :76-95).
+ * PARITY UNPINNED for blur (Neighborhoods.jl 0.1 and ColorVectorSpace are not in the reference tree).
+ * Decisions: neighbours in CartesianIndices order (d1 fastest), left-folded
+ * sum, times (1 / count) -- ColorVectorSpace's RGB / Integer --, count = (2R+1)^2 always, neighbours
+ * outside the image are the zero colour (adding 0.0 is exact: they are skipped), same size out.
+ * in_u8 != 0: `in` holds packed N0f8 RGB (3 B per pixel), else 3 doubles per pixel.  Strides in bytes. */
+void mro_blur(const void* in, int in_u8, int64_t in_stride2, int64_t n1, int64_t n2, int R,
+              double* out, int64_t out_stride2) {
+    const double rcnt = 1.0 / (double)((2 * R + 1) * (2 * R + 1));
+    for (int64_t j = 0; j < n2; ++j)
+        for (int64_t i = 0; i < n1; ++i) {
+            double s[3] = {0.0, 0.0, 0.0};
+            for (int d2 = -R; d2 <= R; ++d2) {
+                const int64_t b = j + d2;
+                if (b < 0 || b >= n2) continue;
+                const uint8_t* line = (const uint8_t*)in + b * in_stride2;
+                for (int d1 = -R; d1 <= R; ++d1) {
+                    const int64_t a = i + d1;
+                    if (a < 0 || a >= n1) continue;
+                    for (int c = 0; c < 3; ++c) {
+                        const double x = in_u8 ? mro_n0f8(line[a * 3 + c]) : ((const double*)line)[a * 3 + c];
+                        s[c] = s[c] + x;
+                    }
+                }
+            }
+            double* o = (double*)((uint8_t*)out + j * out_stride2) + i * 3;
+            for (int c = 0; c < 3; ++c) o[c] = rcnt * s[c];
+        }
+}
+
+void mro_categorize_f64_image(const double* px, int64_t n1, int64_t n2, int64_t stride2, int K,
+                              const double* mean, const double* lo, const double* hi,
+                              int64_t n_known, const int64_t* known_idx, const uint8_t* known_cat,
+                              uint8_t* out, int64_t out_stride2) {
+    for (int64_t j = 0; j < n2; ++j)
+        for (int64_t i = 0; i < n1; ++i) {
+            const double* p = (const double*)((const uint8_t*)px + j * stride2) + i * 3;
+            out[j * out_stride2 + i] = (uint8_t)mro_categorize_f64(p, 3, K, mean, lo, hi, 0);
+        }
+    for (int64_t k = 0; k < n_known; ++k) {
+        const int64_t i = known_idx[k] % n1, j = known_idx[k] / n1;
+        if (j >= n2 || known_cat[k] == 0) continue;
+        const double* p = (const double*)((const uint8_t*)px + j * stride2) + i * 3;
+        out[j * out_stride2 + i] = (uint8_t)mro_categorize_f64(p, 3, K, mean, lo, hi, known_cat[k]);
+    }
+}
+

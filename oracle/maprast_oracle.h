@@ -107,6 +107,16 @@ void mro_fill_gaps(const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride
                    const uint8_t* mask, int64_t mask_stride2,
                    const uint8_t* categories, int n_categories, uint8_t* out, int64_t out_stride2);
 
+/* blur (src/blur.jl:6-14), one pass, RGB{Float64} out; PARITY UNPINNED (decisions in the .c file).
+ * in_u8 != 0: packed N0f8 RGB in, else 3 doubles per pixel.  Strides in bytes. */
+void mro_blur(const void* in, int in_u8, int64_t in_stride2, int64_t n1, int64_t n2, int R,
+              double* out, int64_t out_stride2);
+/* _categorize over an RGB{Float64} image (src/categories.jl:68-73), known points as in mro_categorize_u8 */
+void mro_categorize_f64_image(const double* px, int64_t n1, int64_t n2, int64_t stride2, int K,
+                              const double* mean, const double* lo, const double* hi,
+                              int64_t n_known, const int64_t* known_idx, const uint8_t* known_cat,
+                              uint8_t* out, int64_t out_stride2);
+
 int mro_max_threads(void);
 
 #ifdef __cplusplus

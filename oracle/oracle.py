@@ -63,6 +63,9 @@ def lib():
         L.mro_clean_segments.restype = _i64
         L.mro_fill_gaps.argtypes = [_u8p, _i64, _i64, _i64, _u8p, _i64, C.c_int, C.c_int, C.c_int, _f64p,
                                     C.c_void_p, _i64, C.c_void_p, _i64, _u8p, C.c_int, _u8p, _i64]
+        L.mro_blur.argtypes = [C.c_void_p, C.c_int, _i64, _i64, _i64, C.c_int, C.c_void_p, _i64]
+        L.mro_categorize_f64_image.argtypes = [C.c_void_p, _i64, _i64, _i64, C.c_int, _f64p, _f64p, _f64p, _i64,
+                                               C.c_void_p, C.c_void_p, _u8p, _i64]
         L.mro_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -202,6 +205,39 @@ def fill_gaps(labels, px, mean, categories, known=None, mask=None, repeat=1, col
                             out.ctypes.data, n1)
         cur = out
     return cur if repeat > 0 else labels.copy()
+
+
+def blur(img, R=1, repeat=1):
+    """`blur(A; hood=Window{R}(), repeat)` (src/blur.jl:6-14): img (n2, n1, 3) uint8 (N0f8) or float64 ->
+    (n2, n1, 3) float64."""
+    cur = np.ascontiguousarray(img)
+    assert cur.ndim == 3 and cur.shape[2] == 3 and cur.dtype in (np.uint8, np.float64)
+    n2, n1, _ = cur.shape
+    if repeat == 0:
+        return cur.astype(np.float64) / 255.0 if cur.dtype == np.uint8 else cur.copy()
+    for _ in range(repeat):
+        out = np.empty((n2, n1, 3), dtype=np.float64)
+        u8 = cur.dtype == np.uint8
+        lib().mro_blur(cur.ctypes.data, 1 if u8 else 0, n1 * (3 if u8 else 24), n1, n2, int(R), out.ctypes.data, n1 * 24)
+        cur = out
+    return cur
+
+
+def categorize_f64_image(px, mean, lo, hi, known_idx=None, known_cat=None):
+    """`_categorize` over an RGB{Float64} image: px (n2, n1, 3) float64 -> (n2, n1) uint8 labels."""
+    px = np.ascontiguousarray(px, dtype=np.float64)
+    n2, n1, _ = px.shape
+    mean, lo, hi = _f64(mean), _f64(lo), _f64(hi)
+    out = np.empty((n2, n1), dtype=np.uint8)
+    nk = 0
+    ki = kc = None
+    if known_idx is not None and len(known_idx):
+        ki = np.ascontiguousarray(known_idx, dtype=np.int64)
+        kc = np.ascontiguousarray(known_cat, dtype=np.uint8)
+        nk = ki.size
+    lib().mro_categorize_f64_image(px.ctypes.data, n1, n2, n1 * 24, mean.shape[0], mean, lo, hi, nk,
+                                   ki.ctypes.data if nk else None, kc.ctypes.data if nk else None, out.ctypes.data, n1)
+    return out
 
 
 def philox4x32(c, k):

@@ -32,7 +32,7 @@ for ln in open(disasm):
         op = m.group(2).split()
         op = op[1] if op[0].startswith("@") else op[0]
         addr2op[a] = op
-ALU = ("LOP3", "SHF", "ISETP", "SEL", "VIADD", "IADD3", "PRMT", "PLOP3", "LEA", "R2P", "MOV", "SGXT", "BMSK", "IABS", "VIMNMX", "IMNMX", "CS2R", "P2R", "FSEL", "FSETP", "IADD")
+ALU = ("LOP3", "SHF.", "SHF ", "ISETP", "SEL", "VIADD", "IADD3", "PRMT", "PLOP3", "LEA", "R2P", "MOV", "SGXT", "BMSK", "IABS", "VIMNMX", "IMNMX", "CS2R", "P2R", "FSEL", "FSETP", "IADD")
 def cls(op):
     if op.startswith("U"): return "uni"
     if op.startswith(("IMAD", "IDP", "FFMA", "FMUL", "FADD", "HFMA")): return "fma"

@@ -1,0 +1,95 @@
+"""GPU (-m gpu): blur (/root/reference/src/blur.jl:6-14) and the categoriser on RGB{Float64} pixels through the
+C ABI.  blur: bit-identical Float64 images against the oracle.  Categoriser: the reference's own known-answer
+vectors (test/runtests.jl:6-20 are Float64 colours) go through the PRODUCT's Float64 path here, plus random
+images against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from util import golden_palette, mismatches, random_palette
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("R", [0, 1, 2, 3])
+@pytest.mark.parametrize("shape", [(1, 1), (1, 40), (33, 1), (37, 53), (128, 200)])
+def test_blur_bit_identical(ctx, oracle, R, shape):
+    rng = np.random.default_rng(31 * R + shape[1])
+    img = rng.integers(0, 256, size=shape + (3,), dtype=np.uint8)
+    for rep in (0, 1, 2, 3):
+        got = ctx.blur_host(img, R, rep)
+        want = oracle.blur(img, R, rep)
+        assert got.tobytes() == want.tobytes(), (R, rep)
+    f = rng.random(shape + (3,))
+    assert ctx.blur_host(f, R, 2).tobytes() == oracle.blur(f, R, 2).tobytes()
+
+
+def test_blur_device_entry_with_pitches(ctx, oracle):
+    rng = np.random.default_rng(5)
+    n2, n1, R = 70, 91, 2
+    img = rng.integers(0, 256, size=(n2, n1, 3), dtype=np.uint8)
+    dev = torch.device("cuda", 0)
+    ip, op = 320, (n1 * 24 + 64)
+    d_in = torch.zeros((n2, ip), dtype=torch.uint8, device=dev)
+    d_in[:, :n1 * 3] = torch.from_numpy(img.reshape(n2, n1 * 3)).to(dev)
+    d_out = torch.full((n2, op // 8), -7.0, dtype=torch.float64, device=dev)
+    ctx._ck(ctx._L.mr_blur_dev(ctx._h, d_in.data_ptr(), n1, n2, ip, 3, R, 3, d_out.data_ptr(), op,
+                               torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    got = d_out[:, :n1 * 3].cpu().numpy().reshape(n2, n1, 3)
+    assert got.tobytes() == oracle.blur(img, R, 3).tobytes()
+    assert bool((d_out[:, n1 * 3:] == -7.0).all())        # nothing written outside the lines
+
+
+def test_reference_vectors_through_the_float64_path(ctx, mr, oracle):
+    mean, mn, mx, sd, tol, vectors = golden_palette()
+    pal = mr.Palette(mean, mn, mx, sd, np.full(mean.shape[0], tol))
+    ctx.set_palette(pal.mean, pal.lo, pal.hi)
+    ctx.palette = None
+    ctx.set_known(None)
+    px = np.array([[v["rgb"] for v in vectors]], dtype=np.float64)
+    want = np.array([[v["expected"] for v in vectors]], dtype=np.uint8)
+    assert (ctx.categorize_clean_f64_host(px, 0) == want).all()
+
+
+@pytest.mark.parametrize("R", [0, 1, 2, 4])
+@pytest.mark.parametrize("seed", [0, 1])
+def test_float64_categorise_clean_random(ctx, mr, oracle, R, seed):
+    rng = np.random.default_rng(900 + seed)
+    n2, n1, K = 97, 131, 9
+    mean, mn, mx, sd, tol = random_palette(rng, K)
+    pal = mr.Palette(mean, mn, mx, sd, tol)
+    ctx.set_palette(pal.mean, pal.lo, pal.hi)
+    ctx.palette = None
+    # colours near the means (inside and just outside the boxes) plus uniform noise
+    which = rng.integers(0, K, size=(n2, n1))
+    px = mean[which] + rng.normal(0, 0.05, size=(n2, n1, 3))
+    px[rng.random((n2, n1)) < 0.1] = rng.random(3)
+    idx = np.unique(rng.integers(0, n1 * n2, size=60))
+    cat = rng.integers(1, K + 1, size=idx.size).astype(np.uint8)
+    for known in (False, True):
+        ctx.set_known(idx, cat) if known else ctx.set_known(None)
+        try:
+            got = ctx.categorize_clean_f64_host(px, R)
+        finally:
+            ctx.set_known(None)
+        lab = oracle.categorize_f64_image(px, pal.mean, pal.lo, pal.hi, idx if known else None, cat if known else None)
+        want = oracle.majority(lab, R) if R else lab
+        assert mismatches(got, want) == 0
+
+
+def test_mirror_blur_then_categorize(mr, oracle):
+    rng = np.random.default_rng(7)
+    n2, n1, K = 60, 75, 5
+    pal_rgb = rng.integers(0, 256, size=(K, 3), dtype=np.uint8)
+    img = np.clip(pal_rgb[rng.integers(0, K, size=(n2 // 5, n1 // 5))].repeat(5, 0).repeat(5, 1).astype(np.int32)
+                  + rng.integers(-9, 10, size=(n2, n1, 3)), 0, 255).astype(np.uint8)
+    b = mr.blur(img, hood=mr.Window(1), repeat=2)
+    assert b.dtype == np.float64 and b.tobytes() == oracle.blur(img, 1, 2).tobytes()
+    points = [[(float(5 * x + 3), float(5 * y + 3)) for y in range(n2 // 5) for x in range(n1 // 5)
+               if (img[5 * y + 2, 5 * x + 2].astype(int) - pal_rgb[c]).__abs__().sum() < 30][:8] for c in range(K)]
+    lab = mr.categorize(b, points)
+    pal = mr.Palette.from_points(b, points)
+    assert mismatches(lab, oracle.categorize_f64_image(b, pal.mean, pal.lo, pal.hi)) == 0
+    with pytest.raises(ValueError):
+        mr.categorize(b.astype(np.float32), points)

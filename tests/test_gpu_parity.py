@@ -369,7 +369,21 @@ def test_map_selection_pipeline(ctx, mr, oracle):
     with pytest.raises(ValueError):
         mr.rasterize(scan, mr.MapSelection(settings=dict(segment=True), points=points), ctx=ctx)
     with pytest.raises(ValueError):
-        mr.rasterize(scan, mr.MapSelection(settings=dict(blur_repeat=1), points=points), ctx=ctx)
+        mr.rasterize(scan, mr.MapSelection(settings=dict(match=("color", "std")), points=points), ctx=ctx)
+    # the "fill" stage (src/selectcolors.jl:490-501) on the pruned labels
+    want_fill = oracle.fill_gaps(want_clean, scan, pal.mean, list(sel.kept_categories()), known=known,
+                                 repeat=1)
+    assert mismatches(res["filled"], want_fill) == 0
+    # blur_repeat = 1 (the reference's default): blur -> statistics from the blurred image -> categorise RGB{Float64}
+    sel_b = mr.MapSelection(settings=dict(category_tolerances=tol, category_keep=keep, prune_threshold=30,
+                                          line_threshold=0.02, match=("color",), segment=False, blur_repeat=1),
+                            points=points)
+    res_b = mr.rasterize(scan, sel_b, hood=None, ctx=ctx)
+    blurred = oracle.blur(scan, 1, 1)
+    pal_b = mr.Palette.from_points(blurred, points, tol)
+    want_b = oracle.categorize_f64_image(blurred, pal_b.mean, pal_b.lo, pal_b.hi, known_idx=idx, known_cat=cat)
+    assert mismatches(res_b["categorized"], want_b) == 0
+    assert (res_b["categorized"] != res["categorized"]).any()
 
 
 def test_device_bands_equal_whole(ctx, mr, oracle):

@@ -66,7 +66,7 @@ def test_unsupported_options_raise(mr):
     with pytest.raises(ValueError, match="segmented"):
         mr.categorize(img, pal, segmented=True)
     with pytest.raises(ValueError, match="uint8"):
-        mr.categorize(img.astype(np.float64), pal)
+        mr.categorize(img.astype(np.float32), pal)        # float64 RGB is the blurred-image path, float32 is nothing
     with pytest.raises(ValueError):
         mr.clean(np.zeros((3, 3)))
     with pytest.raises(ValueError):
