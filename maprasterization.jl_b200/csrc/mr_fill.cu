@@ -30,6 +30,7 @@ struct FillParams {
     MrPalette pal;
     double w_diag;            // 1 / sqrt(2), computed by the host in Float64
     uint8_t rank[256];        // position of a category in `categories` (0xFF: not kept)
+    int all_kept_upto;        // every category 1 .. all_kept_upto is kept (0: none): four-pixel fast path
     int vec16;                // lines can be read / written as whole 16-byte chunks
 };
 
@@ -104,17 +105,26 @@ __device__ __forceinline__ unsigned fill_pixel(const FillParams& P, int64_t i, i
     return fill_gap_pixel(P, i, j);
 }
 
+// Few registers (the stencil of a gap pixel is a call and may spill; the pass-through path must not limit
+// the occupancy) and the load of the next line's chunk in flight while this one is processed: the kernel
+// is a stream with very little work per byte, so bytes in flight are what it lives on.
 __global__ void __launch_bounds__(256) k_fill_gaps(const __grid_constant__ FillParams P) {
-    const int64_t chunks = (P.n1 + 15) / 16;
-    const int64_t total = chunks * P.n2;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t j = t / chunks, i0 = (t - j * chunks) * 16;
+    // grid.x covers one line in 16-pixel chunks, grid.y strides over the lines (no 64-bit division per chunk)
+    // (narrow images: blockDim.y lines per block)
+    const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (i0 >= P.n1) return;
+    const int64_t jstep = (int64_t)gridDim.y * blockDim.y;
+    int64_t j = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
+    uint4 nextq = make_uint4(0u, 0u, 0u, 0u);
+    if (P.vec16 && j < P.n2) nextq = __ldg(reinterpret_cast<const uint4*>(P.labels + j * P.stride2 + i0));
+    for (; j < P.n2; j += jstep) {
         const uint8_t* src = P.labels + j * P.stride2 + i0;
         uint8_t* dst = P.out + j * P.out_stride2 + i0;
         const int n = (int)min((int64_t)16, P.n1 - i0);
         uint32_t w[4] = {0u, 0u, 0u, 0u}, mk[4] = {0u, 0u, 0u, 0u};
         if (P.vec16) {
-            const uint4 q = __ldg(reinterpret_cast<const uint4*>(src));
+            const uint4 q = nextq;
+            if (j + jstep < P.n2) nextq = __ldg(reinterpret_cast<const uint4*>(src + jstep * P.stride2));
             w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
             if (P.mask) {
                 const uint4 mq = __ldg(reinterpret_cast<const uint4*>(P.mask + j * P.mask_stride2 + i0));
@@ -127,8 +137,18 @@ __global__ void __launch_bounds__(256) k_fill_gaps(const __grid_constant__ FillP
             }
         }
         uint32_t o[4];
+        // four pixels at a time: unmasked, no gap (no zero byte) and every label in 1 .. all_kept_upto
+        // (no byte above it; bytes >= 128 take the slow path) -> the word passes through unchanged
+        const uint32_t above = (uint32_t)(127 - P.all_kept_upto) * 0x01010101u;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
+            const uint32_t w4 = w[g];
+            const uint32_t zero = ~(((w4 & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w4 | 0x7F7F7F7Fu);   // 0x80 in every zero byte
+            const uint32_t big = (((w4 & 0x7F7F7F7Fu) + above) | w4) & 0x80808080u;          // 0x80 where label > all_kept_upto
+            if (4 * g + 4 <= n && (zero | big | mk[g]) == 0u) {
+                o[g] = w4;
+                continue;
+            }
             uint32_t r = 0u;
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
@@ -177,15 +197,21 @@ cudaError_t mr_launch_fill_gaps(const MrPalette& pal, const uint8_t* labels, int
     P.w_diag = 1.0 / sqrt(2.0);
     for (int c = 0; c < 256; ++c) P.rank[c] = 0xFF;
     for (int k = n_categories - 1; k >= 0; --k) P.rank[categories[k]] = (uint8_t)k;   // first occurrence wins
+    P.all_kept_upto = 0;
+    while (P.all_kept_upto < 127 && P.rank[P.all_kept_upto + 1] != 0xFF) ++P.all_kept_upto;
     P.vec16 = ((uintptr_t)labels % 16 == 0) && ((uintptr_t)out % 16 == 0) && (stride2 % 16 == 0) &&
               (out_stride2 % 16 == 0) && (n1 % 16 == 0) &&
               (!mask || (((uintptr_t)mask % 16 == 0) && (mask_stride2 % 16 == 0)));
-    const int64_t total = ((n1 + 15) / 16) * n2;
-    int64_t grid = (total + 255) / 256;
-    const int64_t cap = (int64_t)sm_count * 16;
-    if (grid > cap) grid = cap;
-    if (grid < 1) grid = 1;
-    k_fill_gaps<<<(unsigned)grid, 256, 0, s>>>(P);
+    const int64_t chunks = (n1 + 15) / 16;
+    int bx = 256;
+    while (bx > 32 && bx / 2 >= chunks) bx /= 2;
+    const int by = 256 / bx;
+    const int64_t gx = (chunks + bx - 1) / bx;
+    int64_t gy = ((int64_t)sm_count * 32 + gx - 1) / gx;   // about 32 blocks per SM in total
+    if (gy > (n2 + by - 1) / by) gy = (n2 + by - 1) / by;
+    if (gy > 65535) gy = 65535;
+    if (gy < 1) gy = 1;
+    k_fill_gaps<<<dim3((unsigned)gx, (unsigned)gy), dim3(bx, by), 0, s>>>(P);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     *n_launches += 1;
