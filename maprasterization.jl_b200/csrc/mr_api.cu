@@ -21,6 +21,7 @@ struct mr_ctx {
     double* d_pal = nullptr;        // mean | lo | hi | lin
     uint8_t* d_lut = nullptr;
     uint8_t* d_coarse = nullptr;
+    double* d_qtab = nullptr;       // squared channel differences per category (table build scratch)
     bool lut_valid = false;
     float build_ms = 0.f;
     // known-category plane (sparse)
@@ -100,6 +101,7 @@ extern "C" mr_ctx* mr_create(int device, int* err) {
     ok = ok && cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_lut, MR_LUT_SIZE) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_coarse, MR_COARSE_SIZE) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_qtab, MR_QTAB_BYTES) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_counters, sizeof(MrCountersDev)) == cudaSuccess;
     ok = ok && cudaMemset(ctx->d_counters, 0, sizeof(MrCountersDev)) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->work.slots, MR_WORK_SLOTS * sizeof(unsigned int)) == cudaSuccess;
@@ -121,7 +123,7 @@ extern "C" void mr_destroy(mr_ctx* ctx) {
     cudaDeviceSynchronize();
     for (auto e : ctx->ev_up) cudaEventDestroy(e);
     for (auto e : ctx->ev_done) cudaEventDestroy(e);
-    cudaFree(ctx->d_pal); cudaFree(ctx->d_lut); cudaFree(ctx->d_coarse);
+    cudaFree(ctx->d_pal); cudaFree(ctx->d_lut); cudaFree(ctx->d_coarse); cudaFree(ctx->d_qtab);
     cudaFree(ctx->d_known_idx); cudaFree(ctx->d_known_cat); cudaFree(ctx->d_counters); cudaFree(ctx->work.slots);
     cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_tmp); cudaFree(ctx->d_rp_in); cudaFree(ctx->d_rp_out); cudaFree(ctx->d_lab); cudaFree(ctx->d_f64); cudaFree(ctx->d_f64b);
     cudaFree(ctx->d_parent); cudaFree(ctx->d_runs); cudaFree(ctx->d_rec); cudaFree(ctx->d_small);
@@ -188,7 +190,7 @@ extern "C" int mr_set_palette(mr_ctx* ctx, int K, const double* mean, const doub
         CK(cudaEventCreate(&b));
         int nl = 0;
         CK(cudaEventRecord(a, ctx->s_main));
-        CK(mr_launch_build_lut(ctx->pal, ctx->d_lut, ctx->d_coarse, ctx->s_main, &nl));
+        CK(mr_launch_build_lut(ctx->pal, ctx->d_lut, ctx->d_coarse, ctx->d_qtab, ctx->s_main, &nl));
         CK(cudaEventRecord(b, ctx->s_main));
         CK(cudaStreamSynchronize(ctx->s_main));
         CK(cudaEventElapsedTime(&ctx->build_ms, a, b));

@@ -53,7 +53,9 @@ struct MrJob {
     MrCountersDev* counters;  // nullptr = do not count
 };
 
-cudaError_t mr_launch_build_lut(const MrPalette& pal, uint8_t* lut, uint8_t* coarse, cudaStream_t s,
+// qtab: scratch of MR_QTAB_BYTES (squared channel differences, RGB colour space); nullptr = one-step build
+#define MR_QTAB_BYTES ((size_t)3 * 254 * 256 * sizeof(double))
+cudaError_t mr_launch_build_lut(const MrPalette& pal, uint8_t* lut, uint8_t* coarse, double* qtab, cudaStream_t s,
                                 int* n_launches);
 cudaError_t mr_launch_generic(const MrJob& job, bool labels_in, int sm_count, cudaStream_t s,
                               int* n_launches);
