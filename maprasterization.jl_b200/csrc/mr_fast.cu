@@ -121,6 +121,9 @@ struct FastParams {
     unsigned int* work_counter;   // this launch's item queue (zero when the launch starts)
     unsigned int* work_reset;     // a slot far ahead in the ring: zeroed here for a later launch (no memset per launch)
     int padded;   // lines are readable / writable up to the next multiple of 16 bytes
+#ifdef MR_TIMELINE
+    unsigned long long* timeline;   // experiment: per warp (start, first vote, end, lines) in ns
+#endif
 };
 
 // one work item as seen by a warp
@@ -1112,6 +1115,10 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
     unsigned c_fine = 0, c_nomatch = 0, c_changed = 0;
     uint32_t parity = 0;
 
+#ifdef MR_TIMELINE
+    unsigned long long t_start, t_first = 0, n_lines_done = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+#endif
     if (blockIdx.x == 0 && tid == 0) *P.work_reset = 0u;
     unsigned next = 0;
     if (lane == 0) next = atomicAdd(P.work_counter, 1u);
@@ -1173,6 +1180,10 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
 #ifdef MR_KO_VOTE   // timing experiment: no vote at all
                 break;
 #endif
+#ifdef MR_TIMELINE
+                if (t_first == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_first));
+                n_lines_done += vend - va;
+#endif
                 int n2 = 0;   // entries round 1 put on the word list
                 const int done = block_vote<R, NB, COUNT>(P, ws, it, va, vend - va, lane, M.vvalid, obytes, hint, c_nomatch,
                                                           c_changed, n2);
@@ -1220,6 +1231,14 @@ __global__ void __launch_bounds__(Cfg<R, NB>::WARPS * 32, 1) k_fast(const FastPa
         next = __shfl_sync(0xffffffffu, next, 0);   // the item fetched in the last block
     }
     if (R > 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // line buffer still in use
+#ifdef MR_TIMELINE
+    if (lane == 0 && P.timeline) {
+        unsigned long long t_end;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+        unsigned long long* o = P.timeline + 4 * ((size_t)blockIdx.x * C::WARPS + warp);
+        o[0] = t_start; o[1] = t_first; o[2] = t_end; o[3] = n_lines_done;
+    }
+#endif
     if (COUNT && P.job.counters) {
         for (int o = 16; o > 0; o >>= 1) {
             c_fine += __shfl_xor_sync(0xffffffffu, c_fine, o);
@@ -1246,7 +1265,10 @@ std::mutex g_cfg_mutex;   // cudaFuncSetAttribute bookkeeping below (contexts ma
 // ---- host: the item schedule.  Class 0 hands out most of the lines (f0) in tall chunks whose item
 // count fills whole "waves" of warps (an item count just above a multiple of the warp count would
 // leave most of the GPU idle at the end of the class); the rest goes out in small chunks that level
-// the finish.  Chunks are multiples of the block height B.  Small jobs: one class of small chunks.
+// the finish: two-block items first, one-block items last.  Small jobs: one class of small chunks.
+// (Measured on B200, scripts/sched_sweep*.sh: tall-class share 0.78 .. 0.96, one to four tail classes
+// down to quarter blocks -- everything within 1.5 %; a per-warp timeline shows the warps ending within
+// 50 us of each other whatever the job size, 5 % of the warp time on a 0.57 ms job.)
 void plan_schedule(FastParams& P, int warps, int B, int R) {
     const long long n2 = P.job.n2;
     const int cols = P.cols;
@@ -1278,6 +1300,39 @@ void plan_schedule(FastParams& P, int warps, int B, int R) {
         y = n0 * H0;
         items = n0 * cols;
         ++k;
+    }
+#ifdef MR_SCHED_ENV   // MAPRAST_TAILS = "frac:lines,frac:lines": classes after the tall one (the last takes the rest)
+    if (const char* e = getenv("MAPRAST_TAILS")) {
+        if (n0 > 0) {
+            const char* p = e;
+            while (*p && k < 3 && y < n2) {
+                const double fr = atof(p);
+                while (*p && *p != ':') ++p;
+                const long long h = *p ? atoll(p + 1) : tail;
+                while (*p && *p != ',') ++p;
+                const bool last = !*p;
+                if (*p) ++p;
+                long long y1 = last ? n2 : y + (long long)(fr * n2) / h * h;
+                if (y1 > n2) y1 = n2;
+                if (y1 <= y) continue;
+                P.cls[k] = SchedClass{(int)y, (int)y1, (int)h, (unsigned)items};
+                items += ((y1 - y + h - 1) / h) * cols;
+                y = y1;
+                ++k;
+            }
+        }
+    }
+#endif
+    if (k == 1 && y < n2 && n2 - y > 4 * B) {   // behind the tall class: half of the rest in two-block items ...
+        const long long h = tail;
+        long long y1 = y + (n2 - y) / 2 / h * h;
+        if (y1 > y) {
+            P.cls[k] = SchedClass{(int)y, (int)y1, (int)h, (unsigned)items};
+            items += ((y1 - y) / h) * cols;
+            y = y1;
+            ++k;
+        }
+        tail = B;                               // ... the last lines in one-block items (1 % on config 2)
     }
     if (y < n2) {
         long long h = tail;
@@ -1346,6 +1401,15 @@ cudaError_t launch_r(FastParams& P, int sm_count, cudaStream_t s) {
 
 }  // namespace
 
+#ifdef MR_TIMELINE
+static unsigned long long* g_timeline_host = nullptr;
+extern "C" int mr_debug_timeline(unsigned long long* out, int n_entries) {   // n_entries x 4 values
+    if (!g_timeline_host) return -1;
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpy(out, g_timeline_host, (size_t)n_entries * 32, cudaMemcpyDeviceToHost);
+}
+#endif
+
 // bpp == 1: label image in (standalone clean); job.pal.K then holds the largest label value
 bool mr_fast_supported(const MrJob& job) {
     if (job.bpp == 1) {
@@ -1379,6 +1443,13 @@ cudaError_t mr_launch_fast(const MrJob& job, int sm_count, cudaStream_t s, int* 
     P.work_counter = ctr;
     P.work_reset = ring->slots + ((seq + MR_WORK_SLOTS / 2) % MR_WORK_SLOTS);
     P.padded = job.padded;
+#ifdef MR_TIMELINE
+    static unsigned long long* g_timeline = nullptr;
+    if (!g_timeline) { cudaMalloc(&g_timeline, 4 * 8 * 148 * 32); }
+    cudaMemsetAsync(g_timeline, 0, 4 * 8 * 148 * 32, s);
+    P.timeline = g_timeline;
+    g_timeline_host = g_timeline;
+#endif
     const int K = job.pal.K;
 #ifdef MR_QUICK   // kernel experiments: only the BASELINE config 1 / 2 / 4 / 5 instantiations (fast to compile)
     if (job.R == 2 && K > 14 && K <= 30) e = launch_c<2, 5>(P, sm_count, s);
