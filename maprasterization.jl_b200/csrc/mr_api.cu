@@ -170,9 +170,9 @@ extern "C" int mr_set_palette(mr_ctx* ctx, int K, const double* mean, const doub
         h[3 * n + i] = (v <= 0.04045) ? v / 12.92 : pow((v + 0.055) / 1.055, 2.4);
     }
     CK(cudaStreamSynchronize(ctx->s_main));
-    cudaFree(ctx->d_pal);
-    ctx->d_pal = nullptr;
-    CK(cudaMalloc(&ctx->d_pal, h.size() * 8));
+    // one allocation for the largest palette (254 categories x 4 channels x 3 arrays + the sRGB table),
+    // made once: a palette change (slider move -> mr_set_palette) costs no cudaMalloc / cudaFree
+    if (!ctx->d_pal) CK(cudaMalloc(&ctx->d_pal, ((size_t)254 * 4 * 3 + 256) * 8));
     CK(cudaMemcpy(ctx->d_pal, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
     ctx->pal.mean = ctx->d_pal;
     ctx->pal.lo = ctx->d_pal + n;
@@ -390,7 +390,7 @@ static int run_clean(mr_ctx* ctx, const MrJob& job, cudaStream_t s, int max_labe
     const bool direct = mr_fast_supported(j), repack = !direct && repack_pays(j);
     if (direct || repack) {   // geometry qualifies (possibly after repacking): the plane count needs the largest label
         if (max_label < 0) {
-            if (!ctx->d_small) CK(cudaMalloc(&ctx->d_small, 512));
+            if (!ctx->d_small) CK(cudaMalloc(&ctx->d_small, 2048));
             unsigned int* d_max = reinterpret_cast<unsigned int*>(ctx->d_small + 264);
             e = mr_launch_max_label(job.px - (int64_t)job.halo_lo * job.stride2, job.n1, job.n2 + job.halo_lo + job.halo_hi,
                                     job.stride2, d_max, ctx->sm_count, s, &nl);
@@ -431,7 +431,7 @@ static int run_rgba(mr_ctx* ctx, const MrJob& job, cudaStream_t s) {
     int rc;
     if ((rc = grow(ctx, &ctx->d_rp_in, &ctx->d_rp_in_cap, (size_t)line_rgb * T))) return rc;
     if ((rc = grow(ctx, &ctx->d_lab, &ctx->d_lab_cap, (size_t)line_lab * T))) return rc;
-    if (!ctx->d_small) CK(cudaMalloc(&ctx->d_small, 512));
+    if (!ctx->d_small) CK(cudaMalloc(&ctx->d_small, 2048));
     unsigned int* d_special = reinterpret_cast<unsigned int*>(ctx->d_small + 268);
     const uint8_t* px0 = job.px - (int64_t)job.halo_lo * job.stride2;
     int nl = 0;
@@ -786,7 +786,7 @@ static int prune_dev(mr_ctx* ctx, const char* fn, const uint8_t* labels_dev, int
     const size_t cb_bytes = mr_prune_cbase_bytes(n1, n2);
     if ((rc = grow(ctx, &ctx->d_parent, &ctx->d_parent_cap, cb_bytes))) return rc;   // chunk bases
     uint32_t* cbase = reinterpret_cast<uint32_t*>(ctx->d_parent);
-    if (!ctx->d_small) CK(cudaMalloc(&ctx->d_small, 512));
+    if (!ctx->d_small) CK(cudaMalloc(&ctx->d_small, 2048));
     unsigned int* d_n_roots = reinterpret_cast<unsigned int*>(ctx->d_small + 256);
     unsigned int* d_conflict = reinterpret_cast<unsigned int*>(ctx->d_small + 260);
     CK(cudaMemcpyAsync(ctx->d_small, keep256, 256, cudaMemcpyHostToDevice, s));
@@ -1090,15 +1090,14 @@ extern "C" int mr_synth_scan_dev(mr_ctx* ctx, uint32_t seed, uint32_t sheet_id, 
         return fail(ctx, MR_ERR_ARG, "mr_synth_scan_dev: bad arguments");
     if (n1 == 0 || nlines == 0) return MR_OK;
     CK(cudaSetDevice(ctx->device));
-    uint8_t* d_pal = nullptr;
-    CK(cudaMalloc(&d_pal, (size_t)K * 3));
+    if (!ctx->d_small) CK(cudaMalloc(&ctx->d_small, 2048));
+    uint8_t* d_pal = ctx->d_small + 1024;   // K * 3 <= 762 bytes; the call synchronises before it returns
     CK(cudaMemcpy(d_pal, palette_rgb_host, (size_t)K * 3, cudaMemcpyHostToDevice));
     int nl = 0;
     cudaError_t e = mr_launch_synth(seed, sheet_id, K, d_pal, n1, line0, nlines, mode, out_dev, out_stride2,
                                     (cudaStream_t)stream, &nl);
     ctx->launches += nl;
     cudaError_t e2 = cudaStreamSynchronize((cudaStream_t)stream);
-    cudaFree(d_pal);
     if (e != cudaSuccess) return fail_cuda(ctx, e, "synth launch");
     if (e2 != cudaSuccess) return fail_cuda(ctx, e2, "synth kernel");
     return MR_OK;

@@ -23,6 +23,22 @@ def sheet_range(n_sheets, world, rank):
     return (rank * n_sheets) // world, ((rank + 1) * n_sheets) // world
 
 
+def set_known_for_band(ctx, lin_idx, cat, n1, n2, R, rank, world):
+    """Known-category points of the WHOLE sheet (lin_idx = i + j * n1, `_set_categories!`,
+    src/selectcolors.jl:670-681) -> the points rank's band can see (its own lines and the R halo lines
+    on both sides), uploaded with the band's first sheet line (mr_set_known_band).  Every rank calls this
+    with the same lists; the following categorize_clean_band / PeerHalos.categorize_clean then applies the
+    override of src/categories.jl:110-112 exactly as a whole-image call would."""
+    import numpy as np
+    a, b = band_range(n2, world, rank)
+    idx = np.asarray(lin_idx, dtype=np.int64).reshape(-1)
+    ct = np.asarray(cat, dtype=np.uint8).reshape(-1)
+    j = idx // max(n1, 1)
+    sel = (j >= a - R) & (j < b + R)
+    ctx.set_known_band(idx[sel], ct[sel], a)
+    return int(sel.sum())
+
+
 def alloc_band(n1, nb, R, bpp=3, device="cuda"):
     """Band buffer with halo slots; `own` is the view of the rank's own lines."""
     buf = torch.empty((nb + 2 * R, n1, bpp), dtype=torch.uint8, device=device)
