@@ -17,6 +17,8 @@
 
 namespace {
 
+constexpr int FILL_GROUP = 16;   // consecutive lines a block processes before it jumps (multiple of every blockDim.y)
+
 struct FillParams {
     const uint8_t* labels;
     int64_t n1, n2, stride2;
@@ -36,17 +38,19 @@ struct FillParams {
 
 // colour error of the original pixel against category c (1-based): categories.jl:91-95, the
 // operations of mr_eval_px (one rounded binary64 operation each, no FMA)
-__device__ __forceinline__ double fill_colour_error(const FillParams& P, const uint8_t* p, int c) {
+// s_n0f8[v] = Float64(N0f8(v)) = v / 255 (correctly rounded), tabulated once per block
+__device__ __forceinline__ double fill_colour_error(const FillParams& P, const double* __restrict__ s_n0f8,
+                                                    const uint8_t* p, int c) {
     const MrPalette& pal = P.pal;
     const int C = pal.C;
     double x0, x1, x2, x3 = 0.0;
     if (pal.colourspace == 1) {
         mr_rgb8_to_lab(pal.lin, p[0], p[1], p[2], x0, x1, x2);
     } else {
-        x0 = __ddiv_rn((double)p[0], 255.0);
-        x1 = __ddiv_rn((double)p[1], 255.0);
-        x2 = __ddiv_rn((double)p[2], 255.0);
-        if (P.bpp == 4) x3 = __ddiv_rn((double)p[3], 255.0);
+        x0 = s_n0f8[p[0]];
+        x1 = s_n0f8[p[1]];
+        x2 = s_n0f8[p[2]];
+        if (P.bpp == 4) x3 = s_n0f8[p[3]];
     }
     const double* m = pal.mean + (size_t)(c - 1) * C;
     const double d0 = __dsub_rn(x0, __ldg(m + 0)), d1 = __dsub_rn(x1, __ldg(m + 1)), d2 = __dsub_rn(x2, __ldg(m + 2));
@@ -58,75 +62,119 @@ __device__ __forceinline__ double fill_colour_error(const FillParams& P, const u
     return e;
 }
 
-// the stencil of one gap pixel (clean.jl:15-34)
-__device__ __noinline__ unsigned fill_gap_pixel(const FillParams& P, int64_t i, int64_t j) {
+// the stencil of one gap pixel (clean.jl:15-34).  The 12 neighbour labels sit in three registers (one byte
+// each); the distinct labels are taken one after the other (first uncounted neighbour), the neighbours that
+// carry the label are found by a byte compare, and their weights are added IN NEIGHBOURHOOD ORDER
+// (clean.jl:43-54: `acc += 1/ds[i]`); best / second best (weight, position in `categories`) are kept
+// (findmax and the reduce of clean.jl:24-27 = first of equal weights).
+__device__ __forceinline__ unsigned fill_gap_pixel(const FillParams& P, const uint8_t* __restrict__ s_rank,
+                                                   const double* __restrict__ s_n0f8, int64_t i, int64_t j) {
     constexpr int D1[12] = {0, -1, 0, 1, -2, -1, 1, 2, -1, 0, 1, 0};
     constexpr int D2[12] = {-2, -1, -1, -1, 0, 0, 0, 0, 1, 1, 1, 2};
-    // distinct kept categories among the neighbours, with their weights (at most 12)
-    unsigned cat[12];
-    double acc[12];
-    int nd = 0, missing = 0;
+    // weight class of neighbour m, two bits each: 0 -> 1 (distance 1), 1 -> 1/sqrt(2), 2 -> 1/2 (distance 2)
+    constexpr unsigned WCLASS = 2u | (1u << 2) | (0u << 4) | (1u << 6) | (2u << 8) | (0u << 10) | (0u << 12) |
+                                (2u << 14) | (1u << 16) | (0u << 18) | (1u << 20) | (2u << 22);
+    uint32_t lw[3] = {0u, 0u, 0u};
+    if (i >= 2 && i + 2 < P.n1 && j >= 2 && j + 2 < P.n2) {   // interior: no bounds tests
+        const uint8_t* c0 = P.labels + j * P.stride2 + i;
 #pragma unroll
-    for (int k = 0; k < 12; ++k) {
-        const int64_t a = i + D1[k], b = j + D2[k];
-        unsigned l = 0;
-        if (a >= 0 && a < P.n1 && b >= 0 && b < P.n2) l = __ldg(P.labels + b * P.stride2 + a);
-        if (l == 0) { ++missing; continue; }
-        if (P.rank[l] == 0xFFu) continue;   // not a kept category: neither missing nor counted
-        const int sq = D1[k] * D1[k] + D2[k] * D2[k];
-        const double w = sq == 1 ? 1.0 : (sq == 2 ? P.w_diag : 0.5);
-        int s = 0;
-        while (s < nd && cat[s] != l) ++s;
-        if (s == nd) { cat[nd] = l; acc[nd] = 0.0; ++nd; }
-        acc[s] = __dadd_rn(acc[s], w);      // clean.jl:49, in neighbourhood order
+        for (int k = 0; k < 12; ++k)
+            lw[k >> 2] |= (uint32_t)__ldg(c0 + D2[k] * P.stride2 + D1[k]) << (8 * (k & 3));
+    } else {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            const int64_t a = i + D1[k], b = j + D2[k];
+            unsigned l = 0u;
+            if (a >= 0 && a < P.n1 && b >= 0 && b < P.n2) l = __ldg(P.labels + b * P.stride2 + a);
+            lw[k >> 2] |= l << (8 * (k & 3));
+        }
     }
-    if (missing > 12 - 12 / 4) return 0u;   // clean.jl:20
-    // findmax = first maximum in the order of `categories`; second = the same among the others
-    int im = -1, is = -1;
-    for (int s = 0; s < nd; ++s)
-        if (im < 0 || acc[s] > acc[im] || (acc[s] == acc[im] && P.rank[cat[s]] < P.rank[cat[im]])) im = s;
-    if (im < 0 || !(acc[im] > 1.0)) return 0u;   // clean.jl:23
-    for (int s = 0; s < nd; ++s) {
-        if (s == im) continue;
-        if (is < 0 || acc[s] > acc[is] || (acc[s] == acc[is] && P.rank[cat[s]] < P.rank[cat[is]])) is = s;
+    auto eq_mask = [&](unsigned c) {      // 12-bit mask of the neighbours whose label is c
+        uint32_t m = 0u;
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+            const uint32_t x = lw[g] ^ (c * 0x01010101u);
+            const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);   // 0x80 in every zero byte
+            m |= ((((z >> 7) * 0x00204081u) >> 21) & 0xFu) << (4 * g);                    // bits 0, 8, 16, 24 -> 0..3
+        }
+        return m;
+    };
+    uint32_t rem = 0xFFFu & ~eq_mask(0u);                 // neighbours that carry a label, not yet counted
+    if (12 - __popc(rem) > 12 - 12 / 4) return 0u;        // clean.jl:20: mostly missing
+    double a1 = 0.0, a2 = 0.0;                            // best / second weight (0: none)
+    unsigned r1 = 0x100u, r2 = 0x100u, c1 = 0u, c2 = 0u;
+    while (rem) {
+        const int k = __ffs(rem) - 1;
+        const uint32_t word = k < 4 ? lw[0] : (k < 8 ? lw[1] : lw[2]);
+        const unsigned c = (word >> (8 * (k & 3))) & 0xFFu;
+        uint32_t mm = eq_mask(c);
+        rem &= ~mm;
+        const unsigned r = s_rank[c];
+        if (r == 0xFFu) continue;                         // not a kept category: neither missing nor counted
+        double acc = 0.0;
+#pragma unroll
+        for (int m = 0; m < 12; ++m) {                    // ascending m = neighbourhood order; predicated additions
+            const unsigned wc = (WCLASS >> (2 * m)) & 3u;
+            if ((mm >> m) & 1u) acc = __dadd_rn(acc, wc == 0u ? 1.0 : (wc == 1u ? P.w_diag : 0.5));
+        }
+        if (acc > a1 || (acc == a1 && r < r1)) {
+            a2 = a1; r2 = r1; c2 = c1;
+            a1 = acc; r1 = r; c1 = c;
+        } else if (acc > a2 || (acc == a2 && r < r2)) {
+            a2 = acc; r2 = r; c2 = c;
+        }
     }
-    if (is >= 0 && acc[is] > 1.0) {              // clean.jl:28-31
+    if (!(a1 > 1.0)) return 0u;                           // clean.jl:23
+    if (a2 > 1.0) {                                       // clean.jl:28-31
         const uint8_t* p = P.px + j * P.px_stride2 + i * P.bpp;
-        const double ea = fill_colour_error(P, p, (int)cat[im]);
-        const double eb = fill_colour_error(P, p, (int)cat[is]);
-        return ea <= eb ? cat[im] : cat[is];
+        const double ea = fill_colour_error(P, s_n0f8, p, (int)c1);
+        const double eb = fill_colour_error(P, s_n0f8, p, (int)c2);
+        return ea <= eb ? c1 : c2;
     }
-    return cat[im];
+    return c1;
 }
 
-__device__ __forceinline__ unsigned fill_pixel(const FillParams& P, int64_t i, int64_t j, unsigned v, unsigned m) {
-    if (m) return v;                                  // clean.jl:13
-    if (v != 0) return P.rank[v] != 0xFFu ? v : 0u;   // clean.jl:16-17, 35-36
-    return fill_gap_pixel(P, i, j);
-}
-
-// Few registers (the stencil of a gap pixel is a call and may spill; the pass-through path must not limit
-// the occupancy) and the load of the next line's chunk in flight while this one is processed: the kernel
-// is a stream with very little work per byte, so bytes in flight are what it lives on.
+// One thread = 16 consecutive pixels of a line; a warp = 512 consecutive pixels.  Words of four pixels that
+// are unmasked, without a gap and entirely inside 1 .. all_kept_upto pass through; the other non-gap pixels
+// map through the rank table; gap pixels are only MARKED, the 16 bytes are stored, and then the warp
+// spreads its gap pixels evenly over its lanes (inclusive scan of the per-lane gap counts, owner by binary
+// search) and patches single bytes -- a sheet with 5 % gaps would otherwise run the stencil on one lane in
+// sixteen.  grid.x covers one line, grid.y strides over the lines; narrow images: blockDim.y lines per block.
 __global__ void __launch_bounds__(256) k_fill_gaps(const __grid_constant__ FillParams P) {
-    // grid.x covers one line in 16-pixel chunks, grid.y strides over the lines (no 64-bit division per chunk)
-    // (narrow images: blockDim.y lines per block)
+    __shared__ uint8_t s_rank[256];
+    __shared__ double s_n0f8[256];
+    for (int t = threadIdx.y * blockDim.x + threadIdx.x; t < 256; t += blockDim.x * blockDim.y) {
+        s_rank[t] = P.rank[t];
+        s_n0f8[t] = __ddiv_rn((double)t, 255.0);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
     const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
-    if (i0 >= P.n1) return;
-    const int64_t jstep = (int64_t)gridDim.y * blockDim.y;
-    int64_t j = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
+    const int n = i0 >= P.n1 ? 0 : (int)min((int64_t)16, P.n1 - i0);
+    // a block walks down GROUPS of FILL_GROUP consecutive lines (the neighbour lines of a gap pixel are then lines
+    // this SM has just read: L1 hits instead of a 32-byte sector from L2 per neighbour), groups stride over grid.y
+    auto advance = [&](int64_t y) {       // the line after y in this thread's sequence
+        const int64_t g0 = y / FILL_GROUP * FILL_GROUP;
+        const int64_t yn = y + blockDim.y;
+        if (yn < g0 + FILL_GROUP) return yn;
+        return g0 + (int64_t)gridDim.y * FILL_GROUP + threadIdx.y;
+    };
+    int64_t j = (int64_t)blockIdx.y * FILL_GROUP + threadIdx.y;
     uint4 nextq = make_uint4(0u, 0u, 0u, 0u);
-    if (P.vec16 && j < P.n2) nextq = __ldg(reinterpret_cast<const uint4*>(P.labels + j * P.stride2 + i0));
-    for (; j < P.n2; j += jstep) {
+    if (P.vec16 && n && j < P.n2) nextq = __ldg(reinterpret_cast<const uint4*>(P.labels + j * P.stride2 + i0));
+    const uint32_t above = (uint32_t)(127 - P.all_kept_upto) * 0x01010101u;
+    const int64_t n2r = (P.n2 + FILL_GROUP - 1) / FILL_GROUP * FILL_GROUP;   // every warp of a block sees the same groups
+    for (; j < n2r; j = advance(j)) {     // warp-uniform: a warp holds consecutive chunks of ONE line
+        const int64_t jn = advance(j);
+        if (j >= P.n2) continue;
         const uint8_t* src = P.labels + j * P.stride2 + i0;
         uint8_t* dst = P.out + j * P.out_stride2 + i0;
-        const int n = (int)min((int64_t)16, P.n1 - i0);
         uint32_t w[4] = {0u, 0u, 0u, 0u}, mk[4] = {0u, 0u, 0u, 0u};
         if (P.vec16) {
             const uint4 q = nextq;
-            if (j + jstep < P.n2) nextq = __ldg(reinterpret_cast<const uint4*>(src + jstep * P.stride2));
+            if (n && jn < P.n2) nextq = __ldg(reinterpret_cast<const uint4*>(P.labels + jn * P.stride2 + i0));
             w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
-            if (P.mask) {
+            if (P.mask && n) {
                 const uint4 mq = __ldg(reinterpret_cast<const uint4*>(P.mask + j * P.mask_stride2 + i0));
                 mk[0] = mq.x; mk[1] = mq.y; mk[2] = mq.z; mk[3] = mq.w;
             }
@@ -137,15 +185,17 @@ __global__ void __launch_bounds__(256) k_fill_gaps(const __grid_constant__ FillP
             }
         }
         uint32_t o[4];
-        // four pixels at a time: unmasked, no gap (no zero byte) and every label in 1 .. all_kept_upto
-        // (no byte above it; bytes >= 128 take the slow path) -> the word passes through unchanged
-        const uint32_t above = (uint32_t)(127 - P.all_kept_upto) * 0x01010101u;
+        uint32_t gaps = 0u;               // bit k: pixel i0 + k is an unmasked gap
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             const uint32_t w4 = w[g];
             const uint32_t zero = ~(((w4 & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w4 | 0x7F7F7F7Fu);   // 0x80 in every zero byte
             const uint32_t big = (((w4 & 0x7F7F7F7Fu) + above) | w4) & 0x80808080u;          // 0x80 where label > all_kept_upto
-            if (4 * g + 4 <= n && (zero | big | mk[g]) == 0u) {
+            if (4 * g + 4 <= n && big == 0u) {
+                // every label of the word is 0 or kept: the bytes pass through; unmasked zero bytes are gaps
+                const uint32_t mz = ~(((mk[g] & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | mk[g] | 0x7F7F7F7Fu);   // 0x80: pixel not masked
+                const uint32_t gz = zero & mz;
+                gaps |= ((((gz >> 7) * 0x00204081u) >> 21) & 0xFu) << (4 * g);
                 o[g] = w4;
                 continue;
             }
@@ -153,16 +203,51 @@ __global__ void __launch_bounds__(256) k_fill_gaps(const __grid_constant__ FillP
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
                 const int k = 4 * g + b;
-                unsigned v = (w[g] >> (8 * b)) & 0xFFu;
-                if (k < n) v = fill_pixel(P, i0 + k, j, v, (mk[g] >> (8 * b)) & 0xFFu);
+                unsigned v = (w4 >> (8 * b)) & 0xFFu;
+                const unsigned m = (mk[g] >> (8 * b)) & 0xFFu;
+                if (k < n && !m) {                                     // clean.jl:13: a masked pixel stays
+                    if (v != 0u) v = s_rank[v] != 0xFFu ? v : 0u;      // clean.jl:16-17, 35-36
+                    else gaps |= 1u << k;
+                }
                 r |= v << (8 * b);
             }
             o[g] = r;
         }
-        if (P.vec16) {
-            *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
-        } else {
-            for (int k = 0; k < n; ++k) dst[k] = (uint8_t)(o[k >> 2] >> (8 * (k & 3)));
+        if (n) {
+            if (P.vec16) {
+                *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+            } else {
+                for (int k = 0; k < n; ++k) dst[k] = (uint8_t)(o[k >> 2] >> (8 * (k & 3)));
+            }
+        }
+        // ---- the warp's gap pixels, spread evenly over its lanes
+        if (!__any_sync(0xffffffffu, gaps != 0u)) continue;
+        __syncwarp();                     // orders the 16-byte stores above before the byte patches below
+        const int c = __popc(gaps);
+        int S = c;                        // inclusive scan of the gap counts
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, S, d);
+            if (lane >= d) S += v;
+        }
+        const int T = __shfl_sync(0xffffffffu, S, 31);
+        for (int t0 = 0; t0 < T; t0 += 32) {
+            const int t = t0 + lane;
+            int owner = 0;                // number of lanes whose inclusive scan is <= t
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const int v = __shfl_sync(0xffffffffu, S, (owner + step - 1) & 31);
+                if (v <= t) owner += step;
+            }
+            owner &= 31;
+            const int before = __shfl_sync(0xffffffffu, S - c, owner);
+            uint32_t m = __shfl_sync(0xffffffffu, gaps, owner);
+            if (t < T) {
+                for (int r = t - before; r > 0; --r) m &= m - 1;       // skip r set bits
+                const int k = __ffs(m) - 1;
+                const int64_t i = i0 + (int64_t)(owner - lane) * 16 + k;
+                P.out[j * P.out_stride2 + i] = (uint8_t)fill_gap_pixel(P, s_rank, s_n0f8, i, j);
+            }
         }
     }
 }
@@ -208,7 +293,8 @@ cudaError_t mr_launch_fill_gaps(const MrPalette& pal, const uint8_t* labels, int
     const int by = 256 / bx;
     const int64_t gx = (chunks + bx - 1) / bx;
     int64_t gy = ((int64_t)sm_count * 32 + gx - 1) / gx;   // about 32 blocks per SM in total
-    if (gy > (n2 + by - 1) / by) gy = (n2 + by - 1) / by;
+    const int64_t groups = (n2 + FILL_GROUP - 1) / FILL_GROUP;
+    if (gy > groups) gy = groups;
     if (gy > 65535) gy = 65535;
     if (gy < 1) gy = 1;
     k_fill_gaps<<<dim3((unsigned)gx, (unsigned)gy), dim3(bx, by), 0, s>>>(P);
