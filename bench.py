@@ -571,6 +571,35 @@ def run_ours(args, rank, world, local_rank):
                     "sample": f"first {lines} lines, sequential C oracle",
                     "label_mismatches_vs_gpu": int((got_f.cpu().numpy() != want_f).sum())}
         del fill_out
+        # blur (src/blur.jl:6-14) and the categoriser on its RGB{Float64} output, on the first lines of the sheet
+        # (24 B per pixel of Float64 colour: 4096 lines = 2 GB)
+        if not batch and stats.colourspace == "rgb":
+            bl = min(nb, 4096)
+            f64 = torch.empty((bl, n1, 3), dtype=torch.float64, device=dev)
+            lab64 = torch.empty((bl, n1), dtype=torch.uint8, device=dev)
+            L = ctx._L
+            def _blur():
+                ctx._ck(L.mr_blur_dev(ctx._h, own.data_ptr(), n1, bl, n1 * 3, 3, 1, 1, f64.data_ptr(), n1 * 24, None))
+            def _cat():
+                ctx._ck(L.mr_categorize_clean_f64_dev(ctx._h, f64.data_ptr(), n1, bl, n1 * 24, 0, lab64.data_ptr(), n1, None))
+            for fn, key, what, bpp_alg in ((_blur, "blur", "blur(A; hood=Window{1}(), repeat=1): RGB{N0f8} in, RGB{Float64} out", 27),
+                                           (_cat, "categorize_f64", "categorise RGB{Float64} pixels (direct Float64 evaluation)", 25)):
+                fn()
+                torch.cuda.synchronize()
+                l0 = ctx.launch_count()
+                e0.record()
+                for _ in range(reps):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / reps
+                res["next_rows"][key] = {
+                    "what": what + f", first {bl} lines, device resident", "value": n1 * bl / (ms * 1e-3) / 1e6, "unit": UNIT,
+                    "ms": ms, "gpu_launches_per_call": (ctx.launch_count() - l0) / reps,
+                    "roofline": {"bound": "hbm" if key == "blur" else "fp64 issue (HBM figure for reference)",
+                                 "algorithmic_bytes_per_px": bpp_alg, "achieved": bpp_alg * n1 * bl / (ms * 1e-3) / 1e9,
+                                 "peak": peak, "unit": "GB/s", "frac": bpp_alg * n1 * bl / (ms * 1e-3) / 1e9 / peak}}
+            del f64, lab64
         # the standalone Window majority filter, clean(labels; hood): categorise-only labels in, device resident
         pre = torch.empty_like(out)
         ctx.categorize_clean_dev(own, n1, nb, n1 * 3, 3, 0, pre, n1)

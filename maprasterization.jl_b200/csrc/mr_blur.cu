@@ -19,62 +19,137 @@
 
 namespace {
 
-// in: u8 (bpp = 3, N0f8) or f64 (3 doubles per pixel); out: 3 doubles per pixel
-template <bool U8IN>
-__global__ void __launch_bounds__(256) k_blur(const void* __restrict__ in, int64_t in_stride2, int64_t n1, int64_t n2,
-                                              int R, double* __restrict__ out, int64_t out_stride2) {
-    const int64_t total = n1 * n2;
+// in: u8 (bpp = 3, N0f8) or f64 (3 doubles per pixel); out: 3 doubles per pixel.
+// One thread = PXT consecutive pixels of a line: the (PXT + 2R) x (2R + 1) neighbourhood colours are fetched
+// once per line into registers (N0f8 -> Float64 through a 256-entry table in shared memory: i / 255 correctly
+// rounded, tabulated once per block), the sums of the PXT pixels then run over registers in the reference's
+// order.  grid.x covers a line, grid.y strides over the lines (no 64-bit division per pixel).
+constexpr int PXT = 4;
+template <bool U8IN, int R>
+__global__ void __launch_bounds__(128) k_blur(const void* __restrict__ in, int64_t in_stride2, int64_t n1, int64_t n2,
+                                              double* __restrict__ out, int64_t out_stride2) {
+    __shared__ double s_n0f8[256];
+    for (int t = threadIdx.x; t < 256; t += blockDim.x) s_n0f8[t] = __ddiv_rn((double)t, 255.0);
+    __syncthreads();
+    constexpr int W = PXT + 2 * R;
     // total / count on an RGB is (one(T) / count) * colour in ColorVectorSpace: reciprocal, then one product per channel
     const double rcnt = __ddiv_rn(1.0, (double)((2 * R + 1) * (2 * R + 1)));
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t j = t / n1, i = t - j * n1;
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * PXT;
+    if (i0 >= n1) return;
+    for (int64_t j = blockIdx.y; j < n2; j += gridDim.y) {
+        double s[PXT][3];
+#pragma unroll
+        for (int p = 0; p < PXT; ++p) s[p][0] = s[p][1] = s[p][2] = 0.0;
+#pragma unroll
         for (int d2 = -R; d2 <= R; ++d2) {
             const int64_t b = j + d2;
-            if (b < 0 || b >= n2) continue;
+            if (b < 0 || b >= n2) continue;                    // outside: the zero colour (adding 0.0 is exact)
             const uint8_t* line = reinterpret_cast<const uint8_t*>(in) + b * in_stride2;
-            for (int d1 = -R; d1 <= R; ++d1) {
-                const int64_t a = i + d1;
-                if (a < 0 || a >= n1) continue;
-                double x0, x1, x2;
-                if (U8IN) {
-                    const uint8_t* p = line + a * 3;
-                    x0 = __ddiv_rn((double)p[0], 255.0);
-                    x1 = __ddiv_rn((double)p[1], 255.0);
-                    x2 = __ddiv_rn((double)p[2], 255.0);
-                } else {
-                    const double* p = reinterpret_cast<const double*>(line) + a * 3;
-                    x0 = p[0]; x1 = p[1]; x2 = p[2];
+            double x[W][3];
+#pragma unroll
+            for (int q = 0; q < W; ++q) {
+                const int64_t a = i0 - R + q;
+                const bool ok = a >= 0 && a < n1;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    double v = 0.0;
+                    if (ok) v = U8IN ? s_n0f8[__ldg(line + a * 3 + c)] : __ldg(reinterpret_cast<const double*>(line) + a * 3 + c);
+                    x[q][c] = v;
                 }
-                s0 = __dadd_rn(s0, x0);
-                s1 = __dadd_rn(s1, x1);
-                s2 = __dadd_rn(s2, x2);
             }
+#pragma unroll
+            for (int p = 0; p < PXT; ++p)
+#pragma unroll
+                for (int d1 = 0; d1 <= 2 * R; ++d1)            // d1 ascending = neighbourhood order within the line
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) s[p][c] = __dadd_rn(s[p][c], x[p + d1][c]);
         }
-        double* o = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(out) + j * out_stride2) + i * 3;
-        o[0] = __dmul_rn(rcnt, s0);
-        o[1] = __dmul_rn(rcnt, s1);
-        o[2] = __dmul_rn(rcnt, s2);
+        double* o = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(out) + j * out_stride2) + i0 * 3;
+        double r[PXT * 3];
+#pragma unroll
+        for (int p = 0; p < PXT; ++p)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) r[3 * p + c] = __dmul_rn(rcnt, s[p][c]);
+        if (i0 + PXT <= n1 && (reinterpret_cast<uintptr_t>(o) & 15u) == 0) {   // 96 contiguous bytes: six 16-byte stores
+#pragma unroll
+            for (int v = 0; v < PXT * 3 / 2; ++v) reinterpret_cast<double2*>(o)[v] = make_double2(r[2 * v], r[2 * v + 1]);
+        } else {
+#pragma unroll
+            for (int p = 0; p < PXT; ++p)
+                if (i0 + p < n1) {
+                    o[3 * p + 0] = r[3 * p + 0];
+                    o[3 * p + 1] = r[3 * p + 1];
+                    o[3 * p + 2] = r[3 * p + 2];
+                }
+        }
     }
 }
 
-// palette means / bounds in shared memory (K <= 254, C = 3): the K-loop reads them for every pixel
-__global__ void __launch_bounds__(256) k_categorize_f64(MrPalette pal, const double* __restrict__ px, int64_t stride2,
+// One thread = four consecutive pixels: the palette row of a category (shared memory, broadcast reads) is
+// fetched once for the four of them.
+__global__ void __launch_bounds__(128) k_categorize_f64(MrPalette pal, const double* __restrict__ px, int64_t stride2,
                                                         int64_t n1, int64_t n2, uint8_t* __restrict__ out,
                                                         int64_t out_stride2, MrCountersDev* counters) {
-    const int64_t total = n1 * n2;
+    __shared__ double s_pal[254 * 9];   // mean | lo | hi, three channels each
+    const int K = pal.K;
+    for (int t = threadIdx.x; t < K * 3; t += blockDim.x) {
+        s_pal[t] = __ldg(pal.mean + t);
+        s_pal[K * 3 + t] = __ldg(pal.lo + t);
+        s_pal[K * 6 + t] = __ldg(pal.hi + t);
+    }
+    __syncthreads();
+    const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     unsigned nomatch = 0;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t j = t / n1, i = t - j * n1;
-        const double* p = reinterpret_cast<const double*>(reinterpret_cast<const uint8_t*>(px) + j * stride2) + i * 3;
-        const int l = mr_eval_f64(pal, p[0], p[1], p[2], 0.0, false, 0);
-        out[j * out_stride2 + i] = (uint8_t)l;
-        nomatch += l == 0;
+    if (i0 < n1) {
+        const int n = (int)min((int64_t)4, n1 - i0);
+        for (int64_t j = blockIdx.y; j < n2; j += gridDim.y) {
+            const double* p = reinterpret_cast<const double*>(reinterpret_cast<const uint8_t*>(px) + j * stride2) + i0 * 3;
+            double x[4][3];
+            if (n == 4 && (reinterpret_cast<uintptr_t>(p) & 15u) == 0) {       // 96 contiguous bytes: six 16-byte loads
+#pragma unroll
+                for (int v = 0; v < 6; ++v) {
+                    const double2 t = __ldg(reinterpret_cast<const double2*>(p) + v);
+                    x[(2 * v) / 3][(2 * v) % 3] = t.x;
+                    x[(2 * v + 1) / 3][(2 * v + 1) % 3] = t.y;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) x[q][c] = q < n ? __ldg(p + 3 * q + c) : 0.0;
+            }
+            int best[4] = {0, 0, 0, 0};
+            double beste[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int c = 0; c < K; ++c) {
+                const double m0 = s_pal[3 * c], m1 = s_pal[3 * c + 1], m2 = s_pal[3 * c + 2];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double d0 = __dsub_rn(x[q][0], m0), d1 = __dsub_rn(x[q][1], m1), d2 = __dsub_rn(x[q][2], m2);
+                    const double e = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
+                    if (c == 0 || e < beste[q]) { beste[q] = e; best[q] = c; }   // first minimum
+                }
+            }
+            uint32_t word = 0u;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double* l = s_pal + K * 3 + 3 * best[q];
+                const double* h = s_pal + K * 6 + 3 * best[q];
+                const bool ok = (x[q][0] >= l[0]) && (x[q][0] <= h[0]) && (x[q][1] >= l[1]) && (x[q][1] <= h[1]) &&
+                                (x[q][2] >= l[2]) && (x[q][2] <= h[2]);
+                const unsigned lab = ok ? (unsigned)(best[q] + 1) : 0u;
+                word |= lab << (8 * q);
+                if (q < n) nomatch += lab == 0u;
+            }
+            uint8_t* o = out + j * out_stride2 + i0;
+            if (n == 4 && (((uintptr_t)o) & 3u) == 0) *reinterpret_cast<uint32_t*>(o) = word;
+            else
+                for (int q = 0; q < n; ++q) o[q] = (uint8_t)(word >> (8 * q));
+        }
     }
     if (counters) {
         for (int o = 16; o > 0; o >>= 1) nomatch += __shfl_xor_sync(0xffffffffu, nomatch, o);
         if ((threadIdx.x & 31) == 0 && nomatch) atomicAdd(&counters->n_nomatch, (unsigned long long)nomatch);
-        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters->n_pixels, (unsigned long long)total);
+        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(&counters->n_pixels, (unsigned long long)(n1 * n2));
     }
 }
 
@@ -89,21 +164,38 @@ __global__ void k_known_fixup_f64(MrPalette pal, const double* __restrict__ px, 
     labels[j * labels_stride2 + i] = (uint8_t)mr_eval_f64(pal, p[0], p[1], p[2], 0.0, false, cat[k]);
 }
 
-unsigned grid_for(int64_t total, int sm_count) {
-    int64_t g = (total + 255) / 256;
-    const int64_t cap = (int64_t)sm_count * 32;
-    if (g > cap) g = cap;
-    return (unsigned)(g < 1 ? 1 : g);
+}  // namespace
+
+static dim3 grid_lines(int64_t n1, int64_t n2, int px_per_thread, int threads, int sm_count) {
+    const int64_t gx = ((n1 + px_per_thread - 1) / px_per_thread + threads - 1) / threads;
+    int64_t gy = ((int64_t)sm_count * 32 + gx - 1) / gx;
+    if (gy > n2) gy = n2;
+    if (gy > 65535) gy = 65535;
+    if (gy < 1) gy = 1;
+    return dim3((unsigned)gx, (unsigned)gy);
 }
 
-}  // namespace
+template <bool U8IN>
+static void launch_blur_r(const void* in, int64_t in_stride2, int64_t n1, int64_t n2, int R, double* out,
+                          int64_t out_stride2, dim3 g, cudaStream_t s) {
+    switch (R) {
+        case 0: k_blur<U8IN, 0><<<g, 128, 0, s>>>(in, in_stride2, n1, n2, out, out_stride2); break;
+        case 1: k_blur<U8IN, 1><<<g, 128, 0, s>>>(in, in_stride2, n1, n2, out, out_stride2); break;
+        case 2: k_blur<U8IN, 2><<<g, 128, 0, s>>>(in, in_stride2, n1, n2, out, out_stride2); break;
+        case 3: k_blur<U8IN, 3><<<g, 128, 0, s>>>(in, in_stride2, n1, n2, out, out_stride2); break;
+        case 4: k_blur<U8IN, 4><<<g, 128, 0, s>>>(in, in_stride2, n1, n2, out, out_stride2); break;
+        case 5: k_blur<U8IN, 5><<<g, 128, 0, s>>>(in, in_stride2, n1, n2, out, out_stride2); break;
+        case 6: k_blur<U8IN, 6><<<g, 128, 0, s>>>(in, in_stride2, n1, n2, out, out_stride2); break;
+        default: k_blur<U8IN, 7><<<g, 128, 0, s>>>(in, in_stride2, n1, n2, out, out_stride2); break;
+    }
+}
 
 cudaError_t mr_launch_blur(const void* in, bool in_is_u8, int64_t in_stride2, int64_t n1, int64_t n2, int R, double* out,
                            int64_t out_stride2, int sm_count, cudaStream_t s, int* n_launches) {
     if (n1 <= 0 || n2 <= 0) return cudaSuccess;
-    const unsigned g = grid_for(n1 * n2, sm_count);
-    if (in_is_u8) k_blur<true><<<g, 256, 0, s>>>(in, in_stride2, n1, n2, R, out, out_stride2);
-    else k_blur<false><<<g, 256, 0, s>>>(in, in_stride2, n1, n2, R, out, out_stride2);
+    const dim3 g = grid_lines(n1, n2, PXT, 128, sm_count);
+    if (in_is_u8) launch_blur_r<true>(in, in_stride2, n1, n2, R, out, out_stride2, g, s);
+    else launch_blur_r<false>(in, in_stride2, n1, n2, R, out, out_stride2, g, s);
     *n_launches += 1;
     return cudaGetLastError();
 }
@@ -113,7 +205,7 @@ cudaError_t mr_launch_categorize_f64(const MrPalette& pal, const double* px, int
                                      int64_t out_stride2, MrCountersDev* counters, int sm_count, cudaStream_t s,
                                      int* n_launches) {
     if (n1 <= 0 || n2 <= 0) return cudaSuccess;
-    k_categorize_f64<<<grid_for(n1 * n2, sm_count), 256, 0, s>>>(pal, px, stride2, n1, n2, out, out_stride2, counters);
+    k_categorize_f64<<<grid_lines(n1, n2, 4, 128, sm_count), 128, 0, s>>>(pal, px, stride2, n1, n2, out, out_stride2, counters);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     *n_launches += 1;
