@@ -831,7 +831,7 @@ extern "C" int mr_clean_segments_dev(mr_ctx* ctx, const uint8_t* labels_dev, int
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
     return prune_dev(ctx, "mr_clean_segments_dev", labels_dev, n1, n2, stride2, keep256, line_threshold,
-                     prune_threshold, out_dev, out_stride2, n_segments, stream ? (cudaStream_t)stream : ctx->s_main);
+                     prune_threshold, out_dev, out_stride2, n_segments, (cudaStream_t)stream);
 }
 
 extern "C" int mr_clean_segments_host(mr_ctx* ctx, const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2,
