@@ -571,6 +571,33 @@ def run_ours(args, rank, world, local_rank):
                     "sample": f"first {lines} lines, sequential C oracle",
                     "label_mismatches_vs_gpu": int((got_f.cpu().numpy() != want_f).sum())}
         del fill_out
+        # the reference's own button sequence (it has no majority filter): categorize -> "clean" (segment prune on
+        # the RAW labels: millions of speckle segments) -> "fill" (one pass), device resident, whole sheet
+        if not batch and stats.colourspace == "rgb":
+            raw = torch.empty_like(out)
+            pruned = torch.empty_like(out)
+            filled = torch.empty_like(out)
+            cats = list(range(1, K + 1))
+            def _pipeline():
+                ctx.categorize_clean_dev(own, n1, nb, n1 * 3, 3, 0, raw, n1)
+                ns = ctx.clean_segments_dev(raw, n1, nb, n1, keep, 0.01, 20, pruned, n1)
+                ctx.fill_gaps_dev(pruned, n1, nb, n1, own, n1 * 3, 3, cats, filled, n1)
+                return ns
+            nseg_raw = _pipeline()
+            torch.cuda.synchronize()
+            l0 = ctx.launch_count()
+            e0.record()
+            for _ in range(reps):
+                _pipeline()
+            e1.record()
+            torch.cuda.synchronize()
+            pl_ms = e0.elapsed_time(e1) / reps
+            res["next_rows"]["reference_pipeline"] = {
+                "what": "categorize (no filter) -> _clean segment prune on the raw labels -> fill_gaps, one pass each, device resident",
+                "value": my_px / (pl_ms * 1e-3) / 1e6, "unit": UNIT, "ms": pl_ms, "segments": nseg_raw,
+                "gap_pixels_after_prune": int((pruned == 0).sum().item()), "gap_pixels_after_fill": int((filled == 0).sum().item()),
+                "gpu_launches_per_call": (ctx.launch_count() - l0) / reps}
+            del raw, pruned, filled
         # blur (src/blur.jl:6-14) and the categoriser on its RGB{Float64} output, on the first lines of the sheet
         # (24 B per pixel of Float64 colour: 4096 lines = 2 GB)
         if not batch and stats.colourspace == "rgb":
