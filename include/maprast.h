@@ -217,8 +217,8 @@ int mr_categorize_clean_f64_dev(mr_ctx* ctx, const double* px_dev, int64_t n1, i
  * inverse-distance weight if that exceeds 1 (:21-23), and when the runner-up also exceeds 1 the one
  * of the two whose mean colour is closer to the ORIGINAL pixel (:24-31, the colour error of
  * categories.jl:91-95 against the palette of mr_set_palette; stats[i] = palette row categories[i]-1).
- * categories: the kept categories, 1..K, in the caller's order (equal weights go to the earlier one,
- * findmax).  px: the pixels the categoriser saw (packed RGB / RGBA, same geometry as labels).
+ * categories: HOST array of the kept categories, 1..K, in the caller's order (equal weights go to the
+ * earlier one, findmax); also for the device variant (it travels in the kernel's parameter block).  px: the pixels the categoriser saw (packed RGB / RGBA, same geometry as labels).
  * mask: optional plane, nonzero = masked (NULL: none).  Neighbours outside the image read as 0;
  * output has the size of the input; not in place.  Asynchronous on `stream` (device variant). */
 int mr_fill_gaps_dev(mr_ctx* ctx, const uint8_t* labels_dev, int64_t n1, int64_t n2, int64_t stride2,
