@@ -77,3 +77,34 @@ def test_banded_oracle_equals_whole(oracle, mr):
         hl, hh = min(2, a), min(2, 64 - b)
         parts.append(oracle.majority(lab[a - hl:b + hh], 2, halo_lo=hl, halo_hi=hh))
     assert np.array_equal(np.concatenate(parts), whole)
+
+
+class _FakeCtx:
+    """records what set_known_for_band uploads (the host-side selection is what is tested here)"""
+
+    def set_known_band(self, idx, cat, first_line):
+        self.idx, self.cat, self.first_line = np.asarray(idx), np.asarray(cat), first_line
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+@pytest.mark.parametrize("R", [0, 2, 3])
+def test_known_points_per_band(world, R):
+    """every rank gets exactly the whole-sheet points its windows can see (own lines +- R) and its first line"""
+    sys.path.insert(0, ROOT)
+    import maprast_b200 as mr
+    D = mr.distributed
+    n1, n2 = 37, 203
+    rng = np.random.default_rng(world * 10 + R)
+    idx = np.unique(rng.integers(0, n1 * n2, size=400))
+    cat = rng.integers(1, 9, size=idx.size).astype(np.uint8)
+    seen = np.zeros(idx.size, dtype=np.int64)
+    for rank in range(world):
+        a, b = D.band_range(n2, world, rank)
+        fake = _FakeCtx()
+        n = D.set_known_for_band(fake, idx, cat, n1, n2, R, rank, world)
+        j = idx // n1
+        want = (j >= a - R) & (j < b + R)
+        assert n == int(want.sum()) and fake.first_line == a
+        assert np.array_equal(fake.idx, idx[want]) and np.array_equal(fake.cat, cat[want])
+        seen += ((j >= a) & (j < b)).astype(np.int64)
+    assert (seen == 1).all()          # every point belongs to exactly one band's own lines
