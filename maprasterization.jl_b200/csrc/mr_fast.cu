@@ -80,8 +80,8 @@ constexpr int best_block(int R, int NB, int warps) {   // largest block that fit
 }
 template <int R, int NB> struct Cfg {
     static constexpr int NBP = R > 0 ? NB : 0;
-#ifdef MR_WARPS
-    static constexpr int WARPS = MR_WARPS;
+#ifdef MR_WARPS   // experiment: warps per CTA for small palettes
+    static constexpr int WARPS = (R > 0 && NB >= 6) ? 12 : MR_WARPS;
 #else
     static constexpr int WARPS = (R > 0 && NB >= 6) ? 12 : 16;
 #endif
