@@ -79,6 +79,64 @@ def ncu_traffic(workload):
     return None
 
 
+class NvmlSampler:
+    """SM clock and throttle reasons through NVML, polled in a thread about every millisecond: the timed region
+    of the headline is ~11 ms, which nvidia-smi's 100 ms loop sees once or twice.  Used beside ClockSampler."""
+
+    def __init__(self, gpu_index):
+        self.ok = False
+        self.sm, self.reasons = [], 0
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it lists plain indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = gpu_index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if gpu_index < len(ids) and ids[gpu_index].isdigit():
+                    phys = int(ids[gpu_index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def start(self):
+        if not self.ok:
+            return
+        self.run = True
+
+        def loop():
+            nv = self.nv
+            while self.run:
+                try:
+                    self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    self.reasons |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                except Exception:
+                    break
+                time.sleep(0.0005)
+        self.t = threading.Thread(target=loop, daemon=True)
+        self.t.start()
+
+    def stop(self):
+        if not self.ok:
+            return None
+        self.run = False
+        self.t.join(timeout=1)
+        nv = self.nv
+        names = []
+        for bit, name in ((getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8), "hw_slowdown"),
+                          (getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40), "hw_thermal_slowdown"),
+                          (getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20), "sw_thermal_slowdown"),
+                          (getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4), "sw_power_cap")):
+            if self.reasons & bit:
+                names.append(name)
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_min_mhz": min(self.sm) if self.sm else None,
+                "sm_max_mhz": self.max, "samples": len(self.sm), "reasons": sorted(names)}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -352,8 +410,10 @@ def run_ours(args, rank, world, local_rank):
         step()
     barrier()
     sampler = ClockSampler(local_rank)
+    nvml = NvmlSampler(local_rank) if rank == 0 else None
     if rank == 0:
         sampler.start()
+        nvml.start()
     launches0 = ctx.launch_count()
     # small workloads would sit in the 126 MB L2 between iterations: flush it (write a 256 MiB buffer)
     # before every timed step and time the steps one by one; big ones are larger than L2 by themselves
@@ -381,6 +441,13 @@ def run_ours(args, rank, world, local_rank):
         step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
     launches = ctx.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        fast = nvml.stop()
+        if fast and fast["samples"]:
+            # the millisecond samples are the ones taken under load; nvidia-smi's line stays beside them
+            clocks = {"sm_mhz": fast["sm_mhz"], "sm_min_mhz": fast["sm_min_mhz"], "sm_max_mhz": fast["sm_max_mhz"],
+                      "samples": fast["samples"], "reasons": sorted(set(fast["reasons"]) | set(clocks.get("reasons") or [])),
+                      "source": "NVML polled every ~0.5 ms over the timed region", "nvidia_smi": clocks}
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
