@@ -196,6 +196,21 @@ int mr_blur_dev(mr_ctx* ctx, const void* px_dev, int64_t n1, int64_t n2, int64_t
                 int bytes_per_px, int R, int repeat, double* out_dev, int64_t out_stride2_bytes,
                 void* stream);
 
+/* _balance(A, points; category_bitindex), src/balance.jl:1-42 (the "balance" button,
+ * src/selectcolors.jl:448-454), per-pixel part: predictions of the fitted cubic trend (`_predict`,
+ * :36-42), their means (:25) and `_final_balance` (:28-35): out = clamp(x - p + mean(p), 0, 1) per channel
+ * in RGB{Float64}.  The least-squares fit (lm(@formula(r ~ i^3 + i^2 + i + j^3 + j^2 + j), ...), :19-23)
+ * stays host code of the caller; coef21 = HOST array, 3 channels x (intercept, i^3, i^2, i, j^3, j^2, j);
+ * (i, j) are the 1-based pixel indices, i the memory-fast axis.  With fewer than 8 points the reference
+ * returns A .* 1.0 (:16-18): that is mr_blur_* with repeat = 0.  Evaluation order and the order of the sum
+ * behind mean(p) are decisions (parity unpinned).  Packed RGB{N0f8} in, RGB{Float64}
+ * out (24 bytes per pixel). */
+int mr_balance_host(mr_ctx* ctx, const uint8_t* px, int64_t n1, int64_t n2, int64_t stride2_bytes,
+                    int bytes_per_px, const double* coef21, double* out, int64_t out_stride2_bytes);
+int mr_balance_dev(mr_ctx* ctx, const uint8_t* px_dev, int64_t n1, int64_t n2, int64_t stride2_bytes,
+                   int bytes_per_px, const double* coef21, double* out_dev, int64_t out_stride2_bytes,
+                   void* stream);
+
 /* The categoriser on RGB{Float64} pixels -- what `blur` / `_balance` hand to
  * _categorize(pixels, points; ...) (src/categories.jl:49-52,68-73; the reference's own known-answer
  * vectors are Float64 colours) -- followed by the Window{R} majority filter.  Direct Float64

@@ -26,6 +26,7 @@ SYMBOLS = [
     "mr_clean_host", "mr_clean_dev", "mr_clean_dev_bounded", "mr_clean_segments_dev", "mr_clean_segments_host",
     "mr_fill_gaps_dev", "mr_fill_gaps_host", "mr_set_known_band",
     "mr_blur_host", "mr_blur_dev", "mr_categorize_clean_f64_host", "mr_categorize_clean_f64_dev",
+    "mr_balance_host", "mr_balance_dev",
     "mr_multi_create", "mr_multi_destroy", "mr_multi_last_error", "mr_multi_device_count", "mr_multi_ctx",
     "mr_multi_band_range", "mr_multi_set_palette", "mr_multi_set_known", "mr_multi_categorize_clean_host",
     "mr_multi_batch_categorize_clean_host", "mr_multi_categorize_clean_dev",
@@ -95,6 +96,8 @@ def load():
     L.mr_fill_gaps_dev.argtypes = [vp, u8p, i64, i64, i64, u8p, i64, i32, u8p, i64, u8p, i32, i32, u8p, i64, vp]
     L.mr_fill_gaps_host.argtypes = [vp, u8p, i64, i64, i64, u8p, i64, i32, u8p, i64, u8p, i32, i32, u8p, i64]
     L.mr_set_known_band.argtypes = [vp, i64, vp, vp, i64]
+    L.mr_balance_host.argtypes = [vp, u8p, i64, i64, i64, i32, vp, vp, i64]
+    L.mr_balance_dev.argtypes = [vp, u8p, i64, i64, i64, i32, vp, vp, i64, vp]
     L.mr_blur_host.argtypes = [vp, vp, i64, i64, i64, i32, i32, i32, vp, i64]
     L.mr_blur_dev.argtypes = [vp, vp, i64, i64, i64, i32, i32, i32, vp, i64, vp]
     L.mr_categorize_clean_f64_host.argtypes = [vp, vp, i64, i64, i64, i32, u8p, i64]
@@ -126,7 +129,7 @@ def load():
                  "mr_batch_categorize_clean_dev", "mr_clean_host", "mr_clean_dev", "mr_clean_segments_dev",
                  "mr_clean_segments_host", "mr_fill_gaps_dev", "mr_fill_gaps_host", "mr_synth_scan_dev",
                  "mr_blur_host", "mr_blur_dev", "mr_categorize_clean_f64_host", "mr_categorize_clean_f64_dev",
-                 "mr_set_known_band", "mr_clean_dev_bounded", "mr_multi_device_count", "mr_multi_band_range", "mr_multi_set_palette",
+                 "mr_balance_host", "mr_balance_dev", "mr_set_known_band", "mr_clean_dev_bounded", "mr_multi_device_count", "mr_multi_band_range", "mr_multi_set_palette",
                  "mr_multi_set_known", "mr_multi_categorize_clean_host", "mr_multi_batch_categorize_clean_host",
                  "mr_multi_categorize_clean_dev"):
         getattr(L, name).restype = i32
@@ -270,6 +273,20 @@ class Context:
         self._ck(self._L.mr_clean_segments_host(self._h, _ptr(labels), n1, n2, n1, _ptr(keep), float(line_threshold),
                                                 float(prune_threshold), _ptr(out), n1, C.byref(nseg)))
         return out, int(nseg.value)
+
+    def balance_host(self, img, coef):
+        """per-pixel part of `_balance` (src/balance.jl:25-42): img (n2, n1, 3) uint8, coef (3, 7) float64
+        (intercept, i^3, i^2, i, j^3, j^2, j per channel) -> (n2, n1, 3) float64."""
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        if img.ndim != 3 or img.shape[2] != 3:
+            raise ValueError("img must be a (n2, n1, 3) uint8 array")
+        coef = np.ascontiguousarray(coef, dtype=np.float64)
+        if coef.shape != (3, 7):
+            raise ValueError("coef must be 3 x 7")
+        n2, n1, _ = img.shape
+        out = np.empty((n2, n1, 3), dtype=np.float64)
+        self._ck(self._L.mr_balance_host(self._h, _ptr(img), n1, n2, n1 * 3, 3, _ptr(coef), _ptr(out), n1 * 24))
+        return out
 
     def blur_host(self, img, R=1, repeat=1):
         """`blur(A; hood=Window{R}(), repeat)` (src/blur.jl:6-14): (n2, n1, 3) uint8 or float64 -> float64."""

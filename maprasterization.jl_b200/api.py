@@ -235,6 +235,51 @@ def blur(A, *, hood=Window(1), repeat=1, ctx=None):
     return ctx.blur_host(A, R, repeat)
 
 
+def balance_fit(img, points, category_bitindex=None):
+    """The host part of `_balance(A, points; category_bitindex)` (src/balance.jl:1-24): the table of colour
+    deviations of the clicked points from their category's mean colour and the least-squares fit of
+    `c ~ i^3 + i^2 + i + j^3 + j^2 + j` per channel.  Returns the 3 x 7 coefficients (intercept first), or
+    None with fewer than 8 points (the reference then returns `A .* 1.0`, :16-18).
+    (numpy's lstsq stands in for GLM's `lm`: same minimiser, last bits may differ.)"""
+    img = np.asarray(img)
+    n2, n1 = img.shape[:2]
+    K = len(points)
+    if category_bitindex is None:
+        category_bitindex = [c == 0 for c in range(K)]       # `category_balance` default: category 1 only (selectcolors.jl:46)
+    rows, resp = [], []
+    for c, pts in enumerate(points):
+        if not category_bitindex[c]:
+            continue
+        pts = np.asarray(pts, dtype=np.float64).reshape(-1, 2)
+        if pts.shape[0] == 0:
+            continue
+        ij = np.rint(pts).astype(np.int64)
+        cols = img[ij[:, 1] - 1, ij[:, 0] - 1, :3].astype(np.float64) / 255.0
+        dev = cols - cols.mean(axis=0)
+        for (i, j), d in zip(pts, dev):
+            rows.append([1.0, i ** 3, i ** 2, i, j ** 3, j ** 2, j])
+            resp.append(d)
+    if len(rows) < 8:
+        return None
+    X, Y = np.asarray(rows), np.asarray(resp)
+    beta, *_ = np.linalg.lstsq(X, Y, rcond=None)
+    return np.ascontiguousarray(beta.T)                       # (3, 7)
+
+
+def balance(img, points, *, category_bitindex=None, ctx=None):
+    """`_balance(A, points; category_bitindex)` (src/balance.jl:1-42): detrend the image with the cubic
+    polynomial fitted to the clicked points' colour deviations; RGB{Float64} out.  The fit is host code, the
+    per-pixel prediction / mean / clamp runs on the GPU."""
+    _check_img(img)
+    if img.shape[2] != 3:
+        raise ValueError("balance takes RGB{N0f8} pixels")
+    ctx = ctx or default_context()
+    coef = balance_fit(img, points, category_bitindex)
+    if coef is None:
+        return ctx.blur_host(img, 0, 0)          # A .* 1.0
+    return ctx.balance_host(img, coef)
+
+
 def categorize_clean(img, points_or_palette, **kw):
     """Same, eltype Int (Julia `Matrix{Int}`, src/categories.jl:69-73)."""
     out = categorize_clean_u8(img, points_or_palette, **kw)
@@ -410,14 +455,20 @@ def rasterize(img, sel, *, hood=None, colourspace="rgb", ctx=None):
     n2, n1 = img.shape[:2]
     tol = sel.tolerances()
     R = 0 if hood is None else (hood.R if isinstance(hood, Window) else int(hood))
-    # "blur" button (src/selectcolors.jl:455-465): blur(balanced; repeat = blur_repeat); `_balance` with fewer
-    # than 8 points is A .* 1.0 (src/balance.jl:16-18), the fitted detrend itself is outside this path
+    # `balanced = _balance(raw, points; category_bitindex = category_balance)` (src/selectcolors.jl:222; default:
+    # the points of category 1), then the "blur" button (:455-465): blur(balanced; repeat = blur_repeat).
+    # With fewer than 8 balance points `_balance` is A .* 1.0 (src/balance.jl:16-18): the N0f8 path.
     blur_repeat = int(st.get("blur_repeat", 0))
     pixels = img
+    coef = None
+    if img.shape[2] == 3 and colourspace == "rgb":
+        coef = balance_fit(img, sel.points, st.get("category_balance"))
+    if coef is not None:
+        pixels = ctx.balance_host(img, coef)
     if blur_repeat > 0:
         if img.shape[2] != 3 or colourspace != "rgb":
             raise ValueError("blur_repeat > 0 needs RGB{N0f8} pixels and RGB matching")
-        pixels = blur(img, repeat=blur_repeat, ctx=ctx)
+        pixels = blur(pixels, repeat=blur_repeat, ctx=ctx)
     categorized = categorize_clean_u8(pixels, sel.points, tolerances=tol, hood=Window(R), colourspace=colourspace,
                                       use_known=True, ctx=ctx)
     idx, cat = _known_from_points(sel.points, n1)

@@ -854,6 +854,58 @@ extern "C" int mr_clean_segments_host(mr_ctx* ctx, const uint8_t* labels, int64_
     return MR_OK;
 }
 
+// ------------------------------------------------------------------ _balance, per-pixel part (src/balance.jl:25-42)
+static int balance_check(mr_ctx* ctx, const char* fn, const void* px, const void* out, int64_t n1, int64_t n2,
+                         int64_t stride2, int bpp, const double* coef, int64_t out_stride2) {
+    std::string f(fn);
+    if (!ctx) return fail(nullptr, MR_ERR_ARG, f + ": null ctx");
+    if (n1 < 0 || n2 < 0) return fail(ctx, MR_ERR_ARG, f + ": negative size");
+    if (bpp != 3) return fail(ctx, MR_ERR_ARG, f + ": pixels must be packed RGB{N0f8} (3 bytes)");
+    if (n1 > 0 && n2 > 0 && (!px || !out)) return fail(ctx, MR_ERR_ARG, f + ": null buffer");
+    if (!coef) return fail(ctx, MR_ERR_ARG, f + ": null coefficients");
+    for (int k = 0; k < 21; ++k)
+        if (!isfinite(coef[k])) return fail(ctx, MR_ERR_ARG, f + ": non-finite coefficient");
+    if (stride2 < n1 * 3 || out_stride2 < n1 * 24 || out_stride2 % 8 != 0) return fail(ctx, MR_ERR_ARG, f + ": bad stride");
+    return MR_OK;
+}
+
+extern "C" int mr_balance_dev(mr_ctx* ctx, const uint8_t* px_dev, int64_t n1, int64_t n2, int64_t stride2, int bytes_per_px,
+                              const double* coef21, double* out_dev, int64_t out_stride2, void* stream) {
+    int rc = balance_check(ctx, "mr_balance_dev", px_dev, out_dev, n1, n2, stride2, bytes_per_px, coef21, out_stride2);
+    if (rc) return rc;
+    if (n1 == 0 || n2 == 0) return MR_OK;
+    CK(cudaSetDevice(ctx->device));
+    if ((rc = grow(ctx, &ctx->d_f64, &ctx->d_f64_cap, mr_balance_scratch_bytes(n1, n2)))) return rc;
+    int nl = 0;
+    cudaError_t e = mr_launch_balance(coef21, px_dev, stride2, n1, n2, reinterpret_cast<double*>(ctx->d_f64), out_dev,
+                                      out_stride2, ctx->sm_count, (cudaStream_t)stream, &nl);
+    ctx->launches += nl;
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "balance launch");
+    return MR_OK;
+}
+
+extern "C" int mr_balance_host(mr_ctx* ctx, const uint8_t* px, int64_t n1, int64_t n2, int64_t stride2, int bytes_per_px,
+                               const double* coef21, double* out, int64_t out_stride2) {
+    int rc = balance_check(ctx, "mr_balance_host", px, out, n1, n2, stride2, bytes_per_px, coef21, out_stride2);
+    if (rc) return rc;
+    if (n1 == 0 || n2 == 0) return MR_OK;
+    CK(cudaSetDevice(ctx->device));
+    const int64_t in_pitch = (n1 * 3 + 15) / 16 * 16, out_pitch = n1 * 24;
+    if ((rc = grow(ctx, &ctx->d_in, &ctx->d_in_cap, (size_t)in_pitch * n2))) return rc;
+    if ((rc = grow(ctx, &ctx->d_f64b, &ctx->d_f64b_cap, (size_t)out_pitch * n2))) return rc;
+    if ((rc = grow(ctx, &ctx->d_f64, &ctx->d_f64_cap, mr_balance_scratch_bytes(n1, n2)))) return rc;
+    cudaStream_t s = ctx->s_main;
+    CK(cudaMemcpy2DAsync(ctx->d_in, in_pitch, px, stride2, n1 * 3, n2, cudaMemcpyHostToDevice, s));
+    int nl = 0;
+    cudaError_t e = mr_launch_balance(coef21, ctx->d_in, in_pitch, n1, n2, reinterpret_cast<double*>(ctx->d_f64),
+                                      reinterpret_cast<double*>(ctx->d_f64b), out_pitch, ctx->sm_count, s, &nl);
+    ctx->launches += nl;
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "balance launch");
+    CK(cudaMemcpy2DAsync(out, out_stride2, ctx->d_f64b, out_pitch, n1 * 24, n2, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return MR_OK;
+}
+
 // ------------------------------------------------------------------ blur + categorise on RGB{Float64}
 static int blur_check(mr_ctx* ctx, const char* fn, const void* in, const void* out, int64_t n1, int64_t n2,
                       int64_t in_stride2, int in_bytes_per_px, int R, int repeat, int64_t out_stride2) {

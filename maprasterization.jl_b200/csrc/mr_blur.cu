@@ -166,6 +166,84 @@ __global__ void k_known_fixup_f64(MrPalette pal, const double* __restrict__ px, 
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------
+// `_balance` (src/balance.jl:25-42), per-pixel part: predictions of the fitted cubic trend, their means,
+// out = clamp(x - p + mean(p), 0, 1).  The sum of the predictions runs in a FIXED order that the oracle
+// repeats: chunks of 256 pixels of a line sequentially, then the chunk sums of a line, then the lines.
+struct BalanceCoef { double b[3][7]; };
+
+__device__ __forceinline__ double balance_pred(const double* b, int64_t i1, int64_t j1) {
+    const double fi = (double)i1, fj = (double)j1;
+    const double i2 = __dmul_rn(fi, fi), i3 = __dmul_rn(i2, fi), j2 = __dmul_rn(fj, fj), j3 = __dmul_rn(j2, fj);
+    double p = __dadd_rn(b[0], __dmul_rn(b[1], i3));
+    p = __dadd_rn(p, __dmul_rn(b[2], i2));
+    p = __dadd_rn(p, __dmul_rn(b[3], fi));
+    p = __dadd_rn(p, __dmul_rn(b[4], j3));
+    p = __dadd_rn(p, __dmul_rn(b[5], j2));
+    p = __dadd_rn(p, __dmul_rn(b[6], fj));
+    return p;
+}
+
+// one thread = one chunk of 256 pixels of one line: partial[(j * chunks + c) * 3 + ch]
+__global__ void k_balance_chunks(BalanceCoef K, int64_t n1, int64_t n2, int64_t chunks, double* __restrict__ partial) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= chunks * n2) return;
+    const int64_t j = t / chunks, c = t - j * chunks;
+    const int64_t i0 = c * 256, i1 = min(i0 + 256, n1);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int64_t i = i0; i < i1; ++i) {
+        s0 = __dadd_rn(s0, balance_pred(K.b[0], i + 1, j + 1));
+        s1 = __dadd_rn(s1, balance_pred(K.b[1], i + 1, j + 1));
+        s2 = __dadd_rn(s2, balance_pred(K.b[2], i + 1, j + 1));
+    }
+    partial[t * 3 + 0] = s0;
+    partial[t * 3 + 1] = s1;
+    partial[t * 3 + 2] = s2;
+}
+// one thread = one line: the chunk sums of the line, in order
+__global__ void k_balance_lines(int64_t n2, int64_t chunks, const double* __restrict__ partial, double* __restrict__ lines) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n2) return;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int64_t c = 0; c < chunks; ++c) {
+        const double* q = partial + (j * chunks + c) * 3;
+        s0 = __dadd_rn(s0, q[0]);
+        s1 = __dadd_rn(s1, q[1]);
+        s2 = __dadd_rn(s2, q[2]);
+    }
+    lines[j * 3 + 0] = s0; lines[j * 3 + 1] = s1; lines[j * 3 + 2] = s2;
+}
+// three threads: the line sums in order, divided by the pixel count
+__global__ void k_balance_total(int64_t n1, int64_t n2, const double* __restrict__ lines, double* __restrict__ means) {
+    const int ch = threadIdx.x;
+    if (ch >= 3) return;
+    double s = 0.0;
+    for (int64_t j = 0; j < n2; ++j) s = __dadd_rn(s, lines[j * 3 + ch]);
+    means[ch] = __ddiv_rn(s, (double)(n1 * n2));
+}
+__global__ void __launch_bounds__(256) k_balance_apply(BalanceCoef K, const uint8_t* __restrict__ px, int64_t stride2,
+                                                       int64_t n1, int64_t n2, const double* __restrict__ means,
+                                                       double* __restrict__ out, int64_t out_stride2) {
+    __shared__ double s_n0f8[256];
+    for (int t = threadIdx.x; t < 256; t += blockDim.x) s_n0f8[t] = __ddiv_rn((double)t, 255.0);
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n1) return;
+    const double m0 = means[0], m1 = means[1], m2 = means[2];
+    for (int64_t j = blockIdx.y; j < n2; j += gridDim.y) {
+        const uint8_t* p = px + j * stride2 + i * 3;
+        double* o = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(out) + j * out_stride2) + i * 3;
+        const double mm[3] = {m0, m1, m2};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double v = __dsub_rn(s_n0f8[p[c]], balance_pred(K.b[c], i + 1, j + 1));
+            v = __dadd_rn(v, mm[c]);
+            v = v > 0.0 ? v : 0.0;
+            o[c] = v < 1.0 ? v : 1.0;
+        }
+    }
+}
+
 static dim3 grid_lines(int64_t n1, int64_t n2, int px_per_thread, int threads, int sm_count) {
     const int64_t gx = ((n1 + px_per_thread - 1) / px_per_thread + threads - 1) / threads;
     int64_t gy = ((int64_t)sm_count * 32 + gx - 1) / gx;
@@ -217,4 +295,33 @@ cudaError_t mr_launch_categorize_f64(const MrPalette& pal, const double* px, int
         *n_launches += 1;
     }
     return cudaSuccess;
+}
+
+// scratch: (ceil(n1 / 256) * n2 + n2 + 1) * 3 doubles
+size_t mr_balance_scratch_bytes(int64_t n1, int64_t n2) {
+    const int64_t chunks = (n1 + 255) / 256;
+    return (size_t)(chunks * n2 + n2 + 1) * 3 * sizeof(double);
+}
+
+cudaError_t mr_launch_balance(const double* coef21, const uint8_t* px, int64_t stride2, int64_t n1, int64_t n2,
+                              double* scratch, double* out, int64_t out_stride2, int sm_count, cudaStream_t s,
+                              int* n_launches) {
+    if (n1 <= 0 || n2 <= 0) return cudaSuccess;
+    BalanceCoef K;
+    for (int c = 0; c < 3; ++c)
+        for (int k = 0; k < 7; ++k) K.b[c][k] = coef21[c * 7 + k];
+    const int64_t chunks = (n1 + 255) / 256;
+    double* partial = scratch;
+    double* lines = scratch + chunks * n2 * 3;
+    double* means = lines + n2 * 3;
+    k_balance_chunks<<<(unsigned)((chunks * n2 + 127) / 128), 128, 0, s>>>(K, n1, n2, chunks, partial);
+    k_balance_lines<<<(unsigned)((n2 + 127) / 128), 128, 0, s>>>(n2, chunks, partial, lines);
+    k_balance_total<<<1, 32, 0, s>>>(n1, n2, lines, means);
+    const int64_t gx = (n1 + 255) / 256;
+    int64_t gy = ((int64_t)sm_count * 16 + gx - 1) / gx;
+    if (gy > n2) gy = n2;
+    if (gy > 65535) gy = 65535;
+    k_balance_apply<<<dim3((unsigned)gx, (unsigned)(gy < 1 ? 1 : gy)), 256, 0, s>>>(K, px, stride2, n1, n2, means, out, out_stride2);
+    *n_launches += 4;
+    return cudaGetLastError();
 }

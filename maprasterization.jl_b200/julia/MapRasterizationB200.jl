@@ -22,7 +22,7 @@ using ColorTypes, FixedPointNumbers, Statistics
 import Neighborhoods: Window
 
 export categorize, clean, categorize_clean, categorize_u8, clean_u8, categorize_clean_u8, clean_segments,
-       clean_segments_u8, fill_gaps, fill_gaps_u8, blur, rasterize, MapSelection, Context, MultiContext, Palette
+       clean_segments_u8, fill_gaps, fill_gaps_u8, blur, balance, rasterize, MapSelection, Context, MultiContext, Palette
 
 const libmaprast = get(ENV, "LIBMAPRAST", joinpath(@__DIR__, "..", "libmaprast.so"))
 const DEFAULT_CATEGORY_TOLERANCE = 2.0            # src/selectcolors.jl:1
@@ -166,6 +166,45 @@ function blur(img::AbstractMatrix{T}; hood=Window{1}(), repeat::Int=1, ctx::Cont
             (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Cint, Cint, Cint, Ptr{Float64}, Int64),
             ctx.ptr, pointer(A), n1, n2, n1 * sizeof(T), sizeof(T), _radius(hood), repeat,
             Ptr{Float64}(pointer(out)), n1 * 24))
+    end
+    return _rebuild(img, out)
+end
+
+"""
+The host part of `_balance(A, points; category_bitindex)` (src/balance.jl:1-24): colour deviations of the
+clicked points from their category's mean colour, least-squares fit of `c ~ i^3 + i^2 + i + j^3 + j^2 + j`
+per channel (`X \\ Y` stands in for GLM's `lm`: same minimiser).  Returns the 7 x 3 coefficients
+(intercept first) or `nothing` with fewer than 8 points (the reference then returns `A .* 1.0`, :16-18).
+"""
+function balance_fit(A::AbstractMatrix{<:Colorant}, points; category_bitindex=[c == 1 for c in 1:length(points)])
+    rows = Vector{NTuple{7,Float64}}(); resp = Vector{NTuple{3,Float64}}()
+    for (c, pv) in enumerate(points)
+        (category_bitindex[c] && length(pv) > 0) || continue
+        cols = [begin px = A[round(Int, p[1]), round(Int, p[2])]; (Float64(px.r), Float64(px.g), Float64(px.b)) end for p in pv]
+        m = ntuple(k -> mean(getindex.(cols, k)), 3)
+        for (p, col) in zip(pv, cols)
+            i, j = Float64(p[1]), Float64(p[2])
+            push!(rows, (1.0, i^3, i^2, i, j^3, j^2, j)); push!(resp, col .- m)
+        end
+    end
+    length(rows) < 8 && return nothing
+    X = [r[k] for r in rows, k in 1:7]; Y = [r[k] for r in resp, k in 1:3]
+    return X \ Y                                   # 7 x 3, column = channel: the layout mr_balance_* reads (3 x 7 row-major)
+end
+
+"`_balance(A, points; category_bitindex)` (src/balance.jl:1-42): RGB{Float64} out; fit on the host, pixels on the GPU."
+function balance(img::AbstractMatrix{RGB{N0f8}}, points; category_bitindex=[c == 1 for c in 1:length(points)],
+        ctx::Context=default_context())
+    A = img isa Matrix ? img : Matrix(img)
+    coef = balance_fit(A, points; category_bitindex)
+    coef === nothing && return blur(img; repeat=0, ctx)          # A .* 1.0
+    n1, n2 = size(A)
+    out = Matrix{RGB{Float64}}(undef, n1, n2)
+    C = Matrix{Float64}(coef)                                       # 7 x 3 column-major = 3 x 7 row-major
+    GC.@preserve A out C begin
+        _check(ctx, ccall((:mr_balance_host, libmaprast), Cint,
+            (Ptr{Cvoid}, Ptr{UInt8}, Int64, Int64, Int64, Cint, Ptr{Float64}, Ptr{Float64}, Int64),
+            ctx.ptr, Ptr{UInt8}(pointer(A)), n1, n2, n1 * 3, 3, pointer(C), Ptr{Float64}(pointer(out)), n1 * 24))
     end
     return _rebuild(img, out)
 end
@@ -329,11 +368,15 @@ known-category override of the clicked points), optional Window majority filter 
 (:479-489), "fill" (:490-501, `fill_repeat` passes of `fill_gaps`; `mask` = the caller's polygon mask).
 Returns `(; categorized, cleaned, filled)`.
 """
-function rasterize(img, sel::MapSelection; hood=Window{0}(), mask=nothing, ctx::Context=default_context())
+function rasterize(img::AbstractMatrix{T}, sel::MapSelection; hood=Window{0}(), mask=nothing, ctx::Context=default_context()) where {T}
     A = img isa Matrix ? img : Matrix(img)
-    # "blur" button (src/selectcolors.jl:455-465); `_balance` with fewer than 8 points is A .* 1.0 (src/balance.jl:16-18)
+    # balanced = _balance(raw, points; category_bitindex = category_balance) (src/selectcolors.jl:222; default:
+    # category 1), then the "blur" button (:455-465).  Fewer than 8 balance points: A .* 1.0 = the N0f8 path.
     blur_repeat = get(sel.settings, :blur_repeat, 0)
-    pixels = blur_repeat > 0 ? blur(A; repeat=blur_repeat, ctx) : A
+    bal = get(sel.settings, :category_balance, [c == 1 for c in 1:length(sel.points)])
+    detrend = T <: RGB{N0f8} && balance_fit(A, sel.points; category_bitindex=collect(Bool, bal)) !== nothing
+    pixels = detrend ? balance(A, sel.points; category_bitindex=collect(Bool, bal), ctx) : A
+    pixels = blur_repeat > 0 ? blur(pixels; repeat=blur_repeat, ctx) : pixels
     pal = Palette(pixels, sel.points; tolerances=collect(Float64, sel.settings.category_tolerances))
     known = _known_plane(size(A), sel.points)
     categorized = categorize_clean_u8(pixels, pal; hood, match=get(sel.settings, :match, (:color,)),

@@ -644,3 +644,57 @@ void mro_categorize_f64_image(const double* px, int64_t n1, int64_t n2, int64_t 
     }
 }
 
+/* =====================================================================================
+ * `_balance` (src/balance.jl:1-42), the per-pixel part: predictions of the fitted cubic trend
+ * (`_predict`, :36-42), their means (:25), and `_final_balance` (:28-42):
+ *   out = clamp(x - p + mean(p), 0, 1) per channel, x = Float64(N0f8), RGB{Float64} out.
+ * The least-squares fit itself (`lm(@formula(r ~ i^3 + i^2 + i + j^3 + j^2 + j), ...)`, :19-23) is host
+ * code of the caller (GLM in Julia, numpy in the Python mirror) and hands over coef[3][7] =
+ * (intercept, i^3, i^2, i, j^3, j^2, j) per channel; (i, j) are the 1-based indices, i the memory-fast axis.
+ * PARITY UNPINNED (GLM's `predict` is a BLAS matrix-vector product and `mean` a pairwise sum: neither
+ * order is visible from the reference tree).  Decisions: p = ((((((b0 + b1 i^3) + b2 i^2) + b3 i) + b4 j^3)
+ * + b5 j^2) + b6 j), every product and sum rounded once, no FMA; mean(p) = sum / (n1 n2) with the sum taken
+ * sequentially over chunks of 256 pixels of a line, then over the chunk sums of the line, then over the lines
+ * (a fixed order that a GPU can reproduce). */
+static double balance_pred(const double* b, int64_t i1, int64_t j1) {
+    const double fi = (double)i1, fj = (double)j1;
+    const double i2 = fi * fi, i3 = i2 * fi, j2 = fj * fj, j3 = j2 * fj;
+    double p = b[0] + b[1] * i3;
+    p = p + b[2] * i2;
+    p = p + b[3] * fi;
+    p = p + b[4] * j3;
+    p = p + b[5] * j2;
+    p = p + b[6] * fj;
+    return p;
+}
+
+void mro_balance(const uint8_t* px, int64_t n1, int64_t n2, int64_t stride2, const double* coef,
+                 double* out, int64_t out_stride2, double means_out[3]) {
+    double mean[3];
+    for (int c = 0; c < 3; ++c) {
+        double total = 0.0;
+        for (int64_t j = 0; j < n2; ++j) {
+            double line = 0.0;
+            for (int64_t i0 = 0; i0 < n1; i0 += 256) {
+                double chunk = 0.0;
+                for (int64_t i = i0; i < n1 && i < i0 + 256; ++i) chunk = chunk + balance_pred(coef + 7 * c, i + 1, j + 1);
+                line = line + chunk;
+            }
+            total = total + line;
+        }
+        mean[c] = total / (double)(n1 * n2);
+        if (means_out) means_out[c] = mean[c];
+    }
+    for (int64_t j = 0; j < n2; ++j)
+        for (int64_t i = 0; i < n1; ++i) {
+            const uint8_t* p = px + j * stride2 + i * 3;
+            double* o = (double*)((uint8_t*)out + j * out_stride2) + i * 3;
+            for (int c = 0; c < 3; ++c) {
+                double v = mro_n0f8(p[c]) - balance_pred(coef + 7 * c, i + 1, j + 1);
+                v = v + mean[c];
+                v = v > 0.0 ? v : 0.0;          /* max(c, 0) */
+                o[c] = v < 1.0 ? v : 1.0;       /* min(1, .) */
+            }
+        }
+}
+

@@ -117,6 +117,11 @@ void mro_categorize_f64_image(const double* px, int64_t n1, int64_t n2, int64_t 
                               int64_t n_known, const int64_t* known_idx, const uint8_t* known_cat,
                               uint8_t* out, int64_t out_stride2);
 
+/* per-pixel part of `_balance` (src/balance.jl:25-42): predictions of the cubic trend coef[3][7], their
+ * means, clamp(x - p + mean, 0, 1); PARITY UNPINNED (decisions in the .c file).  means_out may be NULL. */
+void mro_balance(const uint8_t* px, int64_t n1, int64_t n2, int64_t stride2, const double* coef,
+                 double* out, int64_t out_stride2, double means_out[3]);
+
 int mro_max_threads(void);
 
 #ifdef __cplusplus

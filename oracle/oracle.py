@@ -66,6 +66,7 @@ def lib():
         L.mro_blur.argtypes = [C.c_void_p, C.c_int, _i64, _i64, _i64, C.c_int, C.c_void_p, _i64]
         L.mro_categorize_f64_image.argtypes = [C.c_void_p, _i64, _i64, _i64, C.c_int, _f64p, _f64p, _f64p, _i64,
                                                C.c_void_p, C.c_void_p, _u8p, _i64]
+        L.mro_balance.argtypes = [_u8p, _i64, _i64, _i64, _f64p, C.c_void_p, _i64, C.c_void_p]
         L.mro_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -237,6 +238,16 @@ def categorize_f64_image(px, mean, lo, hi, known_idx=None, known_cat=None):
         nk = ki.size
     lib().mro_categorize_f64_image(px.ctypes.data, n1, n2, n1 * 24, mean.shape[0], mean, lo, hi, nk,
                                    ki.ctypes.data if nk else None, kc.ctypes.data if nk else None, out.ctypes.data, n1)
+    return out
+
+
+def balance(img, coef):
+    """per-pixel part of `_balance` (src/balance.jl:25-42): img (n2, n1, 3) uint8, coef (3, 7) -> (n2, n1, 3) float64."""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    n2, n1, _ = img.shape
+    coef = _f64(coef).reshape(3, 7)
+    out = np.empty((n2, n1, 3), dtype=np.float64)
+    lib().mro_balance(img.ctypes.data, n1, n2, n1 * 3, coef, out.ctypes.data, n1 * 24, None)
     return out
 
 

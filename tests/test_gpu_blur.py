@@ -93,3 +93,34 @@ def test_mirror_blur_then_categorize(mr, oracle):
     assert mismatches(lab, oracle.categorize_f64_image(b, pal.mean, pal.lo, pal.hi)) == 0
     with pytest.raises(ValueError):
         mr.categorize(b.astype(np.float32), points)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (3, 255), (5, 256), (7, 257), (40, 1000), (64, 2049)])
+def test_balance_bit_identical(ctx, oracle, shape):
+    """per-pixel part of `_balance` (src/balance.jl:25-42): predictions, their mean (fixed summation order), clamp"""
+    rng = np.random.default_rng(shape[1])
+    n2, n1 = shape
+    img = rng.integers(0, 256, size=(n2, n1, 3), dtype=np.uint8)
+    coef = np.stack([rng.normal(0, s, size=3) for s in (0.05, 1e-10, 1e-7, 1e-4, 1e-10, 1e-7, 1e-4)], axis=1)   # (3, 7)
+    got = ctx.balance_host(img, coef)
+    want = oracle.balance(img, coef)
+    assert got.tobytes() == want.tobytes()
+    assert got.min() >= 0.0 and got.max() <= 1.0
+    with pytest.raises(Exception):
+        ctx.balance_host(img, np.full((3, 7), np.nan))
+
+
+def test_balance_mirror(mr, oracle):
+    rng = np.random.default_rng(3)
+    n2, n1 = 90, 120
+    yy, xx = np.mgrid[0:n2, 0:n1]
+    img = np.clip(120 + 0.3 * xx[..., None] - 0.2 * yy[..., None] + rng.integers(-5, 6, size=(n2, n1, 3)), 0, 255).astype(np.uint8)
+    pts = [[(float(rng.integers(1, n1 + 1)), float(rng.integers(1, n2 + 1))) for _ in range(12)], []]
+    out = mr.balance(img, pts)
+    coef = mr.balance_fit(img, pts)
+    assert out.tobytes() == oracle.balance(img, coef).tobytes()
+    # fewer than 8 points: A .* 1.0
+    few = mr.balance(img, [pts[0][:5], []])
+    assert few.tobytes() == (img.astype(np.float64) / 255.0).tobytes()
+    # the linear trend is gone: the detrended image varies much less along the axes than the input
+    assert abs(np.polyfit(np.arange(n1), out[:, :, 0].mean(axis=0), 1)[0]) < 0.1 * abs(np.polyfit(np.arange(n1), img[:, :, 0].mean(axis=0) / 255.0, 1)[0])

@@ -350,8 +350,10 @@ def test_map_selection_pipeline(ctx, mr, oracle):
     tol = np.full(K, 2.5)
     keep = [True] * K
     keep[2] = False
+    no_balance = [False] * K      # `category_balance`: no category feeds the detrend -> `_balance` is A .* 1.0
     sel = mr.MapSelection(settings=dict(category_tolerances=tol, category_keep=keep, prune_threshold=30,
-                                        line_threshold=0.02, match=("color",), segment=False, blur_repeat=0),
+                                        line_threshold=0.02, match=("color",), segment=False, blur_repeat=0,
+                                        category_balance=no_balance),
                           points=points)
     # no majority filter: a clicked point then carries its own category or 0 (src/categories.jl:110-112),
     # so two different known categories can only meet in the no-match background
@@ -376,7 +378,8 @@ def test_map_selection_pipeline(ctx, mr, oracle):
     assert mismatches(res["filled"], want_fill) == 0
     # blur_repeat = 1 (the reference's default): blur -> statistics from the blurred image -> categorise RGB{Float64}
     sel_b = mr.MapSelection(settings=dict(category_tolerances=tol, category_keep=keep, prune_threshold=30,
-                                          line_threshold=0.02, match=("color",), segment=False, blur_repeat=1),
+                                          line_threshold=0.02, match=("color",), segment=False, blur_repeat=1,
+                                          category_balance=no_balance),
                             points=points)
     res_b = mr.rasterize(scan, sel_b, hood=None, ctx=ctx)
     blurred = oracle.blur(scan, 1, 1)
@@ -384,6 +387,18 @@ def test_map_selection_pipeline(ctx, mr, oracle):
     want_b = oracle.categorize_f64_image(blurred, pal_b.mean, pal_b.lo, pal_b.hi, known_idx=idx, known_cat=cat)
     assert mismatches(res_b["categorized"], want_b) == 0
     assert (res_b["categorized"] != res["categorized"]).any()
+    # the reference's defaults: `category_balance` = category 1, whose 12 points (>= 8) switch the detrend on
+    # (src/balance.jl:16-24), then blur_repeat = 1: balance -> blur -> statistics from that image -> categorise
+    sel_d = mr.MapSelection(settings=dict(category_tolerances=tol, category_keep=keep, prune_threshold=30,
+                                          line_threshold=0.02, match=("color",), segment=False, blur_repeat=1),
+                            points=points)
+    res_d = mr.rasterize(scan, sel_d, hood=None, ctx=ctx)
+    coef = mr.balance_fit(scan, points)
+    assert coef is not None and coef.shape == (3, 7)
+    pixels = oracle.blur(oracle.balance(scan, coef), 1, 1)
+    pal_d = mr.Palette.from_points(pixels, points, tol)
+    want_d = oracle.categorize_f64_image(pixels, pal_d.mean, pal_d.lo, pal_d.hi, known_idx=idx, known_cat=cat)
+    assert mismatches(res_d["categorized"], want_d) == 0
 
 
 def test_device_bands_equal_whole(ctx, mr, oracle):

@@ -46,3 +46,43 @@ def test_float64_image_categoriser_on_the_reference_vectors(oracle):
     px = np.array([[v["rgb"] for v in vectors]], dtype=np.float64)           # one line of the reference's colours
     want = np.array([[v["expected"] for v in vectors]], dtype=np.uint8)
     assert (oracle.categorize_f64_image(px, mean, lo, hi) == want).all()
+
+
+def test_balance_against_python_reading(oracle):
+    """oracle `_balance` per-pixel part against a direct Python reading of src/balance.jl:25-42 with the stated
+    evaluation and summation order"""
+    rng = np.random.default_rng(11)
+    n2, n1 = 5, 300          # two chunks of 256 pixels per line
+    img = rng.integers(0, 256, size=(n2, n1, 3), dtype=np.uint8)
+    coef = rng.normal(0, 1e-6, size=(3, 7))
+    coef[:, 0] = rng.normal(0, 0.05, size=3)
+
+    def pred(b, i, j):
+        fi, fj = float(i), float(j)
+        i2 = fi * fi
+        i3 = i2 * fi
+        j2 = fj * fj
+        j3 = j2 * fj
+        p = b[0] + b[1] * i3
+        for t in (b[2] * i2, b[3] * fi, b[4] * j3, b[5] * j2, b[6] * fj):
+            p = p + t
+        return p
+    want = np.zeros((n2, n1, 3))
+    for c in range(3):
+        b = [float(v) for v in coef[c]]
+        total = 0.0
+        for j in range(n2):
+            line = 0.0
+            for i0 in range(0, n1, 256):
+                chunk = 0.0
+                for i in range(i0, min(n1, i0 + 256)):
+                    chunk = chunk + pred(b, i + 1, j + 1)
+                line = line + chunk
+            total = total + line
+        mean = total / float(n1 * n2)
+        for j in range(n2):
+            for i in range(n1):
+                v = float(np.float64(img[j, i, c]) / np.float64(255.0)) - pred(b, i + 1, j + 1)
+                v = v + mean
+                want[j, i, c] = min(1.0, max(v, 0.0))
+    assert oracle.balance(img, coef).tobytes() == want.tobytes()
