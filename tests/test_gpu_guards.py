@@ -124,3 +124,13 @@ def test_bands_peer_halos_prune_fill_blur(ctx, mr, oracle):
     bdst.check("blur")
     got = np.frombuffer(bdst.data().tobytes(), dtype=np.float64).reshape(n2o, n1o, 3)
     assert got.tobytes() == oracle.blur(px, 2, 2).tobytes()
+    # _balance (per-pixel part) into a padded Float64 image
+    coef = np.ascontiguousarray(rng.normal(0, 1e-5, size=(3, 7)))
+    coef[:, 0] = rng.normal(0, 0.05, size=3)
+    bal = Guarded(n2o, n1o * 24 + 24, n1o * 24, dev)
+    ctx._ck(ctx._L.mr_balance_dev(ctx._h, psrc.ptr(), n1o, n2o, n1o * 3 + 5, 3, coef.ctypes.data, bal.ptr(), n1o * 24 + 24, None))
+    torch.cuda.synchronize()
+    bal.check("balance")
+    psrc.check("balance (input)")
+    got = np.frombuffer(bal.data().tobytes(), dtype=np.float64).reshape(n2o, n1o, 3)
+    assert got.tobytes() == oracle.balance(px, coef).tobytes()
