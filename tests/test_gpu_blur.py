@@ -124,3 +124,46 @@ def test_balance_mirror(mr, oracle):
     assert few.tobytes() == (img.astype(np.float64) / 255.0).tobytes()
     # the linear trend is gone: the detrended image varies much less along the axes than the input
     assert abs(np.polyfit(np.arange(n1), out[:, :, 0].mean(axis=0), 1)[0]) < 0.1 * abs(np.polyfit(np.arange(n1), img[:, :, 0].mean(axis=0) / 255.0, 1)[0])
+
+
+def test_float64_categoriser_adversarial(ctx, mr, oracle):
+    """adversarial palettes and colours for the Float64 categoriser: duplicate means (first of equal errors
+    wins), exact ties between lattice means, a missing category (+Inf), colours far outside [0, 1], a NaN
+    colour, K = 1 and K = 64.  (A variant that skipped categories which provably cannot win -- triangle
+    inequality on a table of distances between the means -- passed this test too but was 1.7 x slower than
+    evaluating everything: the candidate sets differ from lane to lane.)"""
+    rng = np.random.default_rng(123)
+    n2, n1 = 64, 96
+    for case in range(6):
+        if case == 0:      # duplicates and near-duplicates
+            base = rng.random((5, 3))
+            mean = np.concatenate([base, base, base + 1e-15, base[::-1]])
+        elif case == 1:    # lattice: many exact ties
+            g = np.array([0.25, 0.5, 0.75])
+            mean = np.array([(a, b, c) for a in g for b in g for c in g])
+        elif case == 2:    # a missing category in front and in the middle
+            mean = rng.random((9, 3))
+            mean[0] = np.inf
+            mean[4] = np.inf
+        elif case == 3:
+            mean = rng.random((1, 3))
+        elif case == 4:
+            mean = rng.random((64, 3))
+        else:              # clustered means: the guess is often wrong
+            mean = 0.5 + rng.normal(0, 0.01, size=(40, 3))
+        K = mean.shape[0]
+        lo = np.where(np.isfinite(mean), mean - 0.2, np.nan)
+        hi = np.where(np.isfinite(mean), mean + 0.2, np.nan)
+        ctx.set_palette(mean, lo, hi)
+        ctx.palette = None
+        ctx.set_known(None)
+        fin = np.where(np.isfinite(mean).all(axis=1))[0]
+        px = mean[rng.choice(fin, size=(n2, n1))] + rng.normal(0, 0.02, size=(n2, n1, 3))
+        px[::7, ::5] = mean[fin[0]]                                  # exactly on a mean
+        if case == 1:
+            px[1::3] = np.round(px[1::3] * 8) / 8                      # exactly between lattice means
+        px[3, 3] = (1e6, -1e6, 3.0)
+        px[5, 5] = (np.nan, 0.1, 0.2)
+        got = ctx.categorize_clean_f64_host(px, 0)
+        want = oracle.categorize_f64_image(px, mean, lo, hi)
+        assert mismatches(got, want) == 0, case
