@@ -88,3 +88,29 @@ def test_workload_definitions(mr):
     assert set(np.unique(lat)) <= {32, 96, 160, 224}
     st = synth.make_stats(7, lat, exact_means=True)
     assert np.array_equal(st.mean, lat / 255.0)
+
+
+def test_balance_fit_host_part(mr):
+    """host part of `_balance` (src/balance.jl:1-24): fewer than 8 points -> None (A .* 1.0); otherwise the
+    least-squares cubic through the clicked points' colour deviations from their category mean"""
+    rng = np.random.default_rng(5)
+    n2, n1 = 200, 300
+    img = rng.integers(0, 256, size=(n2, n1, 3), dtype=np.uint8)
+    pts = [(float(rng.integers(1, n1 + 1)), float(rng.integers(1, n2 + 1))) for _ in range(7)]
+    assert mr.balance_fit(img, [pts, []]) is None
+    assert mr.balance_fit(img, [pts, pts], category_bitindex=[True, True]).shape == (3, 7)     # 14 points
+    assert mr.balance_fit(img, [pts, pts * 2]) is None                                             # default: category 1 only
+    # a sheet whose red channel is (mean + a cubic in i): the fit returns that cubic
+    ii = np.arange(1, n1 + 1, dtype=np.float64)
+    trend = 2e-8 * ii ** 3 - 6e-6 * ii ** 2 + 4e-4 * ii
+    sheet = np.zeros((n2, n1, 3))
+    sheet[:, :, 0] = 0.3 + trend[None, :]
+    sheet[:, :, 1:] = 0.5
+    img = np.rint(sheet * 255).astype(np.uint8)
+    pts = [(float(i), float(j)) for i in range(10, n1, 29) for j in (20, 90, 160)]
+    coef = mr.balance_fit(img, [pts])
+    xs = np.array([p[0] for p in pts])
+    got = coef[0, 0] + coef[0, 1] * xs ** 3 + coef[0, 2] * xs ** 2 + coef[0, 3] * xs
+    want = img[0, (xs - 1).astype(int), 0] / 255.0
+    assert np.abs((got - got.mean()) - (want - want.mean())).max() < 3e-3      # up to N0f8 quantisation
+    assert np.abs(coef[1:]).max() < 1e-6                                         # flat channels: no trend
