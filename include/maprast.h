@@ -223,6 +223,51 @@ int mr_categorize_clean_f64_dev(mr_ctx* ctx, const double* px_dev, int64_t n1, i
                                 int64_t stride2_bytes, int R, uint8_t* labels_dev,
                                 int64_t out_stride2, void* stream);
 
+/* Texture features behind the reference's default match = (:color, :std, :stripe), computed
+ * from the blurred RGB{Float64} image by the "blur" button (src/selectcolors.jl:455-465):
+ *   mr_stds_*     _stds(A), src/selectcolors.jl:706-715: per pixel the sum over r, g, b of the sample standard
+ *                 deviation of the channel over Window(2) (5 x 5, centre included), the image divided by its maximum;
+ *                 one double per pixel out;
+ *   mr_stripes_*  _stripes(img; radius), src/stripes.jl:20-35: per pixel (vert - horz, angle45 - angle135) of the
+ *                 directional HSL contrasts (mean over `radius` neighbours per side of (ds^2 + dl^2), the smaller
+ *                 side), the image divided by mean((mean(abs o first), mean(abs o last))); two doubles per pixel out.
+ * px: three doubles per pixel; strides in bytes, multiples of 8.  Neighbours outside the image are the zero
+ * colour; summation orders, the two-pass std and the RGB -> HSL formula are decisions (DESIGN.md section 14:
+ * Neighborhoods.jl, Statistics and Colors.jl are not in the reference tree; parity unpinned). */
+int mr_stds_host(mr_ctx* ctx, const double* px, int64_t n1, int64_t n2, int64_t stride2_bytes,
+                 double* out, int64_t out_stride2_bytes);
+int mr_stds_dev(mr_ctx* ctx, const double* px_dev, int64_t n1, int64_t n2, int64_t stride2_bytes,
+                double* out_dev, int64_t out_stride2_bytes, void* stream);
+int mr_stripes_host(mr_ctx* ctx, const double* px, int64_t n1, int64_t n2, int64_t stride2_bytes,
+                    int radius, double* out, int64_t out_stride2_bytes);
+int mr_stripes_dev(mr_ctx* ctx, const double* px_dev, int64_t n1, int64_t n2, int64_t stride2_bytes,
+                   int radius, double* out_dev, int64_t out_stride2_bytes, void* stream);
+
+/* Statistics of the texture properties per category: `std` and `stripe` of _component_stats(::Vector{<:PixelProp}),
+ * src/categories.jl:10-17 -- mean, and the bounds min - sd * tol / max + sd * tol of src/categories.jl:131-133,
+ * computed by the host like the colour bounds of mr_set_palette.  std_*: K doubles; stripe_*: K x 2 doubles.
+ * Call after mr_set_palette (a new palette drops them). */
+int mr_set_texture_stats(mr_ctx* ctx, int K, const double* std_mean, const double* std_lo, const double* std_hi,
+                         const double* stripe_mean, const double* stripe_lo, const double* stripe_hi);
+
+/* _categorize(pixels::Array{PixelProp}, points; match) (src/categories.jl:45-52,68-82) followed by the Window{R}
+ * majority filter: per pixel the error of a category is the mean over the MATCHED properties, in the order
+ * color, std, stripe, of the colour error (:91-95), (std - mean)^2 (:101) and mean((stripe - mean)^2) (:96-100);
+ * first minimum; accepted when every matched property lies in the winner's box (:106-133) or the pixel is a
+ * clicked point of that category (mr_set_known).  match: bit 0 color, bit 1 std, bit 2 stripe (1 = what
+ * mr_categorize_clean_f64_* does).  px: RGB{Float64}; std plane: one double, stripe plane: two doubles per
+ * pixel (NULL when not matched); strides in bytes, multiples of 8. */
+int mr_categorize_clean_props_host(mr_ctx* ctx, const double* px, int64_t stride2_bytes,
+                                   const double* std_plane, int64_t std_stride2_bytes,
+                                   const double* stripe_plane, int64_t stripe_stride2_bytes,
+                                   int64_t n1, int64_t n2, int match, int R, uint8_t* labels_out,
+                                   int64_t out_stride2);
+int mr_categorize_clean_props_dev(mr_ctx* ctx, const double* px_dev, int64_t stride2_bytes,
+                                  const double* std_dev, int64_t std_stride2_bytes,
+                                  const double* stripe_dev, int64_t stripe_stride2_bytes,
+                                  int64_t n1, int64_t n2, int match, int R, uint8_t* labels_dev,
+                                  int64_t out_stride2, void* stream);
+
 /* fill_gaps(src; categories, neighborhood = VonNeumann{2}(), missingval = 0, stats, match = (:color,),
  * known, original, mask), src/clean.jl:2-54, applied `repeat` times as _fill does
  * (src/selectcolors.jl:683-699; call site :490-501).  Per pixel and pass: a masked pixel stays

@@ -27,6 +27,8 @@ SYMBOLS = [
     "mr_fill_gaps_dev", "mr_fill_gaps_host", "mr_set_known_band",
     "mr_blur_host", "mr_blur_dev", "mr_categorize_clean_f64_host", "mr_categorize_clean_f64_dev",
     "mr_balance_host", "mr_balance_dev",
+    "mr_stds_host", "mr_stds_dev", "mr_stripes_host", "mr_stripes_dev", "mr_set_texture_stats",
+    "mr_categorize_clean_props_host", "mr_categorize_clean_props_dev",
     "mr_multi_create", "mr_multi_destroy", "mr_multi_last_error", "mr_multi_device_count", "mr_multi_ctx",
     "mr_multi_band_range", "mr_multi_set_palette", "mr_multi_set_known", "mr_multi_categorize_clean_host",
     "mr_multi_batch_categorize_clean_host", "mr_multi_categorize_clean_dev",
@@ -102,6 +104,13 @@ def load():
     L.mr_blur_dev.argtypes = [vp, vp, i64, i64, i64, i32, i32, i32, vp, i64, vp]
     L.mr_categorize_clean_f64_host.argtypes = [vp, vp, i64, i64, i64, i32, u8p, i64]
     L.mr_categorize_clean_f64_dev.argtypes = [vp, vp, i64, i64, i64, i32, u8p, i64, vp]
+    L.mr_stds_host.argtypes = [vp, vp, i64, i64, i64, vp, i64]
+    L.mr_stds_dev.argtypes = [vp, vp, i64, i64, i64, vp, i64, vp]
+    L.mr_stripes_host.argtypes = [vp, vp, i64, i64, i64, i32, vp, i64]
+    L.mr_stripes_dev.argtypes = [vp, vp, i64, i64, i64, i32, vp, i64, vp]
+    L.mr_set_texture_stats.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
+    L.mr_categorize_clean_props_host.argtypes = [vp, vp, i64, vp, i64, vp, i64, i64, i64, i32, i32, u8p, i64]
+    L.mr_categorize_clean_props_dev.argtypes = [vp, vp, i64, vp, i64, vp, i64, i64, i64, i32, i32, u8p, i64, vp]
     L.mr_multi_create.argtypes = [vp, i32, C.POINTER(i32)]
     L.mr_multi_create.restype = vp
     L.mr_multi_destroy.argtypes = [vp]
@@ -129,7 +138,9 @@ def load():
                  "mr_batch_categorize_clean_dev", "mr_clean_host", "mr_clean_dev", "mr_clean_segments_dev",
                  "mr_clean_segments_host", "mr_fill_gaps_dev", "mr_fill_gaps_host", "mr_synth_scan_dev",
                  "mr_blur_host", "mr_blur_dev", "mr_categorize_clean_f64_host", "mr_categorize_clean_f64_dev",
-                 "mr_balance_host", "mr_balance_dev", "mr_set_known_band", "mr_clean_dev_bounded", "mr_multi_device_count", "mr_multi_band_range", "mr_multi_set_palette",
+                 "mr_balance_host", "mr_balance_dev", "mr_stds_host", "mr_stds_dev", "mr_stripes_host", "mr_stripes_dev",
+                 "mr_set_texture_stats", "mr_categorize_clean_props_host", "mr_categorize_clean_props_dev",
+                 "mr_set_known_band", "mr_clean_dev_bounded", "mr_multi_device_count", "mr_multi_band_range", "mr_multi_set_palette",
                  "mr_multi_set_known", "mr_multi_categorize_clean_host", "mr_multi_batch_categorize_clean_host",
                  "mr_multi_categorize_clean_dev"):
         getattr(L, name).restype = i32
@@ -307,6 +318,54 @@ class Context:
         n2, n1, _ = px.shape
         out = np.empty((n2, n1), dtype=np.uint8)
         self._ck(self._L.mr_categorize_clean_f64_host(self._h, _ptr(px), n1, n2, n1 * 24, int(R), _ptr(out), n1))
+        return out
+
+    def stds_host(self, px):
+        """`_stds(A)` (src/selectcolors.jl:706-715): (n2, n1, 3) float64 -> (n2, n1) float64."""
+        px = np.ascontiguousarray(px, dtype=np.float64)
+        if px.ndim != 3 or px.shape[2] != 3:
+            raise ValueError("px must be a (n2, n1, 3) float64 array")
+        n2, n1, _ = px.shape
+        out = np.empty((n2, n1), dtype=np.float64)
+        self._ck(self._L.mr_stds_host(self._h, _ptr(px), n1, n2, n1 * 24, _ptr(out), n1 * 8))
+        return out
+
+    def stripes_host(self, px, radius=3):
+        """`_stripes(img; radius)` (src/stripes.jl:20-35): (n2, n1, 3) float64 -> (n2, n1, 2) float64."""
+        px = np.ascontiguousarray(px, dtype=np.float64)
+        if px.ndim != 3 or px.shape[2] != 3:
+            raise ValueError("px must be a (n2, n1, 3) float64 array")
+        n2, n1, _ = px.shape
+        out = np.empty((n2, n1, 2), dtype=np.float64)
+        self._ck(self._L.mr_stripes_host(self._h, _ptr(px), n1, n2, n1 * 24, int(radius), _ptr(out), n1 * 16))
+        return out
+
+    def set_texture_stats(self, std_mean, std_lo, std_hi, stripe_mean, stripe_lo, stripe_hi):
+        """statistics of the `std` / `stripe` properties per category (src/categories.jl:10-17): (K,) and (K, 2)"""
+        a = [np.ascontiguousarray(v, dtype=np.float64).reshape(-1) for v in (std_mean, std_lo, std_hi)]
+        b = [np.ascontiguousarray(v, dtype=np.float64).reshape(-1, 2) for v in (stripe_mean, stripe_lo, stripe_hi)]
+        K = a[0].size
+        if any(v.size != K for v in a) or any(v.shape[0] != K for v in b):
+            raise ValueError("texture statistics must have one row per category")
+        self._ck(self._L.mr_set_texture_stats(self._h, K, *[_ptr(v) for v in a + b]))
+
+    def categorize_clean_props_host(self, px, std, stripe, match_bits, R):
+        """PixelProp categoriser (src/categories.jl:76-133): px (n2, n1, 3), std (n2, n1), stripe (n2, n1, 2) float64
+        (std / stripe may be None when not matched); match_bits: 1 color | 2 std | 4 stripe; labels (n2, n1) uint8."""
+        px = np.ascontiguousarray(px, dtype=np.float64)
+        if px.ndim != 3 or px.shape[2] != 3:
+            raise ValueError("px must be a (n2, n1, 3) float64 array")
+        n2, n1, _ = px.shape
+        std = None if std is None else np.ascontiguousarray(std, dtype=np.float64)
+        stripe = None if stripe is None else np.ascontiguousarray(stripe, dtype=np.float64)
+        if std is not None and std.shape != (n2, n1):
+            raise ValueError("std must be a (n2, n1) float64 array")
+        if stripe is not None and stripe.shape != (n2, n1, 2):
+            raise ValueError("stripe must be a (n2, n1, 2) float64 array")
+        out = np.empty((n2, n1), dtype=np.uint8)
+        self._ck(self._L.mr_categorize_clean_props_host(
+            self._h, _ptr(px), n1 * 24, None if std is None else _ptr(std), n1 * 8,
+            None if stripe is None else _ptr(stripe), n1 * 16, n1, n2, int(match_bits), int(R), _ptr(out), n1))
         return out
 
     def fill_gaps_host(self, labels, px, categories, mask=None, repeat=1):

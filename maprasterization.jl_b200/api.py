@@ -21,7 +21,9 @@ from . import _lib
 from ._lib import Context, MapRastError  # noqa: F401
 
 DEFAULT_CATEGORY_TOLERANCE = 2.0   # src/selectcolors.jl:1
-DEFAULT_MATCH = ("color", "std", "stripe")  # src/scan.jl:1 (the hot path supports ("color",) only)
+DEFAULT_MATCH = ("color", "std", "stripe")  # src/scan.jl:1; ("color",) alone takes the table-driven N0f8 hot path
+MATCH_BITS = {"color": 1, "std": 2, "stripe": 4}   # `match` argument of mr_categorize_clean_props_*
+DEFAULT_STRIPE_RADIUS = 2                   # src/selectcolors.jl:38
 
 
 class Window:
@@ -156,12 +158,70 @@ def default_context(device=0):
 
 
 def _check_match(match, segmented):
+    """-> match bits.  `match` must be a non-empty subset of (color, std, stripe) in that order (the order
+    `_match_from_bools` produces, src/selectcolors.jl:661-668; the error is a left-folded mean over it)."""
     m = tuple(match)
-    if m != ("color",):
-        raise ValueError(f"match={m!r} is not supported by the B200 hot path: only ('color',) "
-                         "(std/stripe texture planes are SURVEY 8(f) 'next' rows)")
+    if not m or any(x not in MATCH_BITS for x in m) or list(m) != [x for x in DEFAULT_MATCH if x in m]:
+        raise ValueError(f"match={m!r}: must be a non-empty subset of ('color', 'std', 'stripe') in that order")
     if segmented:
-        raise ValueError("segmented=True (fast_scanning, src/categories.jl:53-67) is not supported")
+        raise ValueError("segmented=True (fast_scanning, src/categories.jl:53-67: a sequential scan with running "
+                         "segment means) is not supported on the GPU path")
+    return sum(MATCH_BITS[x] for x in m)
+
+
+@dataclass
+class TextureStats:
+    """`std` and `stripe` entries of `_component_stats(::Vector{<:PixelProp})` (src/categories.jl:10-17) per category:
+    mean / min / max / sd of the property at the clicked points; bounds as in src/categories.jl:131-133."""
+    std: dict       # mean, min, max, sd: (K,)
+    stripe: dict    # mean, min, max, sd: (K, 2)
+    tolerances: np.ndarray
+
+    def bounds(self):
+        t = np.asarray(self.tolerances, dtype=np.float64).reshape(-1)
+        with np.errstate(invalid="ignore"):
+            w1, w2 = self.std["sd"] * t, self.stripe["sd"] * t[:, None]
+            return (self.std["min"] - w1, self.std["max"] + w1), (self.stripe["min"] - w2, self.stripe["max"] + w2)
+
+    @classmethod
+    def from_points(cls, std_plane, stripe_plane, points, tolerances=None):
+        """sample the planes at the clicked points (1-based (i, j), `round(Int, p)`); a plane that is None counts
+        as the reference's initial all-zero plane (src/selectcolors.jl:229-231)"""
+        K = len(points)
+        tol = np.full(K, DEFAULT_CATEGORY_TOLERANCE) if tolerances is None else np.asarray(tolerances, dtype=np.float64)
+        std = {k: np.full(K, np.nan) for k in ("mean", "min", "max", "sd")}
+        stripe = {k: np.full((K, 2), np.nan) for k in ("mean", "min", "max", "sd")}
+        for c, pts in enumerate(points):
+            pts = np.asarray(pts, dtype=np.float64).reshape(-1, 2)
+            if pts.shape[0] == 0:
+                continue
+            ij = np.rint(pts).astype(np.int64)
+            i, j = ij[:, 0] - 1, ij[:, 1] - 1
+            a = component_stats(np.zeros(len(i)) if std_plane is None else std_plane[j, i])
+            b = component_stats(np.zeros((len(i), 2)) if stripe_plane is None else stripe_plane[j, i])
+            for k in std:
+                std[k][c] = a[k][0]
+                stripe[k][c] = b[k]
+        return cls(std, stripe, tol)
+
+
+def _upload_texture(ctx, tex):
+    (slo, shi), (tlo, thi) = tex.bounds()
+    ctx.set_texture_stats(tex.std["mean"], slo, shi, tex.stripe["mean"], tlo, thi)
+
+
+def stds(A, *, ctx=None):
+    """`_stds(A)` (src/selectcolors.jl:706-715): the "texture" plane of the blurred RGB{Float64} image."""
+    if not _is_f64_img(A):
+        raise ValueError("stds takes a (n2, n1, 3) float64 image (RGB{Float64}, the output of blur)")
+    return (ctx or default_context()).stds_host(A)
+
+
+def stripes(img, *, radius=3, ctx=None):
+    """`_stripes(img; radius=3)` (src/stripes.jl:20-35): (n2, n1, 2) float64."""
+    if not _is_f64_img(img):
+        raise ValueError("stripes takes a (n2, n1, 3) float64 image (RGB{Float64}, the output of blur)")
+    return (ctx or default_context()).stripes_host(img, radius)
 
 
 def _as_palette(img, points_or_palette, tolerances, colourspace):
@@ -202,14 +262,40 @@ def _check_img(img, f64_ok=False):
 
 def categorize_clean_u8(img, points_or_palette, *, tolerances=None, hood=Window(1), match=("color",),
                         segmented=False, scan_threshold=0.1, colourspace="rgb", use_known=False,
-                        ctx=None, counters=False):
-    """Fused clean(categorize(img)) returning uint8 labels (n2, n1)."""
+                        ctx=None, counters=False, std=None, stripe=None, texture=None):
+    """Fused clean(categorize(img)) returning uint8 labels (n2, n1).
+    A `match` with "std" / "stripe" categorises PixelProp pixels (src/categories.jl:45-48): img must be the
+    RGB{Float64} image, `std` / `stripe` the planes of `stds` / `stripes` (None = the all-zero initial plane of
+    the reference); `texture`: TextureStats (default: from the planes at the clicked points)."""
     del scan_threshold   # only used by the unsupported segmented branch
-    _check_match(match, segmented)
+    bits = _check_match(match, segmented)
     _check_img(img, f64_ok=True)
+    if bits != 1 and (not _is_f64_img(img) or colourspace != "rgb"):
+        raise ValueError(f"match={tuple(match)!r}: std / stripe matching takes RGB{{Float64}} pixels (the blurred "
+                         "image) and RGB statistics")
     ctx = ctx or default_context()
     pal = _as_palette(img, points_or_palette, tolerances, colourspace)
     _upload_palette(ctx, pal)
+    if bits != 1:
+        if counters:
+            raise ValueError("counters are not available for RGB{Float64} pixels")
+        n2, n1 = img.shape[:2]
+        if (bits & 2) and std is None:
+            std = np.zeros((n2, n1))
+        if (bits & 4) and stripe is None:
+            stripe = np.zeros((n2, n1, 2))
+        if texture is None:
+            if isinstance(points_or_palette, Palette):
+                raise ValueError("a Palette needs `texture` (TextureStats) for std / stripe matching")
+            texture = TextureStats.from_points(std if bits & 2 else None, stripe if bits & 4 else None,
+                                               points_or_palette, pal.tolerances)
+        _upload_texture(ctx, texture)
+        if use_known and not isinstance(points_or_palette, Palette):
+            ctx.set_known(*_known_from_points(points_or_palette, n1))
+        else:
+            ctx.set_known(None)
+        R = hood.R if isinstance(hood, Window) else int(hood)
+        return ctx.categorize_clean_props_host(img, std if bits & 2 else None, stripe if bits & 4 else None, bits, R)
     if use_known and not isinstance(points_or_palette, Palette):
         ctx.set_known(*_known_from_points(points_or_palette, img.shape[1]))
     else:
@@ -443,13 +529,14 @@ def rasterize(img, sel, *, hood=None, colourspace="rgb", ctx=None):
     Returns a dict with the uint8 label images `categorized`, `cleaned` and `filled`.
     `blur_repeat > 0` runs `blur` first and categorises its RGB{Float64} output (statistics from the
     blurred image, as the reference does); the tie-break of `fill_gaps` then still reads the unblurred pixel.
-    Settings that select unsupported stages raise ValueError (no CPU fallback): `segment=True`,
-    a `match` other than ("color",)."""
+    A `match` with "std" / "stripe" computes the texture planes from the blurred image (`stds`, `stripes` with
+    `stripe_radius`) and categorises PixelProp pixels (src/categories.jl:45-48).
+    Settings that select unsupported stages raise ValueError (no CPU fallback): `segment=True`."""
     if not isinstance(sel, MapSelection):
         raise ValueError("sel must be a MapSelection")
     st = sel.settings
     match = tuple(st.get("match", ("color",)))
-    _check_match(match, bool(st.get("segment", False)))
+    bits = _check_match(match, bool(st.get("segment", False)))
     _check_img(img)
     ctx = ctx or default_context()
     n2, n1 = img.shape[:2]
@@ -469,8 +556,19 @@ def rasterize(img, sel, *, hood=None, colourspace="rgb", ctx=None):
         if img.shape[2] != 3 or colourspace != "rgb":
             raise ValueError("blur_repeat > 0 needs RGB{N0f8} pixels and RGB matching")
         pixels = blur(pixels, repeat=blur_repeat, ctx=ctx)
+    std_plane = stripe_plane = None
+    if bits != 1:
+        # the "blur" button also refreshes the texture planes of the matched properties (src/selectcolors.jl:457-462)
+        if img.shape[2] != 3 or colourspace != "rgb":
+            raise ValueError("std / stripe matching needs RGB{N0f8} pixels and RGB matching")
+        if not _is_f64_img(pixels):
+            pixels = ctx.blur_host(img, 0, 0)          # A .* 1.0 (src/balance.jl:16-18)
+        if bits & 2:
+            std_plane = stds(pixels, ctx=ctx)
+        if bits & 4:
+            stripe_plane = stripes(pixels, radius=int(st.get("stripe_radius", DEFAULT_STRIPE_RADIUS)), ctx=ctx)
     categorized = categorize_clean_u8(pixels, sel.points, tolerances=tol, hood=Window(R), colourspace=colourspace,
-                                      use_known=True, ctx=ctx)
+                                      use_known=True, ctx=ctx, match=match, std=std_plane, stripe=stripe_plane)
     idx, cat = _known_from_points(sel.points, n1)
     known = np.zeros((n2, n1), dtype=np.uint8)
     known.reshape(-1)[idx] = cat

@@ -45,6 +45,7 @@ struct mr_ctx {
     uint8_t* d_lab = nullptr;    size_t d_lab_cap = 0;     // categorise-only labels of the RGBA path
     uint8_t* d_f64 = nullptr;    size_t d_f64_cap = 0;     // RGB{Float64} scratch images of blur (ping-pong, host staging)
     uint8_t* d_f64b = nullptr;   size_t d_f64b_cap = 0;
+    double* d_tex = nullptr;     bool tex_set = false;     // texture statistics of mr_set_texture_stats (9 K doubles)
     // segment prune scratch: parent array, component records, keep table + two counters
     uint8_t* d_parent = nullptr; size_t d_parent_cap = 0;   // first run of every (line, chunk)
     uint8_t* d_runs = nullptr; size_t d_runs_cap = 0;       // run arrays
@@ -125,7 +126,7 @@ extern "C" void mr_destroy(mr_ctx* ctx) {
     for (auto e : ctx->ev_done) cudaEventDestroy(e);
     cudaFree(ctx->d_pal); cudaFree(ctx->d_lut); cudaFree(ctx->d_coarse); cudaFree(ctx->d_qtab);
     cudaFree(ctx->d_known_idx); cudaFree(ctx->d_known_cat); cudaFree(ctx->d_counters); cudaFree(ctx->work.slots);
-    cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_tmp); cudaFree(ctx->d_rp_in); cudaFree(ctx->d_rp_out); cudaFree(ctx->d_lab); cudaFree(ctx->d_f64); cudaFree(ctx->d_f64b);
+    cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_tmp); cudaFree(ctx->d_rp_in); cudaFree(ctx->d_rp_out); cudaFree(ctx->d_lab); cudaFree(ctx->d_f64); cudaFree(ctx->d_f64b); cudaFree(ctx->d_tex);
     cudaFree(ctx->d_parent); cudaFree(ctx->d_runs); cudaFree(ctx->d_rec); cudaFree(ctx->d_small);
     if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
@@ -182,6 +183,7 @@ extern "C" int mr_set_palette(mr_ctx* ctx, int K, const double* mean, const doub
     ctx->pal.C = channels;
     ctx->pal.colourspace = colourspace;
     ctx->palette_set = true;
+    ctx->tex_set = false;            // texture statistics belong to a palette
     ctx->lut_valid = false;
     ctx->build_ms = 0.f;
     {   // exact label table over the 2^24 colours (4-channel statistics: alpha = 255 in the distance)
@@ -1036,6 +1038,209 @@ extern "C" int mr_categorize_clean_f64_host(mr_ctx* ctx, const double* px, int64
     cudaStream_t s = ctx->s_main;
     CK(cudaMemcpy2DAsync(ctx->d_f64b, pitch, px, stride2, n1 * 24, n2, cudaMemcpyHostToDevice, s));
     rc = cat_f64_dev(ctx, reinterpret_cast<const double*>(ctx->d_f64b), n1, n2, pitch, R, ctx->d_out, line_out, s);
+    if (rc) return rc;
+    CK(cudaMemcpy2DAsync(labels_out, out_stride2, ctx->d_out, line_out, n1, n2, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return MR_OK;
+}
+
+// ------------------------------------------------------------------ texture features + PixelProp categoriser
+// (_stds src/selectcolors.jl:706-715, _stripes src/stripes.jl:1-35, _categorize with a match tuple
+//  src/categories.jl:76-133)
+extern "C" int mr_set_texture_stats(mr_ctx* ctx, int K, const double* std_mean, const double* std_lo, const double* std_hi,
+                                    const double* stripe_mean, const double* stripe_lo, const double* stripe_hi) {
+    if (!ctx) return fail(nullptr, MR_ERR_ARG, "mr_set_texture_stats: null ctx");
+    if (!ctx->palette_set) return fail(ctx, MR_ERR_STATE, "mr_set_texture_stats: mr_set_palette has not been called");
+    if (K != ctx->pal.K) return fail(ctx, MR_ERR_ARG, "mr_set_texture_stats: K differs from the palette's");
+    if (!std_mean || !std_lo || !std_hi || !stripe_mean || !stripe_lo || !stripe_hi)
+        return fail(ctx, MR_ERR_ARG, "mr_set_texture_stats: null statistics");
+    CK(cudaSetDevice(ctx->device));
+    std::vector<double> h((size_t)9 * K);
+    memcpy(h.data(), std_mean, (size_t)K * 8);
+    memcpy(h.data() + K, std_lo, (size_t)K * 8);
+    memcpy(h.data() + 2 * K, std_hi, (size_t)K * 8);
+    memcpy(h.data() + 3 * K, stripe_mean, (size_t)2 * K * 8);
+    memcpy(h.data() + 5 * K, stripe_lo, (size_t)2 * K * 8);
+    memcpy(h.data() + 7 * K, stripe_hi, (size_t)2 * K * 8);
+    CK(cudaStreamSynchronize(ctx->s_main));
+    if (!ctx->d_tex) CK(cudaMalloc(&ctx->d_tex, (size_t)254 * 9 * 8));
+    CK(cudaMemcpy(ctx->d_tex, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
+    ctx->tex_set = true;
+    return MR_OK;
+}
+
+// comp = doubles per pixel of the output plane (1: stds, 2: stripes)
+static int texture_check(mr_ctx* ctx, const char* fn, const void* px, const void* out, int64_t n1, int64_t n2,
+                         int64_t stride2, int comp, int64_t out_stride2) {
+    std::string f(fn);
+    if (!ctx) return fail(nullptr, MR_ERR_ARG, f + ": null ctx");
+    if (n1 < 0 || n2 < 0) return fail(ctx, MR_ERR_ARG, f + ": negative size");
+    if (n1 > 0 && n2 > 0 && (!px || !out)) return fail(ctx, MR_ERR_ARG, f + ": null buffer");
+    if (stride2 < n1 * 24 || out_stride2 < n1 * 8 * comp) return fail(ctx, MR_ERR_ARG, f + ": stride smaller than a line");
+    if (stride2 % 8 != 0 || out_stride2 % 8 != 0) return fail(ctx, MR_ERR_ARG, f + ": Float64 lines must be 8-byte aligned");
+    if (px == out && n1 > 0 && n2 > 0) return fail(ctx, MR_ERR_ARG, f + ": in-place operation is not supported");
+    return MR_OK;
+}
+
+static int stds_dev(mr_ctx* ctx, const double* px, int64_t n1, int64_t n2, int64_t stride2, double* out,
+                    int64_t out_stride2, cudaStream_t s) {
+    if (n1 == 0 || n2 == 0) return MR_OK;
+    int rc;
+    if ((rc = grow(ctx, &ctx->d_f64, &ctx->d_f64_cap, 64))) return rc;
+    int nl = 0;
+    cudaError_t e = mr_launch_stds(px, stride2, n1, n2, out, out_stride2, reinterpret_cast<double*>(ctx->d_f64),
+                                   ctx->sm_count, s, &nl);
+    ctx->launches += nl;
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "stds launch");
+    return MR_OK;
+}
+
+static int stripes_dev(mr_ctx* ctx, const double* px, int64_t n1, int64_t n2, int64_t stride2, int radius, double* out,
+                       int64_t out_stride2, cudaStream_t s) {
+    if (n1 == 0 || n2 == 0) return MR_OK;
+    int rc;
+    if ((rc = grow(ctx, &ctx->d_f64, &ctx->d_f64_cap, mr_stripes_scratch_bytes(n1, n2)))) return rc;
+    int nl = 0;
+    cudaError_t e = mr_launch_stripes(px, stride2, n1, n2, radius, out, out_stride2, reinterpret_cast<double*>(ctx->d_f64),
+                                      ctx->sm_count, s, &nl);
+    ctx->launches += nl;
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "stripes launch");
+    return MR_OK;
+}
+
+extern "C" int mr_stds_dev(mr_ctx* ctx, const double* px_dev, int64_t n1, int64_t n2, int64_t stride2, double* out_dev,
+                           int64_t out_stride2, void* stream) {
+    int rc = texture_check(ctx, "mr_stds_dev", px_dev, out_dev, n1, n2, stride2, 1, out_stride2);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    return stds_dev(ctx, px_dev, n1, n2, stride2, out_dev, out_stride2, (cudaStream_t)stream);
+}
+
+extern "C" int mr_stripes_dev(mr_ctx* ctx, const double* px_dev, int64_t n1, int64_t n2, int64_t stride2, int radius,
+                              double* out_dev, int64_t out_stride2, void* stream) {
+    int rc = texture_check(ctx, "mr_stripes_dev", px_dev, out_dev, n1, n2, stride2, 2, out_stride2);
+    if (rc) return rc;
+    if (radius < 1 || radius > 20) return fail(ctx, MR_ERR_ARG, "mr_stripes_dev: radius must be in 1..20 (the slider's range)");
+    CK(cudaSetDevice(ctx->device));
+    return stripes_dev(ctx, px_dev, n1, n2, stride2, radius, out_dev, out_stride2, (cudaStream_t)stream);
+}
+
+// host variants: pixels -> d_f64b, plane -> d_in (staging), scratch in d_f64
+static int texture_host(mr_ctx* ctx, const char* fn, const double* px, int64_t n1, int64_t n2, int64_t stride2, int comp,
+                        int radius, double* out, int64_t out_stride2) {
+    int rc = texture_check(ctx, fn, px, out, n1, n2, stride2, comp, out_stride2);
+    if (rc) return rc;
+    if (comp == 2 && (radius < 1 || radius > 20)) return fail(ctx, MR_ERR_ARG, std::string(fn) + ": radius must be in 1..20 (the slider's range)");
+    if (n1 == 0 || n2 == 0) return MR_OK;
+    CK(cudaSetDevice(ctx->device));
+    const int64_t pitch = n1 * 24, opitch = n1 * 8 * comp;
+    if ((rc = grow(ctx, &ctx->d_f64b, &ctx->d_f64b_cap, (size_t)pitch * n2))) return rc;
+    if ((rc = grow(ctx, &ctx->d_in, &ctx->d_in_cap, (size_t)opitch * n2))) return rc;
+    cudaStream_t s = ctx->s_main;
+    CK(cudaMemcpy2DAsync(ctx->d_f64b, pitch, px, stride2, n1 * 24, n2, cudaMemcpyHostToDevice, s));
+    double* plane = reinterpret_cast<double*>(ctx->d_in);
+    const double* dpx = reinterpret_cast<const double*>(ctx->d_f64b);
+    rc = comp == 1 ? stds_dev(ctx, dpx, n1, n2, pitch, plane, opitch, s)
+                   : stripes_dev(ctx, dpx, n1, n2, pitch, radius, plane, opitch, s);
+    if (rc) return rc;
+    CK(cudaMemcpy2DAsync(out, out_stride2, plane, opitch, opitch, n2, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return MR_OK;
+}
+
+extern "C" int mr_stds_host(mr_ctx* ctx, const double* px, int64_t n1, int64_t n2, int64_t stride2, double* out,
+                            int64_t out_stride2) {
+    return texture_host(ctx, "mr_stds_host", px, n1, n2, stride2, 1, 0, out, out_stride2);
+}
+
+extern "C" int mr_stripes_host(mr_ctx* ctx, const double* px, int64_t n1, int64_t n2, int64_t stride2, int radius,
+                               double* out, int64_t out_stride2) {
+    return texture_host(ctx, "mr_stripes_host", px, n1, n2, stride2, 2, radius, out, out_stride2);
+}
+
+static int props_check(mr_ctx* ctx, const char* fn, const void* px, int64_t stride2, const void* sd, int64_t sd_stride2,
+                       const void* st, int64_t st_stride2, int64_t n1, int64_t n2, int match, int R, const void* out,
+                       int64_t out_stride2) {
+    std::string f(fn);
+    int rc = check_image_args(ctx, fn, px, out, n1, n2, stride2, 24, out_stride2, R, 0, 0);
+    if (rc) return rc;
+    if (!ctx->palette_set) return fail(ctx, MR_ERR_STATE, f + ": mr_set_palette has not been called");
+    if (ctx->pal.C != 3 || ctx->pal.colourspace != MR_COLOURSPACE_RGB)
+        return fail(ctx, MR_ERR_ARG, f + ": RGB{Float64} pixels take 3-channel RGB statistics");
+    if (match < 1 || match > 7) return fail(ctx, MR_ERR_ARG, f + ": match must be a non-empty subset of color (1) | std (2) | stripe (4)");
+    if ((match & 6) && !ctx->tex_set) return fail(ctx, MR_ERR_STATE, f + ": mr_set_texture_stats has not been called for this palette");
+    if (n1 > 0 && n2 > 0 && (((match & 2) && !sd) || ((match & 4) && !st))) return fail(ctx, MR_ERR_ARG, f + ": a matched texture plane is null");
+    if ((match & 2) && sd_stride2 < n1 * 8) return fail(ctx, MR_ERR_ARG, f + ": std stride smaller than a line");
+    if ((match & 4) && st_stride2 < n1 * 16) return fail(ctx, MR_ERR_ARG, f + ": stripe stride smaller than a line");
+    if (stride2 % 8 != 0 || ((match & 2) && sd_stride2 % 8 != 0) || ((match & 4) && st_stride2 % 8 != 0))
+        return fail(ctx, MR_ERR_ARG, f + ": Float64 lines must be 8-byte aligned");
+    return MR_OK;
+}
+
+// categorise PixelProp pixels (+ known points), then the standalone majority filter
+static int props_dev(mr_ctx* ctx, const double* px, int64_t stride2, const double* sd, int64_t sd_stride2, const double* st,
+                     int64_t st_stride2, int64_t n1, int64_t n2, int match, int R, uint8_t* out, int64_t out_stride2,
+                     cudaStream_t s) {
+    if (n1 == 0 || n2 == 0) return MR_OK;
+    uint8_t* plane = out;
+    int64_t plane_stride = out_stride2;
+    const int64_t line_tmp = (n1 + 15) / 16 * 16;
+    int rc;
+    if (R > 0) {
+        if ((rc = grow(ctx, &ctx->d_tmp, &ctx->d_tmp_cap, (size_t)line_tmp * n2))) return rc;
+        plane = ctx->d_tmp;
+        plane_stride = line_tmp;
+    }
+    int nl = 0;
+    cudaError_t e = mr_launch_categorize_props(ctx->pal, ctx->d_tex, match, px, stride2, (match & 2) ? sd : nullptr, sd_stride2,
+                                               (match & 4) ? st : nullptr, st_stride2, n1, n2, ctx->n_known, ctx->d_known_idx,
+                                               ctx->d_known_cat, plane, plane_stride,
+                                               (ctx->count_on && R == 0) ? ctx->d_counters : nullptr, ctx->sm_count, s, &nl);
+    ctx->launches += nl;
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "PixelProp categorise launch");
+    if (R > 0) {
+        MrJob c = make_job(ctx, plane, out, n1, n2, plane_stride, 1, R, 0, 0, out_stride2);
+        c.lut = nullptr;
+        c.padded = 1;
+        return run_clean(ctx, c, s, ctx->pal.K);
+    }
+    return MR_OK;
+}
+
+extern "C" int mr_categorize_clean_props_dev(mr_ctx* ctx, const double* px_dev, int64_t stride2, const double* std_dev,
+                                             int64_t std_stride2, const double* stripe_dev, int64_t stripe_stride2,
+                                             int64_t n1, int64_t n2, int match, int R, uint8_t* labels_dev,
+                                             int64_t out_stride2, void* stream) {
+    int rc = props_check(ctx, "mr_categorize_clean_props_dev", px_dev, stride2, std_dev, std_stride2, stripe_dev,
+                         stripe_stride2, n1, n2, match, R, labels_dev, out_stride2);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    return props_dev(ctx, px_dev, stride2, std_dev, std_stride2, stripe_dev, stripe_stride2, n1, n2, match, R, labels_dev,
+                     out_stride2, (cudaStream_t)stream);
+}
+
+extern "C" int mr_categorize_clean_props_host(mr_ctx* ctx, const double* px, int64_t stride2, const double* std_plane,
+                                              int64_t std_stride2, const double* stripe_plane, int64_t stripe_stride2,
+                                              int64_t n1, int64_t n2, int match, int R, uint8_t* labels_out,
+                                              int64_t out_stride2) {
+    int rc = props_check(ctx, "mr_categorize_clean_props_host", px, stride2, std_plane, std_stride2, stripe_plane,
+                         stripe_stride2, n1, n2, match, R, labels_out, out_stride2);
+    if (rc) return rc;
+    if (n1 == 0 || n2 == 0) return MR_OK;
+    CK(cudaSetDevice(ctx->device));
+    const int64_t pitch = n1 * 24, line_out = (n1 + 15) / 16 * 16;
+    // pixels -> d_f64b; std plane | stripe plane -> d_f64; labels -> d_out
+    if ((rc = grow(ctx, &ctx->d_f64b, &ctx->d_f64b_cap, (size_t)pitch * n2))) return rc;
+    if ((rc = grow(ctx, &ctx->d_f64, &ctx->d_f64_cap, (size_t)pitch * n2))) return rc;
+    if ((rc = grow(ctx, &ctx->d_out, &ctx->d_out_cap, (size_t)line_out * n2))) return rc;
+    cudaStream_t s = ctx->s_main;
+    double* d_sd = reinterpret_cast<double*>(ctx->d_f64);
+    double* d_st = d_sd + n1 * n2;
+    CK(cudaMemcpy2DAsync(ctx->d_f64b, pitch, px, stride2, n1 * 24, n2, cudaMemcpyHostToDevice, s));
+    if (match & 2) CK(cudaMemcpy2DAsync(d_sd, n1 * 8, std_plane, std_stride2, n1 * 8, n2, cudaMemcpyHostToDevice, s));
+    if (match & 4) CK(cudaMemcpy2DAsync(d_st, n1 * 16, stripe_plane, stripe_stride2, n1 * 16, n2, cudaMemcpyHostToDevice, s));
+    rc = props_dev(ctx, reinterpret_cast<const double*>(ctx->d_f64b), pitch, d_sd, n1 * 8, d_st, n1 * 16, n1, n2, match, R,
+                   ctx->d_out, line_out, s);
     if (rc) return rc;
     CK(cudaMemcpy2DAsync(labels_out, out_stride2, ctx->d_out, line_out, n1, n2, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));

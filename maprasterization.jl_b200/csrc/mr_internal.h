@@ -122,3 +122,15 @@ size_t mr_balance_scratch_bytes(int64_t n1, int64_t n2);
 cudaError_t mr_launch_balance(const double* coef21, const uint8_t* px, int64_t stride2, int64_t n1, int64_t n2,
                               double* scratch, double* out, int64_t out_stride2, int sm_count, cudaStream_t s,
                               int* n_launches);
+
+// texture features of match = (:color, :std, :stripe) and the categoriser on PixelProp pixels (mr_texture.cu)
+cudaError_t mr_launch_stds(const double* px, int64_t stride2, int64_t n1, int64_t n2, double* out, int64_t out_stride2,
+                           double* scratch, int sm_count, cudaStream_t s, int* n_launches);
+size_t mr_stripes_scratch_bytes(int64_t n1, int64_t n2);
+cudaError_t mr_launch_stripes(const double* px, int64_t stride2, int64_t n1, int64_t n2, int radius, double* out,
+                              int64_t out_stride2, double* scratch, int sm_count, cudaStream_t s, int* n_launches);
+cudaError_t mr_launch_categorize_props(const MrPalette& pal, const double* tex, int match, const double* px, int64_t stride2,
+                                       const double* sd, int64_t sd_stride2, const double* st, int64_t st_stride2,
+                                       int64_t n1, int64_t n2, int64_t n_known, const int64_t* known_idx,
+                                       const uint8_t* known_cat, uint8_t* out, int64_t out_stride2,
+                                       MrCountersDev* counters, int sm_count, cudaStream_t s, int* n_launches);

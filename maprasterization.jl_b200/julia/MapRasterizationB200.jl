@@ -22,7 +22,7 @@ using ColorTypes, FixedPointNumbers, Statistics
 import Neighborhoods: Window
 
 export categorize, clean, categorize_clean, categorize_u8, clean_u8, categorize_clean_u8, clean_segments,
-       clean_segments_u8, fill_gaps, fill_gaps_u8, blur, balance, rasterize, MapSelection, Context, MultiContext, Palette
+       clean_segments_u8, fill_gaps, fill_gaps_u8, blur, balance, stds, stripes, rasterize, MapSelection, Context, MultiContext, Palette
 
 const libmaprast = get(ENV, "LIBMAPRAST", joinpath(@__DIR__, "..", "libmaprast.so"))
 const DEFAULT_CATEGORY_TOLERANCE = 2.0            # src/selectcolors.jl:1
@@ -99,10 +99,14 @@ function _upload(ctx::Context, pal::Palette)
         ctx.ptr, K, pal.mean, pal.lo, pal.hi, pal.colourspace, C))
 end
 
+# -> match bits (1 color | 2 std | 4 stripe); `match` must be a non-empty subset of (:color, :std, :stripe) in that
+# order (what `_match_from_bools` produces, src/selectcolors.jl:661-668: the error is a left-folded mean over it)
 _check_match(match, segmented) = begin
     m = match isa Val ? typeof(match).parameters[1] : Tuple(match)
-    m == (:color,) || throw(ArgumentError("match=$m is not supported by the B200 hot path (only (:color,))"))
-    segmented && throw(ArgumentError("segmented=true is not supported by the B200 hot path"))
+    ok = !isempty(m) && all(x -> x in (:color, :std, :stripe), m) && collect(m) == [x for x in (:color, :std, :stripe) if x in m]
+    ok || throw(ArgumentError("match=$m: must be a non-empty subset of (:color, :std, :stripe) in that order"))
+    segmented && throw(ArgumentError("segmented=true (fast_scanning: a sequential scan) is not supported on the GPU path"))
+    return Cint((:color in m) + 2 * (:std in m) + 4 * (:stripe in m))
 end
 
 # ---- known-category plane (`_set_categories!`, src/selectcolors.jl:670-681) ---------------------------
@@ -130,7 +134,7 @@ Fused clean(categorize(img)): UInt8 labels, 0 = no match.  `known`: optional pla
 function categorize_clean_u8(img::AbstractMatrix{T}, points_or_palette; tolerances=nothing,
         hood=Window{1}(), match=(:color,), segmented=false, scan_threshold=0.1, known=nothing,
         ctx::Context=default_context()) where {T<:Union{RGB{N0f8},RGBA{N0f8}}}
-    _check_match(match, segmented)
+    _check_match(match, segmented) == 1 || throw(ArgumentError("std / stripe matching takes the blurred RGB{Float64} image"))
     A = img isa Matrix ? img : Matrix(img)                       # dense, column-major, n1 = size(A, 1)
     pal = points_or_palette isa Palette ? points_or_palette :
           Palette(A, points_or_palette; tolerances=something(tolerances, fill(DEFAULT_CATEGORY_TOLERANCE, length(points_or_palette))))
@@ -209,23 +213,94 @@ function balance(img::AbstractMatrix{RGB{N0f8}}, points; category_bitindex=[c ==
     return _rebuild(img, out)
 end
 
-"Fused clean(categorize(img)) on RGB{Float64} pixels (what `blur` / `_balance` hand to `_categorize`): direct Float64 evaluation."
+"""
+`_stds(A)` (src/selectcolors.jl:706-715): the "texture" plane of the blurred RGB{Float64} image
+(5 x 5 per-channel sample standard deviations, summed, divided by the image maximum).
+"""
+function stds(img::AbstractMatrix{RGB{Float64}}; ctx::Context=default_context())
+    A = img isa Matrix ? img : Matrix(img)
+    n1, n2 = size(A)
+    out = Matrix{Float64}(undef, n1, n2)
+    GC.@preserve A out begin
+        _check(ctx, ccall((:mr_stds_host, libmaprast), Cint,
+            (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Int64),
+            ctx.ptr, Ptr{Float64}(pointer(A)), n1, n2, n1 * 24, pointer(out), n1 * 8))
+    end
+    return _rebuild(img, out)
+end
+
+"`_stripes(img; radius=3)` (src/stripes.jl:20-35): `Matrix{NTuple{2,Float64}}` of (vert - horz, angle45 - angle135)."
+function stripes(img::AbstractMatrix{RGB{Float64}}; radius::Int=3, ctx::Context=default_context())
+    A = img isa Matrix ? img : Matrix(img)
+    n1, n2 = size(A)
+    out = Matrix{NTuple{2,Float64}}(undef, n1, n2)
+    GC.@preserve A out begin
+        _check(ctx, ccall((:mr_stripes_host, libmaprast), Cint,
+            (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Cint, Ptr{Float64}, Int64),
+            ctx.ptr, Ptr{Float64}(pointer(A)), n1, n2, n1 * 24, radius, Ptr{Float64}(pointer(out)), n1 * 16))
+    end
+    return _rebuild(img, out)
+end
+
+# `std` / `stripe` of _component_stats(::Vector{<:PixelProp}) (src/categories.jl:10-17) at the clicked points,
+# bounds as in :131-133; rows of a `missing` category stay NaN (its colour mean is +Inf)
+function _upload_texture(ctx::Context, std, stripe, points, tolerances)
+    K = length(points)
+    sm = fill(NaN, K); slo = fill(NaN, K); shi = fill(NaN, K)
+    tm = fill(NaN, 2, K); tlo = fill(NaN, 2, K); thi = fill(NaN, 2, K)
+    stat(v, t) = (mean(v), minimum(v) - std_(v) * t, maximum(v) + std_(v) * t)
+    std_(v) = Statistics.std(v)
+    for (k, pv) in enumerate(points)
+        length(pv) == 0 && continue
+        idx = [CartesianIndex(round(Int, p[1]), round(Int, p[2])) for p in pv]
+        sm[k], slo[k], shi[k] = stat([std === nothing ? 0.0 : std[i] for i in idx], tolerances[k])
+        for e in 1:2
+            tm[e, k], tlo[e, k], thi[e, k] = stat([stripe === nothing ? 0.0 : stripe[i][e] for i in idx], tolerances[k])
+        end
+    end
+    _check(ctx, ccall((:mr_set_texture_stats, libmaprast), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        ctx.ptr, K, sm, slo, shi, tm, tlo, thi))
+end
+
+"""
+Fused clean(categorize(img)) on RGB{Float64} pixels (what `blur` / `_balance` hand to `_categorize`): direct
+Float64 evaluation.  With `:std` / `:stripe` in `match` the pixels are PixelProps (src/categories.jl:45-48):
+`std` / `stripe` are the planes of `stds` / `stripes` (`nothing` = the reference's initial all-zero plane) and
+`points_or_palette` must be the clicked points (the texture statistics are sampled at them).
+"""
 function categorize_clean_u8(img::AbstractMatrix{RGB{Float64}}, points_or_palette; tolerances=nothing,
         hood=Window{1}(), match=(:color,), segmented=false, scan_threshold=0.1, known=nothing,
-        ctx::Context=default_context())
-    _check_match(match, segmented)
+        std=nothing, stripe=nothing, ctx::Context=default_context())
+    bits = _check_match(match, segmented)
     A = img isa Matrix ? img : Matrix(img)
-    pal = points_or_palette isa Palette ? points_or_palette :
-          Palette(A, points_or_palette; tolerances=something(tolerances, fill(DEFAULT_CATEGORY_TOLERANCE, length(points_or_palette))))
+    tol = points_or_palette isa Palette ? nothing :
+          something(tolerances, fill(DEFAULT_CATEGORY_TOLERANCE, length(points_or_palette)))
+    pal = points_or_palette isa Palette ? points_or_palette : Palette(A, points_or_palette; tolerances=tol)
     _upload(ctx, pal)
     n1, n2 = size(A)
     out = Matrix{UInt8}(undef, n1, n2)
+    S = (bits & 2) != 0 ? Matrix{Float64}(std === nothing ? zeros(n1, n2) : std) : nothing
+    P = (bits & 4) != 0 ? Matrix{NTuple{2,Float64}}(stripe === nothing ? fill((0.0, 0.0), n1, n2) : stripe) : nothing
+    if bits != 1
+        points_or_palette isa Palette && throw(ArgumentError("std / stripe matching needs the clicked points, not a Palette"))
+        _upload_texture(ctx, S, P, points_or_palette, tol)
+    end
     _set_known(ctx, known, size(A))
     try
-        GC.@preserve A out begin
-            _check(ctx, ccall((:mr_categorize_clean_f64_host, libmaprast), Cint,
-                (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Cint, Ptr{UInt8}, Int64),
-                ctx.ptr, Ptr{Float64}(pointer(A)), n1, n2, n1 * 24, _radius(hood), pointer(out), n1))
+        GC.@preserve A out S P begin
+            if bits == 1
+                _check(ctx, ccall((:mr_categorize_clean_f64_host, libmaprast), Cint,
+                    (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Cint, Ptr{UInt8}, Int64),
+                    ctx.ptr, Ptr{Float64}(pointer(A)), n1, n2, n1 * 24, _radius(hood), pointer(out), n1))
+            else
+                _check(ctx, ccall((:mr_categorize_clean_props_host, libmaprast), Cint,
+                    (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Int64, Int64, Cint, Cint,
+                     Ptr{UInt8}, Int64),
+                    ctx.ptr, Ptr{Float64}(pointer(A)), n1 * 24, S === nothing ? Ptr{Float64}(C_NULL) : pointer(S), n1 * 8,
+                    P === nothing ? Ptr{Float64}(C_NULL) : Ptr{Float64}(pointer(P)), n1 * 16, n1, n2, bits, _radius(hood),
+                    pointer(out), n1))
+            end
         end
     finally
         known === nothing || _clear_known(ctx)
@@ -377,10 +452,20 @@ function rasterize(img::AbstractMatrix{T}, sel::MapSelection; hood=Window{0}(), 
     detrend = T <: RGB{N0f8} && balance_fit(A, sel.points; category_bitindex=collect(Bool, bal)) !== nothing
     pixels = detrend ? balance(A, sel.points; category_bitindex=collect(Bool, bal), ctx) : A
     pixels = blur_repeat > 0 ? blur(pixels; repeat=blur_repeat, ctx) : pixels
-    pal = Palette(pixels, sel.points; tolerances=collect(Float64, sel.settings.category_tolerances))
+    tol = collect(Float64, sel.settings.category_tolerances)
+    pal = Palette(pixels, sel.points; tolerances=tol)
     known = _known_plane(size(A), sel.points)
-    categorized = categorize_clean_u8(pixels, pal; hood, match=get(sel.settings, :match, (:color,)),
-        segmented=get(sel.settings, :segment, false), known, ctx)
+    match = get(sel.settings, :match, (:color,))
+    bits = _check_match(match, get(sel.settings, :segment, false))
+    if bits == 1
+        categorized = categorize_clean_u8(pixels, pal; hood, match, known, ctx)
+    else
+        # the "blur" button refreshes the texture planes of the matched properties (src/selectcolors.jl:457-462)
+        eltype(pixels) <: RGB{Float64} || (pixels = blur(pixels; repeat=0, ctx))      # A .* 1.0
+        S = (bits & 2) != 0 ? stds(pixels; ctx) : nothing
+        P = (bits & 4) != 0 ? stripes(pixels; radius=get(sel.settings, :stripe_radius, 2), ctx) : nothing
+        categorized = categorize_clean_u8(pixels, sel.points; tolerances=tol, hood, match, known, std=S, stripe=P, ctx)
+    end
     keep = get(sel.settings, :category_keep, fill(true, length(sel.points)))
     kept = _kept_categories(collect(Bool, keep))
     cleaned = clean_segments_u8(categorized, known; categories=kept,

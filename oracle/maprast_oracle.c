@@ -698,3 +698,192 @@ void mro_balance(const uint8_t* px, int64_t n1, int64_t n2, int64_t stride2, con
         }
 }
 
+
+/* =====================================================================================
+ * Texture features of the reference's default match = (:color, :std, :stripe):
+ *   _stds(A)            src/selectcolors.jl:706-715  (computed from the blurred RGB{Float64} image, :458)
+ *   _stripes(img; radius) src/stripes.jl:1-35        (:461)
+ *   _categorize on PixelProp with a match tuple   src/categories.jl:76-133 (:85-87, :96-101, :106-114, :122-133)
+ * PARITY UNPINNED: Neighborhoods.jl 0.1, Statistics' reduction order over a neighbourhood and Colors.jl's
+ * RGB -> HSL are not in the reference tree.  Decisions:
+ *  - neighbours outside the image are the zero colour (as for blur), their number is fixed;
+ *  - _stds: Window(2) = 5 x 5 incl. the centre in CartesianIndices order (d1 fastest); per channel
+ *    std = sqrt(sum((x - m)^2) / 24) with m = sum(x) / 25, both sums left-folded (the two-pass `varm` of an
+ *    array); pixel value (rs + gs) + bs; the image is divided by its maximum (0 / 0 = NaN as in Julia);
+ *  - HSL (only s and l are used): mx = max(r, g, b), mn = min(r, g, b), l = (mx + mn) / 2,
+ *    s = 0 if mx == mn, (mx - mn) / (mx + mn) if l < 0.5, else (mx - mn) / ((2 - mx) - mn);
+ *  - _stripes: direction (di, dj) in vert (1, 0), horz (0, 1), angle45 (1, 1), angle135 (1, -1) (d1, d2);
+ *    side a = offsets x (di, dj), x = -radius .. -1, side b = x = 1 .. radius; mean over a side =
+ *    left-folded sum of ((s - s_n)^2 + (l - l_n)^2) divided by radius; direction value = min(a, b);
+ *    pixel value (vert - horz, angle45 - angle135); the image is divided by
+ *    m = (mean(abs first) + mean(abs last)) / 2, each mean = sum / (n1 n2) with the sum taken in the fixed
+ *    order of mro_balance (chunks of 256 pixels of a line, the chunk sums of a line, the lines). */
+static void hsl_sl(const double* rgb, double* s, double* l) {
+    const double r = rgb[0], g = rgb[1], b = rgb[2];
+    double mx = r > g ? r : g, mn = r < g ? r : g;
+    mx = mx > b ? mx : b;
+    mn = mn < b ? mn : b;
+    *l = (mx + mn) / 2.0;
+    if (mx == mn) *s = 0.0;
+    else if (*l < 0.5) *s = (mx - mn) / (mx + mn);
+    else *s = (mx - mn) / ((2.0 - mx) - mn);
+}
+
+static const double ZERO3[3] = {0.0, 0.0, 0.0};
+static const double* px_or_zero(const double* px, int64_t n1, int64_t n2, int64_t stride2, int64_t a, int64_t b) {
+    if (a < 0 || a >= n1 || b < 0 || b >= n2) return ZERO3;
+    return (const double*)((const uint8_t*)px + b * stride2) + a * 3;
+}
+
+/* raw: the un-normalised plane (may be NULL); returns the maximum */
+void mro_stds(const double* px, int64_t n1, int64_t n2, int64_t stride2, double* out, int64_t out_stride2) {
+    double mxv = 0.0;
+    int have = 0;
+    for (int64_t j = 0; j < n2; ++j)
+        for (int64_t i = 0; i < n1; ++i) {
+            double sd[3];
+            for (int c = 0; c < 3; ++c) {
+                double sum = 0.0;
+                for (int d2 = -2; d2 <= 2; ++d2)
+                    for (int d1 = -2; d1 <= 2; ++d1) sum = sum + px_or_zero(px, n1, n2, stride2, i + d1, j + d2)[c];
+                const double m = sum / 25.0;
+                double ss = 0.0;
+                for (int d2 = -2; d2 <= 2; ++d2)
+                    for (int d1 = -2; d1 <= 2; ++d1) {
+                        const double d = px_or_zero(px, n1, n2, stride2, i + d1, j + d2)[c] - m;
+                        ss = ss + d * d;
+                    }
+                sd[c] = sqrt(ss / 24.0);
+            }
+            const double v = (sd[0] + sd[1]) + sd[2];
+            ((double*)((uint8_t*)out + j * out_stride2))[i] = v;
+            if (!have || v > mxv) { mxv = v; have = 1; }       /* maximum (no NaN can occur: finite colours) */
+        }
+    for (int64_t j = 0; j < n2; ++j)
+        for (int64_t i = 0; i < n1; ++i) {
+            double* o = (double*)((uint8_t*)out + j * out_stride2) + i;
+            *o = *o / mxv;
+        }
+}
+
+void mro_stripes(const double* px, int64_t n1, int64_t n2, int64_t stride2, int radius, double* out,
+                 int64_t out_stride2) {
+    static const int DI[4] = {1, 0, 1, 1}, DJ[4] = {0, 1, 1, -1};   /* vert, horz, angle45, angle135 */
+    for (int64_t j = 0; j < n2; ++j)
+        for (int64_t i = 0; i < n1; ++i) {
+            double s0, l0, dir[4];
+            hsl_sl(px_or_zero(px, n1, n2, stride2, i, j), &s0, &l0);
+            for (int k = 0; k < 4; ++k) {
+                double side[2];
+                for (int sd = 0; sd < 2; ++sd) {
+                    double acc = 0.0;
+                    for (int t = 0; t < radius; ++t) {
+                        const int x = sd == 0 ? -radius + t : 1 + t;
+                        double sn, ln;
+                        hsl_sl(px_or_zero(px, n1, n2, stride2, i + DI[k] * x, j + DJ[k] * x), &sn, &ln);
+                        const double a = s0 - sn, b = l0 - ln;
+                        acc = acc + (a * a + b * b);
+                    }
+                    side[sd] = acc / (double)radius;
+                }
+                dir[k] = side[1] < side[0] ? side[1] : side[0];
+            }
+            double* o = (double*)((uint8_t*)out + j * out_stride2) + 2 * i;
+            o[0] = dir[0] - dir[1];
+            o[1] = dir[2] - dir[3];
+        }
+    double mean2[2];
+    for (int e = 0; e < 2; ++e) {
+        double total = 0.0;
+        for (int64_t j = 0; j < n2; ++j) {
+            double line = 0.0;
+            for (int64_t i0 = 0; i0 < n1; i0 += 256) {
+                double chunk = 0.0;
+                for (int64_t i = i0; i < n1 && i < i0 + 256; ++i)
+                    chunk = chunk + fabs(((const double*)((const uint8_t*)out + j * out_stride2))[2 * i + e]);
+                line = line + chunk;
+            }
+            total = total + line;
+        }
+        mean2[e] = total / (double)(n1 * n2);
+    }
+    const double m = (mean2[0] + mean2[1]) / 2.0;
+    for (int64_t j = 0; j < n2; ++j)
+        for (int64_t i = 0; i < 2 * n1; ++i) {
+            double* o = (double*)((uint8_t*)out + j * out_stride2) + i;
+            *o = *o / m;
+        }
+}
+
+/* _categorize(x::PixelProp, categories, tolerances, match) (src/categories.jl:76-82):
+ * error = mean over the matched properties, in the order (:color, :std, :stripe), of
+ *   color  ((r - mr)^2 + (g - mg)^2) + (b - mb)^2                        (:91-95)
+ *   std    (v - m)^2                                                      (:101)
+ *   stripe ((v1 - m1)^2 + (v2 - m2)^2) / 2                                (:96-100)
+ * (mean of a tuple = left-folded sum / count); first minimum; accepted when the pixel carries the
+ * winner's category (:110-112) or every matched property lies in the winner's box (:113, :122-133).
+ * match: bit 0 color, bit 1 std, bit 2 stripe.  A `missing` category has a colour mean of +Inf. */
+int mro_categorize_props(const double* rgb, double sd, const double* stripe, int match, int K,
+                         const double* mean, const double* lo, const double* hi,
+                         const double* sd_mean, const double* sd_lo, const double* sd_hi,
+                         const double* st_mean, const double* st_lo, const double* st_hi, int known) {
+    const int cnt = (match & 1) + ((match >> 1) & 1) + ((match >> 2) & 1);
+    int best = 0;
+    double beste = 0.0;
+    for (int c = 0; c < K; ++c) {
+        double e = 0.0;
+        int first = 1;
+        if (mean[3 * c] == INFINITY) e = INFINITY;                       /* ismissing(cat) ? typemax(Float64) */
+        else {
+            if (match & 1) {
+                const double d0 = rgb[0] - mean[3 * c], d1 = rgb[1] - mean[3 * c + 1], d2 = rgb[2] - mean[3 * c + 2];
+                const double t = (d0 * d0 + d1 * d1) + d2 * d2;
+                e = t; first = 0;
+            }
+            if (match & 2) {
+                const double d = sd - sd_mean[c];
+                const double t = d * d;
+                e = first ? t : e + t; first = 0;
+            }
+            if (match & 4) {
+                const double d0 = stripe[0] - st_mean[2 * c], d1 = stripe[1] - st_mean[2 * c + 1];
+                const double t = (d0 * d0 + d1 * d1) / 2.0;
+                e = first ? t : e + t; first = 0;
+            }
+            e = e / (double)cnt;
+        }
+        if (c == 0 || e < beste) { beste = e; best = c; }
+    }
+    if (known != 0) return best + 1 == known ? best + 1 : 0;
+    int ok = 1;
+    if (match & 1)
+        for (int k = 0; k < 3; ++k) ok = ok && rgb[k] >= lo[3 * best + k] && rgb[k] <= hi[3 * best + k];
+    if (match & 2) ok = ok && sd >= sd_lo[best] && sd <= sd_hi[best];
+    if (match & 4)
+        for (int k = 0; k < 2; ++k) ok = ok && stripe[k] >= st_lo[2 * best + k] && stripe[k] <= st_hi[2 * best + k];
+    return ok ? best + 1 : 0;
+}
+
+void mro_categorize_props_image(const double* px, int64_t stride2, const double* sd, int64_t sd_stride2,
+                                const double* stripe, int64_t st_stride2, int64_t n1, int64_t n2, int match, int K,
+                                const double* mean, const double* lo, const double* hi,
+                                const double* sd_mean, const double* sd_lo, const double* sd_hi,
+                                const double* st_mean, const double* st_lo, const double* st_hi,
+                                int64_t n_known, const int64_t* known_idx, const uint8_t* known_cat,
+                                uint8_t* out, int64_t out_stride2) {
+    for (int pass = 0; pass < 2; ++pass) {
+        const int64_t n = pass == 0 ? n1 * n2 : n_known;
+        for (int64_t k = 0; k < n; ++k) {
+            const int64_t lin = pass == 0 ? k : known_idx[k];
+            const int kn = pass == 0 ? 0 : known_cat[k];
+            const int64_t i = lin % n1, j = lin / n1;
+            if (j >= n2 || (pass == 1 && kn == 0)) continue;
+            const double* p = (const double*)((const uint8_t*)px + j * stride2) + i * 3;
+            const double v = sd ? ((const double*)((const uint8_t*)sd + j * sd_stride2))[i] : 0.0;
+            const double zero2[2] = {0.0, 0.0};
+            const double* s = stripe ? (const double*)((const uint8_t*)stripe + j * st_stride2) + 2 * i : zero2;
+            out[j * out_stride2 + i] = (uint8_t)mro_categorize_props(p, v, s, match, K, mean, lo, hi, sd_mean, sd_lo,
+                                                                      sd_hi, st_mean, st_lo, st_hi, kn);
+        }
+    }
+}

@@ -124,6 +124,26 @@ void mro_balance(const uint8_t* px, int64_t n1, int64_t n2, int64_t stride2, con
 
 int mro_max_threads(void);
 
+/* Texture features of match = (:color, :std, :stripe); PARITY UNPINNED (decisions in
+ * the .c file).  px: RGB{Float64}, 3 doubles per pixel; strides in bytes.
+ * mro_stds: src/selectcolors.jl:706-715, one double per pixel out.
+ * mro_stripes: src/stripes.jl:20-35, two doubles per pixel out. */
+void mro_stds(const double* px, int64_t n1, int64_t n2, int64_t stride2, double* out, int64_t out_stride2);
+void mro_stripes(const double* px, int64_t n1, int64_t n2, int64_t stride2, int radius, double* out,
+                 int64_t out_stride2);
+/* src/categories.jl:76-133 on a PixelProp; match: bit 0 color, bit 1 std, bit 2 stripe */
+int mro_categorize_props(const double* rgb, double sd, const double* stripe, int match, int K,
+                         const double* mean, const double* lo, const double* hi,
+                         const double* sd_mean, const double* sd_lo, const double* sd_hi,
+                         const double* st_mean, const double* st_lo, const double* st_hi, int known);
+void mro_categorize_props_image(const double* px, int64_t stride2, const double* sd, int64_t sd_stride2,
+                                const double* stripe, int64_t st_stride2, int64_t n1, int64_t n2, int match, int K,
+                                const double* mean, const double* lo, const double* hi,
+                                const double* sd_mean, const double* sd_lo, const double* sd_hi,
+                                const double* st_mean, const double* st_lo, const double* st_hi,
+                                int64_t n_known, const int64_t* known_idx, const uint8_t* known_cat,
+                                uint8_t* out, int64_t out_stride2);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,6 +67,11 @@ def lib():
         L.mro_categorize_f64_image.argtypes = [C.c_void_p, _i64, _i64, _i64, C.c_int, _f64p, _f64p, _f64p, _i64,
                                                C.c_void_p, C.c_void_p, _u8p, _i64]
         L.mro_balance.argtypes = [_u8p, _i64, _i64, _i64, _f64p, C.c_void_p, _i64, C.c_void_p]
+        L.mro_stds.argtypes = [C.c_void_p, _i64, _i64, _i64, C.c_void_p, _i64]
+        L.mro_stripes.argtypes = [C.c_void_p, _i64, _i64, _i64, C.c_int, C.c_void_p, _i64]
+        L.mro_categorize_props_image.argtypes = [C.c_void_p, _i64, C.c_void_p, _i64, C.c_void_p, _i64, _i64, _i64,
+                                                 C.c_int, C.c_int] + [_f64p] * 9 + [_i64, C.c_void_p, C.c_void_p,
+                                                                                    C.c_void_p, _i64]
         L.mro_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -238,6 +243,54 @@ def categorize_f64_image(px, mean, lo, hi, known_idx=None, known_cat=None):
         nk = ki.size
     lib().mro_categorize_f64_image(px.ctypes.data, n1, n2, n1 * 24, mean.shape[0], mean, lo, hi, nk,
                                    ki.ctypes.data if nk else None, kc.ctypes.data if nk else None, out.ctypes.data, n1)
+    return out
+
+
+def stds(px):
+    """`_stds(A)` (src/selectcolors.jl:706-715): px (n2, n1, 3) float64 -> (n2, n1) float64."""
+    px = np.ascontiguousarray(px, dtype=np.float64)
+    n2, n1, _ = px.shape
+    out = np.empty((n2, n1), dtype=np.float64)
+    lib().mro_stds(px.ctypes.data, n1, n2, n1 * 24, out.ctypes.data, n1 * 8)
+    return out
+
+
+def stripes(px, radius=3):
+    """`_stripes(img; radius)` (src/stripes.jl:20-35): px (n2, n1, 3) float64 -> (n2, n1, 2) float64."""
+    px = np.ascontiguousarray(px, dtype=np.float64)
+    n2, n1, _ = px.shape
+    out = np.empty((n2, n1, 2), dtype=np.float64)
+    lib().mro_stripes(px.ctypes.data, n1, n2, n1 * 24, int(radius), out.ctypes.data, n1 * 16)
+    return out
+
+
+MATCH_BITS = {"color": 1, "std": 2, "stripe": 4}
+
+
+def categorize_props_image(px, sd, stripe, match, mean, lo, hi, sd_stats, st_stats, known_idx=None, known_cat=None):
+    """`_categorize` over PixelProp pixels with a match tuple (src/categories.jl:76-133).  sd_stats / st_stats:
+    (mean, lo, hi) of shape (K,) / (K, 2).  -> (n2, n1) uint8 labels."""
+    px = np.ascontiguousarray(px, dtype=np.float64)
+    n2, n1, _ = px.shape
+    bits = sum(MATCH_BITS[m] for m in match)
+    sd = None if sd is None else np.ascontiguousarray(sd, dtype=np.float64)
+    stripe = None if stripe is None else np.ascontiguousarray(stripe, dtype=np.float64)
+    mean, lo, hi = _f64(mean), _f64(lo), _f64(hi)
+    K = mean.shape[0]
+    sdm, sdl, sdh = (_f64(np.asarray(a, dtype=np.float64).reshape(K)) for a in sd_stats)
+    stm, stl, sth = (_f64(np.asarray(a, dtype=np.float64).reshape(K, 2)) for a in st_stats)
+    out = np.empty((n2, n1), dtype=np.uint8)
+    nk = 0
+    ki = kc = None
+    if known_idx is not None and len(known_idx):
+        ki = np.ascontiguousarray(known_idx, dtype=np.int64)
+        kc = np.ascontiguousarray(known_cat, dtype=np.uint8)
+        nk = ki.size
+    lib().mro_categorize_props_image(px.ctypes.data, n1 * 24, None if sd is None else sd.ctypes.data, n1 * 8,
+                                     None if stripe is None else stripe.ctypes.data, n1 * 16, n1, n2, bits, K,
+                                     mean, lo, hi, sdm, sdl, sdh, stm, stl, sth, nk,
+                                     ki.ctypes.data if nk else None, kc.ctypes.data if nk else None,
+                                     out.ctypes.data, n1)
     return out
 
 

@@ -1,0 +1,163 @@
+"""GPU (-m gpu): the texture features of the reference's default match = (:color, :std, :stripe) --
+`_stds` (/root/reference/src/selectcolors.jl:706-715), `_stripes` (src/stripes.jl:20-35) -- and the categoriser on
+PixelProp pixels (src/categories.jl:76-133 with a match tuple) through the C ABI: Float64 planes bit-identical
+to the oracle, labels identical.  Parity unpinned by reference fixtures (none exist)."""
+import numpy as np
+import pytest
+import torch
+
+from util import mismatches, random_palette
+
+pytestmark = pytest.mark.gpu
+
+
+def blurred_like(rng, shape):
+    """a plausible blurred scan: smooth patches + noise, some grey and some bright pixels"""
+    n2, n1 = shape
+    base = rng.random((n2 // 8 + 2, n1 // 8 + 2, 3))
+    img = np.repeat(np.repeat(base, 8, axis=0), 8, axis=1)[:n2, :n1] * 0.8 + rng.random((n2, n1, 3)) * 0.2
+    img[rng.random((n2, n1)) < 0.05] = rng.random()            # grey pixels: the s = 0 branch of HSL
+    return np.ascontiguousarray(img)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (1, 40), (33, 1), (37, 53), (70, 600)])
+def test_stds_bit_identical(ctx, oracle, shape):
+    rng = np.random.default_rng(shape[0] * 7 + shape[1])
+    px = blurred_like(rng, shape)
+    with np.errstate(invalid="ignore"):
+        want = oracle.stds(px)
+    got = ctx.stds_host(px)
+    assert got.tobytes() == want.tobytes()
+
+
+def test_stds_of_a_flat_image_is_nan_like_julia(ctx, oracle):
+    px = np.zeros((9, 12, 3))          # every std is 0: 0 / maximum = 0 / 0 = NaN
+    with np.errstate(invalid="ignore"):
+        want = oracle.stds(px)
+    got = ctx.stds_host(px)
+    assert np.isnan(got).all() and got.tobytes() == want.tobytes()
+
+
+@pytest.mark.parametrize("radius", [1, 2, 3, 7])
+@pytest.mark.parametrize("shape", [(1, 1), (1, 300), (33, 2), (37, 53), (40, 600)])
+def test_stripes_bit_identical(ctx, oracle, radius, shape):
+    rng = np.random.default_rng(radius * 1000 + shape[0] * 7 + shape[1])
+    px = blurred_like(rng, shape)
+    px[0, 0] = (0.9, 0.95, 0.99)       # l >= 0.5 branch
+    with np.errstate(invalid="ignore", divide="ignore"):
+        want = oracle.stripes(px, radius)
+    got = ctx.stripes_host(px, radius)
+    assert got.tobytes() == want.tobytes()
+
+
+def test_texture_device_entries_with_pitches(ctx, oracle):
+    rng = np.random.default_rng(17)
+    n2, n1 = 45, 77
+    px = blurred_like(rng, (n2, n1))
+    dev = torch.device("cuda", 0)
+    ip = n1 * 24 + 40
+    d_in = torch.zeros((n2, ip // 8), dtype=torch.float64, device=dev)
+    d_in[:, :n1 * 3] = torch.from_numpy(px.reshape(n2, n1 * 3)).to(dev)
+    s = torch.cuda.current_stream().cuda_stream
+    op = n1 * 8 + 24
+    d_out = torch.full((n2, op // 8), -7.0, dtype=torch.float64, device=dev)
+    ctx._ck(ctx._L.mr_stds_dev(ctx._h, d_in.data_ptr(), n1, n2, ip, d_out.data_ptr(), op, s))
+    torch.cuda.synchronize()
+    assert d_out[:, :n1].cpu().numpy().tobytes() == oracle.stds(px).tobytes()
+    assert bool((d_out[:, n1:] == -7.0).all())              # nothing written outside the lines
+    op = n1 * 16 + 8
+    d_out = torch.full((n2, op // 8), -7.0, dtype=torch.float64, device=dev)
+    ctx._ck(ctx._L.mr_stripes_dev(ctx._h, d_in.data_ptr(), n1, n2, ip, 2, d_out.data_ptr(), op, s))
+    torch.cuda.synchronize()
+    assert d_out[:, :2 * n1].cpu().numpy().reshape(n2, n1, 2).tobytes() == oracle.stripes(px, 2).tobytes()
+    assert bool((d_out[:, 2 * n1:] == -7.0).all())
+
+
+MATCHES = [("color",), ("color", "std"), ("color", "stripe"), ("color", "std", "stripe"), ("std", "stripe"), ("std",),
+           ("stripe",)]
+
+
+@pytest.mark.parametrize("match", MATCHES)
+@pytest.mark.parametrize("R", [0, 2])
+def test_props_categorise_clean_random(ctx, mr, oracle, match, R):
+    rng = np.random.default_rng(1300 + len(match) * 10 + R + len(match[0]))
+    n2, n1, K = 83, 121, 7
+    mean, mn, mx, sd, tol = random_palette(rng, K)
+    mean[4] = np.inf                                          # a `missing` category
+    pal = mr.Palette(mean, mn, mx, sd, tol)
+    ctx.set_palette(pal.mean, pal.lo, pal.hi)
+    ctx.palette = None
+    sdm = rng.random(K) * 0.6
+    stm = rng.normal(0, 1, (K, 2))
+    sds = (sdm, sdm - 0.1 - rng.random(K) * 0.3, sdm + 0.1 + rng.random(K) * 0.3)
+    sts = (stm, stm - 0.4 - rng.random((K, 2)), stm + 0.4 + rng.random((K, 2)))
+    ctx.set_texture_stats(*sds, *sts)
+    which = rng.integers(0, K, size=(n2, n1))
+    which[which == 4] = 0
+    px = mean[which] + rng.normal(0, 0.03, size=(n2, n1, 3))
+    px[rng.random((n2, n1)) < 0.1] = rng.random(3)
+    std = sdm[which] + rng.normal(0, 0.1, size=(n2, n1))
+    stripe = stm[which] + rng.normal(0, 0.35, size=(n2, n1, 2))
+    idx = np.unique(rng.integers(0, n1 * n2, size=60))
+    cat = rng.integers(1, K + 1, size=idx.size).astype(np.uint8)
+    bits = sum(mr.api.MATCH_BITS[m] for m in match)
+    for known in (False, True):
+        ctx.set_known(idx, cat) if known else ctx.set_known(None)
+        try:
+            got = ctx.categorize_clean_props_host(px, std if bits & 2 else None, stripe if bits & 4 else None, bits, R)
+        finally:
+            ctx.set_known(None)
+        lab = oracle.categorize_props_image(px, std, stripe, match, pal.mean, pal.lo, pal.hi, sds, sts,
+                                            idx if known else None, cat if known else None)
+        want = oracle.majority(lab, R) if R else lab
+        assert mismatches(got, want) == 0
+        assert R > 0 or len(np.unique(got)) > 2
+    if match == ("color",):                                   # bit 1 alone = the RGB{Float64} categoriser
+        assert mismatches(ctx.categorize_clean_props_host(px, None, None, 1, R), ctx.categorize_clean_f64_host(px, R)) == 0
+
+
+def test_props_need_texture_stats_and_planes(ctx, mr):
+    mean, mn, mx, sd, tol = random_palette(np.random.default_rng(1), 3)
+    pal = mr.Palette(mean, mn, mx, sd, tol)
+    ctx.set_palette(pal.mean, pal.lo, pal.hi)                 # a new palette drops the texture statistics
+    ctx.palette = None
+    px = np.zeros((4, 5, 3))
+    with pytest.raises(mr.MapRastError, match="mr_set_texture_stats"):
+        ctx.categorize_clean_props_host(px, np.zeros((4, 5)), None, 3, 0)
+    z1, z2 = np.zeros(3), np.zeros((3, 2))
+    ctx.set_texture_stats(z1, z1, z1, z2, z2, z2)
+    with pytest.raises(mr.MapRastError, match="null"):
+        ctx.categorize_clean_props_host(px, None, None, 3, 0)
+    with pytest.raises(mr.MapRastError, match="match"):
+        ctx.categorize_clean_props_host(px, None, None, 0, 0)
+    with pytest.raises(mr.MapRastError, match="radius"):
+        ctx.stripes_host(px, 0)
+    assert ctx.stds_host(np.zeros((0, 0, 3))).shape == (0, 0)
+
+
+def test_rasterize_with_the_default_match(ctx, mr, oracle):
+    """the reference's DEFAULT settings (match = (:color, :std, :stripe), blur_repeat = 1, stripe_radius = 2)
+    through `rasterize`: balance (too few points: A .* 1.0) -> blur -> stds / stripes -> statistics at the clicked
+    points -> PixelProp categorise, against the same chain on the oracle"""
+    from maprast_b200 import synth
+    seed, pal_rgb, stats, spec = synth.config_workload(1)
+    n1, n2 = 240, 180
+    img = oracle.synth_scan(seed, 0, pal_rgb, n1, n2)
+    rng = np.random.default_rng(4)
+    K = 4
+    points = [[(float(rng.integers(3, n1 - 2)), float(rng.integers(3, n2 - 2))) for _ in range(6)] for _ in range(K)]
+    tol = np.full(K, 3.0)
+    sel = mr.MapSelection(settings={"match": ("color", "std", "stripe"), "blur_repeat": 1, "stripe_radius": 2,
+                                    "category_tolerances": tol, "category_balance": [False] * K,
+                                    "prune_threshold": 0, "line_threshold": 0.0, "fill_repeat": 0}, points=points)
+    got = mr.rasterize(img, sel, ctx=ctx)["categorized"]
+    blurred = oracle.blur(img, 1, 1)
+    std, stripe = oracle.stds(blurred), oracle.stripes(blurred, 2)
+    pal = mr.Palette.from_points(blurred, points, tol)
+    tex = mr.TextureStats.from_points(std, stripe, points, tol)
+    (slo, shi), (tlo, thi) = tex.bounds()
+    kidx, kcat = mr.api._known_from_points(points, n1)
+    want = oracle.categorize_props_image(blurred, std, stripe, ("color", "std", "stripe"), pal.mean, pal.lo, pal.hi,
+                                         (tex.std["mean"], slo, shi), (tex.stripe["mean"], tlo, thi), kidx, kcat)
+    assert mismatches(got, want) == 0
+    assert (got != 0).sum() > 0

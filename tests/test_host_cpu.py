@@ -62,7 +62,11 @@ def test_unsupported_options_raise(mr):
     img = np.zeros((4, 4, 3), dtype=np.uint8)
     pal = mr.Palette([[0.5] * 3], [[0.4] * 3], [[0.6] * 3], [[0.1] * 3])
     with pytest.raises(ValueError, match="match"):
-        mr.categorize(img, pal, match=("color", "std", "stripe"))
+        mr.categorize(img, pal, match=("color", "std", "stripe"))      # texture matching takes the RGB{Float64} image
+    with pytest.raises(ValueError, match="match"):
+        mr.categorize(img, pal, match=("std", "color"))                # not the order of _match_from_bools
+    with pytest.raises(ValueError, match="match"):
+        mr.categorize(img, pal, match=())
     with pytest.raises(ValueError, match="segmented"):
         mr.categorize(img, pal, segmented=True)
     with pytest.raises(ValueError, match="uint8"):
