@@ -371,7 +371,7 @@ def test_map_selection_pipeline(ctx, mr, oracle):
     with pytest.raises(ValueError):
         mr.rasterize(scan, mr.MapSelection(settings=dict(segment=True), points=points), ctx=ctx)
     with pytest.raises(ValueError):
-        mr.rasterize(scan, mr.MapSelection(settings=dict(match=("color", "std")), points=points), ctx=ctx)
+        mr.rasterize(scan, mr.MapSelection(settings=dict(match=("std", "color")), points=points), ctx=ctx)   # order
     # the "fill" stage (src/selectcolors.jl:490-501) on the pruned labels
     want_fill = oracle.fill_gaps(want_clean, scan, pal.mean, list(sel.kept_categories()), known=known,
                                  repeat=1)
