@@ -693,7 +693,39 @@ def run_ours(args, rank, world, local_rank):
                     "roofline": {"bound": "hbm" if key == "blur" else "fp64 issue (HBM figure for reference)",
                                  "algorithmic_bytes_per_px": bpp_alg, "achieved": bpp_alg * n1 * bl / (ms * 1e-3) / 1e9,
                                  "peak": peak, "unit": "GB/s", "frac": bpp_alg * n1 * bl / (ms * 1e-3) / 1e9 / peak}}
-            del f64, lab64
+            # texture features of the default match = (:color, :std, :stripe) on the blurred image
+            # (_stds src/selectcolors.jl:706-715, _stripes src/stripes.jl:20-35, PixelProp categoriser)
+            sdp = torch.empty((bl, n1), dtype=torch.float64, device=dev)
+            stp = torch.empty((bl, n1, 2), dtype=torch.float64, device=dev)
+            K_ = stats.K
+            z1, z2 = np.full(K_, 0.5), np.zeros((K_, 2))
+            ctx.set_texture_stats(z1, z1 - 0.6, z1 + 0.6, z2, z2 - 50.0, z2 + 50.0)
+            def _stds():
+                ctx._ck(L.mr_stds_dev(ctx._h, f64.data_ptr(), n1, bl, n1 * 24, sdp.data_ptr(), n1 * 8, None))
+            def _stripes():
+                ctx._ck(L.mr_stripes_dev(ctx._h, f64.data_ptr(), n1, bl, n1 * 24, 2, stp.data_ptr(), n1 * 16, None))
+            def _props():
+                ctx._ck(L.mr_categorize_clean_props_dev(ctx._h, f64.data_ptr(), n1 * 24, sdp.data_ptr(), n1 * 8, stp.data_ptr(),
+                                                        n1 * 16, n1, bl, 7, 0, lab64.data_ptr(), n1, None))
+            for fn, key, what, bpp_alg in ((_stds, "stds", "_stds(blurred): RGB{Float64} in, Float64 plane out", 32),
+                                           (_stripes, "stripes", "_stripes(blurred; radius=2): RGB{Float64} in, 2 x Float64 out", 40),
+                                           (_props, "categorize_props", "categorise PixelProp pixels, match = (:color, :std, :stripe)", 49)):
+                fn()
+                torch.cuda.synchronize()
+                l0 = ctx.launch_count()
+                e0.record()
+                for _ in range(reps):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / reps
+                res["next_rows"][key] = {
+                    "what": what + f", first {bl} lines, device resident", "value": n1 * bl / (ms * 1e-3) / 1e6, "unit": UNIT,
+                    "ms": ms, "gpu_launches_per_call": (ctx.launch_count() - l0) / reps,
+                    "roofline": {"bound": "fp64 issue (HBM figure for reference)",
+                                 "algorithmic_bytes_per_px": bpp_alg, "achieved": bpp_alg * n1 * bl / (ms * 1e-3) / 1e9,
+                                 "peak": peak, "unit": "GB/s", "frac": bpp_alg * n1 * bl / (ms * 1e-3) / 1e9 / peak}}
+            del f64, lab64, sdp, stp
         # the standalone Window majority filter, clean(labels; hood): categorise-only labels in, device resident
         pre = torch.empty_like(out)
         ctx.categorize_clean_dev(own, n1, nb, n1 * 3, 3, 0, pre, n1)

@@ -992,9 +992,10 @@ static int cat_f64_dev(mr_ctx* ctx, const double* px, int64_t n1, int64_t n2, in
         plane_stride = line_tmp;
     }
     int nl = 0;
-    cudaError_t e = mr_launch_categorize_f64(ctx->pal, px, stride2, n1, n2, ctx->n_known, ctx->d_known_idx, ctx->d_known_cat,
-                                             plane, plane_stride, (ctx->count_on && R == 0) ? ctx->d_counters : nullptr,
-                                             ctx->sm_count, s, &nl);
+    // colour-only matching = the PixelProp categoriser with match = color (mr_texture.cu)
+    cudaError_t e = mr_launch_categorize_props(ctx->pal, nullptr, 1, px, stride2, nullptr, 0, nullptr, 0, n1, n2, ctx->n_known,
+                                               ctx->d_known_idx, ctx->d_known_cat, plane, plane_stride,
+                                               (ctx->count_on && R == 0) ? ctx->d_counters : nullptr, ctx->sm_count, s, &nl);
     ctx->launches += nl;
     if (e != cudaSuccess) return fail_cuda(ctx, e, "Float64 categorise launch");
     if (R > 0) {

@@ -1,8 +1,8 @@
 // mr_blur.cu -- the colour pre-smoothing of the reference and the categoriser on its output:
 //   blur(A; hood = Window{R}(), repeat)   src/blur.jl:6-14: every pass replaces a pixel by
 //       mean(neighbors(h)) of its Window{R} (centre included), in RGB{Float64};
-//   _categorize on RGB{Float64} pixels       src/categories.jl:68-73,76-95 (what `blur` / `_balance` hand it;
-//       the reference's own known-answer vectors are Float64 colours).
+// (The categoriser on RGB{Float64} pixels, src/categories.jl:68-73,76-95, is the PixelProp categoriser of
+//  mr_texture.cu with match = color.)
 // The exact-table trick of the N0f8 path does not apply (the colour is no longer one of 2^24 values):
 // every pixel is evaluated directly in Float64 with the operations of mr_device.cuh.
 //
@@ -12,8 +12,7 @@
 // (1 / count) * colour), neighbours outside the image contribute the zero colour
 // (boundary = Remove(zero)), output of the size of the input.  Adding 0.0 is exact, so skipping the
 // outside neighbours IS adding them.
-// Bound: FP64 issue (9 .. 49 additions per channel and pixel) for the blur, FP64 issue (about 9 K
-// operations per pixel) for the categoriser; both stream 24 B per pixel of Float64 colour.
+// Bound: FP64 issue (9 .. 49 additions per channel and pixel); streams 24 B per pixel of Float64 colour.
 #include "mr_device.cuh"
 #include "mr_internal.h"
 
@@ -83,85 +82,6 @@ __global__ void __launch_bounds__(128) k_blur(const void* __restrict__ in, int64
                 }
         }
     }
-}
-
-// One thread = four consecutive pixels: the palette row of a category (shared memory, broadcast reads) is
-// fetched once for the four of them.
-__global__ void __launch_bounds__(128) k_categorize_f64(MrPalette pal, const double* __restrict__ px, int64_t stride2,
-                                                        int64_t n1, int64_t n2, uint8_t* __restrict__ out,
-                                                        int64_t out_stride2, MrCountersDev* counters) {
-    __shared__ double s_pal[254 * 9];   // mean | lo | hi, three channels each
-    const int K = pal.K;
-    for (int t = threadIdx.x; t < K * 3; t += blockDim.x) {
-        s_pal[t] = __ldg(pal.mean + t);
-        s_pal[K * 3 + t] = __ldg(pal.lo + t);
-        s_pal[K * 6 + t] = __ldg(pal.hi + t);
-    }
-    __syncthreads();
-    const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    unsigned nomatch = 0;
-    if (i0 < n1) {
-        const int n = (int)min((int64_t)4, n1 - i0);
-        for (int64_t j = blockIdx.y; j < n2; j += gridDim.y) {
-            const double* p = reinterpret_cast<const double*>(reinterpret_cast<const uint8_t*>(px) + j * stride2) + i0 * 3;
-            double x[4][3];
-            if (n == 4 && (reinterpret_cast<uintptr_t>(p) & 15u) == 0) {       // 96 contiguous bytes: six 16-byte loads
-#pragma unroll
-                for (int v = 0; v < 6; ++v) {
-                    const double2 t = __ldg(reinterpret_cast<const double2*>(p) + v);
-                    x[(2 * v) / 3][(2 * v) % 3] = t.x;
-                    x[(2 * v + 1) / 3][(2 * v + 1) % 3] = t.y;
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) x[q][c] = q < n ? __ldg(p + 3 * q + c) : 0.0;
-            }
-            int best[4] = {0, 0, 0, 0};
-            double beste[4] = {0.0, 0.0, 0.0, 0.0};
-            for (int c = 0; c < K; ++c) {
-                const double m0 = s_pal[3 * c], m1 = s_pal[3 * c + 1], m2 = s_pal[3 * c + 2];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const double d0 = __dsub_rn(x[q][0], m0), d1 = __dsub_rn(x[q][1], m1), d2 = __dsub_rn(x[q][2], m2);
-                    const double e = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
-                    if (c == 0 || e < beste[q]) { beste[q] = e; best[q] = c; }   // first minimum
-                }
-            }
-            uint32_t word = 0u;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const double* l = s_pal + K * 3 + 3 * best[q];
-                const double* h = s_pal + K * 6 + 3 * best[q];
-                const bool ok = (x[q][0] >= l[0]) && (x[q][0] <= h[0]) && (x[q][1] >= l[1]) && (x[q][1] <= h[1]) &&
-                                (x[q][2] >= l[2]) && (x[q][2] <= h[2]);
-                const unsigned lab = ok ? (unsigned)(best[q] + 1) : 0u;
-                word |= lab << (8 * q);
-                if (q < n) nomatch += lab == 0u;
-            }
-            uint8_t* o = out + j * out_stride2 + i0;
-            if (n == 4 && (((uintptr_t)o) & 3u) == 0) *reinterpret_cast<uint32_t*>(o) = word;
-            else
-                for (int q = 0; q < n; ++q) o[q] = (uint8_t)(word >> (8 * q));
-        }
-    }
-    if (counters) {
-        for (int o = 16; o > 0; o >>= 1) nomatch += __shfl_xor_sync(0xffffffffu, nomatch, o);
-        if ((threadIdx.x & 31) == 0 && nomatch) atomicAdd(&counters->n_nomatch, (unsigned long long)nomatch);
-        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(&counters->n_pixels, (unsigned long long)(n1 * n2));
-    }
-}
-
-__global__ void k_known_fixup_f64(MrPalette pal, const double* __restrict__ px, int64_t stride2, int64_t n1, int64_t n2,
-                                  int64_t n_known, const int64_t* __restrict__ idx, const uint8_t* __restrict__ cat,
-                                  uint8_t* __restrict__ labels, int64_t labels_stride2) {
-    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (k >= n_known) return;
-    if (idx[k] < 0 || idx[k] >= n1 * n2 || cat[k] == 0) return;
-    const int64_t i = idx[k] % n1, j = idx[k] / n1;
-    const double* p = reinterpret_cast<const double*>(reinterpret_cast<const uint8_t*>(px) + j * stride2) + i * 3;
-    labels[j * labels_stride2 + i] = (uint8_t)mr_eval_f64(pal, p[0], p[1], p[2], 0.0, false, cat[k]);
 }
 
 }  // namespace
@@ -276,25 +196,6 @@ cudaError_t mr_launch_blur(const void* in, bool in_is_u8, int64_t in_stride2, in
     else launch_blur_r<false>(in, in_stride2, n1, n2, R, out, out_stride2, g, s);
     *n_launches += 1;
     return cudaGetLastError();
-}
-
-cudaError_t mr_launch_categorize_f64(const MrPalette& pal, const double* px, int64_t stride2, int64_t n1, int64_t n2,
-                                     int64_t n_known, const int64_t* known_idx, const uint8_t* known_cat, uint8_t* out,
-                                     int64_t out_stride2, MrCountersDev* counters, int sm_count, cudaStream_t s,
-                                     int* n_launches) {
-    if (n1 <= 0 || n2 <= 0) return cudaSuccess;
-    k_categorize_f64<<<grid_lines(n1, n2, 4, 128, sm_count), 128, 0, s>>>(pal, px, stride2, n1, n2, out, out_stride2, counters);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    *n_launches += 1;
-    if (n_known > 0) {
-        k_known_fixup_f64<<<(unsigned)((n_known + 127) / 128), 128, 0, s>>>(pal, px, stride2, n1, n2, n_known, known_idx,
-                                                                             known_cat, out, out_stride2);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        *n_launches += 1;
-    }
-    return cudaSuccess;
 }
 
 // scratch: (ceil(n1 / 256) * n2 + n2 + 1) * 3 doubles

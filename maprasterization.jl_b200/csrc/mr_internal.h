@@ -109,13 +109,9 @@ cudaError_t mr_launch_fill_gaps(const MrPalette& pal, const uint8_t* labels, int
                                 const int64_t* known_idx, const uint8_t* known_cat, uint8_t* out, int64_t out_stride2,
                                 int sm_count, cudaStream_t s, int* n_launches);
 
-// blur (src/blur.jl:6-14) and the categoriser on RGB{Float64} pixels (mr_blur.cu)
+// blur (src/blur.jl:6-14) (mr_blur.cu)
 cudaError_t mr_launch_blur(const void* in, bool in_is_u8, int64_t in_stride2, int64_t n1, int64_t n2, int R, double* out,
                            int64_t out_stride2, int sm_count, cudaStream_t s, int* n_launches);
-cudaError_t mr_launch_categorize_f64(const MrPalette& pal, const double* px, int64_t stride2, int64_t n1, int64_t n2,
-                                     int64_t n_known, const int64_t* known_idx, const uint8_t* known_cat, uint8_t* out,
-                                     int64_t out_stride2, MrCountersDev* counters, int sm_count, cudaStream_t s,
-                                     int* n_launches);
 
 // per-pixel part of `_balance` (src/balance.jl:25-42): cubic trend coef21 = 3 x 7 doubles (host memory)
 size_t mr_balance_scratch_bytes(int64_t n1, int64_t n2);

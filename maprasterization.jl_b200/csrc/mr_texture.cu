@@ -205,8 +205,11 @@ __device__ __forceinline__ int eval_props(const double* sp, int K, int match, co
     const double* sdm = sp + 9 * K;
     const double* stm = sp + 12 * K;
     const double cnt = (double)((match & 1) + ((match >> 1) & 1) + ((match >> 2) & 1));
+    // The error is sum / count; the division (FP64, slow) is monotone, so a category can only become the new
+    // first minimum when its undivided sum is smaller than the best one so far: only then are the two
+    // quotients formed and compared (the strict < on the rounded quotients is what decides, as in the oracle).
     int best = 0;
-    double beste = 0.0;
+    double bests = 0.0, beste = 0.0;   // undivided sum and error of the best category so far
     for (int c = 0; c < K; ++c) {
         double e = 0.0;
         if (cm[3 * c] == CUDART_INF) e = CUDART_INF;   // `missing` category: typemax(Float64)
@@ -225,12 +228,15 @@ __device__ __forceinline__ int eval_props(const double* sp, int K, int match, co
             }
             if (match & 4) {
                 const double d0 = __dsub_rn(x.s0, stm[2 * c]), d1 = __dsub_rn(x.s1, stm[2 * c + 1]);
-                const double t = __ddiv_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), 2.0);
+                const double t = __dmul_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), 0.5);   // / 2: exact either way
                 e = first ? t : __dadd_rn(e, t);
             }
-            e = __ddiv_rn(e, cnt);
         }
-        if (c == 0 || e < beste) { beste = e; best = c; }   // first minimum
+        if (c == 0) { bests = e; beste = __ddiv_rn(e, cnt); }
+        else if (e < bests) {
+            const double q = __ddiv_rn(e, cnt);
+            if (q < beste) { beste = q; bests = e; best = c; }   // first minimum of the quotients
+        }
     }
     if (known != 0) return best + 1 == known ? best + 1 : 0;
     bool ok = true;
@@ -269,11 +275,13 @@ __device__ __forceinline__ void load_stats(double* sp, const MrPalette& pal, con
         sp[3 * K + t] = __ldg(pal.lo + t);
         sp[6 * K + t] = __ldg(pal.hi + t);
     }
-    for (int t = threadIdx.x; t < 9 * K; t += blockDim.x) sp[9 * K + t] = __ldg(tex + t);
+    if (tex)   // nullptr: colour-only matching, no texture statistics
+        for (int t = threadIdx.x; t < 9 * K; t += blockDim.x) sp[9 * K + t] = __ldg(tex + t);
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) k_categorize_props(MrPalette pal, const double* __restrict__ tex, int match,
+template <int match>
+__global__ void __launch_bounds__(256) k_categorize_props(MrPalette pal, const double* __restrict__ tex,
                                                           const double* __restrict__ px, int64_t stride2,
                                                           const double* __restrict__ sd, int64_t sd_stride2,
                                                           const double* __restrict__ st, int64_t st_stride2, int64_t n1,
@@ -297,7 +305,8 @@ __global__ void __launch_bounds__(256) k_categorize_props(MrPalette pal, const d
 }
 
 // clicked points: the known-category override of src/categories.jl:110-112
-__global__ void __launch_bounds__(256) k_known_props(MrPalette pal, const double* __restrict__ tex, int match,
+template <int match>
+__global__ void __launch_bounds__(256) k_known_props(MrPalette pal, const double* __restrict__ tex,
                                                      const double* __restrict__ px, int64_t stride2,
                                                      const double* __restrict__ sd, int64_t sd_stride2,
                                                      const double* __restrict__ st, int64_t st_stride2, int64_t n1, int64_t n2,
@@ -370,18 +379,21 @@ cudaError_t mr_launch_categorize_props(const MrPalette& pal, const double* tex, 
                                        MrCountersDev* counters, int sm_count, cudaStream_t s, int* n_launches) {
     if (n1 <= 0 || n2 <= 0) return cudaSuccess;
     const size_t smem = (size_t)pal.K * 18 * sizeof(double);   // <= 254 * 144 B = 36.6 KB
-    k_categorize_props<<<grid_cols(n1, n2, 256, sm_count), 256, smem, s>>>(pal, tex, match, px, stride2, sd, sd_stride2, st,
-                                                                           st_stride2, n1, n2, out, out_stride2, counters);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    *n_launches += 1;
-    if (n_known > 0) {
-        k_known_props<<<(unsigned)((n_known + 255) / 256), 256, smem, s>>>(pal, tex, match, px, stride2, sd, sd_stride2, st,
-                                                                           st_stride2, n1, n2, n_known, known_idx, known_cat,
-                                                                           out, out_stride2);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        *n_launches += 1;
+    const dim3 g = grid_cols((n1 + 3) / 4, n2, 256, sm_count);
+    const unsigned gk = (unsigned)((n_known + 255) / 256);
+#define MR_PROPS_CASE(M)                                                                                              \
+    case M:                                                                                                           \
+        k_categorize_props<M><<<g, 256, smem, s>>>(pal, tex, px, stride2, sd, sd_stride2, st, st_stride2, n1, n2, out, \
+                                                   out_stride2, counters);                                            \
+        if (n_known > 0)                                                                                              \
+            k_known_props<M><<<gk, 256, smem, s>>>(pal, tex, px, stride2, sd, sd_stride2, st, st_stride2, n1, n2,      \
+                                                   n_known, known_idx, known_cat, out, out_stride2);                  \
+        break;
+    switch (match) {
+        MR_PROPS_CASE(1) MR_PROPS_CASE(2) MR_PROPS_CASE(3) MR_PROPS_CASE(4) MR_PROPS_CASE(5) MR_PROPS_CASE(6) MR_PROPS_CASE(7)
+        default: return cudaErrorInvalidValue;
     }
-    return cudaSuccess;
+#undef MR_PROPS_CASE
+    *n_launches += n_known > 0 ? 2 : 1;
+    return cudaGetLastError();
 }
