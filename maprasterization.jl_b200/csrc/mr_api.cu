@@ -50,6 +50,7 @@ struct mr_ctx {
     uint8_t* d_parent = nullptr; size_t d_parent_cap = 0;   // first run of every (line, chunk)
     uint8_t* d_runs = nullptr; size_t d_runs_cap = 0;       // run arrays
     uint8_t* d_rec = nullptr; size_t d_rec_cap = 0;
+    uint8_t* d_stage = nullptr; size_t d_stage_cap = 0;     // per-chunk staging of the run-count pass
     uint8_t* d_small = nullptr;     // 256-byte keep table | n_roots | conflict
     std::vector<cudaEvent_t> ev_up, ev_done;
     std::string err;
@@ -127,7 +128,7 @@ extern "C" void mr_destroy(mr_ctx* ctx) {
     cudaFree(ctx->d_pal); cudaFree(ctx->d_lut); cudaFree(ctx->d_coarse); cudaFree(ctx->d_qtab);
     cudaFree(ctx->d_known_idx); cudaFree(ctx->d_known_cat); cudaFree(ctx->d_counters); cudaFree(ctx->work.slots);
     cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_tmp); cudaFree(ctx->d_rp_in); cudaFree(ctx->d_rp_out); cudaFree(ctx->d_lab); cudaFree(ctx->d_f64); cudaFree(ctx->d_f64b); cudaFree(ctx->d_tex);
-    cudaFree(ctx->d_parent); cudaFree(ctx->d_runs); cudaFree(ctx->d_rec); cudaFree(ctx->d_small);
+    cudaFree(ctx->d_parent); cudaFree(ctx->d_runs); cudaFree(ctx->d_rec); cudaFree(ctx->d_stage); cudaFree(ctx->d_small);
     if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
@@ -788,12 +789,13 @@ static int prune_dev(mr_ctx* ctx, const char* fn, const uint8_t* labels_dev, int
     const size_t cb_bytes = mr_prune_cbase_bytes(n1, n2);
     if ((rc = grow(ctx, &ctx->d_parent, &ctx->d_parent_cap, cb_bytes))) return rc;   // chunk bases
     uint32_t* cbase = reinterpret_cast<uint32_t*>(ctx->d_parent);
+    if ((rc = grow(ctx, &ctx->d_stage, &ctx->d_stage_cap, mr_prune_stage_bytes(n1, n2)))) return rc;
     if (!ctx->d_small) CK(cudaMalloc(&ctx->d_small, 2048));
     unsigned int* d_n_roots = reinterpret_cast<unsigned int*>(ctx->d_small + 256);
     unsigned int* d_conflict = reinterpret_cast<unsigned int*>(ctx->d_small + 260);
     CK(cudaMemcpyAsync(ctx->d_small, keep256, 256, cudaMemcpyHostToDevice, s));
     int nl = 0;
-    cudaError_t e = mr_launch_prune_count(labels_dev, n1, n2, stride2, cbase, s, &nl);
+    cudaError_t e = mr_launch_prune_count(labels_dev, n1, n2, stride2, cbase, ctx->d_stage, s, &nl);
     ctx->launches += nl;
     if (e != cudaSuccess) return fail_cuda(ctx, e, "segment prune (run count)");
     unsigned int n_runs = 0;
@@ -802,7 +804,7 @@ static int prune_dev(mr_ctx* ctx, const char* fn, const uint8_t* labels_dev, int
     CK(cudaStreamSynchronize(s));
     if ((rc = grow(ctx, &ctx->d_runs, &ctx->d_runs_cap, mr_prune_run_bytes(n_runs)))) return rc;
     nl = 0;
-    e = mr_launch_prune_components(labels_dev, n1, n2, stride2, cbase, ctx->d_runs, n_runs, d_n_roots, s, &nl);
+    e = mr_launch_prune_components(n1, n2, cbase, ctx->d_stage, ctx->d_runs, n_runs, d_n_roots, s, &nl);
     ctx->launches += nl;
     if (e != cudaSuccess) return fail_cuda(ctx, e, "segment prune (components)");
     unsigned int n_roots = 0;
@@ -810,7 +812,7 @@ static int prune_dev(mr_ctx* ctx, const char* fn, const uint8_t* labels_dev, int
     CK(cudaStreamSynchronize(s));
     if ((rc = grow(ctx, &ctx->d_rec, &ctx->d_rec_cap, mr_prune_rec_bytes(n_roots)))) return rc;
     nl = 0;
-    e = mr_launch_prune_apply(labels_dev, n1, n2, stride2, cbase, ctx->d_runs, n_runs, ctx->d_rec, n_roots, ctx->n_known,
+    e = mr_launch_prune_apply(n1, n2, cbase, ctx->d_stage, ctx->d_runs, n_runs, ctx->d_rec, n_roots, ctx->n_known,
                               ctx->d_known_idx, ctx->d_known_cat, ctx->d_small, line_threshold, prune_threshold, out_dev,
                               out_stride2, d_conflict, s, &nl);
     ctx->launches += nl;

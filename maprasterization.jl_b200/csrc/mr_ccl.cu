@@ -14,9 +14,11 @@
 // RUN based: a cleaned map has long horizontal runs of equal labels (~30 pixels on the synthetic
 // sheets), so everything after the first two passes works on runs, not pixels:
 //
-//   k_count    (line, 4096-pixel chunk): number of run starts            } 16 pixels per thread,
+//   k_count    (line, 4096-pixel chunk): number of run starts; per thread (16 pixels, one 16-byte load) the
+//              run-start mask and its offset in the chunk (`info`, 4 B per 16 pixels); the chunk's run starts
+//              and labels compacted into the chunk's staging slot.  THE ONLY PASS THAT READS THE LABELS.
 //   k_scan     exclusive scan of the chunk counts -> first run of every chunk / line
-//   k_fill     run start x, label, parent = self                         } 16-byte loads
+//   k_fill     staging slots -> run arrays (start x, label, parent = self): work per run, not per pixel
 //   k_merge    one block per line: every run finds the runs of the previous line that overlap it
 //              (binary search in the sorted run starts) and unites with those of equal label
 //              (lock-free union-find, atomicMin links towards the smaller run index)
@@ -25,11 +27,12 @@
 //   k_known    known-category plane (sparse list): pixel -> run (binary search) -> component
 //   k_decide   per component: the rule of clean.jl:65-88 (Float64 arithmetic as written there)
 //   k_runout   per run: the label it will be painted with
-//   k_paint    (line, chunk) again: pixel -> run -> label, 16-byte stores
+//   k_paint    (line, chunk) again: `info` -> run -> label, 16-byte stores (no label read, no block scan)
 //
 // Run / pixel indices fit 31 bits (n1 * n2 < 2^31; bit 31 tags a numbered root).
-// Bound: HBM; algorithmic traffic 2 B/pixel (label in, label out); this version reads the labels
-// three times and writes them once (4 B/pixel) plus ~10 B per run.
+// Bound: HBM; algorithmic traffic 2 B/pixel (label in, label out); the labels are read once and written
+// once, plus 0.5 B per pixel of `info` (written, read) and ~25 B per run.  The streaming kernels handle
+// UB chunks per block (independent loads in flight, one barrier pair for all of them).
 #include "mr_internal.h"
 
 namespace {
@@ -38,6 +41,14 @@ constexpr uint32_t TAG = 0x80000000u;
 constexpr int PT = 16;            // pixels per thread
 constexpr int BT = 256;           // threads per block
 constexpr int CH = PT * BT;       // pixels per chunk
+constexpr int UB = 4;             // chunks per block in the streaming kernels
+
+// per-chunk staging written by k_count: the only pass over the label plane
+struct Stage {
+    uint32_t* info;             // [chunk][BT]: run-start mask of the thread's 16 pixels | offset of its first run in the chunk << 16
+    uint16_t* sx;               // [chunk][CH]: x - chunk start of the chunk's runs, in order (first `count` entries)
+    uint8_t* sl;                // [chunk][CH]: their labels
+};
 
 struct SegRec {                 // one per component
     unsigned int count;
@@ -106,45 +117,92 @@ __device__ __forceinline__ uint32_t load_starts(const uint8_t* __restrict__ line
     return m;
 }
 
-// exclusive prefix of v over the block (BT = 256 threads); total in *tot
-__device__ __forceinline__ uint32_t block_exclusive(uint32_t v, uint32_t* tot) {
-    __shared__ uint32_t wsum[BT / 32];
+// exclusive prefix over the block (BT = 256 threads) of UB independent values per thread (one barrier pair for all of them)
+__device__ __forceinline__ void block_exclusive_ub(const uint32_t (&v)[UB], uint32_t (&excl)[UB], uint32_t (&tot)[UB]) {
+    __shared__ uint32_t wsum[UB][BT / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t s = v;
+    uint32_t s[UB];
+#pragma unroll
+    for (int u = 0; u < UB; ++u) s[u] = v[u];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, s, o);
-        if (lane >= o) s += t;
-    }
-    if (lane == 31) wsum[warp] = s;
-    __syncthreads();
-    uint32_t base = 0, all = 0;
 #pragma unroll
-    for (int w = 0; w < BT / 32; ++w) {
-        const uint32_t t = wsum[w];
-        if (w < warp) base += t;
-        all += t;
+        for (int u = 0; u < UB; ++u) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, s[u], o);
+            if (lane >= o) s[u] += t;
+        }
+    }
+    if (lane == 31) {
+#pragma unroll
+        for (int u = 0; u < UB; ++u) wsum[u][warp] = s[u];
     }
     __syncthreads();
-    *tot = all;
-    return base + s - v;
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+        uint32_t base = 0, all = 0;
+#pragma unroll
+        for (int w = 0; w < BT / 32; ++w) {
+            const uint32_t t = wsum[u][w];
+            if (w < warp) base += t;
+            all += t;
+        }
+        tot[u] = all;
+        excl[u] = base + s[u] - v[u];
+    }
 }
 
-// grid: chunks * n2 blocks, block = (line y, chunk c)
-__global__ void __launch_bounds__(BT) k_count(const uint8_t* __restrict__ lab, int64_t stride2, uint32_t n1, bool al16,
-                                              uint32_t chunks, uint32_t* __restrict__ cnt) {
-    const uint32_t y = blockIdx.x / chunks, c = blockIdx.x - y * chunks, x = c * CH + threadIdx.x * PT;
-    uint8_t px[PT];
-    int nv;
-    const uint32_t m = load_starts(lab + (int64_t)y * stride2, x, n1, al16, px, nv);
-    uint32_t tot;
-    block_exclusive(__popc(m), &tot);
-    if (threadIdx.x == 0) cnt[blockIdx.x] = tot;
+// grid: ceil(chunks * n2 / UB) blocks; block = UB consecutive (line y, chunk c) units
+__global__ void __launch_bounds__(BT) k_count_stage(const uint8_t* __restrict__ lab, int64_t stride2, uint32_t n1, bool al16,
+                                                    uint32_t chunks, uint32_t n_units, uint32_t* __restrict__ cnt, Stage G) {
+    uint8_t px[UB][PT];
+    uint32_t m[UB], pc[UB], excl[UB], tot[UB];
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+        const uint32_t unit = blockIdx.x * UB + u;
+        m[u] = 0u;
+        if (unit < n_units) {   // block-uniform
+            const uint32_t y = unit / chunks, c = unit - y * chunks, x = c * CH + threadIdx.x * PT;
+            int nv;
+            m[u] = load_starts(lab + (int64_t)y * stride2, x, n1, al16, px[u], nv);
+        }
+        pc[u] = __popc(m[u]);
+    }
+    block_exclusive_ub(pc, excl, tot);
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+        const uint32_t unit = blockIdx.x * UB + u;
+        if (unit >= n_units) break;
+        G.info[(size_t)unit * BT + threadIdx.x] = m[u] | (excl[u] << 16);
+        if (threadIdx.x == 0) cnt[unit] = tot[u];
+        uint16_t* sx = G.sx + (size_t)unit * CH + excl[u];
+        uint8_t* sl = G.sl + (size_t)unit * CH + excl[u];
+        uint32_t mm = m[u];
+#pragma unroll
+        for (int k = 0; k < PT; ++k)
+            if ((mm >> k) & 1u) {
+                *sx++ = (uint16_t)(threadIdx.x * PT + k);
+                *sl++ = px[u][k];
+            }
+    }
 }
 
-// in-place exclusive scan of n counts, total appended at a[n]; one block, 8 entries per thread and step
+// staging slots -> run arrays; one block per chunk unit
+__global__ void __launch_bounds__(BT) k_fill_runs(Runs R, Stage G) {
+    const uint32_t unit = blockIdx.x;
+    const uint32_t base = R.cbase[unit], n = R.cbase[unit + 1] - base;
+    const uint32_t x0 = (unit % R.chunks) * CH;
+    const uint16_t* sx = G.sx + (size_t)unit * CH;
+    const uint8_t* sl = G.sl + (size_t)unit * CH;
+    for (uint32_t j = threadIdx.x; j < n; j += BT) {
+        R.start[base + j] = x0 + sx[j];
+        R.label[base + j] = sl[j];
+        R.parent[base + j] = base + j;
+    }
+}
+
+// in-place exclusive scan of n counts, total appended at a[n]; one block, 32 entries per thread and step
 __global__ void __launch_bounds__(1024) k_scan(uint32_t* __restrict__ a, uint64_t n) {
-    constexpr int E = 8;
+    constexpr int E = 32;
     __shared__ uint32_t wsum[32];
     __shared__ uint32_t carry;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -179,24 +237,6 @@ __global__ void __launch_bounds__(1024) k_scan(uint32_t* __restrict__ a, uint64_
         __syncthreads();
     }
     if (threadIdx.x == 0) a[n] = carry;
-}
-
-__global__ void __launch_bounds__(BT) k_fill(const uint8_t* __restrict__ lab, int64_t stride2, uint32_t n1, bool al16,
-                                             Runs R) {
-    const uint32_t y = blockIdx.x / R.chunks, c = blockIdx.x - y * R.chunks, x = c * CH + threadIdx.x * PT;
-    uint8_t px[PT];
-    int nv;
-    uint32_t m = load_starts(lab + (int64_t)y * stride2, x, n1, al16, px, nv);
-    uint32_t tot;
-    uint32_t idx = R.cbase[blockIdx.x] + block_exclusive(__popc(m), &tot);
-    while (m) {
-        const int k = __ffs(m) - 1;
-        m &= m - 1;
-        R.start[idx] = x + k;
-        R.label[idx] = px[k];
-        R.parent[idx] = idx;
-        ++idx;
-    }
 }
 
 // one block per line y >= 1 (blockIdx.x = y - 1)
@@ -259,19 +299,34 @@ __global__ void k_init_recs(SegRec* rec, unsigned int n) {
     rec[i] = r;
 }
 
-// one block per line
+// one block per line.  Neighbouring runs of a line alternate between a few components, so the runs of a warp
+// are grouped by component (match.any) and reduced inside the warp (redux) before ONE lane per group touches
+// the component's record: an order of magnitude fewer same-address atomics.
 __global__ void __launch_bounds__(128) k_stats(uint32_t n1, Runs R, SegRec* __restrict__ rec) {
     const uint32_t y = blockIdx.x;
     const uint32_t c0 = R.cbase[(uint64_t)y * R.chunks], c1 = R.cbase[(uint64_t)(y + 1) * R.chunks];
-    for (uint32_t i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
-        const uint32_t s = R.start[i], e = (i + 1 < c1) ? R.start[i + 1] : n1;
-        SegRec* r = rec + comp_id(R.parent, i);
-        atomicAdd(&r->count, e - s);
-        if (r->xmin > s) atomicMin(&r->xmin, s);
-        if (r->xmax < e - 1) atomicMax(&r->xmax, e - 1);
-        if (r->ymin > y) atomicMin(&r->ymin, y);
-        if (r->ymax < y) atomicMax(&r->ymax, y);
-        if (R.parent[i] & TAG) r->label = R.label[i];   // the root run writes the component's label
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t i0 = c0 + (threadIdx.x & ~31u); i0 < c1; i0 += blockDim.x) {   // warp-uniform trip count
+        const uint32_t i = i0 + lane;
+        const bool valid = i < c1;
+        uint32_t s = 0, e = 1, comp = 0xFFFFFF00u + lane;      // idle lanes: groups of their own
+        if (valid) {
+            s = R.start[i];
+            e = (i + 1 < c1) ? R.start[i + 1] : n1;
+            comp = comp_id(R.parent, i);
+            if (R.parent[i] & TAG) rec[comp].label = R.label[i];   // the root run writes the component's label
+        }
+        const uint32_t grp = __match_any_sync(0xffffffffu, comp);
+        const uint32_t cnt = __reduce_add_sync(grp, e - s);
+        const uint32_t lo = __reduce_min_sync(grp, s), hi = __reduce_max_sync(grp, e - 1);
+        if (valid && lane == (uint32_t)(__ffs(grp) - 1)) {
+            SegRec* r = rec + comp;
+            atomicAdd(&r->count, cnt);
+            if (r->xmin > lo) atomicMin(&r->xmin, lo);
+            if (r->xmax < hi) atomicMax(&r->xmax, hi);
+            if (r->ymin > y) atomicMin(&r->ymin, y);
+            if (r->ymax < y) atomicMax(&r->ymax, y);
+        }
     }
 }
 
@@ -323,28 +378,48 @@ __global__ void k_runout(Runs R, uint32_t n, const SegRec* __restrict__ rec) {
     if (i < n) R.out[i] = (uint8_t)rec[comp_id(R.parent, i)].label;
 }
 
-__global__ void __launch_bounds__(BT) k_paint(const uint8_t* __restrict__ lab, int64_t stride2, uint32_t n1, bool al16,
-                                              Runs R, uint8_t* __restrict__ out, int64_t out_stride2, bool out_al16) {
-    const uint32_t y = blockIdx.x / R.chunks, c = blockIdx.x - y * R.chunks, x = c * CH + threadIdx.x * PT;
-    uint8_t px[PT];
-    int nv;
-    const uint32_t m = load_starts(lab + (int64_t)y * stride2, x, n1, al16, px, nv);
-    uint32_t tot;
-    uint32_t run = R.cbase[blockIdx.x] + block_exclusive(__popc(m), &tot);   // next run to start
-    if (nv == 0) return;
-    uint8_t cur = (m & 1u) ? (uint8_t)0 : R.out[run - 1];   // the run that continues into this thread
-    uint32_t w[4] = {0u, 0u, 0u, 0u};
+// UB chunk units per block; per thread: `info` word -> first run and run-start mask of its 16 pixels
+__global__ void __launch_bounds__(BT) k_paint(uint32_t n1, uint32_t n_units, Runs R, Stage G, uint8_t* __restrict__ out,
+                                              int64_t out_stride2, bool out_al16) {
+    uint32_t inf[UB];
 #pragma unroll
-    for (int k = 0; k < PT; ++k) {
-        if ((m >> k) & 1u) cur = R.out[run++];
-        w[k >> 2] |= (uint32_t)cur << (8 * (k & 3));
+    for (int u = 0; u < UB; ++u) {
+        const uint32_t unit = blockIdx.x * UB + u;
+        inf[u] = unit < n_units ? G.info[(size_t)unit * BT + threadIdx.x] : 0u;
     }
-    uint8_t* dst = out + (int64_t)y * out_stride2 + x;
-    if (nv == PT && out_al16) {
-        *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-    } else {
-        for (int k = 0; k < nv; ++k) dst[k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+        const uint32_t unit = blockIdx.x * UB + u;
+        if (unit >= n_units) break;
+        const uint32_t y = unit / R.chunks, c = unit - y * R.chunks, x = c * CH + threadIdx.x * PT;
+        if (x >= n1) continue;
+        const int nv = n1 - x < (uint32_t)PT ? (int)(n1 - x) : PT;
+        const uint32_t m = inf[u] & 0xFFFFu;
+        uint32_t run = R.cbase[unit] + (inf[u] >> 16);          // next run to start
+        uint8_t cur = (m & 1u) ? (uint8_t)0 : R.out[run - 1];   // the run that continues into this thread
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int k = 0; k < PT; ++k) {
+            if ((m >> k) & 1u) cur = R.out[run++];
+            w[k >> 2] |= (uint32_t)cur << (8 * (k & 3));
+        }
+        uint8_t* dst = out + (int64_t)y * out_stride2 + x;
+        if (nv == PT && out_al16) {
+            *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+        } else {
+            for (int k = 0; k < nv; ++k) dst[k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+        }
     }
+}
+
+Stage make_stage(void* stage_mem, int64_t n1, int64_t n2) {
+    const size_t units = (size_t)((n1 + CH - 1) / CH) * (size_t)n2;
+    Stage G;
+    uint8_t* p = reinterpret_cast<uint8_t*>(stage_mem);
+    G.info = reinterpret_cast<uint32_t*>(p);
+    G.sx = reinterpret_cast<uint16_t*>(p + units * BT * 4);
+    G.sl = p + units * BT * 4 + units * CH * 2;
+    return G;
 }
 
 Runs make_runs(void* run_mem, unsigned int n_runs, const uint32_t* cbase, int64_t n1) {
@@ -367,28 +442,34 @@ bool aligned16(const void* p, int64_t stride) { return ((uintptr_t)p % 16 == 0) 
 size_t mr_prune_cbase_bytes(int64_t n1, int64_t n2) {
     return ((size_t)((n1 + CH - 1) / CH) * (size_t)n2 + 1) * sizeof(uint32_t);
 }
+// staging of k_count: 4 B per 16 pixels (`info`) + 3 B per pixel slot of the chunk's compacted run starts / labels
+size_t mr_prune_stage_bytes(int64_t n1, int64_t n2) {
+    const size_t units = (size_t)((n1 + CH - 1) / CH) * (size_t)n2;
+    return units * ((size_t)BT * 4 + (size_t)CH * 3) + 16;
+}
 size_t mr_prune_run_bytes(unsigned int n_runs) { return (((size_t)n_runs + 3) / 4 * 4) * 10 + 16; }
 size_t mr_prune_rec_bytes(unsigned int n_segments) { return ((size_t)n_segments + 1) * sizeof(SegRec); }
 
 // phase 1: run starts per (line, chunk) and their exclusive scan; the number of runs ends up in
 // cbase[chunks * n2] (device)
 cudaError_t mr_launch_prune_count(const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2, uint32_t* cbase,
-                                  cudaStream_t s, int* n_launches) {
+                                  void* stage_mem, cudaStream_t s, int* n_launches) {
     const uint32_t chunks = (uint32_t)((n1 + CH - 1) / CH);
-    k_count<<<chunks * (unsigned)n2, BT, 0, s>>>(labels, stride2, (uint32_t)n1, aligned16(labels, stride2), chunks, cbase);
+    const uint32_t n_units = chunks * (uint32_t)n2;
+    k_count_stage<<<(n_units + UB - 1) / UB, BT, 0, s>>>(labels, stride2, (uint32_t)n1, aligned16(labels, stride2), chunks,
+                                                        n_units, cbase, make_stage(stage_mem, n1, n2));
     k_scan<<<1, 1024, 0, s>>>(cbase, (uint64_t)chunks * (uint64_t)n2);
     *n_launches += 2;
     return cudaGetLastError();
 }
 
 // phase 2: runs, vertical merges, component numbering; the number of components ends up in *d_n_roots
-cudaError_t mr_launch_prune_components(const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2,
-                                       const uint32_t* cbase, void* run_mem, unsigned int n_runs,
-                                       unsigned int* d_n_roots, cudaStream_t s, int* n_launches) {
+cudaError_t mr_launch_prune_components(int64_t n1, int64_t n2, const uint32_t* cbase, const void* stage_mem, void* run_mem,
+                                       unsigned int n_runs, unsigned int* d_n_roots, cudaStream_t s, int* n_launches) {
     const Runs R = make_runs(run_mem, n_runs, cbase, n1);
     cudaError_t e = cudaMemsetAsync(d_n_roots, 0, sizeof(unsigned int), s);
     if (e != cudaSuccess) return e;
-    k_fill<<<R.chunks * (unsigned)n2, BT, 0, s>>>(labels, stride2, (uint32_t)n1, aligned16(labels, stride2), R);
+    k_fill_runs<<<R.chunks * (unsigned)n2, BT, 0, s>>>(R, make_stage(const_cast<void*>(stage_mem), n1, n2));
     *n_launches += 1;
     if (n2 > 1) {
         k_merge<<<(unsigned)(n2 - 1), 128, 0, s>>>((uint32_t)n1, R);
@@ -401,8 +482,8 @@ cudaError_t mr_launch_prune_components(const uint8_t* labels, int64_t n1, int64_
 
 // phase 3: statistics, rule, output.  *d_conflict (device) becomes non-zero when a segment holds
 // two different known categories.
-cudaError_t mr_launch_prune_apply(const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2,
-                                  const uint32_t* cbase, void* run_mem, unsigned int n_runs, void* rec,
+cudaError_t mr_launch_prune_apply(int64_t n1, int64_t n2, const uint32_t* cbase, const void* stage_mem, void* run_mem,
+                                  unsigned int n_runs, void* rec,
                                   unsigned int n_segments, int64_t n_known, const int64_t* known_idx,
                                   const uint8_t* known_cat, const uint8_t* keep_dev, double line_threshold,
                                   double prune_threshold, uint8_t* out, int64_t out_stride2,
@@ -421,8 +502,9 @@ cudaError_t mr_launch_prune_apply(const uint8_t* labels, int64_t n1, int64_t n2,
     }
     k_decide<<<(n_segments + 255) / 256, 256, 0, s>>>(r, n_segments, keep_dev, line_threshold, prune_threshold, d_conflict);
     k_runout<<<(n_runs + 255) / 256, 256, 0, s>>>(R, n_runs, r);
-    k_paint<<<R.chunks * (unsigned)n2, BT, 0, s>>>(labels, stride2, (uint32_t)n1, aligned16(labels, stride2), R, out,
-                                                       out_stride2, aligned16(out, out_stride2));
+    const uint32_t n_units = R.chunks * (uint32_t)n2;
+    k_paint<<<(n_units + UB - 1) / UB, BT, 0, s>>>((uint32_t)n1, n_units, R, make_stage(const_cast<void*>(stage_mem), n1, n2), out,
+                                                  out_stride2, aligned16(out, out_stride2));
     *n_launches += 3;
     return cudaGetLastError();
 }

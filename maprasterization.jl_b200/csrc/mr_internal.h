@@ -87,18 +87,17 @@ cudaError_t mr_launch_synth(uint32_t seed, uint32_t sheet, int K, const uint8_t*
 // segment prune (`_clean`, src/clean.jl:59-93): run-based connected components + per-component rule
 // (mr_ccl.cu).  Three phases with a host read-back between them (run count, component count).
 size_t mr_prune_cbase_bytes(int64_t n1, int64_t n2);
+size_t mr_prune_stage_bytes(int64_t n1, int64_t n2);
 size_t mr_prune_run_bytes(unsigned int n_runs);
 size_t mr_prune_rec_bytes(unsigned int n_segments);
 cudaError_t mr_launch_prune_count(const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2, uint32_t* cbase,
-                                  cudaStream_t s, int* n_launches);
-cudaError_t mr_launch_prune_components(const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2,
-                                       const uint32_t* cbase, void* run_mem, unsigned int n_runs,
-                                       unsigned int* d_n_roots, cudaStream_t s, int* n_launches);
-cudaError_t mr_launch_prune_apply(const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2,
-                                  const uint32_t* cbase, void* run_mem, unsigned int n_runs, void* rec,
-                                  unsigned int n_segments, int64_t n_known, const int64_t* known_idx,
-                                  const uint8_t* known_cat, const uint8_t* keep_dev, double line_threshold,
-                                  double prune_threshold, uint8_t* out, int64_t out_stride2,
+                                  void* stage_mem, cudaStream_t s, int* n_launches);
+cudaError_t mr_launch_prune_components(int64_t n1, int64_t n2, const uint32_t* cbase, const void* stage_mem, void* run_mem,
+                                       unsigned int n_runs, unsigned int* d_n_roots, cudaStream_t s, int* n_launches);
+cudaError_t mr_launch_prune_apply(int64_t n1, int64_t n2, const uint32_t* cbase, const void* stage_mem, void* run_mem,
+                                  unsigned int n_runs, void* rec, unsigned int n_segments, int64_t n_known,
+                                  const int64_t* known_idx, const uint8_t* known_cat, const uint8_t* keep_dev,
+                                  double line_threshold, double prune_threshold, uint8_t* out, int64_t out_stride2,
                                   unsigned int* d_conflict, cudaStream_t s, int* n_launches);
 
 // fill_gaps (src/clean.jl:2-54), one pass; the known-category override (clean.jl:14) runs as a second,

@@ -200,58 +200,112 @@ __global__ void k_abs_total(int64_t n1, int64_t n2, const double* __restrict__ l
 struct PropPx {
     double r, g, b, sd, s0, s1;
 };
-__device__ __forceinline__ int eval_props(const double* sp, int K, int match, const PropPx& x, int known) {
-    const double* cm = sp;
-    const double* sdm = sp + 9 * K;
-    const double* stm = sp + 12 * K;
-    const double cnt = (double)((match & 1) + ((match >> 1) & 1) + ((match >> 2) & 1));
-    // The error is sum / count; the division (FP64, slow) is monotone, so a category can only become the new
-    // first minimum when its undivided sum is smaller than the best one so far: only then are the two
-    // quotients formed and compared (the strict < on the rounded quotients is what decides, as in the oracle).
-    int best = 0;
-    double bests = 0.0, beste = 0.0;   // undivided sum and error of the best category so far
+// undivided error sum of one pixel against category c: the matched terms in the order color, std, stripe
+template <int match>
+__device__ __forceinline__ double props_sum(const double* sp, int K, int c, const PropPx& x) {
+    const double* cm = sp + 3 * c;
+    if (cm[0] == CUDART_INF) return CUDART_INF;       // `missing` category: typemax(Float64)
+    double e = 0.0;
+    if (match & 1) {
+        const double d0 = __dsub_rn(x.r, cm[0]), d1 = __dsub_rn(x.g, cm[1]), d2 = __dsub_rn(x.b, cm[2]);
+        e = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
+    }
+    if (match & 2) {
+        const double d = __dsub_rn(x.sd, sp[9 * K + c]);
+        const double t = __dmul_rn(d, d);
+        e = (match & 1) ? __dadd_rn(e, t) : t;
+    }
+    if (match & 4) {
+        const double d0 = __dsub_rn(x.s0, sp[12 * K + 2 * c]), d1 = __dsub_rn(x.s1, sp[12 * K + 2 * c + 1]);
+        const double t = __dmul_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), 0.5);   // / 2: exact either way
+        e = (match & 3) ? __dadd_rn(e, t) : t;
+    }
+    return e;
+}
+
+// P pixels at once: the statistics of a category (shared memory, broadcast reads) are fetched once for all of them.
+// match (compile time): bit 0 color, bit 1 std, bit 2 stripe.
+//
+// The error of a category is sum / count (count = number of matched properties) and the reference takes the
+// FIRST minimum of the rounded quotients.  The quotient is monotone in the sum, so the winner is the first
+// minimum of the undivided sums -- unless an EARLIER category has a sum one ulp above the minimum whose quotient
+// rounds to the same double (dividing by 3 can merge adjacent doubles, never doubles two apart; dividing by 2
+// is exact).  The loop therefore runs without the (slow, FP64) division and remembers that one possible rival;
+// two divisions at the end settle it.  Sums so small that their quotients are subnormal (where spacing
+// arguments fail) take a plain loop with one division per category.
+template <int P, int match>
+__device__ __forceinline__ void eval_props(const double* sp, int K, const PropPx (&x)[P], const int (&known)[P],
+                                           int (&lab)[P]) {
+    constexpr int CNT = (match & 1) + ((match >> 1) & 1) + ((match >> 2) & 1);
+    int c1[P], c2[P];            // first minimum of the sums; earlier category one ulp above it (-1: none)
+    double s1[P], s2[P];
+#pragma unroll
+    for (int q = 0; q < P; ++q) { c1[q] = 0; c2[q] = -1; s1[q] = s2[q] = 0.0; }
     for (int c = 0; c < K; ++c) {
-        double e = 0.0;
-        if (cm[3 * c] == CUDART_INF) e = CUDART_INF;   // `missing` category: typemax(Float64)
-        else {
-            bool first = true;
+        // the category's statistics once for the P pixels
+        const double m0 = sp[3 * c], m1 = sp[3 * c + 1], m2 = sp[3 * c + 2];
+        const double ms = (match & 2) ? sp[9 * K + c] : 0.0;
+        const double t0 = (match & 4) ? sp[12 * K + 2 * c] : 0.0, t1 = (match & 4) ? sp[12 * K + 2 * c + 1] : 0.0;
+        const bool missing = m0 == CUDART_INF;          // `missing` category: typemax(Float64)
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+            double e = 0.0;
             if (match & 1) {
-                const double d0 = __dsub_rn(x.r, cm[3 * c]), d1 = __dsub_rn(x.g, cm[3 * c + 1]), d2 = __dsub_rn(x.b, cm[3 * c + 2]);
+                const double d0 = __dsub_rn(x[q].r, m0), d1 = __dsub_rn(x[q].g, m1), d2 = __dsub_rn(x[q].b, m2);
                 e = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
-                first = false;
             }
             if (match & 2) {
-                const double d = __dsub_rn(x.sd, sdm[c]);
+                const double d = __dsub_rn(x[q].sd, ms);
                 const double t = __dmul_rn(d, d);
-                e = first ? t : __dadd_rn(e, t);
-                first = false;
+                e = (match & 1) ? __dadd_rn(e, t) : t;
             }
             if (match & 4) {
-                const double d0 = __dsub_rn(x.s0, stm[2 * c]), d1 = __dsub_rn(x.s1, stm[2 * c + 1]);
+                const double d0 = __dsub_rn(x[q].s0, t0), d1 = __dsub_rn(x[q].s1, t1);
                 const double t = __dmul_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), 0.5);   // / 2: exact either way
-                e = first ? t : __dadd_rn(e, t);
+                e = (match & 3) ? __dadd_rn(e, t) : t;
+            }
+            // colour alone: (x - Inf)^2 = Inf by itself; with texture terms their statistics may be NaN -> explicit
+            if ((match & 6) && missing) e = CUDART_INF;
+            if (c == 0) s1[q] = e;
+            else if (e < s1[q]) {
+                if (CNT > 1) {
+                    const double up = __longlong_as_double(__double_as_longlong(e) + 1);   // next double above e >= 0
+                    if (s1[q] <= up) { s2[q] = s1[q]; c2[q] = c1[q]; } else c2[q] = -1;
+                }
+                s1[q] = e;
+                c1[q] = c;
             }
         }
-        if (c == 0) { bests = e; beste = __ddiv_rn(e, cnt); }
-        else if (e < bests) {
-            const double q = __ddiv_rn(e, cnt);
-            if (q < beste) { beste = q; bests = e; best = c; }   // first minimum of the quotients
+    }
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+        int bq = c1[q];
+        if (CNT > 1) {
+            if (s1[q] < 1e-290) {          // quotients near the subnormal range: the literal loop
+                double beste = 0.0;
+                for (int c = 0; c < K; ++c) {
+                    const double e = __ddiv_rn(props_sum<match>(sp, K, c, x[q]), (double)CNT);
+                    if (c == 0 || e < beste) { beste = e; bq = c; }
+                }
+            } else if (c2[q] >= 0 && __ddiv_rn(s2[q], (double)CNT) == __ddiv_rn(s1[q], (double)CNT)) {
+                bq = c2[q];
+            }
         }
+        if (known[q] != 0) { lab[q] = bq + 1 == known[q] ? bq + 1 : 0; continue; }
+        bool ok = true;
+        if (match & 1) {
+            const double* l = sp + 3 * K + 3 * bq;
+            const double* h = sp + 6 * K + 3 * bq;
+            ok = ok && x[q].r >= l[0] && x[q].r <= h[0] && x[q].g >= l[1] && x[q].g <= h[1] && x[q].b >= l[2] && x[q].b <= h[2];
+        }
+        if (match & 2) ok = ok && x[q].sd >= sp[10 * K + bq] && x[q].sd <= sp[11 * K + bq];
+        if (match & 4) {
+            const double* l = sp + 14 * K + 2 * bq;
+            const double* h = sp + 16 * K + 2 * bq;
+            ok = ok && x[q].s0 >= l[0] && x[q].s0 <= h[0] && x[q].s1 >= l[1] && x[q].s1 <= h[1];
+        }
+        lab[q] = ok ? bq + 1 : 0;
     }
-    if (known != 0) return best + 1 == known ? best + 1 : 0;
-    bool ok = true;
-    if (match & 1) {
-        const double* l = sp + 3 * K + 3 * best;
-        const double* h = sp + 6 * K + 3 * best;
-        ok = ok && x.r >= l[0] && x.r <= h[0] && x.g >= l[1] && x.g <= h[1] && x.b >= l[2] && x.b <= h[2];
-    }
-    if (match & 2) ok = ok && x.sd >= sp[10 * K + best] && x.sd <= sp[11 * K + best];
-    if (match & 4) {
-        const double* l = sp + 14 * K + 2 * best;
-        const double* h = sp + 16 * K + 2 * best;
-        ok = ok && x.s0 >= l[0] && x.s0 <= h[0] && x.s1 >= l[1] && x.s1 <= h[1];
-    }
-    return ok ? best + 1 : 0;
 }
 
 __device__ __forceinline__ PropPx load_props(const double* px, int64_t stride2, const double* sd, int64_t sd_stride2,
@@ -281,7 +335,7 @@ __device__ __forceinline__ void load_stats(double* sp, const MrPalette& pal, con
 }
 
 template <int match>
-__global__ void __launch_bounds__(256) k_categorize_props(MrPalette pal, const double* __restrict__ tex,
+__global__ void __launch_bounds__(128) k_categorize_props(MrPalette pal, const double* __restrict__ tex,
                                                           const double* __restrict__ px, int64_t stride2,
                                                           const double* __restrict__ sd, int64_t sd_stride2,
                                                           const double* __restrict__ st, int64_t st_stride2, int64_t n1,
@@ -289,14 +343,52 @@ __global__ void __launch_bounds__(256) k_categorize_props(MrPalette pal, const d
                                                           MrCountersDev* counters) {
     extern __shared__ double sp[];
     load_stats(sp, pal, tex);
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int P = 4;
+    const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * P;
     unsigned nomatch = 0;
-    if (i < n1)
+    if (i0 < n1) {
+        const int n = (int)min((int64_t)P, n1 - i0);
         for (int64_t j = blockIdx.y; j < n2; j += gridDim.y) {
-            const int lab = eval_props(sp, pal.K, match, load_props(px, stride2, sd, sd_stride2, st, st_stride2, i, j), 0);
-            out[j * out_stride2 + i] = (uint8_t)lab;
-            nomatch += lab == 0;
+            PropPx x[P];
+            int lab[P];
+            const int known[P] = {0, 0, 0, 0};
+            const double* pc = reinterpret_cast<const double*>(reinterpret_cast<const uint8_t*>(px) + j * stride2) + i0 * 3;
+            const double* ps = sd ? reinterpret_cast<const double*>(reinterpret_cast<const uint8_t*>(sd) + j * sd_stride2) + i0 : nullptr;
+            const double* pt = st ? reinterpret_cast<const double*>(reinterpret_cast<const uint8_t*>(st) + j * st_stride2) + 2 * i0 : nullptr;
+            const uintptr_t al = reinterpret_cast<uintptr_t>(pc) | reinterpret_cast<uintptr_t>(ps) | reinterpret_cast<uintptr_t>(pt);
+            if (n == P && (al & 15u) == 0) {      // whole 16-byte loads: 96 + 32 + 64 contiguous bytes per thread
+                double v[12];
+#pragma unroll
+                for (int t = 0; t < 6; ++t) {
+                    const double2 d = __ldg(reinterpret_cast<const double2*>(pc) + t);
+                    v[2 * t] = d.x; v[2 * t + 1] = d.y;
+                }
+#pragma unroll
+                for (int q = 0; q < P; ++q) { x[q].r = v[3 * q]; x[q].g = v[3 * q + 1]; x[q].b = v[3 * q + 2]; x[q].sd = x[q].s0 = x[q].s1 = 0.0; }
+                if (ps) {
+                    const double2 a = __ldg(reinterpret_cast<const double2*>(ps)), b = __ldg(reinterpret_cast<const double2*>(ps) + 1);
+                    x[0].sd = a.x; x[1].sd = a.y; x[2].sd = b.x; x[3].sd = b.y;
+                }
+                if (pt) {
+#pragma unroll
+                    for (int q = 0; q < P; ++q) {
+                        const double2 d = __ldg(reinterpret_cast<const double2*>(pt) + q);
+                        x[q].s0 = d.x; x[q].s1 = d.y;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < P; ++q) x[q] = load_props(px, stride2, sd, sd_stride2, st, st_stride2, q < n ? i0 + q : i0, j);
+            }
+            eval_props<P, match>(sp, pal.K, x, known, lab);
+            uint8_t* o = out + j * out_stride2 + i0;
+            const uint32_t word = (uint32_t)lab[0] | ((uint32_t)lab[1] << 8) | ((uint32_t)lab[2] << 16) | ((uint32_t)lab[3] << 24);
+            if (n == P && (((uintptr_t)o) & 3u) == 0) *reinterpret_cast<uint32_t*>(o) = word;
+            else
+                for (int q = 0; q < n; ++q) o[q] = (uint8_t)lab[q];
+            for (int q = 0; q < n; ++q) nomatch += lab[q] == 0;
         }
+    }
     if (counters) {
         for (int o = 16; o > 0; o >>= 1) nomatch += __shfl_xor_sync(0xffffffffu, nomatch, o);
         if ((threadIdx.x & 31) == 0 && nomatch) atomicAdd(&counters->n_nomatch, (unsigned long long)nomatch);
@@ -319,7 +411,11 @@ __global__ void __launch_bounds__(256) k_known_props(MrPalette pal, const double
     if (k >= n_known) return;
     if (idx[k] < 0 || idx[k] >= n1 * n2 || cat[k] == 0) return;
     const int64_t i = idx[k] % n1, j = idx[k] / n1;
-    out[j * out_stride2 + i] = (uint8_t)eval_props(sp, pal.K, match, load_props(px, stride2, sd, sd_stride2, st, st_stride2, i, j), cat[k]);
+    const PropPx x[1] = {load_props(px, stride2, sd, sd_stride2, st, st_stride2, i, j)};
+    const int known[1] = {cat[k]};
+    int lab[1];
+    eval_props<1, match>(sp, pal.K, x, known, lab);
+    out[j * out_stride2 + i] = (uint8_t)lab[0];
 }
 
 dim3 grid_cols(int64_t width, int64_t n2, int threads, int sm_count) {
@@ -379,11 +475,11 @@ cudaError_t mr_launch_categorize_props(const MrPalette& pal, const double* tex, 
                                        MrCountersDev* counters, int sm_count, cudaStream_t s, int* n_launches) {
     if (n1 <= 0 || n2 <= 0) return cudaSuccess;
     const size_t smem = (size_t)pal.K * 18 * sizeof(double);   // <= 254 * 144 B = 36.6 KB
-    const dim3 g = grid_cols((n1 + 3) / 4, n2, 256, sm_count);
+    const dim3 g = grid_cols((n1 + 3) / 4, n2, 128, sm_count * 2);
     const unsigned gk = (unsigned)((n_known + 255) / 256);
 #define MR_PROPS_CASE(M)                                                                                              \
     case M:                                                                                                           \
-        k_categorize_props<M><<<g, 256, smem, s>>>(pal, tex, px, stride2, sd, sd_stride2, st, st_stride2, n1, n2, out, \
+        k_categorize_props<M><<<g, 128, smem, s>>>(pal, tex, px, stride2, sd, sd_stride2, st, st_stride2, n1, n2, out, \
                                                    out_stride2, counters);                                            \
         if (n_known > 0)                                                                                              \
             k_known_props<M><<<gk, 256, smem, s>>>(pal, tex, px, stride2, sd, sd_stride2, st, st_stride2, n1, n2,      \

@@ -116,6 +116,35 @@ def test_props_categorise_clean_random(ctx, mr, oracle, match, R):
         assert mismatches(ctx.categorize_clean_props_host(px, None, None, 1, R), ctx.categorize_clean_f64_host(px, R)) == 0
 
 
+@pytest.mark.parametrize("n1", [1023, 1300, 4100])
+def test_props_wide_lines(ctx, mr, oracle, n1):
+    """lines wider than one block of threads (several blocks per line, ragged last word)"""
+    rng = np.random.default_rng(n1)
+    n2, K = 5, 6
+    mean, mn, mx, sd, tol = random_palette(rng, K)
+    pal = mr.Palette(mean, mn, mx, sd, tol)
+    ctx.set_palette(pal.mean, pal.lo, pal.hi)
+    ctx.palette = None
+    ctx.set_known(None)
+    sdm, stm = rng.random(K), rng.normal(0, 1, (K, 2))
+    sds, sts = (sdm, sdm - 0.3, sdm + 0.3), (stm, stm - 1.0, stm + 1.0)
+    ctx.set_texture_stats(*sds, *sts)
+    which = rng.integers(0, K, size=(n2, n1))
+    px = mean[which] + rng.normal(0, 0.03, size=(n2, n1, 3))
+    std = sdm[which] + rng.normal(0, 0.1, size=(n2, n1))
+    stripe = stm[which] + rng.normal(0, 0.35, size=(n2, n1, 2))
+    for match in (("color",), ("color", "std", "stripe")):
+        bits = sum(mr.api.MATCH_BITS[m] for m in match)
+        got = ctx.categorize_clean_props_host(px, std if bits & 2 else None, stripe if bits & 4 else None, bits, 0)
+        want = oracle.categorize_props_image(px, std, stripe, match, pal.mean, pal.lo, pal.hi, sds, sts)
+        assert mismatches(got, want) == 0
+        assert (got[:, -8:] != 0).any() and (got[:, :8] != 0).any()
+    assert mismatches(ctx.categorize_clean_f64_host(px, 0), oracle.categorize_f64_image(px, pal.mean, pal.lo, pal.hi)) == 0
+    with np.errstate(invalid="ignore", divide="ignore"):
+        assert ctx.stds_host(px).tobytes() == oracle.stds(px).tobytes()
+        assert ctx.stripes_host(px, 3).tobytes() == oracle.stripes(px, 3).tobytes()
+
+
 def test_props_need_texture_stats_and_planes(ctx, mr):
     mean, mn, mx, sd, tol = random_palette(np.random.default_rng(1), 3)
     pal = mr.Palette(mean, mn, mx, sd, tol)
