@@ -41,7 +41,7 @@ constexpr uint32_t TAG = 0x80000000u;
 constexpr int PT = 16;            // pixels per thread
 constexpr int BT = 256;           // threads per block
 constexpr int CH = PT * BT;       // pixels per chunk
-constexpr int UB = 4;             // chunks per block in the streaming kernels
+constexpr int UB = 2;             // chunks per block in the streaming kernels (count: 12 KB of shared memory each)
 
 // per-chunk staging written by k_count: the only pass over the label plane
 struct Stage {
@@ -89,34 +89,6 @@ __device__ __forceinline__ void unite(uint32_t* parent, uint32_t a, uint32_t b) 
     }
 }
 
-// 16 pixels of a line starting at x (thread t of chunk c: x = c * CH + t * PT); px[k] valid for k < nv.
-// Returns the run-start mask: bit k <=> pixel x + k starts a run (x + k == 0 or label differs from x + k - 1).
-__device__ __forceinline__ uint32_t load_starts(const uint8_t* __restrict__ line, uint32_t x, uint32_t n1, bool al16,
-                                                uint8_t (&px)[PT], int& nv) {
-    nv = x >= n1 ? 0 : (n1 - x < (uint32_t)PT ? (int)(n1 - x) : PT);
-    if (nv == PT && al16) {
-        const uint4 v = *reinterpret_cast<const uint4*>(line + x);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int k = 0; k < PT; ++k) px[k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
-    } else {
-#pragma unroll
-        for (int k = 0; k < PT; ++k) px[k] = k < nv ? line[x + k] : (uint8_t)0;
-    }
-    // label of the pixel before this thread's first one: the previous thread's last pixel
-    int prev = __shfl_up_sync(0xffffffffu, (int)px[PT - 1], 1);
-    if ((threadIdx.x & 31) == 0) prev = (x > 0 && nv > 0) ? (int)line[x - 1] : -1;
-    if (x == 0) prev = -1;
-    uint32_t m = 0;
-#pragma unroll
-    for (int k = 0; k < PT; ++k) {
-        const int cur = px[k];
-        if (k < nv && cur != prev) m |= 1u << k;
-        prev = cur;
-    }
-    return m;
-}
-
 // exclusive prefix over the block (BT = 256 threads) of UB independent values per thread (one barrier pair for all of them)
 __device__ __forceinline__ void block_exclusive_ub(const uint32_t (&v)[UB], uint32_t (&excl)[UB], uint32_t (&tot)[UB]) {
     __shared__ uint32_t wsum[UB][BT / 32];
@@ -151,19 +123,49 @@ __device__ __forceinline__ void block_exclusive_ub(const uint32_t (&v)[UB], uint
     }
 }
 
-// grid: ceil(chunks * n2 / UB) blocks; block = UB consecutive (line y, chunk c) units
+// run-start mask of the 16 pixels in w[0..3] (byte-parallel): bit k <=> pixel k differs from the pixel before it;
+// prev = label of the pixel before w[0]'s first one (any value > 255: none)
+__device__ __forceinline__ uint32_t starts16(const uint32_t (&w)[4], uint32_t prev) {
+    uint32_t m = 0u;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t sh = i == 0 ? ((w[0] << 8) | (prev & 0xFFu)) : __funnelshift_l(w[i - 1], w[i], 8);
+        const uint32_t t = w[i] ^ sh;
+        const uint32_t nz = ((((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) >> 7) & 0x01010101u;   // byte != 0 -> bit 0 of the byte
+        m |= ((nz * 0x10204080u) >> 28) << (4 * i);                                        // bits 0, 8, 16, 24 -> a nibble
+    }
+    if (prev > 0xFFu) m |= 1u;
+    return m;
+}
+
+// grid: ceil(chunks * n2 / UB) blocks; block = UB consecutive (line y, chunk c) units.  The 16-byte loads of all
+// units are issued first; one block scan for all of them; the run starts / labels of a unit are compacted in
+// shared memory and leave as contiguous, coalesced stores.
 __global__ void __launch_bounds__(BT) k_count_stage(const uint8_t* __restrict__ lab, int64_t stride2, uint32_t n1, bool al16,
                                                     uint32_t chunks, uint32_t n_units, uint32_t* __restrict__ cnt, Stage G) {
-    uint8_t px[UB][PT];
-    uint32_t m[UB], pc[UB], excl[UB], tot[UB];
+    __shared__ uint16_t s_x[UB][CH];
+    __shared__ uint8_t s_l[UB][CH];
+    uint32_t w[UB][4], m[UB], pc[UB], excl[UB], tot[UB];
 #pragma unroll
     for (int u = 0; u < UB; ++u) {
         const uint32_t unit = blockIdx.x * UB + u;
         m[u] = 0u;
+        w[u][0] = w[u][1] = w[u][2] = w[u][3] = 0u;
         if (unit < n_units) {   // block-uniform
             const uint32_t y = unit / chunks, c = unit - y * chunks, x = c * CH + threadIdx.x * PT;
-            int nv;
-            m[u] = load_starts(lab + (int64_t)y * stride2, x, n1, al16, px[u], nv);
+            const uint8_t* line = lab + (int64_t)y * stride2;
+            const int nv = x >= n1 ? 0 : (n1 - x < (uint32_t)PT ? (int)(n1 - x) : PT);
+            if (nv == PT && al16) {
+                const uint4 v = *reinterpret_cast<const uint4*>(line + x);
+                w[u][0] = v.x; w[u][1] = v.y; w[u][2] = v.z; w[u][3] = v.w;
+            } else {
+                for (int k = 0; k < nv; ++k) w[u][k >> 2] |= (uint32_t)line[x + k] << (8 * (k & 3));
+            }
+            // label of the pixel before this thread's first one: the previous thread's last pixel
+            uint32_t prev = __shfl_up_sync(0xffffffffu, w[u][3] >> 24, 1);
+            if ((threadIdx.x & 31) == 0) prev = (x > 0 && nv > 0) ? (uint32_t)line[x - 1] : 0x100u;
+            if (x == 0) prev = 0x100u;
+            m[u] = starts16(w[u], prev) & (nv == PT ? 0xFFFFu : ((1u << nv) - 1u));
         }
         pc[u] = __popc(m[u]);
     }
@@ -174,15 +176,26 @@ __global__ void __launch_bounds__(BT) k_count_stage(const uint8_t* __restrict__ 
         if (unit >= n_units) break;
         G.info[(size_t)unit * BT + threadIdx.x] = m[u] | (excl[u] << 16);
         if (threadIdx.x == 0) cnt[unit] = tot[u];
-        uint16_t* sx = G.sx + (size_t)unit * CH + excl[u];
-        uint8_t* sl = G.sl + (size_t)unit * CH + excl[u];
-        uint32_t mm = m[u];
+        uint32_t mm = m[u], pos = excl[u];
+        while (mm) {
+            const int k = __ffs(mm) - 1;
+            mm &= mm - 1;
+            s_x[u][pos] = (uint16_t)(threadIdx.x * PT + k);
+            s_l[u][pos] = (uint8_t)(w[u][k >> 2] >> (8 * (k & 3)));
+            ++pos;
+        }
+    }
+    __syncthreads();
 #pragma unroll
-        for (int k = 0; k < PT; ++k)
-            if ((mm >> k) & 1u) {
-                *sx++ = (uint16_t)(threadIdx.x * PT + k);
-                *sl++ = px[u][k];
-            }
+    for (int u = 0; u < UB; ++u) {
+        const uint32_t unit = blockIdx.x * UB + u;
+        if (unit >= n_units) break;
+        uint16_t* sx = G.sx + (size_t)unit * CH;
+        uint8_t* sl = G.sl + (size_t)unit * CH;
+        for (uint32_t j = threadIdx.x; j < tot[u]; j += BT) {
+            sx[j] = s_x[u][j];
+            sl[j] = s_l[u][j];
+        }
     }
 }
 
@@ -200,9 +213,9 @@ __global__ void __launch_bounds__(BT) k_fill_runs(Runs R, Stage G) {
     }
 }
 
-// in-place exclusive scan of n counts, total appended at a[n]; one block, 32 entries per thread and step
+// in-place exclusive scan of n counts, total appended at a[n]; one block, 8 entries per thread and step
 __global__ void __launch_bounds__(1024) k_scan(uint32_t* __restrict__ a, uint64_t n) {
-    constexpr int E = 32;
+    constexpr int E = 8;
     __shared__ uint32_t wsum[32];
     __shared__ uint32_t carry;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -299,34 +312,21 @@ __global__ void k_init_recs(SegRec* rec, unsigned int n) {
     rec[i] = r;
 }
 
-// one block per line.  Neighbouring runs of a line alternate between a few components, so the runs of a warp
-// are grouped by component (match.any) and reduced inside the warp (redux) before ONE lane per group touches
-// the component's record: an order of magnitude fewer same-address atomics.
+// one block per line.  (Grouping the runs of a warp by component -- match.any + redux -- before touching the
+// records was measured: 280 -> 367 us; the conditional min / max atomics are almost always skipped and the
+// count is a fire-and-forget reduction.)
 __global__ void __launch_bounds__(128) k_stats(uint32_t n1, Runs R, SegRec* __restrict__ rec) {
     const uint32_t y = blockIdx.x;
     const uint32_t c0 = R.cbase[(uint64_t)y * R.chunks], c1 = R.cbase[(uint64_t)(y + 1) * R.chunks];
-    const uint32_t lane = threadIdx.x & 31;
-    for (uint32_t i0 = c0 + (threadIdx.x & ~31u); i0 < c1; i0 += blockDim.x) {   // warp-uniform trip count
-        const uint32_t i = i0 + lane;
-        const bool valid = i < c1;
-        uint32_t s = 0, e = 1, comp = 0xFFFFFF00u + lane;      // idle lanes: groups of their own
-        if (valid) {
-            s = R.start[i];
-            e = (i + 1 < c1) ? R.start[i + 1] : n1;
-            comp = comp_id(R.parent, i);
-            if (R.parent[i] & TAG) rec[comp].label = R.label[i];   // the root run writes the component's label
-        }
-        const uint32_t grp = __match_any_sync(0xffffffffu, comp);
-        const uint32_t cnt = __reduce_add_sync(grp, e - s);
-        const uint32_t lo = __reduce_min_sync(grp, s), hi = __reduce_max_sync(grp, e - 1);
-        if (valid && lane == (uint32_t)(__ffs(grp) - 1)) {
-            SegRec* r = rec + comp;
-            atomicAdd(&r->count, cnt);
-            if (r->xmin > lo) atomicMin(&r->xmin, lo);
-            if (r->xmax < hi) atomicMax(&r->xmax, hi);
-            if (r->ymin > y) atomicMin(&r->ymin, y);
-            if (r->ymax < y) atomicMax(&r->ymax, y);
-        }
+    for (uint32_t i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
+        const uint32_t s = R.start[i], e = (i + 1 < c1) ? R.start[i + 1] : n1;
+        SegRec* r = rec + comp_id(R.parent, i);
+        atomicAdd(&r->count, e - s);
+        if (r->xmin > s) atomicMin(&r->xmin, s);
+        if (r->xmax < e - 1) atomicMax(&r->xmax, e - 1);
+        if (r->ymin > y) atomicMin(&r->ymin, y);
+        if (r->ymax < y) atomicMax(&r->ymax, y);
+        if (R.parent[i] & TAG) r->label = R.label[i];   // the root run writes the component's label
     }
 }
 
