@@ -138,6 +138,8 @@ __device__ __forceinline__ uint32_t starts16(const uint32_t (&w)[4], uint32_t pr
     return m;
 }
 
+// (A persistent variant that loads the next group of units while the current one is processed was measured:
+// 226 -> 275 us, twice the registers and half the resident blocks.)
 // grid: ceil(chunks * n2 / UB) blocks; block = UB consecutive (line y, chunk c) units.  The 16-byte loads of all
 // units are issued first; one block scan for all of them; the run starts / labels of a unit are compacted in
 // shared memory and leave as contiguous, coalesced stores.
@@ -199,17 +201,22 @@ __global__ void __launch_bounds__(BT) k_count_stage(const uint8_t* __restrict__ 
     }
 }
 
-// staging slots -> run arrays; one block per chunk unit
-__global__ void __launch_bounds__(BT) k_fill_runs(Runs R, Stage G) {
-    const uint32_t unit = blockIdx.x;
-    const uint32_t base = R.cbase[unit], n = R.cbase[unit + 1] - base;
-    const uint32_t x0 = (unit % R.chunks) * CH;
-    const uint16_t* sx = G.sx + (size_t)unit * CH;
-    const uint8_t* sl = G.sl + (size_t)unit * CH;
+// staging slots -> run arrays; FU chunk units per block (a unit holds ~140 runs on a filtered sheet: one block
+// per unit left half of its threads idle)
+constexpr int FU = 8;
+__global__ void __launch_bounds__(BT) k_fill_runs(Runs R, Stage G, uint32_t n_units) {
+    const uint32_t u0 = blockIdx.x * FU, u1 = min(u0 + FU, n_units);
+    const uint32_t base0 = R.cbase[u0], n = R.cbase[u1] - base0;
     for (uint32_t j = threadIdx.x; j < n; j += BT) {
-        R.start[base + j] = x0 + sx[j];
-        R.label[base + j] = sl[j];
-        R.parent[base + j] = base + j;
+        const uint32_t i = base0 + j;
+        uint32_t u = u0;                                  // the unit that owns run i (FU - 1 comparisons)
+#pragma unroll
+        for (int k = 1; k < FU; ++k)
+            if (u0 + k < u1 && R.cbase[u0 + k] <= i) u = u0 + k;
+        const uint32_t off = i - R.cbase[u];
+        R.start[i] = (u % R.chunks) * CH + G.sx[(size_t)u * CH + off];
+        R.label[i] = G.sl[(size_t)u * CH + off];
+        R.parent[i] = i;
     }
 }
 
@@ -322,10 +329,13 @@ __global__ void __launch_bounds__(128) k_stats(uint32_t n1, Runs R, SegRec* __re
         const uint32_t s = R.start[i], e = (i + 1 < c1) ? R.start[i + 1] : n1;
         SegRec* r = rec + comp_id(R.parent, i);
         atomicAdd(&r->count, e - s);
-        if (r->xmin > s) atomicMin(&r->xmin, s);
-        if (r->xmax < e - 1) atomicMax(&r->xmax, e - 1);
-        if (r->ymin > y) atomicMin(&r->ymin, y);
-        if (r->ymax < y) atomicMax(&r->ymax, y);
+        // the box so far in two reads (a stale copy only costs a redundant atomic: min / max are monotone)
+        const uint4 a = *reinterpret_cast<const uint4*>(r);          // count, xmin, xmax, ymin
+        const uint32_t ymax = r->ymax;
+        if (a.y > s) atomicMin(&r->xmin, s);
+        if (a.z < e - 1) atomicMax(&r->xmax, e - 1);
+        if (a.w > y) atomicMin(&r->ymin, y);
+        if (ymax < y) atomicMax(&r->ymax, y);
         if (R.parent[i] & TAG) r->label = R.label[i];   // the root run writes the component's label
     }
 }
@@ -469,7 +479,8 @@ cudaError_t mr_launch_prune_components(int64_t n1, int64_t n2, const uint32_t* c
     const Runs R = make_runs(run_mem, n_runs, cbase, n1);
     cudaError_t e = cudaMemsetAsync(d_n_roots, 0, sizeof(unsigned int), s);
     if (e != cudaSuccess) return e;
-    k_fill_runs<<<R.chunks * (unsigned)n2, BT, 0, s>>>(R, make_stage(const_cast<void*>(stage_mem), n1, n2));
+    const uint32_t n_units = R.chunks * (uint32_t)n2;
+    k_fill_runs<<<(n_units + FU - 1) / FU, BT, 0, s>>>(R, make_stage(const_cast<void*>(stage_mem), n1, n2), n_units);
     *n_launches += 1;
     if (n2 > 1) {
         k_merge<<<(unsigned)(n2 - 1), 128, 0, s>>>((uint32_t)n1, R);
