@@ -22,7 +22,7 @@
 //   k_merge    one block per line: every run finds the runs of the previous line that overlap it
 //              (binary search in the sorted run starts) and unites with those of equal label
 //              (lock-free union-find, atomicMin links towards the smaller run index)
-//   k_flatnum  parent = root; roots take a compact component id (tagged into the root's entry)
+//   k_number_roots / k_flatten   roots take a compact component id; every run's parent entry becomes TAG | id
 //   k_stats    per run: count, bounding box, label -> atomics on the component's record
 //   k_known    known-category plane (sparse list): pixel -> run (binary search) -> component
 //   k_decide   per component: the rule of clean.jl:65-88 (Float64 arithmetic as written there)
@@ -59,9 +59,10 @@ struct SegRec {                 // one per component
 
 struct Runs {
     uint32_t* start;            // x of the first pixel
-    uint32_t* parent;           // union-find over run indices; after k_flatnum: root index, or TAG | id in a root
+    uint32_t* parent;           // union-find over run indices; after k_number_roots / k_flatten: TAG | component id
     uint8_t* label;
     uint8_t* out;               // label the run is painted with
+    uint32_t* rootof;           // component id -> its root run (first n_segments entries)
     const uint32_t* cbase;      // first run of every (line, chunk); cbase[n2 * chunks] = number of runs
     uint32_t chunks;            // chunks per line
 };
@@ -278,35 +279,52 @@ __global__ void __launch_bounds__(128) k_merge(uint32_t n1, Runs R) {
     }
 }
 
-__global__ void k_flatnum(uint32_t* __restrict__ parent, uint32_t n, unsigned int* n_roots) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool root = false;
-    if (i < n) {
-        // read-only walk (see the note in DESIGN.md: a path-halving write could land after the owner's store);
-        // a root may already carry its tag
-        uint32_t r = i, p = parent[r];
-        root = (p == i);
-        while (!(p & TAG) && p != r) {
-            r = p;
-            p = parent[r];
-        }
-        if (!root) parent[i] = r;
+// roots take a compact component id: parent[root] = TAG | id, rootof[id] = root.  Four entries per thread
+// (one 16-byte load; the run arrays are 16-byte aligned and padded to a multiple of four entries).
+__global__ void k_number_roots(uint32_t* __restrict__ parent, uint32_t n, unsigned int* n_roots, uint32_t* __restrict__ rootof) {
+    const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    uint32_t rm = 0u;
+    if (i0 < n) {
+        const uint4 v = *reinterpret_cast<const uint4*>(parent + i0);
+        rm = (v.x == i0 ? 1u : 0u) | (v.y == i0 + 1 && i0 + 1 < n ? 2u : 0u) | (v.z == i0 + 2 && i0 + 2 < n ? 4u : 0u) |
+             (v.w == i0 + 3 && i0 + 3 < n ? 8u : 0u);
     }
-    const uint32_t m = __ballot_sync(0xffffffffu, root);
-    if (!m) return;
-    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t c = __popc(rm), lane = threadIdx.x & 31;
+    uint32_t sc = c;                                   // inclusive scan of the counts over the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, sc, o);
+        if (lane >= o) sc += t;
+    }
+    const uint32_t tot = __shfl_sync(0xffffffffu, sc, 31);
+    if (!tot) return;
     uint32_t base = 0;
-    if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(n_roots, (unsigned)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-    if (root) parent[i] = TAG | (base + __popc(m & ((1u << lane) - 1u)));
+    if (lane == 0) base = atomicAdd(n_roots, tot);
+    uint32_t id = __shfl_sync(0xffffffffu, base, 0) + sc - c;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if ((rm >> k) & 1u) {
+            parent[i0 + k] = TAG | id;
+            rootof[id] = i0 + k;
+            ++id;
+        }
 }
 
-__device__ __forceinline__ uint32_t comp_id(const uint32_t* parent, uint32_t run) {
-    const uint32_t v = parent[run];
-    return (v & TAG) ? (v & ~TAG) : (parent[v] & ~TAG);
+// every run takes its component's id: walk towards the root until an entry carries a tag (the root's, or the one
+// another thread has already written into a run on the way: same component), then parent[i] = TAG | id.
+// Afterwards the component of a run is ONE coalesced read (no second, random read of the root's entry).
+__global__ void k_flatten(uint32_t* parent, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t p = parent[i];
+    if (p & TAG) return;
+    while (!(p & TAG)) p = parent[p];   // a stale cached entry is still a valid link of the same component
+    parent[i] = p;
 }
 
-__global__ void k_init_recs(SegRec* rec, unsigned int n) {
+__device__ __forceinline__ uint32_t comp_id(const uint32_t* parent, uint32_t run) { return parent[run] & ~TAG; }
+
+__global__ void k_init_recs(SegRec* rec, unsigned int n, Runs R) {
     const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     SegRec r;
@@ -315,7 +333,7 @@ __global__ void k_init_recs(SegRec* rec, unsigned int n) {
     r.xmax = r.ymax = 0;
     r.cmin = 0xffffffffu;
     r.cmax = 0;
-    r.label = 0;
+    r.label = R.label[R.rootof[i]];   // the component's label = the label of any of its runs
     rec[i] = r;
 }
 
@@ -336,7 +354,6 @@ __global__ void __launch_bounds__(128) k_stats(uint32_t n1, Runs R, SegRec* __re
         if (a.z < e - 1) atomicMax(&r->xmax, e - 1);
         if (a.w > y) atomicMin(&r->ymin, y);
         if (ymax < y) atomicMax(&r->ymax, y);
-        if (R.parent[i] & TAG) r->label = R.label[i];   // the root run writes the component's label
     }
 }
 
@@ -440,6 +457,7 @@ Runs make_runs(void* run_mem, unsigned int n_runs, const uint32_t* cbase, int64_
     R.parent = reinterpret_cast<uint32_t*>(p + n4 * 4);
     R.label = p + n4 * 8;
     R.out = p + n4 * 9;
+    R.rootof = reinterpret_cast<uint32_t*>(p + n4 * 10);
     R.cbase = cbase;
     R.chunks = (uint32_t)((n1 + CH - 1) / CH);
     return R;
@@ -457,7 +475,7 @@ size_t mr_prune_stage_bytes(int64_t n1, int64_t n2) {
     const size_t units = (size_t)((n1 + CH - 1) / CH) * (size_t)n2;
     return units * ((size_t)BT * 4 + (size_t)CH * 3) + 16;
 }
-size_t mr_prune_run_bytes(unsigned int n_runs) { return (((size_t)n_runs + 3) / 4 * 4) * 10 + 16; }
+size_t mr_prune_run_bytes(unsigned int n_runs) { return (((size_t)n_runs + 3) / 4 * 4) * 14 + 16; }
 size_t mr_prune_rec_bytes(unsigned int n_segments) { return ((size_t)n_segments + 1) * sizeof(SegRec); }
 
 // phase 1: run starts per (line, chunk) and their exclusive scan; the number of runs ends up in
@@ -486,8 +504,9 @@ cudaError_t mr_launch_prune_components(int64_t n1, int64_t n2, const uint32_t* c
         k_merge<<<(unsigned)(n2 - 1), 128, 0, s>>>((uint32_t)n1, R);
         *n_launches += 1;
     }
-    k_flatnum<<<(n_runs + 255) / 256, 256, 0, s>>>(R.parent, n_runs, d_n_roots);
-    *n_launches += 1;
+    k_number_roots<<<(n_runs + 1023) / 1024, 256, 0, s>>>(R.parent, n_runs, d_n_roots, R.rootof);
+    k_flatten<<<(n_runs + 255) / 256, 256, 0, s>>>(R.parent, n_runs);
+    *n_launches += 2;
     return cudaGetLastError();
 }
 
@@ -503,7 +522,7 @@ cudaError_t mr_launch_prune_apply(int64_t n1, int64_t n2, const uint32_t* cbase,
     SegRec* r = reinterpret_cast<SegRec*>(rec);
     cudaError_t e = cudaMemsetAsync(d_conflict, 0, sizeof(unsigned int), s);
     if (e != cudaSuccess) return e;
-    k_init_recs<<<(n_segments + 255) / 256, 256, 0, s>>>(r, n_segments);
+    k_init_recs<<<(n_segments + 255) / 256, 256, 0, s>>>(r, n_segments, R);
     k_stats<<<(unsigned)n2, 128, 0, s>>>((uint32_t)n1, R, r);
     *n_launches += 2;
     if (n_known > 0) {
