@@ -133,13 +133,20 @@ __global__ void k_balance_lines(int64_t n2, int64_t chunks, const double* __rest
     }
     lines[j * 3 + 0] = s0; lines[j * 3 + 1] = s1; lines[j * 3 + 2] = s2;
 }
-// three threads: the line sums in order, divided by the pixel count
-__global__ void k_balance_total(int64_t n1, int64_t n2, const double* __restrict__ lines, double* __restrict__ means) {
-    const int ch = threadIdx.x;
-    if (ch >= 3) return;
+// three threads add the line sums in order (the block stages them in shared memory, 256 lines at a time, so that
+// the serial chain is additions only), divided by the pixel count
+__global__ void __launch_bounds__(256) k_balance_total(int64_t n1, int64_t n2, const double* __restrict__ lines, double* __restrict__ means) {
+    __shared__ double s_v[768];
     double s = 0.0;
-    for (int64_t j = 0; j < n2; ++j) s = __dadd_rn(s, lines[j * 3 + ch]);
-    means[ch] = __ddiv_rn(s, (double)(n1 * n2));
+    for (int64_t j0 = 0; j0 < n2; j0 += 256) {
+        const int n = (int)min((int64_t)256, n2 - j0);
+        for (int k = threadIdx.x; k < 3 * n; k += blockDim.x) s_v[k] = lines[j0 * 3 + k];
+        __syncthreads();
+        if (threadIdx.x < 3)
+            for (int k = 0; k < n; ++k) s = __dadd_rn(s, s_v[3 * k + threadIdx.x]);
+        __syncthreads();
+    }
+    if (threadIdx.x < 3) means[threadIdx.x] = __ddiv_rn(s, (double)(n1 * n2));
 }
 __global__ void __launch_bounds__(256) k_balance_apply(BalanceCoef K, const uint8_t* __restrict__ px, int64_t stride2,
                                                        int64_t n1, int64_t n2, const double* __restrict__ means,
@@ -217,7 +224,7 @@ cudaError_t mr_launch_balance(const double* coef21, const uint8_t* px, int64_t s
     double* means = lines + n2 * 3;
     k_balance_chunks<<<(unsigned)((chunks * n2 + 127) / 128), 128, 0, s>>>(K, n1, n2, chunks, partial);
     k_balance_lines<<<(unsigned)((n2 + 127) / 128), 128, 0, s>>>(n2, chunks, partial, lines);
-    k_balance_total<<<1, 32, 0, s>>>(n1, n2, lines, means);
+    k_balance_total<<<1, 256, 0, s>>>(n1, n2, lines, means);
     const int64_t gx = (n1 + 255) / 256;
     int64_t gy = ((int64_t)sm_count * 16 + gx - 1) / gx;
     if (gy > n2) gy = n2;

@@ -121,6 +121,8 @@ __global__ void __launch_bounds__(256) k_stripes_raw(const double2* __restrict__
                                                      double* __restrict__ out, int64_t out_stride2) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n1) return;
+    const bool pow2 = (radius & (radius - 1)) == 0;
+    const double rinv = 1.0 / (double)radius;
     for (int64_t j = blockIdx.y; j < n2; j += gridDim.y) {
         const double2 c = __ldg(sl + j * n1 + i);
         double dir[4];
@@ -139,7 +141,7 @@ __global__ void __launch_bounds__(256) k_stripes_raw(const double2* __restrict__
                     const double ds = __dsub_rn(c.x, n.x), dl = __dsub_rn(c.y, n.y);
                     acc = __dadd_rn(acc, __dadd_rn(__dmul_rn(ds, ds), __dmul_rn(dl, dl)));
                 }
-                side[sd] = __ddiv_rn(acc, (double)radius);
+                side[sd] = pow2 ? __dmul_rn(acc, rinv) : __ddiv_rn(acc, (double)radius);   // a power of two: the product is the quotient
             }
             dir[k] = side[1] < side[0] ? side[1] : side[0];
         }
@@ -182,17 +184,24 @@ __global__ void k_abs_lines(int64_t n2, int64_t chunks, const double* __restrict
     lines[j * 2] = s0;
     lines[j * 2 + 1] = s1;
 }
-// m = mean((mean(abs o first), mean(abs o last))) = (M0 + M1) / 2
-__global__ void k_abs_total(int64_t n1, int64_t n2, const double* __restrict__ lines, double* __restrict__ m_out) {
+// m = mean((mean(abs o first), mean(abs o last))) = (M0 + M1) / 2.  The line sums are added in order by one
+// thread per component; the block fetches them 512 lines at a time into shared memory (coalesced) so that the
+// serial chain is additions only, not dependent global loads.
+__global__ void __launch_bounds__(256) k_abs_total(int64_t n1, int64_t n2, const double* __restrict__ lines, double* __restrict__ m_out) {
+    __shared__ double s_v[1024];
     __shared__ double s_m[2];
-    const int e = threadIdx.x;
-    if (e < 2) {
-        double s = 0.0;
-        for (int64_t j = 0; j < n2; ++j) s = __dadd_rn(s, lines[j * 2 + e]);
-        s_m[e] = __ddiv_rn(s, (double)(n1 * n2));
+    double s = 0.0;
+    for (int64_t j0 = 0; j0 < n2; j0 += 512) {
+        const int n = (int)min((int64_t)512, n2 - j0);
+        for (int k = threadIdx.x; k < 2 * n; k += blockDim.x) s_v[k] = lines[j0 * 2 + k];
+        __syncthreads();
+        if (threadIdx.x < 2)
+            for (int k = 0; k < n; ++k) s = __dadd_rn(s, s_v[2 * k + threadIdx.x]);
+        __syncthreads();
     }
+    if (threadIdx.x < 2) s_m[threadIdx.x] = __ddiv_rn(s, (double)(n1 * n2));
     __syncthreads();
-    if (e == 0) *m_out = __ddiv_rn(__dadd_rn(s_m[0], s_m[1]), 2.0);
+    if (threadIdx.x == 0) *m_out = __ddiv_rn(__dadd_rn(s_m[0], s_m[1]), 2.0);
 }
 
 // ---- the categoriser on PixelProp pixels.  Statistics in shared memory:
@@ -461,7 +470,7 @@ cudaError_t mr_launch_stripes(const double* px, int64_t stride2, int64_t n1, int
     k_stripes_raw<<<g, 256, 0, s>>>(sl, n1, n2, radius, out, out_stride2);
     k_abs_chunks<<<(unsigned)((chunks * n2 + 7) / 8), 256, 0, s>>>(out, out_stride2, n1, n2, chunks, partial);
     k_abs_lines<<<(unsigned)((n2 + 127) / 128), 128, 0, s>>>(n2, chunks, partial, lines);
-    k_abs_total<<<1, 32, 0, s>>>(n1, n2, lines, m);
+    k_abs_total<<<1, 256, 0, s>>>(n1, n2, lines, m);
     k_div_plane<<<grid_cols(2 * n1, n2, 256, sm_count), 256, 0, s>>>(out, out_stride2, 2 * n1, n2, m);
     *n_launches += 6;
     return cudaGetLastError();

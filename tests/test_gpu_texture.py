@@ -73,6 +73,43 @@ def test_texture_device_entries_with_pitches(ctx, oracle):
     assert bool((d_out[:, 2 * n1:] == -7.0).all())
 
 
+def test_props_device_entry_with_pitches(ctx, mr, oracle):
+    """device-resident planes with padded lines; nothing is written outside the label lines"""
+    rng = np.random.default_rng(23)
+    n2, n1, K = 41, 203, 5
+    mean, mn, mx, sd, tol = random_palette(rng, K)
+    pal = mr.Palette(mean, mn, mx, sd, tol)
+    ctx.set_palette(pal.mean, pal.lo, pal.hi)
+    ctx.palette = None
+    ctx.set_known(None)
+    sdm, stm = rng.random(K), rng.normal(0, 1, (K, 2))
+    sds, sts = (sdm, sdm - 0.3, sdm + 0.3), (stm, stm - 1.0, stm + 1.0)
+    ctx.set_texture_stats(*sds, *sts)
+    which = rng.integers(0, K, size=(n2, n1))
+    px = mean[which] + rng.normal(0, 0.03, size=(n2, n1, 3))
+    std = sdm[which] + rng.normal(0, 0.1, size=(n2, n1))
+    stripe = stm[which] + rng.normal(0, 0.35, size=(n2, n1, 2))
+    dev = torch.device("cuda", 0)
+
+    def padded(a, extra):
+        flat = a.reshape(n2, -1)
+        t = torch.full((n2, flat.shape[1] + extra), 9.0, dtype=torch.float64, device=dev)
+        t[:, :flat.shape[1]] = torch.from_numpy(flat).to(dev)
+        return t
+    d_px, d_sd, d_st = padded(px, 5), padded(std, 3), padded(stripe, 7)
+    s = torch.cuda.current_stream().cuda_stream
+    for R in (0, 2):
+        d_out = torch.full((n2, n1 + 29), 77, dtype=torch.uint8, device=dev)
+        ctx._ck(ctx._L.mr_categorize_clean_props_dev(ctx._h, d_px.data_ptr(), d_px.shape[1] * 8, d_sd.data_ptr(), d_sd.shape[1] * 8,
+                                                     d_st.data_ptr(), d_st.shape[1] * 8, n1, n2, 7, R, d_out.data_ptr(),
+                                                     d_out.shape[1], s))
+        torch.cuda.synchronize()
+        lab = oracle.categorize_props_image(px, std, stripe, ("color", "std", "stripe"), pal.mean, pal.lo, pal.hi, sds, sts)
+        want = oracle.majority(lab, R) if R else lab
+        assert mismatches(d_out[:, :n1].cpu().numpy(), want) == 0
+        assert bool((d_out[:, n1:] == 77).all())
+
+
 MATCHES = [("color",), ("color", "std"), ("color", "stripe"), ("color", "std", "stripe"), ("std", "stripe"), ("std",),
            ("stripe",)]
 
