@@ -405,30 +405,49 @@ __global__ void k_runout(Runs R, uint32_t n, const SegRec* __restrict__ rec) {
     if (i < n) R.out[i] = (uint8_t)rec[comp_id(R.parent, i)].label;
 }
 
-// UB chunk units per block; per thread: `info` word -> first run and run-start mask of its 16 pixels
+// PU chunk units per block; per thread: `info` word -> first run and run-start mask of its 16 pixels.  The info
+// words, chunk bases and first output labels of all PU units are fetched before any of them is used (three
+// dependent loads per unit: independent chains in flight).
+constexpr int PU = 4;
 __global__ void __launch_bounds__(BT) k_paint(uint32_t n1, uint32_t n_units, Runs R, Stage G, uint8_t* __restrict__ out,
                                               int64_t out_stride2, bool out_al16) {
-    uint32_t inf[UB];
+    uint32_t inf[PU], run[PU];
+    uint8_t cur[PU];
 #pragma unroll
-    for (int u = 0; u < UB; ++u) {
-        const uint32_t unit = blockIdx.x * UB + u;
+    for (int u = 0; u < PU; ++u) {
+        const uint32_t unit = blockIdx.x * PU + u;
         inf[u] = unit < n_units ? G.info[(size_t)unit * BT + threadIdx.x] : 0u;
+        run[u] = unit < n_units ? R.cbase[unit] : 0u;
     }
 #pragma unroll
-    for (int u = 0; u < UB; ++u) {
-        const uint32_t unit = blockIdx.x * UB + u;
+    for (int u = 0; u < PU; ++u) {
+        run[u] += inf[u] >> 16;                                  // next run to start
+        // the run that continues into this thread (none when its first pixel starts one, or outside the sheet)
+        cur[u] = ((inf[u] & 1u) || run[u] == 0u || blockIdx.x * PU + u >= n_units) ? (uint8_t)0 : R.out[run[u] - 1];
+    }
+#pragma unroll
+    for (int u = 0; u < PU; ++u) {
+        const uint32_t unit = blockIdx.x * PU + u;
         if (unit >= n_units) break;
         const uint32_t y = unit / R.chunks, c = unit - y * R.chunks, x = c * CH + threadIdx.x * PT;
         if (x >= n1) continue;
         const int nv = n1 - x < (uint32_t)PT ? (int)(n1 - x) : PT;
         const uint32_t m = inf[u] & 0xFFFFu;
-        uint32_t run = R.cbase[unit] + (inf[u] >> 16);          // next run to start
-        uint8_t cur = (m & 1u) ? (uint8_t)0 : R.out[run - 1];   // the run that continues into this thread
-        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        // the continuing run's label everywhere, then every run start (0.5 per thread on a filtered sheet)
+        // overwrites the bytes from its pixel on: work per run, not per pixel
+        uint32_t r = run[u], mm = m;
+        uint32_t w[4];
+        w[0] = w[1] = w[2] = w[3] = (uint32_t)cur[u] * 0x01010101u;
+        while (mm) {
+            const int k = __ffs(mm) - 1;
+            mm &= mm - 1;
+            const uint32_t L4 = (uint32_t)R.out[r++] * 0x01010101u;
 #pragma unroll
-        for (int k = 0; k < PT; ++k) {
-            if ((m >> k) & 1u) cur = R.out[run++];
-            w[k >> 2] |= (uint32_t)cur << (8 * (k & 3));
+            for (int j = 0; j < 4; ++j) {
+                const int d = k - 4 * j;                                  // first byte of word j to overwrite
+                const uint32_t keep = d <= 0 ? 0u : (d >= 4 ? 0xFFFFFFFFu : (0xFFFFFFFFu >> (8 * (4 - d))));
+                w[j] = (w[j] & keep) | (L4 & ~keep);
+            }
         }
         uint8_t* dst = out + (int64_t)y * out_stride2 + x;
         if (nv == PT && out_al16) {
@@ -533,7 +552,7 @@ cudaError_t mr_launch_prune_apply(int64_t n1, int64_t n2, const uint32_t* cbase,
     k_decide<<<(n_segments + 255) / 256, 256, 0, s>>>(r, n_segments, keep_dev, line_threshold, prune_threshold, d_conflict);
     k_runout<<<(n_runs + 255) / 256, 256, 0, s>>>(R, n_runs, r);
     const uint32_t n_units = R.chunks * (uint32_t)n2;
-    k_paint<<<(n_units + UB - 1) / UB, BT, 0, s>>>((uint32_t)n1, n_units, R, make_stage(const_cast<void*>(stage_mem), n1, n2), out,
+    k_paint<<<(n_units + PU - 1) / PU, BT, 0, s>>>((uint32_t)n1, n_units, R, make_stage(const_cast<void*>(stage_mem), n1, n2), out,
                                                   out_stride2, aligned16(out, out_stride2));
     *n_launches += 3;
     return cudaGetLastError();
