@@ -110,17 +110,18 @@ __device__ __forceinline__ void block_exclusive_ub(const uint32_t (&v)[UB], uint
         for (int u = 0; u < UB; ++u) wsum[u][warp] = s[u];
     }
     __syncthreads();
+    // the BT / 32 = 8 warp totals: lane l < 8 takes one, inclusive scan over those lanes, broadcast
 #pragma unroll
     for (int u = 0; u < UB; ++u) {
-        uint32_t base = 0, all = 0;
+        uint32_t t = lane < BT / 32 ? wsum[u][lane] : 0u;
 #pragma unroll
-        for (int w = 0; w < BT / 32; ++w) {
-            const uint32_t t = wsum[u][w];
-            if (w < warp) base += t;
-            all += t;
+        for (int o = 1; o < BT / 32; o <<= 1) {
+            const uint32_t q = __shfl_up_sync(0xffffffffu, t, o);
+            if (lane >= o) t += q;
         }
-        tot[u] = all;
-        excl[u] = base + s[u] - v[u];
+        tot[u] = __shfl_sync(0xffffffffu, t, BT / 32 - 1);
+        const uint32_t before = __shfl_sync(0xffffffffu, t, (warp + 31) & 31);   // inclusive total of the warps below
+        excl[u] = (warp ? before : 0u) + s[u] - v[u];
     }
 }
 
@@ -141,7 +142,7 @@ __device__ __forceinline__ uint32_t starts16(const uint32_t (&w)[4], uint32_t pr
 
 // (A persistent variant that loads the next group of units while the current one is processed was measured:
 // 226 -> 275 us, twice the registers and half the resident blocks.)
-// grid: ceil(chunks * n2 / UB) blocks; block = UB consecutive (line y, chunk c) units.  The 16-byte loads of all
+// grid: n2 * ceil(chunks / UB) blocks; block = UB consecutive chunks of one line.  The 16-byte loads of all
 // units are issued first; one block scan for all of them; the run starts / labels of a unit are compacted in
 // shared memory and leave as contiguous, coalesced stores.
 __global__ void __launch_bounds__(BT) k_count_stage(const uint8_t* __restrict__ lab, int64_t stride2, uint32_t n1, bool al16,
@@ -150,12 +151,14 @@ __global__ void __launch_bounds__(BT) k_count_stage(const uint8_t* __restrict__ 
     __shared__ uint8_t s_l[UB][CH];
     uint32_t w[UB][4], m[UB], pc[UB], excl[UB], tot[UB];
 #pragma unroll
+    const uint32_t groups = (chunks + UB - 1) / UB;          // blocks per line
+    const uint32_t y = blockIdx.x / groups, c0 = (blockIdx.x - y * groups) * UB;   // line, first chunk of this block (uniform)
+    const uint32_t unit0 = y * chunks + c0;
     for (int u = 0; u < UB; ++u) {
-        const uint32_t unit = blockIdx.x * UB + u;
         m[u] = 0u;
         w[u][0] = w[u][1] = w[u][2] = w[u][3] = 0u;
-        if (unit < n_units) {   // block-uniform
-            const uint32_t y = unit / chunks, c = unit - y * chunks, x = c * CH + threadIdx.x * PT;
+        if (c0 + u < chunks) {   // block-uniform
+            const uint32_t x = (c0 + u) * CH + threadIdx.x * PT;
             const uint8_t* line = lab + (int64_t)y * stride2;
             const int nv = x >= n1 ? 0 : (n1 - x < (uint32_t)PT ? (int)(n1 - x) : PT);
             if (nv == PT && al16) {
@@ -175,8 +178,8 @@ __global__ void __launch_bounds__(BT) k_count_stage(const uint8_t* __restrict__ 
     block_exclusive_ub(pc, excl, tot);
 #pragma unroll
     for (int u = 0; u < UB; ++u) {
-        const uint32_t unit = blockIdx.x * UB + u;
-        if (unit >= n_units) break;
+        const uint32_t unit = unit0 + u;
+        if (c0 + u >= chunks) break;
         G.info[(size_t)unit * BT + threadIdx.x] = m[u] | (excl[u] << 16);
         if (threadIdx.x == 0) cnt[unit] = tot[u];
         uint32_t mm = m[u], pos = excl[u];
@@ -184,15 +187,16 @@ __global__ void __launch_bounds__(BT) k_count_stage(const uint8_t* __restrict__ 
             const int k = __ffs(mm) - 1;
             mm &= mm - 1;
             s_x[u][pos] = (uint16_t)(threadIdx.x * PT + k);
-            s_l[u][pos] = (uint8_t)(w[u][k >> 2] >> (8 * (k & 3)));
+            // byte k of the 16: the 8-byte half by two selects, the byte by one permute
+            s_l[u][pos] = (uint8_t)__byte_perm(k < 8 ? w[u][0] : w[u][2], k < 8 ? w[u][1] : w[u][3], (uint32_t)(k & 7));
             ++pos;
         }
     }
     __syncthreads();
 #pragma unroll
     for (int u = 0; u < UB; ++u) {
-        const uint32_t unit = blockIdx.x * UB + u;
-        if (unit >= n_units) break;
+        const uint32_t unit = unit0 + u;
+        if (c0 + u >= chunks) break;
         uint16_t* sx = G.sx + (size_t)unit * CH;
         uint8_t* sl = G.sl + (size_t)unit * CH;
         for (uint32_t j = threadIdx.x; j < tot[u]; j += BT) {
@@ -503,7 +507,7 @@ cudaError_t mr_launch_prune_count(const uint8_t* labels, int64_t n1, int64_t n2,
                                   void* stage_mem, cudaStream_t s, int* n_launches) {
     const uint32_t chunks = (uint32_t)((n1 + CH - 1) / CH);
     const uint32_t n_units = chunks * (uint32_t)n2;
-    k_count_stage<<<(n_units + UB - 1) / UB, BT, 0, s>>>(labels, stride2, (uint32_t)n1, aligned16(labels, stride2), chunks,
+    k_count_stage<<<(unsigned)n2 * ((chunks + UB - 1) / UB), BT, 0, s>>>(labels, stride2, (uint32_t)n1, aligned16(labels, stride2), chunks,
                                                         n_units, cbase, make_stage(stage_mem, n1, n2));
     k_scan<<<1, 1024, 0, s>>>(cbase, (uint64_t)chunks * (uint64_t)n2);
     *n_launches += 2;
