@@ -51,8 +51,8 @@ struct Stage {
 };
 
 struct SegRec {                 // one per component
+    unsigned int xmin, xmax, ymin, ymax;   // the box: one 16-byte read in k_stats
     unsigned int count;
-    unsigned int xmin, xmax, ymin, ymax;
     unsigned int cmin, cmax;    // known categories present: min / max of the non-zero ones
     unsigned int label;         // input label, later (k_decide) the output label
 };
@@ -359,17 +359,40 @@ __global__ void k_init_recs(SegRec* rec, unsigned int n, Runs R) {
 __global__ void __launch_bounds__(128) k_stats(uint32_t n1, Runs R, SegRec* __restrict__ rec) {
     const uint32_t y = blockIdx.x;
     const uint32_t c0 = R.cbase[(uint64_t)y * R.chunks], c1 = R.cbase[(uint64_t)(y + 1) * R.chunks];
-    for (uint32_t i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
-        const uint32_t s = R.start[i], e = (i + 1 < c1) ? R.start[i + 1] : n1;
-        SegRec* r = rec + comp_id(R.parent, i);
-        atomicAdd(&r->count, e - s);
-        // the box so far in two reads (a stale copy only costs a redundant atomic: min / max are monotone)
-        const uint4 a = *reinterpret_cast<const uint4*>(r);          // count, xmin, xmax, ymin
-        const uint32_t ymax = r->ymax;
-        if (a.y > s) atomicMin(&r->xmin, s);
-        if (a.z < e - 1) atomicMax(&r->xmax, e - 1);
-        if (a.w > y) atomicMin(&r->ymin, y);
-        if (ymax < y) atomicMax(&r->ymax, y);
+    // two runs per thread and step: their component reads and box reads are in flight together
+    for (uint32_t ib = c0 + threadIdx.x; ib < c1; ib += 2 * blockDim.x) {
+        uint32_t s[2], e[2];
+        SegRec* r[2];
+        bool on[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const uint32_t i = ib + k * blockDim.x;
+            on[k] = i < c1;
+            s[k] = 0; e[k] = 1; r[k] = rec;
+            if (on[k]) {
+                s[k] = R.start[i];
+                e[k] = (i + 1 < c1) ? R.start[i + 1] : n1;
+                r[k] = rec + comp_id(R.parent, i);
+            }
+        }
+        uint4 box[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            box[k] = make_uint4(0u, 0xffffffffu, 0u, 0xffffffffu);
+            if (on[k]) {
+                atomicAdd(&r[k]->count, e[k] - s[k]);
+                // the box so far in one 16-byte read (a stale copy only costs a redundant atomic: min / max are monotone)
+                box[k] = *reinterpret_cast<const uint4*>(&r[k]->xmin);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            if (on[k]) {
+                if (box[k].x > s[k]) atomicMin(&r[k]->xmin, s[k]);
+                if (box[k].y < e[k] - 1) atomicMax(&r[k]->xmax, e[k] - 1);
+                if (box[k].z > y) atomicMin(&r[k]->ymin, y);
+                if (box[k].w < y) atomicMax(&r[k]->ymax, y);
+            }
     }
 }
 
