@@ -118,3 +118,27 @@ def test_balance_fit_host_part(mr):
     want = img[0, (xs - 1).astype(int), 0] / 255.0
     assert np.abs((got - got.mean()) - (want - want.mean())).max() < 3e-3      # up to N0f8 quantisation
     assert np.abs(coef[1:]).max() < 1e-6                                         # flat channels: no trend
+
+
+def test_texture_stats_from_points(mr, oracle):
+    """`std` / `stripe` entries of `_component_stats(::Vector{<:PixelProp})` (src/categories.jl:10-17) at the clicked
+    points, bounds as in :131-133; a plane that is None is the reference's initial all-zero plane"""
+    rng = np.random.default_rng(2)
+    n2, n1 = 12, 17
+    std, stripe = rng.random((n2, n1)), rng.normal(0, 1, (n2, n1, 2))
+    pts = [[(2.5, 3.5), (10.2, 7.9), (17.0, 12.0)], [], [(1.0, 1.0)]]
+    tol = np.array([2.0, 1.0, 3.0])
+    tex = mr.TextureStats.from_points(std, stripe, pts, tol)
+    ij = [(4 - 1, 2 - 1), (8 - 1, 10 - 1), (12 - 1, 17 - 1)]                 # (j, i) 0-based; 2.5 -> 2, 3.5 -> 4
+    want = oracle.component_stats(np.array([std[j, i] for j, i in ij]))
+    assert np.allclose([tex.std[k][0] for k in ("mean", "min", "max", "sd")], want, rtol=1e-15, atol=0)
+    for e in range(2):
+        want = oracle.component_stats(np.array([stripe[j, i, e] for j, i in ij]))
+        assert np.allclose([tex.stripe[k][0, e] for k in ("mean", "min", "max", "sd")], want, rtol=1e-15, atol=0)
+    assert np.isnan(tex.std["mean"][1]) and np.isnan(tex.stripe["mean"][1]).all()      # `missing` category
+    assert np.isnan(tex.std["sd"][2])                                                     # one point -> sd NaN
+    (slo, shi), (tlo, thi) = tex.bounds()
+    assert slo[0] == tex.std["min"][0] - tex.std["sd"][0] * 2.0 and shi[0] == tex.std["max"][0] + tex.std["sd"][0] * 2.0
+    assert np.array_equal(tlo[0], tex.stripe["min"][0] - tex.stripe["sd"][0] * 2.0)
+    zero = mr.TextureStats.from_points(None, None, pts, tol)
+    assert zero.std["mean"][0] == 0.0 and (zero.stripe["max"][0] == 0.0).all()
