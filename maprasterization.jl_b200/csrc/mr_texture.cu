@@ -116,38 +116,57 @@ __global__ void __launch_bounds__(256) k_sl_plane(const double* __restrict__ px,
     }
 }
 
-// ---- _stripes, un-normalised: one thread per pixel over the (s, l) plane; outside = the zero colour (s = l = 0)
+// ---- _stripes, un-normalised: one thread per pixel over the (s, l) plane; outside = the zero colour (s = l = 0).
+// RT > 0: the radius as a template parameter (unrolled); INNER: every neighbour of the line's pixels this thread
+// can reach lies inside the image (no bounds tests, plain pointer offsets).
+template <int RT, bool INNER>
+__device__ __forceinline__ void stripes_px(const double2* __restrict__ sl, int64_t n1, int64_t n2, int radius, int64_t i, int64_t j,
+                                           bool pow2, double rinv, double* __restrict__ o) {
+    const int rad = RT > 0 ? RT : radius;
+    const double2* ctr = sl + j * n1 + i;
+    const double2 c = __ldg(ctr);
+    double dir[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {   // vert (1, 0), horz (0, 1), angle45 (1, 1), angle135 (1, -1)
+        const int di = k == 1 ? 0 : 1, dj = k == 0 ? 0 : (k == 3 ? -1 : 1);
+        const int64_t step = (int64_t)dj * n1 + di;          // element offset of one step along the direction
+        double side[2];
+#pragma unroll
+        for (int sd = 0; sd < 2; ++sd) {
+            double acc = 0.0;
+#pragma unroll
+            for (int t = 0; t < rad; ++t) {
+                const int x = sd == 0 ? -rad + t : 1 + t;
+                double2 n = make_double2(0.0, 0.0);
+                if (INNER) n = __ldg(ctr + x * step);
+                else {
+                    const int64_t a = i + di * x, b = j + dj * x;
+                    if (a >= 0 && a < n1 && b >= 0 && b < n2) n = __ldg(ctr + x * step);
+                }
+                const double ds = __dsub_rn(c.x, n.x), dl = __dsub_rn(c.y, n.y);
+                acc = __dadd_rn(acc, __dadd_rn(__dmul_rn(ds, ds), __dmul_rn(dl, dl)));
+            }
+            side[sd] = pow2 ? __dmul_rn(acc, rinv) : __ddiv_rn(acc, (double)rad);   // a power of two: the product is the quotient
+        }
+        dir[k] = side[1] < side[0] ? side[1] : side[0];
+    }
+    o[0] = __dsub_rn(dir[0], dir[1]);
+    o[1] = __dsub_rn(dir[2], dir[3]);
+}
+
+template <int RT>
 __global__ void __launch_bounds__(256) k_stripes_raw(const double2* __restrict__ sl, int64_t n1, int64_t n2, int radius,
                                                      double* __restrict__ out, int64_t out_stride2) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n1) return;
-    const bool pow2 = (radius & (radius - 1)) == 0;
-    const double rinv = 1.0 / (double)radius;
+    const int rad = RT > 0 ? RT : radius;
+    const bool pow2 = (rad & (rad - 1)) == 0;
+    const double rinv = 1.0 / (double)rad;
+    const bool inner_i = i >= rad && i + rad < n1;
     for (int64_t j = blockIdx.y; j < n2; j += gridDim.y) {
-        const double2 c = __ldg(sl + j * n1 + i);
-        double dir[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {   // vert (1, 0), horz (0, 1), angle45 (1, 1), angle135 (1, -1)
-            const int di = k == 1 ? 0 : 1, dj = k == 0 ? 0 : (k == 3 ? -1 : 1);
-            double side[2];
-#pragma unroll
-            for (int sd = 0; sd < 2; ++sd) {
-                double acc = 0.0;
-                for (int t = 0; t < radius; ++t) {
-                    const int x = sd == 0 ? -radius + t : 1 + t;
-                    const int64_t a = i + di * x, b = j + dj * x;
-                    double2 n = make_double2(0.0, 0.0);
-                    if (a >= 0 && a < n1 && b >= 0 && b < n2) n = __ldg(sl + b * n1 + a);
-                    const double ds = __dsub_rn(c.x, n.x), dl = __dsub_rn(c.y, n.y);
-                    acc = __dadd_rn(acc, __dadd_rn(__dmul_rn(ds, ds), __dmul_rn(dl, dl)));
-                }
-                side[sd] = pow2 ? __dmul_rn(acc, rinv) : __ddiv_rn(acc, (double)radius);   // a power of two: the product is the quotient
-            }
-            dir[k] = side[1] < side[0] ? side[1] : side[0];
-        }
         double* o = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(out) + j * out_stride2) + 2 * i;
-        o[0] = __dsub_rn(dir[0], dir[1]);
-        o[1] = __dsub_rn(dir[2], dir[3]);
+        if (inner_i && j >= rad && j + rad < n2) stripes_px<RT, true>(sl, n1, n2, radius, i, j, pow2, rinv, o);
+        else stripes_px<RT, false>(sl, n1, n2, radius, i, j, pow2, rinv, o);
     }
 }
 
@@ -467,7 +486,13 @@ cudaError_t mr_launch_stripes(const double* px, int64_t stride2, int64_t n1, int
     double* m = lines + n2 * 2;
     const dim3 g = grid_cols(n1, n2, 256, sm_count);
     k_sl_plane<<<g, 256, 0, s>>>(px, stride2, n1, n2, sl);
-    k_stripes_raw<<<g, 256, 0, s>>>(sl, n1, n2, radius, out, out_stride2);
+    switch (radius) {   // the usual radii unrolled (default 3, the GUI's slider starts at 2)
+        case 1: k_stripes_raw<1><<<g, 256, 0, s>>>(sl, n1, n2, radius, out, out_stride2); break;
+        case 2: k_stripes_raw<2><<<g, 256, 0, s>>>(sl, n1, n2, radius, out, out_stride2); break;
+        case 3: k_stripes_raw<3><<<g, 256, 0, s>>>(sl, n1, n2, radius, out, out_stride2); break;
+        case 4: k_stripes_raw<4><<<g, 256, 0, s>>>(sl, n1, n2, radius, out, out_stride2); break;
+        default: k_stripes_raw<0><<<g, 256, 0, s>>>(sl, n1, n2, radius, out, out_stride2); break;
+    }
     k_abs_chunks<<<(unsigned)((chunks * n2 + 7) / 8), 256, 0, s>>>(out, out_stride2, n1, n2, chunks, partial);
     k_abs_lines<<<(unsigned)((n2 + 127) / 128), 128, 0, s>>>(n2, chunks, partial, lines);
     k_abs_total<<<1, 256, 0, s>>>(n1, n2, lines, m);
