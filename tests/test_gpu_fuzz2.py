@@ -91,3 +91,42 @@ def test_multi_random_geometry(mr, oracle, seed):
         assert mismatches(got, want) == 0, dict(seed=seed, ndev=ndev, n1=n1, n2=n2, R=R, K=K)
     finally:
         m.close()
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_texture_random_geometry(ctx, mr, oracle, seed):
+    """_stds / _stripes planes bit-identical and PixelProp labels identical on seeded random shapes, radii, match
+    subsets, window radii and known points (host entry points)"""
+    rng = np.random.default_rng(7000 + seed)
+    n1 = int(rng.choice([1, 2, 3, 4, 5, 7, 16, 31, 255, 256, 257, 513, 1025]))
+    n2 = int(rng.choice([1, 2, 3, 5, 8, 13, 40]))
+    K = int(rng.integers(1, 10))
+    radius = int(rng.choice([1, 2, 3, 4, 5, 8]))
+    px = rng.random((n2, n1, 3))
+    px[rng.random((n2, n1)) < 0.1] = rng.random()          # grey pixels
+    with np.errstate(invalid="ignore", divide="ignore"):
+        std_want, st_want = oracle.stds(px), oracle.stripes(px, radius)
+    std, st = ctx.stds_host(px), ctx.stripes_host(px, radius)
+    assert std.tobytes() == std_want.tobytes() and st.tobytes() == st_want.tobytes()
+    if not (np.isfinite(std).all() and np.isfinite(st).all()):
+        return                                              # one-pixel / flat images: NaN planes (0 / 0), as in Julia
+    mean, mn, mx, sd, tol = random_palette(rng, K, spread=0.3)
+    pal = mr.Palette(mean, mn, mx, sd, tol)
+    ctx.set_palette(pal.mean, pal.lo, pal.hi)
+    ctx.palette = None
+    sdm, stm = rng.random(K), rng.normal(0, 1, (K, 2))
+    sds, sts = (sdm, sdm - rng.random(K), sdm + rng.random(K)), (stm, stm - 2 * rng.random((K, 2)), stm + 2 * rng.random((K, 2)))
+    ctx.set_texture_stats(*sds, *sts)
+    names = ("color", "std", "stripe")
+    bits = int(rng.integers(1, 8))
+    match = tuple(n for k, n in enumerate(names) if bits >> k & 1)
+    R = int(rng.choice([0, 1, 2, 3]))
+    idx = np.unique(rng.integers(0, n1 * n2, size=5))
+    cat = rng.integers(1, K + 1, size=idx.size).astype(np.uint8)
+    ctx.set_known(idx, cat)
+    try:
+        got = ctx.categorize_clean_props_host(px, std if bits & 2 else None, st if bits & 4 else None, bits, R)
+    finally:
+        ctx.set_known(None)
+    lab = oracle.categorize_props_image(px, std, st, match, pal.mean, pal.lo, pal.hi, sds, sts, idx, cat)
+    assert mismatches(got, oracle.majority(lab, R) if R else lab) == 0
