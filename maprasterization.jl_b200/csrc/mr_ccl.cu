@@ -225,43 +225,55 @@ __global__ void __launch_bounds__(BT) k_fill_runs(Runs R, Stage G, uint32_t n_un
     }
 }
 
-// in-place exclusive scan of n counts, total appended at a[n]; one block, 8 entries per thread and step
-__global__ void __launch_bounds__(1024) k_scan(uint32_t* __restrict__ a, uint64_t n) {
-    constexpr int E = 8;
+// in-place exclusive scan of n counts, total appended at a[n]; one block.  Every thread owns one contiguous
+// segment (a multiple of four entries, 16-byte loads): it sums the segment, the block scans the 1024 sums, the
+// thread walks its segment again writing the running prefix.  (The first version walked the array in 13 steps of
+// 8192 entries with three barriers and a round trip to L2 each: 57 us for 100 k entries.)
+__global__ void __launch_bounds__(1024) k_scan(uint32_t* a, uint64_t n) {
     __shared__ uint32_t wsum[32];
-    __shared__ uint32_t carry;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (uint64_t i0 = 0; i0 < n; i0 += 1024 * E) {
-        const uint64_t i = i0 + (uint64_t)threadIdx.x * E;
-        uint32_t v[E], mine = 0;
-#pragma unroll
-        for (int k = 0; k < E; ++k) {
-            v[k] = i + k < n ? a[i + k] : 0u;
-            mine += v[k];
-        }
-        uint32_t s = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, s, o);
-            if (lane >= o) s += t;
-        }
-        if (lane == 31) wsum[warp] = s;
-        __syncthreads();
-        uint32_t base = carry;
-        for (int w = 0; w < warp; ++w) base += wsum[w];
-        uint32_t run = base + s - mine;
-#pragma unroll
-        for (int k = 0; k < E; ++k) {
-            if (i + k < n) a[i + k] = run;
-            run += v[k];
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = base + s;
-        __syncthreads();
+    const uint64_t seg = ((n + 1023) / 1024 + 3) & ~(uint64_t)3;
+    const uint64_t b = min((uint64_t)threadIdx.x * seg, n), e = min(b + seg, n);
+    const uint64_t e4 = b + ((e - b) & ~(uint64_t)3);
+    uint32_t mine = 0;
+#pragma unroll 8
+    for (uint64_t i = b; i < e4; i += 4) {
+        const uint4 v = *reinterpret_cast<const uint4*>(a + i);
+        mine += v.x + v.y + v.z + v.w;
     }
-    if (threadIdx.x == 0) a[n] = carry;
+    for (uint64_t i = e4; i < e; ++i) mine += a[i];
+    uint32_t s = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, s, o);
+        if (lane >= o) s += t;
+    }
+    if (lane == 31) wsum[warp] = s;
+    __syncthreads();
+    uint32_t base = 0, total = 0;
+    for (int w = 0; w < 32; ++w) {
+        const uint32_t t = wsum[w];
+        if (w < warp) base += t;
+        total += t;
+    }
+    __syncthreads();                       // every segment has been summed before any entry is overwritten
+    uint32_t run = base + s - mine;
+#pragma unroll 8
+    for (uint64_t i = b; i < e4; i += 4) {
+        const uint4 v = *reinterpret_cast<const uint4*>(a + i);
+        uint4 o;
+        o.x = run; run += v.x;
+        o.y = run; run += v.y;
+        o.z = run; run += v.z;
+        o.w = run; run += v.w;
+        *reinterpret_cast<uint4*>(a + i) = o;
+    }
+    for (uint64_t i = e4; i < e; ++i) {
+        const uint32_t v = a[i];
+        a[i] = run;
+        run += v;
+    }
+    if (threadIdx.x == 0) a[n] = total;
 }
 
 // one block per line y >= 1 (blockIdx.x = y - 1)
