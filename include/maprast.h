@@ -268,6 +268,23 @@ int mr_categorize_clean_props_dev(mr_ctx* ctx, const double* px_dev, int64_t str
                                   int64_t n1, int64_t n2, int match, int R, uint8_t* labels_dev,
                                   int64_t out_stride2, void* stream);
 
+/* Polygon masks and polygon painting of the "clean" / "fill" buttons (src/selectcolors.jl:480-481, 491-497):
+ *   fill == NULL   plane = _polymask(polygons, A) (:559-563: Rasters.boolmask(...; shape = :polygon)): 1 inside any
+ *                  ring, 0 elsewhere;
+ *   fill != NULL   plane[inside ring p] = fill[p], ring after ring (later rings win), other pixels unchanged:
+ *                  rasterize!(fill_raster, p; fill = i, shape = :polygon) with fill = the category of the ring;
+ *                  fill = 0 for every ring is `(1 .- mask) .* A`.
+ * Rings: HOST arrays; ring p = vertices offsets[p] .. offsets[p + 1] of xy (two doubles each: the 1-based (d1, d2)
+ * coordinates of the GUI, Point2{Float32} widened); also for the device variant (packed and uploaded per call).
+ * Pixel (i, j) is the point (i, j); even-odd rule over the closed ring, an edge (a, b) is crossed when
+ * (a2 > j) != (b2 > j) and i < a1 + (b1 - a1) * ((j - a2) / (b2 - a2)); rings with fewer than three vertices are
+ * empty (the GUI's placeholder polygon).  Rasters.jl is not in the reference tree: the rule is a decision
+ * (parity unpinned).  In place on `plane`. */
+int mr_polygons_host(mr_ctx* ctx, int n_rings, const int32_t* offsets, const double* xy, const uint8_t* fill,
+                     int64_t n1, int64_t n2, uint8_t* plane, int64_t stride2);
+int mr_polygons_dev(mr_ctx* ctx, int n_rings, const int32_t* offsets, const double* xy, const uint8_t* fill,
+                    int64_t n1, int64_t n2, uint8_t* plane_dev, int64_t stride2, void* stream);
+
 /* fill_gaps(src; categories, neighborhood = VonNeumann{2}(), missingval = 0, stats, match = (:color,),
  * known, original, mask), src/clean.jl:2-54, applied `repeat` times as _fill does
  * (src/selectcolors.jl:683-699; call site :490-501).  Per pixel and pass: a masked pixel stays

@@ -28,7 +28,7 @@ SYMBOLS = [
     "mr_blur_host", "mr_blur_dev", "mr_categorize_clean_f64_host", "mr_categorize_clean_f64_dev",
     "mr_balance_host", "mr_balance_dev",
     "mr_stds_host", "mr_stds_dev", "mr_stripes_host", "mr_stripes_dev", "mr_set_texture_stats",
-    "mr_categorize_clean_props_host", "mr_categorize_clean_props_dev",
+    "mr_categorize_clean_props_host", "mr_categorize_clean_props_dev", "mr_polygons_host", "mr_polygons_dev",
     "mr_multi_create", "mr_multi_destroy", "mr_multi_last_error", "mr_multi_device_count", "mr_multi_ctx",
     "mr_multi_band_range", "mr_multi_set_palette", "mr_multi_set_known", "mr_multi_categorize_clean_host",
     "mr_multi_batch_categorize_clean_host", "mr_multi_categorize_clean_dev",
@@ -111,6 +111,8 @@ def load():
     L.mr_set_texture_stats.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
     L.mr_categorize_clean_props_host.argtypes = [vp, vp, i64, vp, i64, vp, i64, i64, i64, i32, i32, u8p, i64]
     L.mr_categorize_clean_props_dev.argtypes = [vp, vp, i64, vp, i64, vp, i64, i64, i64, i32, i32, u8p, i64, vp]
+    L.mr_polygons_host.argtypes = [vp, i32, vp, vp, vp, i64, i64, u8p, i64]
+    L.mr_polygons_dev.argtypes = [vp, i32, vp, vp, vp, i64, i64, u8p, i64, vp]
     L.mr_multi_create.argtypes = [vp, i32, C.POINTER(i32)]
     L.mr_multi_create.restype = vp
     L.mr_multi_destroy.argtypes = [vp]
@@ -140,6 +142,7 @@ def load():
                  "mr_blur_host", "mr_blur_dev", "mr_categorize_clean_f64_host", "mr_categorize_clean_f64_dev",
                  "mr_balance_host", "mr_balance_dev", "mr_stds_host", "mr_stds_dev", "mr_stripes_host", "mr_stripes_dev",
                  "mr_set_texture_stats", "mr_categorize_clean_props_host", "mr_categorize_clean_props_dev",
+                 "mr_polygons_host", "mr_polygons_dev",
                  "mr_set_known_band", "mr_clean_dev_bounded", "mr_multi_device_count", "mr_multi_band_range", "mr_multi_set_palette",
                  "mr_multi_set_known", "mr_multi_categorize_clean_host", "mr_multi_batch_categorize_clean_host",
                  "mr_multi_categorize_clean_dev"):
@@ -366,6 +369,31 @@ class Context:
         self._ck(self._L.mr_categorize_clean_props_host(
             self._h, _ptr(px), n1 * 24, None if std is None else _ptr(std), n1 * 8,
             None if stripe is None else _ptr(stripe), n1 * 16, n1, n2, int(match_bits), int(R), _ptr(out), n1))
+        return out
+
+    def polygons_host(self, rings, shape, fill=None, plane=None):
+        """rings: list of vertex lists ((d1, d2), 1-based GUI coordinates).  fill None: the 0 / 1 mask of shape
+        (n2, n1) (`_polymask`, src/selectcolors.jl:559-563); else `plane` with fill[p] painted inside ring p."""
+        off = np.zeros(len(rings) + 1, dtype=np.int32)
+        pts = []
+        for k, r in enumerate(rings):
+            r = np.asarray(r, dtype=np.float32).astype(np.float64).reshape(-1, 2)     # Point2{Float32}
+            pts.append(r)
+            off[k + 1] = off[k] + r.shape[0]
+        xy = np.ascontiguousarray(np.concatenate(pts) if pts else np.zeros((0, 2)))
+        n2, n1 = shape
+        if fill is None:
+            out = np.empty((n2, n1), dtype=np.uint8)
+            f = None
+        else:
+            out = np.ascontiguousarray(plane, dtype=np.uint8).copy()
+            if out.shape != (n2, n1):
+                raise ValueError("plane must have the given shape")
+            f = np.ascontiguousarray(fill, dtype=np.uint8)
+            if f.size != len(rings):
+                raise ValueError("one fill value per ring")
+        self._ck(self._L.mr_polygons_host(self._h, len(rings), _ptr(off), _ptr(xy) if xy.size else None,
+                                          None if f is None else _ptr(f), n1, n2, _ptr(out), n1))
         return out
 
     def fill_gaps_host(self, labels, px, categories, mask=None, repeat=1):

@@ -497,6 +497,36 @@ def fill_gaps(src, **kw):
     return fill_gaps_u8(src, **kw).astype(np.int64)
 
 
+def _rings_of(polygons):
+    """`polygons`: per category a list of rings (src/selectcolors.jl:35: Vector{Vector{Vector{Point2}}}) ->
+    (rings, category of every ring)"""
+    rings, cats = [], []
+    for c, polys in enumerate(polygons or []):
+        for r in polys:
+            rings.append(r)
+            cats.append(c + 1)
+    return rings, cats
+
+
+def polymask(polygons, shape, *, ctx=None):
+    """`_polymask(polygons, A)` (src/selectcolors.jl:559-563): boolean mask (n2, n1) of the pixels inside any polygon."""
+    rings, _ = _rings_of(polygons)
+    return (ctx or default_context()).polygons_host(rings, tuple(shape)) != 0
+
+
+def paint_polygons(labels, polygons, *, fill=None, ctx=None):
+    """`rasterize!(raster, p; fill = i, shape = :polygon)` for the polygons of every category i
+    (src/selectcolors.jl:494-496); `fill=0` paints zeros: `(1 .- mask) .* labels` (:481).  Returns uint8 labels."""
+    rings, cats = _rings_of(polygons)
+    labels = np.asarray(labels)
+    if labels.ndim != 2 or not np.issubdtype(labels.dtype, np.integer):
+        raise ValueError("labels must be a 2-D integer array")
+    if labels.size and (labels.min() < 0 or labels.max() > 254):
+        raise ValueError("labels must be in 0..254")
+    f = np.asarray(cats, dtype=np.uint8) if fill is None else np.full(len(rings), fill, dtype=np.uint8)
+    return (ctx or default_context()).polygons_host(rings, labels.shape, fill=f, plane=labels.astype(np.uint8))
+
+
 @dataclass
 class MapSelection:
     """`MapSelection` (src/selectcolors.jl:3-8): what `selectcolors` returns -- the clicked points per
@@ -506,6 +536,7 @@ class MapSelection:
     removals: list = field(default_factory=list)
     points: list = field(default_factory=list)
     output: object = None
+    polygons: list = field(default_factory=list)   # per category a list of rings (src/selectcolors.jl:35, :124)
 
     def tolerances(self):
         t = self.settings.get("category_tolerances")
@@ -572,11 +603,19 @@ def rasterize(img, sel, *, hood=None, colourspace="rgb", ctx=None):
     idx, cat = _known_from_points(sel.points, n1)
     known = np.zeros((n2, n1), dtype=np.uint8)
     known.reshape(-1)[idx] = cat
-    cleaned = clean_segments_u8(categorized, known, categories=sel.kept_categories(),
+    # "clean" (src/selectcolors.jl:479-489): masked = (1 .- mask) .* categorized, mask = the drawn polygons
+    polygons = sel.polygons or st.get("polygons")        # the reference keeps them in `settings` (:124)
+    have_polys = any(len(r) >= 3 for polys in (polygons or []) for r in polys)
+    mask = polymask(polygons, (n2, n1), ctx=ctx) if have_polys else None
+    masked = paint_polygons(categorized, polygons, fill=0, ctx=ctx) if have_polys else categorized
+    cleaned = clean_segments_u8(masked, known, categories=sel.kept_categories(),
                                 line_threshold=float(st.get("line_threshold", 0.01)),
                                 prune_threshold=float(st.get("prune_threshold", 20)), ctx=ctx)
     # `_component_stats(original, points[categories])` (selectcolors.jl:689): the rows of the kept categories
     pal = ctx.palette if isinstance(ctx.palette, Palette) else _as_palette(img, sel.points, tol, colourspace)
+    # "fill" (:490-501): fill_gaps with the polygon mask, then every polygon painted with its category
     filled = fill_gaps_u8(cleaned, categories=sel.kept_categories(), stats=pal, original=img, known=known,
-                          mask=None, repeat=int(st.get("fill_repeat", 1)), ctx=ctx)
+                          mask=mask, repeat=int(st.get("fill_repeat", 1)), ctx=ctx)
+    if have_polys:
+        filled = paint_polygons(filled, polygons, ctx=ctx)
     return {"categorized": categorized, "cleaned": cleaned, "filled": filled}

@@ -51,6 +51,7 @@ struct mr_ctx {
     uint8_t* d_runs = nullptr; size_t d_runs_cap = 0;       // run arrays
     uint8_t* d_rec = nullptr; size_t d_rec_cap = 0;
     uint8_t* d_stage = nullptr; size_t d_stage_cap = 0;     // per-chunk staging of the run-count pass
+    uint8_t* d_poly = nullptr; size_t d_poly_cap = 0;       // packed rings of mr_polygons_*
     uint8_t* d_small = nullptr;     // 256-byte keep table | n_roots | conflict
     std::vector<cudaEvent_t> ev_up, ev_done;
     std::string err;
@@ -128,7 +129,7 @@ extern "C" void mr_destroy(mr_ctx* ctx) {
     cudaFree(ctx->d_pal); cudaFree(ctx->d_lut); cudaFree(ctx->d_coarse); cudaFree(ctx->d_qtab);
     cudaFree(ctx->d_known_idx); cudaFree(ctx->d_known_cat); cudaFree(ctx->d_counters); cudaFree(ctx->work.slots);
     cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_tmp); cudaFree(ctx->d_rp_in); cudaFree(ctx->d_rp_out); cudaFree(ctx->d_lab); cudaFree(ctx->d_f64); cudaFree(ctx->d_f64b); cudaFree(ctx->d_tex);
-    cudaFree(ctx->d_parent); cudaFree(ctx->d_runs); cudaFree(ctx->d_rec); cudaFree(ctx->d_stage); cudaFree(ctx->d_small);
+    cudaFree(ctx->d_parent); cudaFree(ctx->d_runs); cudaFree(ctx->d_rec); cudaFree(ctx->d_stage); cudaFree(ctx->d_poly); cudaFree(ctx->d_small);
     if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
@@ -1246,6 +1247,71 @@ extern "C" int mr_categorize_clean_props_host(mr_ctx* ctx, const double* px, int
                    ctx->d_out, line_out, s);
     if (rc) return rc;
     CK(cudaMemcpy2DAsync(labels_out, out_stride2, ctx->d_out, line_out, n1, n2, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return MR_OK;
+}
+
+// ------------------------------------------------------------------ polygon masks / polygon painting
+// (_polymask src/selectcolors.jl:559-563; (1 .- mask) .* A :480-481; rasterize!(...; fill = i) :494-496)
+static int polygons_dev(mr_ctx* ctx, const char* fn, int n_rings, const int32_t* offsets, const double* xy, const uint8_t* fill,
+                        int64_t n1, int64_t n2, uint8_t* plane_dev, int64_t stride2, cudaStream_t s) {
+    std::string f(fn);
+    if (n_rings < 0) return fail(ctx, MR_ERR_ARG, f + ": negative ring count");
+    if (n_rings > 0 && (!offsets || !xy)) return fail(ctx, MR_ERR_ARG, f + ": null ring arrays");
+    if (n_rings > 0 && offsets[0] != 0) return fail(ctx, MR_ERR_ARG, f + ": offsets[0] must be 0");
+    for (int p = 0; p < n_rings; ++p)
+        if (offsets[p + 1] < offsets[p]) return fail(ctx, MR_ERR_ARG, f + ": offsets must not decrease");
+    const int64_t nv = n_rings > 0 ? offsets[n_rings] : 0;
+    for (int64_t k = 0; k < 2 * nv; ++k)
+        if (!isfinite(xy[k])) return fail(ctx, MR_ERR_ARG, f + ": vertex coordinates must be finite");
+    if (n1 == 0 || n2 == 0) return MR_OK;
+    // pack: off | xy | ext | fill (8-byte aligned parts)
+    const size_t off_b = ((size_t)(n_rings + 1) * 4 + 7) / 8 * 8, xy_b = (size_t)nv * 16, ext_b = (size_t)n_rings * 16;
+    std::vector<uint8_t> h(off_b + xy_b + ext_b + (size_t)n_rings + 8, 0);
+    if (n_rings > 0) memcpy(h.data(), offsets, (size_t)(n_rings + 1) * 4);
+    if (nv > 0) memcpy(h.data() + off_b, xy, xy_b);
+    double* ext = reinterpret_cast<double*>(h.data() + off_b + xy_b);
+    for (int p = 0; p < n_rings; ++p) {
+        double lo = INFINITY, hi = -INFINITY;
+        for (int k = offsets[p]; k < offsets[p + 1]; ++k) { lo = fmin(lo, xy[2 * k + 1]); hi = fmax(hi, xy[2 * k + 1]); }
+        ext[2 * p] = lo; ext[2 * p + 1] = hi;
+    }
+    if (fill && n_rings > 0) memcpy(h.data() + off_b + xy_b + ext_b, fill, (size_t)n_rings);
+    int rc;
+    if ((rc = grow(ctx, &ctx->d_poly, &ctx->d_poly_cap, h.size()))) return rc;
+    CK(cudaMemcpyAsync(ctx->d_poly, h.data(), h.size(), cudaMemcpyHostToDevice, s));   // pageable: staged before it returns
+    int nl = 0;
+    cudaError_t e = mr_launch_polygons(n_rings, reinterpret_cast<const int32_t*>(ctx->d_poly),
+                                       reinterpret_cast<const double*>(ctx->d_poly + off_b),
+                                       reinterpret_cast<const double*>(ctx->d_poly + off_b + xy_b),
+                                       fill ? ctx->d_poly + off_b + xy_b + ext_b : nullptr, n1, n2, plane_dev, stride2,
+                                       ctx->sm_count, s, &nl);
+    ctx->launches += nl;
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "polygon launch");
+    return MR_OK;
+}
+
+extern "C" int mr_polygons_dev(mr_ctx* ctx, int n_rings, const int32_t* offsets, const double* xy, const uint8_t* fill,
+                               int64_t n1, int64_t n2, uint8_t* plane_dev, int64_t stride2, void* stream) {
+    int rc = check_image_args(ctx, "mr_polygons_dev", plane_dev, plane_dev, n1, n2, stride2, 1, stride2, 0, 0, 0);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    return polygons_dev(ctx, "mr_polygons_dev", n_rings, offsets, xy, fill, n1, n2, plane_dev, stride2, (cudaStream_t)stream);
+}
+
+extern "C" int mr_polygons_host(mr_ctx* ctx, int n_rings, const int32_t* offsets, const double* xy, const uint8_t* fill,
+                                int64_t n1, int64_t n2, uint8_t* plane, int64_t stride2) {
+    int rc = check_image_args(ctx, "mr_polygons_host", plane, plane, n1, n2, stride2, 1, stride2, 0, 0, 0);
+    if (rc) return rc;
+    if (n1 == 0 || n2 == 0) return MR_OK;
+    CK(cudaSetDevice(ctx->device));
+    const int64_t pitch = (n1 + 15) / 16 * 16;
+    if ((rc = grow(ctx, &ctx->d_out, &ctx->d_out_cap, (size_t)pitch * n2))) return rc;
+    cudaStream_t s = ctx->s_main;
+    if (fill) CK(cudaMemcpy2DAsync(ctx->d_out, pitch, plane, stride2, n1, n2, cudaMemcpyHostToDevice, s));   // painting keeps the rest
+    rc = polygons_dev(ctx, "mr_polygons_host", n_rings, offsets, xy, fill, n1, n2, ctx->d_out, pitch, s);
+    if (rc) return rc;
+    CK(cudaMemcpy2DAsync(plane, stride2, ctx->d_out, pitch, n1, n2, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return MR_OK;
 }

@@ -129,3 +129,8 @@ cudaError_t mr_launch_categorize_props(const MrPalette& pal, const double* tex, 
                                        int64_t n1, int64_t n2, int64_t n_known, const int64_t* known_idx,
                                        const uint8_t* known_cat, uint8_t* out, int64_t out_stride2,
                                        MrCountersDev* counters, int sm_count, cudaStream_t s, int* n_launches);
+
+// polygon masks / polygon painting (mr_polygon.cu); all pointers device memory
+cudaError_t mr_launch_polygons(int n_rings, const int32_t* off, const double* xy, const double* ext, const uint8_t* fill,
+                               int64_t n1, int64_t n2, uint8_t* plane, int64_t stride2, int sm_count, cudaStream_t s,
+                               int* n_launches);

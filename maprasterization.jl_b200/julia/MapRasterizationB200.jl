@@ -22,7 +22,7 @@ using ColorTypes, FixedPointNumbers, Statistics
 import Neighborhoods: Window
 
 export categorize, clean, categorize_clean, categorize_u8, clean_u8, categorize_clean_u8, clean_segments,
-       clean_segments_u8, fill_gaps, fill_gaps_u8, blur, balance, stds, stripes, rasterize, MapSelection, Context, MultiContext, Palette
+       clean_segments_u8, fill_gaps, fill_gaps_u8, blur, balance, stds, stripes, polymask, paint_polygons, rasterize, MapSelection, Context, MultiContext, Palette
 
 const libmaprast = get(ENV, "LIBMAPRAST", joinpath(@__DIR__, "..", "libmaprast.so"))
 const DEFAULT_CATEGORY_TOLERANCE = 2.0            # src/selectcolors.jl:1
@@ -411,6 +411,40 @@ function fill_gaps_u8(src::AbstractMatrix{<:Integer}; categories, stats::Palette
 end
 fill_gaps(src; kw...) = _rewrap(src, fill_gaps_u8(src; kw...))
 
+# ---- polygons (src/selectcolors.jl:480-481, 491-497, 559-563) ------------------------------------------
+# `polygons`: per category a vector of rings, a ring = vector of points (the reference's
+# Vector{Vector{Vector{Point2{Float32}}}}, src/selectcolors.jl:35, :60).  -> offsets, coordinates, category per ring
+function _rings(polygons)
+    off = Int32[0]; xy = Float64[]; cats = UInt8[]
+    for (c, polys) in enumerate(polygons), r in polys
+        for p in r
+            push!(xy, Float64(Float32(p[1])), Float64(Float32(p[2])))
+        end
+        push!(off, Int32(length(xy) ÷ 2)); push!(cats, UInt8(c))
+    end
+    return off, xy, cats
+end
+
+function _polygons!(plane::Matrix{UInt8}, polygons, fill; ctx::Context=default_context())
+    off, xy, cats = _rings(polygons)
+    f = fill === nothing ? nothing : (fill === :category ? cats : Base.fill(UInt8(fill), length(cats)))
+    n1, n2 = size(plane)
+    GC.@preserve plane off xy f begin
+        _check(ctx, ccall((:mr_polygons_host, libmaprast), Cint,
+            (Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Float64}, Ptr{UInt8}, Int64, Int64, Ptr{UInt8}, Int64),
+            ctx.ptr, length(cats), pointer(off), isempty(xy) ? Ptr{Float64}(C_NULL) : pointer(xy),
+            f === nothing ? Ptr{UInt8}(C_NULL) : pointer(f), n1, n2, pointer(plane), n1))
+    end
+    return plane
+end
+
+"`_polymask(polygons, A)` (src/selectcolors.jl:559-563): `Matrix{Bool}` of the pixels inside any polygon."
+polymask(polygons, sz::Tuple{Int,Int}; ctx::Context=default_context()) =
+    _polygons!(Matrix{UInt8}(undef, sz), polygons, nothing; ctx) .!= 0
+"`rasterize!(raster, p; fill = i, shape = :polygon)` for the polygons of every category i (:494-496); `fill = 0`: `(1 .- mask) .* A` (:481)."
+paint_polygons(labels::AbstractMatrix{<:Integer}, polygons; fill=:category, ctx::Context=default_context()) =
+    _polygons!(Matrix{UInt8}(labels), polygons, fill; ctx)
+
 # ---- MapSelection: the non-interactive entry (src/selectcolors.jl:3-8, 21-24, 111-127) ------------
 "Same fields as the reference's `MapSelection`; `settings` is the NamedTuple built at src/selectcolors.jl:111-125."
 struct MapSelection{S<:NamedTuple,O}
@@ -468,11 +502,17 @@ function rasterize(img::AbstractMatrix{T}, sel::MapSelection; hood=Window{0}(), 
     end
     keep = get(sel.settings, :category_keep, fill(true, length(sel.points)))
     kept = _kept_categories(collect(Bool, keep))
-    cleaned = clean_segments_u8(categorized, known; categories=kept,
+    # "clean" (src/selectcolors.jl:479-489): masked = (1 .- mask) .* categorized, mask = the drawn polygons
+    polys = get(sel.settings, :polygons, nothing)
+    drawn = polys !== nothing && any(r -> length(r) >= 3, (r for ps in polys for r in ps))
+    mask === nothing && drawn && (mask = polymask(polys, size(A); ctx))
+    masked = drawn ? paint_polygons(categorized, polys; fill=0, ctx) : categorized
+    cleaned = clean_segments_u8(masked, known; categories=kept,
         line_threshold=get(sel.settings, :line_threshold, 0.01),
         prune_threshold=get(sel.settings, :prune_threshold, 20), ctx)
     filled = fill_gaps_u8(cleaned; categories=kept, stats=pal, original=A, known, mask,
         repeat=get(sel.settings, :fill_repeat, 1), ctx)
+    drawn && (filled = paint_polygons(filled, polys; ctx))      # rasterize!(fill_raster, p; fill = i) (:494-496)
     return (; categorized=_rewrap(img, categorized), cleaned=_rewrap(img, cleaned), filled=_rewrap(img, filled))
 end
 

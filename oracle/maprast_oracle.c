@@ -887,3 +887,45 @@ void mro_categorize_props_image(const double* px, int64_t stride2, const double*
         }
     }
 }
+
+/* =====================================================================================
+ * Polygon masks of the "clean" / "fill" buttons (src/selectcolors.jl:480-481, 491-497):
+ *   mask = _polymask(polygons, A)  (:559-563: Rasters.boolmask(polygons; to = raster, shape = :polygon))
+ *   masked = (1 .- mask) .* categorized;   rasterize!(fill_raster, p; fill = i, shape = :polygon)
+ * PARITY UNPINNED: the rule lives in Rasters.jl 0.4 (PolygonInbounds), not in the reference tree.  Decisions
+ * (DESIGN.md section 15): the raster's lookups are the index ranges (`X(ax[1])`, `Y(ax[2])`, points), so pixel (i, j)
+ * (1-based) is the POINT (i, j) in polygon coordinates; a pixel belongs to a polygon when the crossing number of
+ * the ray towards +d1 is odd (even-odd rule over the closed ring, the last vertex joined to the first); an edge
+ * (a, b) is crossed when (a2 > j) != (b2 > j) and i < a1 + (b1 - a1) * ((j - a2) / (b2 - a2)), every operation one
+ * rounded Float64 operation in that order; a ring with fewer than three vertices (the GUI's placeholder
+ * [[Point2(100, 100)]], :35) is empty.  Vertices are Float32 points converted to Float64.
+ * off[p] .. off[p + 1]: the vertices of ring p in xy (2 doubles each, (d1, d2)). */
+static int in_ring(const double* xy, int nv, double pi, double pj) {
+    if (nv < 3) return 0;
+    int in = 0;
+    for (int a = 0, b = nv - 1; a < nv; b = a++) {
+        const double a1 = xy[2 * a], a2 = xy[2 * a + 1], b1 = xy[2 * b], b2 = xy[2 * b + 1];
+        if ((a2 > pj) != (b2 > pj)) {
+            const double t = (pj - a2) / (b2 - a2);
+            const double x = a1 + (b1 - a1) * t;
+            if (pi < x) in = !in;
+        }
+    }
+    return in;
+}
+
+/* fill == NULL: plane[j][i] = 1 inside any ring, else 0 (the mask).
+ * fill != NULL: plane[j][i] = fill[p] for the LAST ring p that contains the pixel; other pixels keep their value
+ * (rasterize!(…; fill = i) ring after ring; fill = 0 everywhere is `(1 .- mask) .* A`). */
+void mro_polygons(int n_rings, const int32_t* off, const double* xy, const uint8_t* fill, int64_t n1, int64_t n2,
+                  uint8_t* plane, int64_t stride2) {
+    for (int64_t j = 0; j < n2; ++j)
+        for (int64_t i = 0; i < n1; ++i) {
+            int hit = -1;
+            for (int p = 0; p < n_rings; ++p)
+                if (in_ring(xy + 2 * (int64_t)off[p], off[p + 1] - off[p], (double)(i + 1), (double)(j + 1))) hit = p;
+            uint8_t* o = plane + j * stride2 + i;
+            if (!fill) *o = hit >= 0;
+            else if (hit >= 0) *o = fill[hit];
+        }
+}

@@ -144,6 +144,11 @@ void mro_categorize_props_image(const double* px, int64_t stride2, const double*
                                 int64_t n_known, const int64_t* known_idx, const uint8_t* known_cat,
                                 uint8_t* out, int64_t out_stride2);
 
+/* polygon masks / polygon painting of the "clean" and "fill" buttons (src/selectcolors.jl:480-481, 491-497, 559-563);
+ * PARITY UNPINNED (Rasters.jl's rule; decisions in the .c file).  fill == NULL: 0 / 1 mask; else paint. */
+void mro_polygons(int n_rings, const int32_t* off, const double* xy, const uint8_t* fill, int64_t n1, int64_t n2,
+                  uint8_t* plane, int64_t stride2);
+
 #ifdef __cplusplus
 }
 #endif

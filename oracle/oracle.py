@@ -67,6 +67,7 @@ def lib():
         L.mro_categorize_f64_image.argtypes = [C.c_void_p, _i64, _i64, _i64, C.c_int, _f64p, _f64p, _f64p, _i64,
                                                C.c_void_p, C.c_void_p, _u8p, _i64]
         L.mro_balance.argtypes = [_u8p, _i64, _i64, _i64, _f64p, C.c_void_p, _i64, C.c_void_p]
+        L.mro_polygons.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, _i64, _i64, C.c_void_p, _i64]
         L.mro_stds.argtypes = [C.c_void_p, _i64, _i64, _i64, C.c_void_p, _i64]
         L.mro_stripes.argtypes = [C.c_void_p, _i64, _i64, _i64, C.c_int, C.c_void_p, _i64]
         L.mro_categorize_props_image.argtypes = [C.c_void_p, _i64, C.c_void_p, _i64, C.c_void_p, _i64, _i64, _i64,
@@ -243,6 +244,29 @@ def categorize_f64_image(px, mean, lo, hi, known_idx=None, known_cat=None):
         nk = ki.size
     lib().mro_categorize_f64_image(px.ctypes.data, n1, n2, n1 * 24, mean.shape[0], mean, lo, hi, nk,
                                    ki.ctypes.data if nk else None, kc.ctypes.data if nk else None, out.ctypes.data, n1)
+    return out
+
+
+def flatten_rings(rings):
+    """list of rings (each a sequence of (d1, d2) vertices) -> (offsets int32 (n + 1), xy float64 (nv, 2))"""
+    off = np.zeros(len(rings) + 1, dtype=np.int32)
+    pts = []
+    for k, r in enumerate(rings):
+        r = np.asarray(r, dtype=np.float32).astype(np.float64).reshape(-1, 2)     # Point2{Float32} vertices
+        pts.append(r)
+        off[k + 1] = off[k] + r.shape[0]
+    xy = np.ascontiguousarray(np.concatenate(pts) if pts else np.zeros((0, 2)))
+    return off, xy
+
+
+def polygons(rings, shape, fill=None, plane=None):
+    """mask (fill None) or painted label plane of the rings; shape = (n2, n1)"""
+    off, xy = flatten_rings(rings)
+    n2, n1 = shape
+    out = np.zeros((n2, n1), dtype=np.uint8) if plane is None else np.ascontiguousarray(plane, dtype=np.uint8).copy()
+    f = None if fill is None else np.ascontiguousarray(fill, dtype=np.uint8)
+    lib().mro_polygons(len(rings), off.ctypes.data, xy.ctypes.data, None if f is None else f.ctypes.data, n1, n2,
+                       out.ctypes.data, n1)
     return out
 
 

@@ -45,7 +45,7 @@ def prototypes():
 
 JL_SCALAR = {"Cint": "i32", "Int32": "i32", "Int64": "i64", "Float64": "f64", "UInt32": "u32", "Cuint": "u32",
              "Csize_t": "size", "Cvoid": "void", "Cfloat": "f32"}
-JL_POINTEE = {"UInt8": {"uint8_t"}, "Int64": {"int64_t"}, "Float64": {"double"}, "Cint": {"int"}, "Cfloat": {"float"},
+JL_POINTEE = {"UInt8": {"uint8_t"}, "Int64": {"int64_t"}, "Int32": {"int32_t"}, "Float64": {"double"}, "Cint": {"int"}, "Cfloat": {"float"},
               "MRCounters": {"mr_counters"}, "Cvoid": None}   # Ptr{Cvoid}: any pointer
 
 
