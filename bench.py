@@ -726,6 +726,37 @@ def run_ours(args, rank, world, local_rank):
                                  "algorithmic_bytes_per_px": bpp_alg, "achieved": bpp_alg * n1 * bl / (ms * 1e-3) / 1e9,
                                  "peak": peak, "unit": "GB/s", "frac": bpp_alg * n1 * bl / (ms * 1e-3) / 1e9 / peak}}
             del f64, lab64, sdp, stp
+        # polygon mask of the "clean" / "fill" buttons (src/selectcolors.jl:559-563): 16 rings of 12 vertices over the sheet
+        if not batch:
+            prng = np.random.default_rng(17)
+            rings_xy, offs = [], [0]
+            for _ in range(16):
+                c = prng.random(2) * (n1, nb)
+                ang = np.sort(prng.random(12)) * 2 * np.pi
+                rad = (0.05 + 0.15 * prng.random(12)) * min(n1, nb)
+                rings_xy.append(np.stack([c[0] + rad * np.cos(ang), c[1] + rad * np.sin(ang)], axis=1))
+                offs.append(offs[-1] + 12)
+            pxy = np.ascontiguousarray(np.concatenate(rings_xy).astype(np.float32).astype(np.float64))
+            poff = np.asarray(offs, dtype=np.int32)
+            pmask = torch.empty((nb, n1), dtype=torch.uint8, device=dev)
+            def _poly():
+                ctx._ck(ctx._L.mr_polygons_dev(ctx._h, 16, poff.ctypes.data, pxy.ctypes.data, None, n1, nb, pmask.data_ptr(), n1, None))
+            _poly()
+            torch.cuda.synchronize()
+            l0 = ctx.launch_count()
+            e0.record()
+            for _ in range(reps):
+                _poly()
+            e1.record()
+            torch.cuda.synchronize()
+            pm_ms = e0.elapsed_time(e1) / reps
+            res["next_rows"]["polygons"] = {
+                "what": "_polymask: 16 rings of 12 vertices over the sheet, device resident (per call: rings packed and uploaded, one kernel)",
+                "value": my_px / (pm_ms * 1e-3) / 1e6, "unit": UNIT, "ms": pm_ms, "inside_fraction": float(pmask.float().mean().item()),
+                "gpu_launches_per_call": (ctx.launch_count() - l0) / reps,
+                "roofline": {"bound": "hbm", "algorithmic_bytes_per_px": 1, "achieved": my_px / (pm_ms * 1e-3) / 1e9, "peak": peak,
+                             "unit": "GB/s", "frac": my_px / (pm_ms * 1e-3) / 1e9 / peak}}
+            del pmask
         # the standalone Window majority filter, clean(labels; hood): categorise-only labels in, device resident
         pre = torch.empty_like(out)
         ctx.categorize_clean_dev(own, n1, nb, n1 * 3, 3, 0, pre, n1)

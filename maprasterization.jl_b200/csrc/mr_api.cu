@@ -1265,26 +1265,32 @@ static int polygons_dev(mr_ctx* ctx, const char* fn, int n_rings, const int32_t*
     for (int64_t k = 0; k < 2 * nv; ++k)
         if (!isfinite(xy[k])) return fail(ctx, MR_ERR_ARG, f + ": vertex coordinates must be finite");
     if (n1 == 0 || n2 == 0) return MR_OK;
-    // pack: off | xy | ext | fill (8-byte aligned parts)
+    // pack: off | xy | ext | ring_of | fill (8-byte aligned parts)
     const size_t off_b = ((size_t)(n_rings + 1) * 4 + 7) / 8 * 8, xy_b = (size_t)nv * 16, ext_b = (size_t)n_rings * 16;
-    std::vector<uint8_t> h(off_b + xy_b + ext_b + (size_t)n_rings + 8, 0);
+    const size_t ro_b = ((size_t)nv * 4 + 7) / 8 * 8;
+    std::vector<uint8_t> h(off_b + xy_b + ext_b + ro_b + (size_t)n_rings + 8, 0);
     if (n_rings > 0) memcpy(h.data(), offsets, (size_t)(n_rings + 1) * 4);
     if (nv > 0) memcpy(h.data() + off_b, xy, xy_b);
     double* ext = reinterpret_cast<double*>(h.data() + off_b + xy_b);
+    int32_t* ring_of = reinterpret_cast<int32_t*>(h.data() + off_b + xy_b + ext_b);
     for (int p = 0; p < n_rings; ++p) {
         double lo = INFINITY, hi = -INFINITY;
-        for (int k = offsets[p]; k < offsets[p + 1]; ++k) { lo = fmin(lo, xy[2 * k + 1]); hi = fmax(hi, xy[2 * k + 1]); }
+        for (int k = offsets[p]; k < offsets[p + 1]; ++k) {
+            lo = fmin(lo, xy[2 * k + 1]); hi = fmax(hi, xy[2 * k + 1]);
+            ring_of[k] = offsets[p + 1] - offsets[p] >= 3 ? p : -1;
+        }
         ext[2 * p] = lo; ext[2 * p + 1] = hi;
     }
-    if (fill && n_rings > 0) memcpy(h.data() + off_b + xy_b + ext_b, fill, (size_t)n_rings);
+    if (fill && n_rings > 0) memcpy(h.data() + off_b + xy_b + ext_b + ro_b, fill, (size_t)n_rings);
     int rc;
     if ((rc = grow(ctx, &ctx->d_poly, &ctx->d_poly_cap, h.size()))) return rc;
     CK(cudaMemcpyAsync(ctx->d_poly, h.data(), h.size(), cudaMemcpyHostToDevice, s));   // pageable: staged before it returns
     int nl = 0;
-    cudaError_t e = mr_launch_polygons(n_rings, reinterpret_cast<const int32_t*>(ctx->d_poly),
+    cudaError_t e = mr_launch_polygons(n_rings, (int)nv, reinterpret_cast<const int32_t*>(ctx->d_poly),
                                        reinterpret_cast<const double*>(ctx->d_poly + off_b),
                                        reinterpret_cast<const double*>(ctx->d_poly + off_b + xy_b),
-                                       fill ? ctx->d_poly + off_b + xy_b + ext_b : nullptr, n1, n2, plane_dev, stride2,
+                                       reinterpret_cast<const int32_t*>(ctx->d_poly + off_b + xy_b + ext_b),
+                                       fill ? ctx->d_poly + off_b + xy_b + ext_b + ro_b : nullptr, n1, n2, plane_dev, stride2,
                                        ctx->sm_count, s, &nl);
     ctx->launches += nl;
     if (e != cudaSuccess) return fail_cuda(ctx, e, "polygon launch");

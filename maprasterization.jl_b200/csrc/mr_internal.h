@@ -131,6 +131,6 @@ cudaError_t mr_launch_categorize_props(const MrPalette& pal, const double* tex, 
                                        MrCountersDev* counters, int sm_count, cudaStream_t s, int* n_launches);
 
 // polygon masks / polygon painting (mr_polygon.cu); all pointers device memory
-cudaError_t mr_launch_polygons(int n_rings, const int32_t* off, const double* xy, const double* ext, const uint8_t* fill,
-                               int64_t n1, int64_t n2, uint8_t* plane, int64_t stride2, int sm_count, cudaStream_t s,
-                               int* n_launches);
+cudaError_t mr_launch_polygons(int n_rings, int n_edges, const int32_t* off, const double* xy, const double* ext,
+                               const int32_t* ring_of, const uint8_t* fill, int64_t n1, int64_t n2, uint8_t* plane,
+                               int64_t stride2, int sm_count, cudaStream_t s, int* n_launches);

@@ -46,19 +46,108 @@ __global__ void __launch_bounds__(256) k_polygons(int n_rings, const int32_t* __
     }
 }
 
+// The crossings of a line are the same for all of its pixels: per (block, line) the edges are evaluated once
+// (one thread per edge; the x of every crossed edge is appended to its ring's segment in shared memory -- the
+// order inside a segment does not matter, parity is commutative), then a pixel only compares its d1 coordinate
+// with the few crossings of each ring the line crosses.
+constexpr int PXL = 8;          // pixels per thread: two groups of four consecutive pixels (one 32-bit store each)
+__global__ void __launch_bounds__(256) k_polygons_lines(int n_rings, int n_edges, const int32_t* __restrict__ off,
+                                                        const double* __restrict__ xy, const int32_t* __restrict__ ring_of,
+                                                        const uint8_t* __restrict__ fill, int64_t n1, int64_t n2,
+                                                        uint8_t* __restrict__ plane, int64_t stride2) {
+    extern __shared__ double s_x[];                        // [n_edges] crossings, ring p in [off[p], off[p] + s_cnt[p])
+    int* s_cnt = reinterpret_cast<int*>(s_x + n_edges);    // [n_rings]
+    int* s_off = s_cnt + n_rings;                          // [n_rings]
+    int* s_act = s_off + n_rings;                          // [n_rings] rings with crossings on this line, ascending
+    __shared__ int s_nact;
+    for (int p = threadIdx.x; p < n_rings; p += blockDim.x) s_off[p] = __ldg(off + p);
+    const int64_t i0 = ((int64_t)blockIdx.x * (256 * (PXL / 4)) + threadIdx.x) * 4;
+    for (int64_t j = blockIdx.y; j < n2; j += gridDim.y) {
+        const double pj = (double)(j + 1);
+        for (int p = threadIdx.x; p < n_rings; p += blockDim.x) s_cnt[p] = 0;
+        __syncthreads();
+        for (int e = threadIdx.x; e < n_edges; e += blockDim.x) {
+            const int p = __ldg(ring_of + e);
+            if (p < 0) continue;                           // ring with fewer than three vertices
+            const int v0 = __ldg(off + p), v1 = __ldg(off + p + 1);
+            const int eb = e == v0 ? v1 - 1 : e - 1;       // edge (a, b): vertex e and the vertex before it in the ring
+            const double a1 = __ldg(xy + 2 * e), a2 = __ldg(xy + 2 * e + 1), b1 = __ldg(xy + 2 * eb), b2 = __ldg(xy + 2 * eb + 1);
+            if ((a2 > pj) != (b2 > pj)) {
+                const double t = __ddiv_rn(__dsub_rn(pj, a2), __dsub_rn(b2, a2));
+                const double x = __dadd_rn(a1, __dmul_rn(__dsub_rn(b1, a1), t));
+                s_x[v0 + atomicAdd(&s_cnt[p], 1)] = x;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {                            // the rings this line crosses, in ring order (later rings win)
+            int n = 0;
+            for (int p = 0; p < n_rings; ++p)
+                if (s_cnt[p]) s_act[n++] = p;
+            s_nact = n;
+        }
+        __syncthreads();
+        const int nact = s_nact;
+        uint8_t* row = plane + j * stride2;
+#pragma unroll 1
+        for (int g = 0; g < PXL / 4; ++g) {
+            const int64_t i = i0 + (int64_t)g * 1024;      // 256 threads x 4 pixels per group
+            if (i >= n1) break;
+            int hit[4] = {-1, -1, -1, -1};
+            for (int a = 0; a < nact; ++a) {
+                const int p = s_act[a], c = s_cnt[p];
+                const double* x = s_x + s_off[p];
+                unsigned in = 0u;
+                for (int q = 0; q < c; ++q) {
+                    const double xq = x[q];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) in ^= ((double)(i + k + 1) < xq ? 1u : 0u) << k;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if ((in >> k) & 1u) hit[k] = p;
+            }
+            uint8_t* o = row + i;
+            if (i + 4 <= n1 && (reinterpret_cast<uintptr_t>(o) & 3u) == 0) {
+                uint32_t w = fill ? *reinterpret_cast<const uint32_t*>(o) : 0u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (!fill) w |= (uint32_t)(hit[k] >= 0) << (8 * k);
+                    else if (hit[k] >= 0) w = (w & ~(0xFFu << (8 * k))) | ((uint32_t)__ldg(fill + hit[k]) << (8 * k));
+                }
+                *reinterpret_cast<uint32_t*>(o) = w;
+            } else {
+                for (int k = 0; k < 4 && i + k < n1; ++k) {
+                    if (!fill) o[k] = hit[k] >= 0;
+                    else if (hit[k] >= 0) o[k] = __ldg(fill + hit[k]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace
 
-// dev: off (n_rings + 1 int32) | pad to 8 | xy (2 nv doubles) | ext (2 n_rings doubles) | fill (n_rings bytes), see
-// mr_polygon_pack_bytes / the packing in mr_api.cu
-cudaError_t mr_launch_polygons(int n_rings, const int32_t* off, const double* xy, const double* ext, const uint8_t* fill,
-                               int64_t n1, int64_t n2, uint8_t* plane, int64_t stride2, int sm_count, cudaStream_t s,
-                               int* n_launches) {
+// all pointers device memory; ring_of[e] = ring of vertex / edge e (-1: its ring has fewer than three vertices)
+cudaError_t mr_launch_polygons(int n_rings, int n_edges, const int32_t* off, const double* xy, const double* ext,
+                               const int32_t* ring_of, const uint8_t* fill, int64_t n1, int64_t n2, uint8_t* plane,
+                               int64_t stride2, int sm_count, cudaStream_t s, int* n_launches) {
     if (n1 <= 0 || n2 <= 0) return cudaSuccess;
-    const int64_t gx = (n1 + 255) / 256;
-    int64_t gy = ((int64_t)sm_count * 8 + gx - 1) / gx;
-    if (gy > n2) gy = n2;
-    if (gy > 65535) gy = 65535;
-    k_polygons<<<dim3((unsigned)gx, (unsigned)(gy < 1 ? 1 : gy)), 256, 0, s>>>(n_rings, off, xy, ext, fill, n1, n2, plane, stride2);
+    const size_t smem = (size_t)n_edges * 8 + (size_t)n_rings * 12 + 16;
+    if (smem <= 40 * 1024) {          // the usual case: a handful of hand-drawn polygons
+        const int64_t gx = (n1 + 256 * PXL - 1) / (256 * PXL);
+        int64_t gy = ((int64_t)sm_count * 8 + gx - 1) / gx;
+        if (gy > n2) gy = n2;
+        if (gy > 65535) gy = 65535;
+        k_polygons_lines<<<dim3((unsigned)gx, (unsigned)(gy < 1 ? 1 : gy)), 256, smem, s>>>(n_rings, n_edges, off, xy, ring_of, fill,
+                                                                                            n1, n2, plane, stride2);
+    } else {                          // thousands of vertices: every pixel walks the rings itself
+        const int64_t gx = (n1 + 255) / 256;
+        int64_t gy = ((int64_t)sm_count * 8 + gx - 1) / gx;
+        if (gy > n2) gy = n2;
+        if (gy > 65535) gy = 65535;
+        k_polygons<<<dim3((unsigned)gx, (unsigned)(gy < 1 ? 1 : gy)), 256, 0, s>>>(n_rings, off, xy, ext, fill, n1, n2, plane, stride2);
+    }
     *n_launches += 1;
     return cudaGetLastError();
 }

@@ -25,6 +25,16 @@ def test_polygons_random(ctx, oracle, seed):
     assert ctx.polygons_host([], (n2, n1)).sum() == 0
 
 
+def test_polygon_with_thousands_of_vertices(ctx, oracle):
+    """more edges than the shared-memory crossing lists hold: the per-pixel kernel"""
+    n1, n2 = 130, 90
+    ang = np.linspace(0, 2 * np.pi, 6000, endpoint=False)
+    ring = np.stack([65 + 50 * np.cos(ang) * (1 + 0.2 * np.sin(7 * ang)), 45 + 35 * np.sin(ang)], axis=1).tolist()
+    rings = [ring, [(10.0, 10.0), (40.0, 12.0), (20.0, 50.0)]]
+    got = ctx.polygons_host(rings, (n2, n1))
+    assert mismatches(got, oracle.polygons(rings, (n2, n1))) == 0 and 1000 < got.sum() < n1 * n2
+
+
 def test_polygons_device_entry_with_pitch(ctx, oracle):
     rng = np.random.default_rng(5)
     n1, n2 = 301, 77
