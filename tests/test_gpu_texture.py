@@ -182,6 +182,76 @@ def test_props_wide_lines(ctx, mr, oracle, n1):
         assert ctx.stripes_host(px, 3).tobytes() == oracle.stripes(px, 3).tobytes()
 
 
+@pytest.mark.parametrize("bits", [3, 5, 7])
+def test_props_near_ties_and_tiny_sums(ctx, mr, oracle, bits):
+    """adversarial for the division-free loop of the PixelProp categoriser: pairs of categories whose undivided error
+    sums are equal or a few ulps apart (the quotient by 2 / 3 may or may not merge them: the FIRST minimum of the
+    rounded quotients decides), and sums near the subnormal range (the literal loop)"""
+    rng = np.random.default_rng(bits)
+    K, n2, n1 = 6, 64, 512
+    base = rng.random(3) * 0.5 + 0.25
+    d = 0.0625
+    mean = np.stack([base + (d, 0, 0), base - (d, 0, 0), base + (0, d, 0), base - (0, d, 0), base + (0, 0, d), base - (0, 0, d)])
+    lo, hi = mean - 1.0, mean + 1.0
+    pal = mr.Palette(mean, lo, hi, np.zeros((K, 3)))
+    ctx.set_palette(pal.mean, pal.lo, pal.hi)
+    ctx.palette = None
+    ctx.set_known(None)
+    sdm, stm = np.full(K, 0.3), np.tile([0.1, -0.2], (K, 1))
+    sds, sts = (sdm, sdm - 9, sdm + 9), (stm, stm - 9, stm + 9)
+    ctx.set_texture_stats(*sds, *sts)
+    # pixels at the centre +- a few ulps per channel: the six errors are equal up to rounding
+    ulps = rng.integers(-3, 4, size=(n2, n1, 3))
+    px = base + ulps * np.spacing(base)
+    px[: n2 // 4] = mean[rng.integers(0, K, size=(n2 // 4, n1))] + rng.integers(-2, 3, size=(n2 // 4, n1, 3)) * 1e-155   # tiny sums
+    std = 0.3 + rng.integers(-2, 3, size=(n2, n1)) * np.spacing(0.3)
+    stripe = np.array([0.1, -0.2]) + rng.integers(-2, 3, size=(n2, n1, 2)) * np.spacing(0.1)
+    std[: n2 // 4] = 0.3
+    stripe[: n2 // 4] = (0.1, -0.2)
+    match = tuple(n for k, n in enumerate(("color", "std", "stripe")) if bits >> k & 1)
+    got = ctx.categorize_clean_props_host(px, std if bits & 2 else None, stripe if bits & 4 else None, bits, 0)
+    want = oracle.categorize_props_image(px, std, stripe, match, pal.mean, pal.lo, pal.hi, sds, sts)
+    assert mismatches(got, want) == 0
+    assert len(np.unique(got)) >= 4
+
+
+def test_props_quotient_rounding_decides_the_first_minimum(ctx, mr, oracle):
+    """categories that differ only by two ulps of one stripe mean: their undivided sums are equal or one ulp apart,
+    and dividing by 3 merges some of those pairs -- then the EARLIER category wins although its sum is larger.
+    The division-free loop must reproduce that (its remembered rival); the test first checks that the data holds
+    such pixels."""
+    rng = np.random.default_rng(5)
+    K, n2, n1 = 4, 100, 2000
+    cm = np.tile(rng.random(3), (K, 1))
+    pal = mr.Palette(cm, cm - 9, cm + 9, np.zeros((K, 3)))
+    ctx.set_palette(pal.mean, pal.lo, pal.hi)
+    ctx.palette = None
+    ctx.set_known(None)
+    sdm = np.full(K, 0.3)
+    stm = np.tile([0.1, -0.2], (K, 1)).astype(np.float64)
+    for c in range(K):
+        stm[c, 0] = 0.1 + (K - 1 - c) * 2 * np.spacing(0.1)
+    sds, sts = (sdm, sdm - 9, sdm + 9), (stm, stm - 9, stm + 9)
+    ctx.set_texture_stats(*sds, *sts)
+    px = cm[0] + rng.normal(0, 0.3, (n2, n1, 3))
+    std = 0.3 + rng.normal(0, 0.2, (n2, n1))
+    st = np.array([0.1, -0.2]) + rng.normal(0, 0.3, (n2, n1, 2))
+    sums = []
+    for c in range(K):
+        dd = px - cm[c]
+        e = (dd[..., 0] * dd[..., 0] + dd[..., 1] * dd[..., 1]) + dd[..., 2] * dd[..., 2]
+        t = std - sdm[c]
+        e = e + t * t
+        t0, t1 = st[..., 0] - stm[c, 0], st[..., 1] - stm[c, 1]
+        sums.append(e + (t0 * t0 + t1 * t1) * 0.5)
+    S = np.stack(sums)
+    assert int((S.argmin(0) != (S / 3).argmin(0)).sum()) > 1000         # the rounding of the quotient matters here
+    got = ctx.categorize_clean_props_host(px, std, st, 7, 0)
+    want = oracle.categorize_props_image(px, std, st, ("color", "std", "stripe"), pal.mean, pal.lo, pal.hi, sds, sts)
+    assert mismatches(got, want) == 0
+    assert mismatches(want, (S / 3).argmin(0) + 1) == 0                      # and the oracle is the literal rule
+
+
 def test_props_need_texture_stats_and_planes(ctx, mr):
     mean, mn, mx, sd, tol = random_palette(np.random.default_rng(1), 3)
     pal = mr.Palette(mean, mn, mx, sd, tol)
