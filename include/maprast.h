@@ -268,6 +268,16 @@ int mr_categorize_clean_props_dev(mr_ctx* ctx, const double* px_dev, int64_t str
                                   int64_t n1, int64_t n2, int match, int R, uint8_t* labels_dev,
                                   int64_t out_stride2, void* stream);
 
+/* _shrink_grow(A, i, j) (src/clean.jl:132-140): n_erode passes of the categorical erosion `_erode` (:121-129: a pixel
+ * whose 8 Moore neighbours all equal it becomes 0) followed by n_dilate passes of the categorical dilation `_dilate`
+ * (:96-118: a 0 pixel takes the neighbour that occurs most often among its 8 neighbours -- first maximum in
+ * neighbourhood order --, or, if that is 0, the first neighbour that is not 0).  Neighbours outside the image are 0;
+ * Moore(1) in CartesianIndices order (decisions; parity unpinned).  Not in place. */
+int mr_shrink_grow_host(mr_ctx* ctx, const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2,
+                        int n_erode, int n_dilate, uint8_t* out, int64_t out_stride2);
+int mr_shrink_grow_dev(mr_ctx* ctx, const uint8_t* labels_dev, int64_t n1, int64_t n2, int64_t stride2,
+                       int n_erode, int n_dilate, uint8_t* out_dev, int64_t out_stride2, void* stream);
+
 /* Polygon masks and polygon painting of the "clean" / "fill" buttons (src/selectcolors.jl:480-481, 491-497):
  *   fill == NULL   plane = _polymask(polygons, A) (:559-563: Rasters.boolmask(...; shape = :polygon)): 1 inside any
  *                  ring, 0 elsewhere;

@@ -497,6 +497,35 @@ def fill_gaps(src, **kw):
     return fill_gaps_u8(src, **kw).astype(np.int64)
 
 
+def _labels_u8(labels):
+    labels = np.asarray(labels)
+    if labels.ndim != 2 or not np.issubdtype(labels.dtype, np.integer):
+        raise ValueError("labels must be a 2-D integer array")
+    if labels.size and (labels.min() < 0 or labels.max() > 254):
+        raise ValueError("labels must be in 0..254")
+    return labels.astype(np.uint8)
+
+
+def shrink_grow(A, i, j, *, missingval=0, ctx=None):
+    """`_shrink_grow(A, i, j; missingval=0)` (src/clean.jl:132-140): `i` categorical erosions (`_erode`, :121-129), then
+    `j` categorical dilations (`_dilate`, :96-118).  Returns labels, eltype Int."""
+    if missingval != 0:
+        raise ValueError("shrink_grow: only missingval = 0 is supported")
+    if i < 0 or j < 0:
+        raise ValueError("pass counts must be >= 0")
+    return (ctx or default_context()).shrink_grow_host(_labels_u8(A), i, j).astype(np.int64)
+
+
+def erode(A, *, missingval=0, ctx=None):
+    """`_erode(A; missingval=0)` (src/clean.jl:121-129)"""
+    return shrink_grow(A, 1, 0, missingval=missingval, ctx=ctx)
+
+
+def dilate(A, *, missingval=0, ctx=None):
+    """`_dilate(A; missingval=0)` (src/clean.jl:96-118)"""
+    return shrink_grow(A, 0, 1, missingval=missingval, ctx=ctx)
+
+
 def _rings_of(polygons):
     """`polygons`: per category a list of rings (src/selectcolors.jl:35: Vector{Vector{Vector{Point2}}}) ->
     (rings, category of every ring)"""

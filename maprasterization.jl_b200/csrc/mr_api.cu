@@ -1251,6 +1251,70 @@ extern "C" int mr_categorize_clean_props_host(mr_ctx* ctx, const double* px, int
     return MR_OK;
 }
 
+// ------------------------------------------------------------------ _shrink_grow (src/clean.jl:96-140)
+// n_erode passes of _erode, then n_dilate passes of _dilate; ping-pong between `out` and a scratch plane so that the
+// last pass writes `out`
+static int shrink_grow_dev(mr_ctx* ctx, const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2, int n_erode,
+                           int n_dilate, uint8_t* out, int64_t out_stride2, cudaStream_t s) {
+    if (n1 == 0 || n2 == 0) return MR_OK;
+    const int passes = n_erode + n_dilate;
+    if (passes == 0) {
+        CK(cudaMemcpy2DAsync(out, out_stride2, labels, stride2, n1, n2, cudaMemcpyDeviceToDevice, s));
+        return MR_OK;
+    }
+    const int64_t pitch = (n1 + 15) / 16 * 16;
+    int rc;
+    if (passes > 1 && (rc = grow(ctx, &ctx->d_lab, &ctx->d_lab_cap, (size_t)pitch * n2))) return rc;
+    const uint8_t* src = labels;
+    int64_t src_stride = stride2;
+    for (int it = 0; it < passes; ++it) {
+        const bool to_out = ((passes - 1 - it) % 2) == 0;
+        uint8_t* dst = to_out ? out : ctx->d_lab;
+        const int64_t dst_stride = to_out ? out_stride2 : pitch;
+        int nl = 0;
+        cudaError_t e = mr_launch_morph(it >= n_erode, src, src_stride, n1, n2, dst, dst_stride, ctx->sm_count, s, &nl);
+        ctx->launches += nl;
+        if (e != cudaSuccess) return fail_cuda(ctx, e, "erode / dilate launch");
+        src = dst; src_stride = dst_stride;
+    }
+    return MR_OK;
+}
+
+static int shrink_grow_check(mr_ctx* ctx, const char* fn, const void* labels, const void* out, int64_t n1, int64_t n2,
+                             int64_t stride2, int n_erode, int n_dilate, int64_t out_stride2) {
+    int rc = check_image_args(ctx, fn, labels, out, n1, n2, stride2, 1, out_stride2, 0, 0, 0);
+    if (rc) return rc;
+    if (n_erode < 0 || n_dilate < 0) return fail(ctx, MR_ERR_ARG, std::string(fn) + ": negative pass count");
+    if (labels == out && n1 > 0 && n2 > 0) return fail(ctx, MR_ERR_ARG, std::string(fn) + ": in-place operation is not supported");
+    return MR_OK;
+}
+
+extern "C" int mr_shrink_grow_dev(mr_ctx* ctx, const uint8_t* labels_dev, int64_t n1, int64_t n2, int64_t stride2, int n_erode,
+                                  int n_dilate, uint8_t* out_dev, int64_t out_stride2, void* stream) {
+    int rc = shrink_grow_check(ctx, "mr_shrink_grow_dev", labels_dev, out_dev, n1, n2, stride2, n_erode, n_dilate, out_stride2);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    return shrink_grow_dev(ctx, labels_dev, n1, n2, stride2, n_erode, n_dilate, out_dev, out_stride2, (cudaStream_t)stream);
+}
+
+extern "C" int mr_shrink_grow_host(mr_ctx* ctx, const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2, int n_erode,
+                                   int n_dilate, uint8_t* out, int64_t out_stride2) {
+    int rc = shrink_grow_check(ctx, "mr_shrink_grow_host", labels, out, n1, n2, stride2, n_erode, n_dilate, out_stride2);
+    if (rc) return rc;
+    if (n1 == 0 || n2 == 0) return MR_OK;
+    CK(cudaSetDevice(ctx->device));
+    const int64_t pitch = (n1 + 15) / 16 * 16;
+    if ((rc = grow(ctx, &ctx->d_in, &ctx->d_in_cap, (size_t)pitch * n2))) return rc;
+    if ((rc = grow(ctx, &ctx->d_out, &ctx->d_out_cap, (size_t)pitch * n2))) return rc;
+    cudaStream_t s = ctx->s_main;
+    CK(cudaMemcpy2DAsync(ctx->d_in, pitch, labels, stride2, n1, n2, cudaMemcpyHostToDevice, s));
+    rc = shrink_grow_dev(ctx, ctx->d_in, n1, n2, pitch, n_erode, n_dilate, ctx->d_out, pitch, s);
+    if (rc) return rc;
+    CK(cudaMemcpy2DAsync(out, out_stride2, ctx->d_out, pitch, n1, n2, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return MR_OK;
+}
+
 // ------------------------------------------------------------------ polygon masks / polygon painting
 // (_polymask src/selectcolors.jl:559-563; (1 .- mask) .* A :480-481; rasterize!(...; fill = i) :494-496)
 static int polygons_dev(mr_ctx* ctx, const char* fn, int n_rings, const int32_t* offsets, const double* xy, const uint8_t* fill,

@@ -134,3 +134,7 @@ cudaError_t mr_launch_categorize_props(const MrPalette& pal, const double* tex, 
 cudaError_t mr_launch_polygons(int n_rings, int n_edges, const int32_t* off, const double* xy, const double* ext,
                                const int32_t* ring_of, const uint8_t* fill, int64_t n1, int64_t n2, uint8_t* plane,
                                int64_t stride2, int sm_count, cudaStream_t s, int* n_launches);
+
+// categorical erosion / dilation, one pass (mr_morph.cu)
+cudaError_t mr_launch_morph(bool dilate, const uint8_t* a, int64_t stride2, int64_t n1, int64_t n2, uint8_t* out,
+                            int64_t out_stride2, int sm_count, cudaStream_t s, int* n_launches);

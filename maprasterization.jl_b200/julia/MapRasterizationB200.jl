@@ -22,7 +22,7 @@ using ColorTypes, FixedPointNumbers, Statistics
 import Neighborhoods: Window
 
 export categorize, clean, categorize_clean, categorize_u8, clean_u8, categorize_clean_u8, clean_segments,
-       clean_segments_u8, fill_gaps, fill_gaps_u8, blur, balance, stds, stripes, polymask, paint_polygons, rasterize, MapSelection, Context, MultiContext, Palette
+       clean_segments_u8, fill_gaps, fill_gaps_u8, blur, balance, stds, stripes, polymask, paint_polygons, shrink_grow, erode, dilate, rasterize, MapSelection, Context, MultiContext, Palette
 
 const libmaprast = get(ENV, "LIBMAPRAST", joinpath(@__DIR__, "..", "libmaprast.so"))
 const DEFAULT_CATEGORY_TOLERANCE = 2.0            # src/selectcolors.jl:1
@@ -410,6 +410,23 @@ function fill_gaps_u8(src::AbstractMatrix{<:Integer}; categories, stats::Palette
     return out
 end
 fill_gaps(src; kw...) = _rewrap(src, fill_gaps_u8(src; kw...))
+
+# ---- categorical erosion / dilation (src/clean.jl:96-140) ------------------------------------------------
+"`_shrink_grow(A, i, j)` (src/clean.jl:132-140): `i` passes of `_erode` (:121-129), then `j` passes of `_dilate` (:96-118)."
+function shrink_grow_u8(A::AbstractMatrix{<:Integer}, i::Int, j::Int; ctx::Context=default_context())
+    L = Matrix{UInt8}(A)
+    n1, n2 = size(L)
+    out = similar(L)
+    GC.@preserve L out begin
+        _check(ctx, ccall((:mr_shrink_grow_host, libmaprast), Cint,
+            (Ptr{Cvoid}, Ptr{UInt8}, Int64, Int64, Int64, Cint, Cint, Ptr{UInt8}, Int64),
+            ctx.ptr, pointer(L), n1, n2, n1, i, j, pointer(out), n1))
+    end
+    return out
+end
+shrink_grow(A, i::Int, j::Int; kw...) = _rewrap(A, shrink_grow_u8(A, i, j; kw...))
+erode(A; kw...) = shrink_grow(A, 1, 0; kw...)
+dilate(A; kw...) = shrink_grow(A, 0, 1; kw...)
 
 # ---- polygons (src/selectcolors.jl:480-481, 491-497, 559-563) ------------------------------------------
 # `polygons`: per category a vector of rings, a ring = vector of points (the reference's

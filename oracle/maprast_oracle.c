@@ -929,3 +929,49 @@ void mro_polygons(int n_rings, const int32_t* off, const double* xy, const uint8
             else if (hit >= 0) *o = fill[hit];
         }
 }
+
+/* =====================================================================================
+ * Categorical erosion / dilation, `_shrink_grow(A, i, j)` (src/clean.jl:96-140; its call sites in the reference are
+ * commented out, src/selectcolors.jl:699, :703).  PARITY UNPINNED (Neighborhoods.jl 0.1 is not in the tree).
+ * Decisions: Moore(1) = the 8 neighbours without the centre in CartesianIndices order (d1 fastest); neighbours
+ * outside the image are missingval = 0; output of the size of the input.
+ *   _erode  (:121-129): all 8 neighbours equal the pixel -> 0, else the pixel (as written: it empties interiors);
+ *   _dilate (:96-118):  a pixel != 0 stays; for a 0 pixel counts[k] = number of neighbours equal to neighbour k,
+ *                       v = the neighbour at the FIRST maximum of counts; v != 0 -> v, else the first neighbour
+ *                       that is not 0 (0 when there is none). */
+static const int MO1[8] = {-1, 0, 1, -1, 1, -1, 0, 1}, MO2[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
+static void moore8(const uint8_t* a, int64_t n1, int64_t n2, int64_t stride2, int64_t i, int64_t j, int h[8]) {
+    for (int k = 0; k < 8; ++k) {
+        const int64_t x = i + MO1[k], y = j + MO2[k];
+        h[k] = (x >= 0 && x < n1 && y >= 0 && y < n2) ? a[y * stride2 + x] : 0;
+    }
+}
+void mro_erode(const uint8_t* a, int64_t n1, int64_t n2, int64_t stride2, uint8_t* out, int64_t out_stride2) {
+    for (int64_t j = 0; j < n2; ++j)
+        for (int64_t i = 0; i < n1; ++i) {
+            int h[8], all = 1;
+            const int x = a[j * stride2 + i];
+            moore8(a, n1, n2, stride2, i, j, h);
+            for (int k = 0; k < 8; ++k) all = all && h[k] == x;
+            out[j * out_stride2 + i] = all ? 0 : (uint8_t)x;
+        }
+}
+void mro_dilate(const uint8_t* a, int64_t n1, int64_t n2, int64_t stride2, uint8_t* out, int64_t out_stride2) {
+    for (int64_t j = 0; j < n2; ++j)
+        for (int64_t i = 0; i < n1; ++i) {
+            const int x = a[j * stride2 + i];
+            if (x != 0) { out[j * out_stride2 + i] = (uint8_t)x; continue; }
+            int h[8], best = 0, bc = -1;
+            moore8(a, n1, n2, stride2, i, j, h);
+            for (int k = 0; k < 8; ++k) {
+                int c = 0;
+                for (int q = 0; q < 8; ++q) c += h[q] == h[k];
+                if (c > bc) { bc = c; best = k; }                 /* findmax: first maximum */
+            }
+            int v = h[best];
+            if (v == 0)
+                for (int k = 0; k < 8; ++k)
+                    if (h[k] != 0) { v = h[k]; break; }           /* findfirst(!=(missingval), hood) */
+            out[j * out_stride2 + i] = (uint8_t)v;
+        }
+}

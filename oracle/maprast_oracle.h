@@ -149,6 +149,10 @@ void mro_categorize_props_image(const double* px, int64_t stride2, const double*
 void mro_polygons(int n_rings, const int32_t* off, const double* xy, const uint8_t* fill, int64_t n1, int64_t n2,
                   uint8_t* plane, int64_t stride2);
 
+/* categorical erosion / dilation over Moore(1), one pass (src/clean.jl:96-129); PARITY UNPINNED (decisions in the .c file) */
+void mro_erode(const uint8_t* a, int64_t n1, int64_t n2, int64_t stride2, uint8_t* out, int64_t out_stride2);
+void mro_dilate(const uint8_t* a, int64_t n1, int64_t n2, int64_t stride2, uint8_t* out, int64_t out_stride2);
+
 #ifdef __cplusplus
 }
 #endif

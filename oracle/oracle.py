@@ -67,6 +67,8 @@ def lib():
         L.mro_categorize_f64_image.argtypes = [C.c_void_p, _i64, _i64, _i64, C.c_int, _f64p, _f64p, _f64p, _i64,
                                                C.c_void_p, C.c_void_p, _u8p, _i64]
         L.mro_balance.argtypes = [_u8p, _i64, _i64, _i64, _f64p, C.c_void_p, _i64, C.c_void_p]
+        L.mro_erode.argtypes = [_u8p, _i64, _i64, _i64, _u8p, _i64]
+        L.mro_dilate.argtypes = [_u8p, _i64, _i64, _i64, _u8p, _i64]
         L.mro_polygons.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, _i64, _i64, C.c_void_p, _i64]
         L.mro_stds.argtypes = [C.c_void_p, _i64, _i64, _i64, C.c_void_p, _i64]
         L.mro_stripes.argtypes = [C.c_void_p, _i64, _i64, _i64, C.c_int, C.c_void_p, _i64]
@@ -245,6 +247,17 @@ def categorize_f64_image(px, mean, lo, hi, known_idx=None, known_cat=None):
     lib().mro_categorize_f64_image(px.ctypes.data, n1, n2, n1 * 24, mean.shape[0], mean, lo, hi, nk,
                                    ki.ctypes.data if nk else None, kc.ctypes.data if nk else None, out.ctypes.data, n1)
     return out
+
+
+def shrink_grow(labels, n_erode, n_dilate):
+    """`_shrink_grow(A, i, j)` (src/clean.jl:132-140): i passes of `_erode`, then j passes of `_dilate`."""
+    cur = np.ascontiguousarray(labels, dtype=np.uint8)
+    n2, n1 = cur.shape
+    for k in range(n_erode + n_dilate):
+        out = np.empty_like(cur)
+        (lib().mro_erode if k < n_erode else lib().mro_dilate)(cur.ctypes.data, n1, n2, n1, out.ctypes.data, n1)
+        cur = out
+    return cur.copy()
 
 
 def flatten_rings(rings):
