@@ -6,67 +6,128 @@
 //   erode:  all 8 neighbours equal the pixel -> 0, else the pixel (as written in the reference: it empties interiors)
 //   dilate: a pixel != 0 stays; a 0 pixel takes the neighbour at the FIRST maximum of "how many neighbours equal
 //           neighbour k"; if that is 0, the first neighbour that is not 0 (0 when there is none)
-// One thread = four consecutive pixels of a line (one 32-bit store); the 3 x 6 neighbourhood bytes come through L1.
 // Bound: HBM, 2 B per pixel and pass.
 #include "mr_internal.h"
 
 namespace {
 
+// bytes of a 16-pixel row segment shifted by one pixel: pixel x-1 (left) / x+1 (right) at the position of pixel x;
+// lb / rb = the pixels just outside the segment
+__device__ __forceinline__ void shift_px(const uint32_t (&w)[4], uint32_t lb, uint32_t rb, uint32_t (&l)[4], uint32_t (&r)[4]) {
+    l[0] = (w[0] << 8) | lb;
+    l[1] = __funnelshift_l(w[0], w[1], 8);
+    l[2] = __funnelshift_l(w[1], w[2], 8);
+    l[3] = __funnelshift_l(w[2], w[3], 8);
+    r[0] = __funnelshift_r(w[0], w[1], 8);
+    r[1] = __funnelshift_r(w[1], w[2], 8);
+    r[2] = __funnelshift_r(w[2], w[3], 8);
+    r[3] = (w[3] >> 8) | (rb << 24);
+}
+// 0xFF in every byte of t that is not zero
+__device__ __forceinline__ uint32_t nz_bytes(uint32_t t) {
+    return (((((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) >> 7) & 0x01010101u) * 0xFFu;
+}
+
+// One thread = 16 consecutive pixels of a line (16-byte loads of the three rows when the lines are 16-byte aligned,
+// the two pixels beside the segment as byte loads).  Erode is byte-parallel: xor of the pixel word with its eight
+// shifted neighbour words, the bytes that stay zero are the pixels to clear.  Dilate copies words without a 0 pixel
+// and runs the counting rule only for the 0 pixels.
 template <bool DILATE>
 __global__ void __launch_bounds__(256) k_morph(const uint8_t* __restrict__ a, int64_t stride2, int64_t n1, int64_t n2,
-                                               uint8_t* __restrict__ out, int64_t out_stride2) {
-    const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+                                               uint8_t* __restrict__ out, int64_t out_stride2, bool al16, bool out_al16) {
+    const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
     if (i0 >= n1) return;
+    const int nv = n1 - i0 < 16 ? (int)(n1 - i0) : 16;
     for (int64_t j = blockIdx.y; j < n2; j += gridDim.y) {
-        // rows j-1, j, j+1, columns i0-1 .. i0+4 (0 outside the image)
-        uint8_t w[3][6];
+        uint32_t w[3][4], lb[3], rb[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             const int64_t y = j + r - 1;
-            const bool oky = y >= 0 && y < n2;
-            const uint8_t* line = a + (oky ? y : 0) * stride2;
-#pragma unroll
-            for (int q = 0; q < 6; ++q) {
-                const int64_t x = i0 - 1 + q;
-                w[r][q] = (oky && x >= 0 && x < n1) ? __ldg(line + x) : (uint8_t)0;
-            }
-        }
-        uint8_t res[4];
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            // neighbours in CartesianIndices order: (-1,-1) (0,-1) (1,-1) (-1,0) (1,0) (-1,1) (0,1) (1,1)
-            const uint8_t h[8] = {w[0][p], w[0][p + 1], w[0][p + 2], w[1][p], w[1][p + 2], w[2][p], w[2][p + 1], w[2][p + 2]};
-            const uint8_t x = w[1][p + 1];
-            if (!DILATE) {
-                bool all = true;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) all = all && h[k] == x;
-                res[p] = all ? (uint8_t)0 : x;
-            } else if (x != 0) {
-                res[p] = x;
+            w[r][0] = w[r][1] = w[r][2] = w[r][3] = 0u;
+            lb[r] = rb[r] = 0u;
+            if (y < 0 || y >= n2) continue;                    // outside: 0
+            const uint8_t* line = a + y * stride2;
+            if (nv == 16 && al16) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(line + i0));
+                w[r][0] = v.x; w[r][1] = v.y; w[r][2] = v.z; w[r][3] = v.w;
             } else {
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    if (k < nv) w[r][k >> 2] |= (uint32_t)__ldg(line + i0 + k) << (8 * (k & 3));
+            }
+            if (i0 > 0) lb[r] = __ldg(line + i0 - 1);
+            if (i0 + 16 < n1) rb[r] = __ldg(line + i0 + 16);
+        }
+        uint32_t res[4];
+        if (!DILATE) {
+            uint32_t l[3][4], rr[3][4];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) shift_px(w[r], lb[r], rb[r], l[r], rr[r]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t m = w[1][q];
+                const uint32_t d = (l[0][q] ^ m) | (w[0][q] ^ m) | (rr[0][q] ^ m) | (l[1][q] ^ m) | (rr[1][q] ^ m) | (l[2][q] ^ m) |
+                                   (w[2][q] ^ m) | (rr[2][q] ^ m);
+                res[q] = m & nz_bytes(d);                      // a pixel whose eight neighbours all equal it becomes 0
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) res[q] = w[1][q];
+            uint32_t zero = 0u;                                // bit k: pixel k is 0
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t z = ~nz_bytes(w[1][q]) & 0x01010101u;
+                zero |= ((z * 0x10204080u) >> 28) << (4 * q);
+            }
+            zero &= nv == 16 ? 0xFFFFu : ((1u << nv) - 1u);
+            if (zero) {   // a 0 pixel whose eight neighbours are all 0 stays 0: drop those first (byte-parallel)
+                uint32_t l[3][4], rr[3][4];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) shift_px(w[r], lb[r], rb[r], l[r], rr[r]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t any = l[0][q] | w[0][q] | rr[0][q] | l[1][q] | rr[1][q] | l[2][q] | w[2][q] | rr[2][q];
+                    const uint32_t nzb = nz_bytes(any) & 0x01010101u;       // pixels with a neighbour that is not 0
+                    zero &= ~(0xFu << (4 * q)) | (((nzb * 0x10204080u) >> 28) << (4 * q));
+                }
+            }
+            while (zero) {
+                const int k = __ffs(zero) - 1;
+                zero &= zero - 1;
+                // the byte at segment position p (-1 .. 16) of row r
+                auto px = [&](int r, int p) -> uint32_t {
+                    if (p < 0) return lb[r];
+                    if (p > 15) return rb[r];
+                    const uint32_t ww = p < 8 ? (p < 4 ? w[r][0] : w[r][1]) : (p < 12 ? w[r][2] : w[r][3]);
+                    return (ww >> (8 * (p & 3))) & 0xFFu;
+                };
+                // neighbours in CartesianIndices order: (-1,-1) (0,-1) (1,-1) (-1,0) (1,0) (-1,1) (0,1) (1,1)
+                const uint32_t h[8] = {px(0, k - 1), px(0, k), px(0, k + 1), px(1, k - 1), px(1, k + 1), px(2, k - 1), px(2, k), px(2, k + 1)};
                 int best = 0, bc = -1;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
+                for (int t = 0; t < 8; ++t) {
                     int c = 0;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) c += h[q] == h[k];
-                    if (c > bc) { bc = c; best = k; }           // findmax: first maximum
+                    for (int q = 0; q < 8; ++q) c += h[q] == h[t];
+                    if (c > bc) { bc = c; best = t; }           // findmax: first maximum
                 }
-                uint8_t v = 0, first = 0;
+                uint32_t v = 0, first = 0;
 #pragma unroll
-                for (int k = 7; k >= 0; --k) {
-                    if (k == best) v = h[k];
-                    if (h[k] != 0) first = h[k];                 // ends as the first neighbour that is not 0
+                for (int t = 7; t >= 0; --t) {
+                    if (t == best) v = h[t];
+                    if (h[t] != 0) first = h[t];                 // ends as the first neighbour that is not 0
                 }
-                res[p] = v != 0 ? v : first;
+                const uint32_t val = v != 0 ? v : first;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if ((k >> 2) == q) res[q] |= val << (8 * (k & 3));
             }
         }
         uint8_t* o = out + j * out_stride2 + i0;
-        if (i0 + 4 <= n1 && (reinterpret_cast<uintptr_t>(o) & 3u) == 0) {
-            *reinterpret_cast<uint32_t*>(o) = (uint32_t)res[0] | ((uint32_t)res[1] << 8) | ((uint32_t)res[2] << 16) | ((uint32_t)res[3] << 24);
+        if (nv == 16 && out_al16) {
+            *reinterpret_cast<uint4*>(o) = make_uint4(res[0], res[1], res[2], res[3]);
         } else {
-            for (int p = 0; p < 4 && i0 + p < n1; ++p) o[p] = res[p];
+            for (int k = 0; k < nv; ++k) o[k] = (uint8_t)(res[k >> 2] >> (8 * (k & 3)));
         }
     }
 }
@@ -76,13 +137,14 @@ __global__ void __launch_bounds__(256) k_morph(const uint8_t* __restrict__ a, in
 cudaError_t mr_launch_morph(bool dilate, const uint8_t* a, int64_t stride2, int64_t n1, int64_t n2, uint8_t* out,
                             int64_t out_stride2, int sm_count, cudaStream_t s, int* n_launches) {
     if (n1 <= 0 || n2 <= 0) return cudaSuccess;
-    const int64_t gx = ((n1 + 3) / 4 + 255) / 256;
+    const int64_t gx = ((n1 + 15) / 16 + 255) / 256;
     int64_t gy = ((int64_t)sm_count * 8 + gx - 1) / gx;
     if (gy > n2) gy = n2;
     if (gy > 65535) gy = 65535;
     const dim3 g((unsigned)gx, (unsigned)(gy < 1 ? 1 : gy));
-    if (dilate) k_morph<true><<<g, 256, 0, s>>>(a, stride2, n1, n2, out, out_stride2);
-    else k_morph<false><<<g, 256, 0, s>>>(a, stride2, n1, n2, out, out_stride2);
+    const bool al = ((uintptr_t)a % 16 == 0) && (stride2 % 16 == 0), oal = ((uintptr_t)out % 16 == 0) && (out_stride2 % 16 == 0);
+    if (dilate) k_morph<true><<<g, 256, 0, s>>>(a, stride2, n1, n2, out, out_stride2, al, oal);
+    else k_morph<false><<<g, 256, 0, s>>>(a, stride2, n1, n2, out, out_stride2, al, oal);
     *n_launches += 1;
     return cudaGetLastError();
 }
