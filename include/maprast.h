@@ -268,6 +268,16 @@ int mr_categorize_clean_props_dev(mr_ctx* ctx, const double* px_dev, int64_t str
                                   int64_t n1, int64_t n2, int match, int R, uint8_t* labels_dev,
                                   int64_t out_stride2, void* stream);
 
+/* _recolor(categories, source, points) (src/selectcolors.jl:650-655), the display layers of the GUI (:378-388):
+ * label c >= 1 -> RGBA(colors[c]), colors[c] = _mean_color(source, points[c]) (:701-704: the mean r, g, b of the
+ * category's clicked points, computed by the host) with alpha 1; label 0 -> RGBA(RGB(0), 0).  colors: HOST array,
+ * K x 3 doubles; out: RGBA{Float64}, 4 doubles per pixel, stride in bytes (multiple of 8).  A label above K (a
+ * BoundsError in the reference) gives the transparent pixel. */
+int mr_recolor_host(mr_ctx* ctx, const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2, int K,
+                    const double* colors, double* out, int64_t out_stride2_bytes);
+int mr_recolor_dev(mr_ctx* ctx, const uint8_t* labels_dev, int64_t n1, int64_t n2, int64_t stride2, int K,
+                   const double* colors, double* out_dev, int64_t out_stride2_bytes, void* stream);
+
 /* _shrink_grow(A, i, j) (src/clean.jl:132-140): n_erode passes of the categorical erosion `_erode` (:121-129: a pixel
  * whose 8 Moore neighbours all equal it becomes 0) followed by n_dilate passes of the categorical dilation `_dilate`
  * (:96-118: a 0 pixel takes the neighbour that occurs most often among its 8 neighbours -- first maximum in

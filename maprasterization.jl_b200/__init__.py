@@ -7,4 +7,4 @@ from . import _lib, api, distributed, synth  # noqa: F401
 from ._lib import Context, Counters, MapRastError, MultiContext, LIB_PATH  # noqa: F401
 from .api import (DEFAULT_CATEGORY_TOLERANCE, MapSelection, Palette, Window, balance, balance_fit, blur, rasterize, categorize, categorize_clean,  # noqa: F401
                   categorize_clean_u8, categorize_u8, clean, clean_segments, clean_segments_u8, clean_u8,
-                  component_stats, default_context, fill_gaps, fill_gaps_u8, stds, stripes, TextureStats, polymask, paint_polygons, shrink_grow, erode, dilate)
+                  component_stats, default_context, fill_gaps, fill_gaps_u8, stds, stripes, TextureStats, polymask, paint_polygons, shrink_grow, erode, dilate, recolor, mean_color)

@@ -29,7 +29,7 @@ SYMBOLS = [
     "mr_balance_host", "mr_balance_dev",
     "mr_stds_host", "mr_stds_dev", "mr_stripes_host", "mr_stripes_dev", "mr_set_texture_stats",
     "mr_categorize_clean_props_host", "mr_categorize_clean_props_dev", "mr_polygons_host", "mr_polygons_dev",
-    "mr_shrink_grow_host", "mr_shrink_grow_dev",
+    "mr_shrink_grow_host", "mr_shrink_grow_dev", "mr_recolor_host", "mr_recolor_dev",
     "mr_multi_create", "mr_multi_destroy", "mr_multi_last_error", "mr_multi_device_count", "mr_multi_ctx",
     "mr_multi_band_range", "mr_multi_set_palette", "mr_multi_set_known", "mr_multi_categorize_clean_host",
     "mr_multi_batch_categorize_clean_host", "mr_multi_categorize_clean_dev",
@@ -112,6 +112,8 @@ def load():
     L.mr_set_texture_stats.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
     L.mr_categorize_clean_props_host.argtypes = [vp, vp, i64, vp, i64, vp, i64, i64, i64, i32, i32, u8p, i64]
     L.mr_categorize_clean_props_dev.argtypes = [vp, vp, i64, vp, i64, vp, i64, i64, i64, i32, i32, u8p, i64, vp]
+    L.mr_recolor_host.argtypes = [vp, u8p, i64, i64, i64, i32, vp, vp, i64]
+    L.mr_recolor_dev.argtypes = [vp, u8p, i64, i64, i64, i32, vp, vp, i64, vp]
     L.mr_shrink_grow_host.argtypes = [vp, u8p, i64, i64, i64, i32, i32, u8p, i64]
     L.mr_shrink_grow_dev.argtypes = [vp, u8p, i64, i64, i64, i32, i32, u8p, i64, vp]
     L.mr_polygons_host.argtypes = [vp, i32, vp, vp, vp, i64, i64, u8p, i64]
@@ -145,7 +147,7 @@ def load():
                  "mr_blur_host", "mr_blur_dev", "mr_categorize_clean_f64_host", "mr_categorize_clean_f64_dev",
                  "mr_balance_host", "mr_balance_dev", "mr_stds_host", "mr_stds_dev", "mr_stripes_host", "mr_stripes_dev",
                  "mr_set_texture_stats", "mr_categorize_clean_props_host", "mr_categorize_clean_props_dev",
-                 "mr_polygons_host", "mr_polygons_dev", "mr_shrink_grow_host", "mr_shrink_grow_dev",
+                 "mr_polygons_host", "mr_polygons_dev", "mr_shrink_grow_host", "mr_shrink_grow_dev", "mr_recolor_host", "mr_recolor_dev",
                  "mr_set_known_band", "mr_clean_dev_bounded", "mr_multi_device_count", "mr_multi_band_range", "mr_multi_set_palette",
                  "mr_multi_set_known", "mr_multi_categorize_clean_host", "mr_multi_batch_categorize_clean_host",
                  "mr_multi_categorize_clean_dev"):
@@ -372,6 +374,15 @@ class Context:
         self._ck(self._L.mr_categorize_clean_props_host(
             self._h, _ptr(px), n1 * 24, None if std is None else _ptr(std), n1 * 8,
             None if stripe is None else _ptr(stripe), n1 * 16, n1, n2, int(match_bits), int(R), _ptr(out), n1))
+        return out
+
+    def recolor_host(self, labels, colors):
+        """`_recolor` (src/selectcolors.jl:650-655): labels (n2, n1) uint8, colors (K, 3) float64 -> (n2, n1, 4) float64"""
+        labels = np.ascontiguousarray(labels, dtype=np.uint8)
+        colors = np.ascontiguousarray(colors, dtype=np.float64).reshape(-1, 3)
+        n2, n1 = labels.shape
+        out = np.empty((n2, n1, 4), dtype=np.float64)
+        self._ck(self._L.mr_recolor_host(self._h, _ptr(labels), n1, n2, n1, colors.shape[0], _ptr(colors), _ptr(out), n1 * 32))
         return out
 
     def shrink_grow_host(self, labels, n_erode, n_dilate):

@@ -506,6 +506,23 @@ def _labels_u8(labels):
     return labels.astype(np.uint8)
 
 
+def mean_color(A, pointvec):
+    """`_mean_color(A, pointvec)` (src/selectcolors.jl:701-704): mean colour of the clicked points; zero colour when the
+    category has no points"""
+    pal = Palette.from_points(np.asarray(A), [pointvec])
+    return np.zeros(3) if np.isinf(pal.mean[0, 0]) else pal.mean[0, :3].copy()
+
+
+def recolor(categories, source, points, *, ctx=None):
+    """`_recolor(categories, source, points)` (src/selectcolors.jl:650-655): the RGBA{Float64} display layer of a label
+    image: the category's mean colour at its clicked points (alpha 1), transparent black for label 0.
+    Returns (n2, n1, 4) float64."""
+    colors = np.stack([mean_color(source, ps) for ps in points]) if len(points) else np.zeros((0, 3))
+    if colors.shape[0] == 0:
+        raise ValueError("recolor needs at least one category")
+    return (ctx or default_context()).recolor_host(_labels_u8(categories), colors)
+
+
 def shrink_grow(A, i, j, *, missingval=0, ctx=None):
     """`_shrink_grow(A, i, j; missingval=0)` (src/clean.jl:132-140): `i` categorical erosions (`_erode`, :121-129), then
     `j` categorical dilations (`_dilate`, :96-118).  Returns labels, eltype Int."""

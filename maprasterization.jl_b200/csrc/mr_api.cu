@@ -1315,6 +1315,51 @@ extern "C" int mr_shrink_grow_host(mr_ctx* ctx, const uint8_t* labels, int64_t n
     return MR_OK;
 }
 
+// ------------------------------------------------------------------ _recolor (src/selectcolors.jl:650-655)
+static int recolor_dev(mr_ctx* ctx, const char* fn, const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2, int K,
+                       const double* colors, double* out, int64_t out_stride2, cudaStream_t s) {
+    std::string f(fn);
+    if (K < 1 || K > 254) return fail(ctx, MR_ERR_ARG, f + ": K must be in 1..254");
+    if (!colors) return fail(ctx, MR_ERR_ARG, f + ": null colour table");
+    if (out_stride2 < n1 * 32 || out_stride2 % 8 != 0) return fail(ctx, MR_ERR_ARG, f + ": output lines hold 32 bytes per pixel, 8-byte aligned");
+    if (n1 == 0 || n2 == 0) return MR_OK;
+    int rc;
+    if ((rc = grow(ctx, &ctx->d_poly, &ctx->d_poly_cap, (size_t)K * 24))) return rc;
+    CK(cudaMemcpyAsync(ctx->d_poly, colors, (size_t)K * 24, cudaMemcpyHostToDevice, s));   // pageable: staged before it returns
+    int nl = 0;
+    cudaError_t e = mr_launch_recolor(labels, stride2, n1, n2, K, reinterpret_cast<const double*>(ctx->d_poly), out, out_stride2,
+                                      ctx->sm_count, s, &nl);
+    ctx->launches += nl;
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "recolor launch");
+    return MR_OK;
+}
+
+extern "C" int mr_recolor_dev(mr_ctx* ctx, const uint8_t* labels_dev, int64_t n1, int64_t n2, int64_t stride2, int K,
+                              const double* colors, double* out_dev, int64_t out_stride2, void* stream) {
+    int rc = check_image_args(ctx, "mr_recolor_dev", labels_dev, out_dev, n1, n2, stride2, 1, n1, 0, 0, 0);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    return recolor_dev(ctx, "mr_recolor_dev", labels_dev, n1, n2, stride2, K, colors, out_dev, out_stride2, (cudaStream_t)stream);
+}
+
+extern "C" int mr_recolor_host(mr_ctx* ctx, const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2, int K,
+                               const double* colors, double* out, int64_t out_stride2) {
+    int rc = check_image_args(ctx, "mr_recolor_host", labels, out, n1, n2, stride2, 1, n1, 0, 0, 0);
+    if (rc) return rc;
+    if (n1 == 0 || n2 == 0) return MR_OK;
+    CK(cudaSetDevice(ctx->device));
+    const int64_t pitch = (n1 + 15) / 16 * 16, opitch = n1 * 32;
+    if ((rc = grow(ctx, &ctx->d_in, &ctx->d_in_cap, (size_t)pitch * n2))) return rc;
+    if ((rc = grow(ctx, &ctx->d_f64b, &ctx->d_f64b_cap, (size_t)opitch * n2))) return rc;
+    cudaStream_t s = ctx->s_main;
+    CK(cudaMemcpy2DAsync(ctx->d_in, pitch, labels, stride2, n1, n2, cudaMemcpyHostToDevice, s));
+    rc = recolor_dev(ctx, "mr_recolor_host", ctx->d_in, n1, n2, pitch, K, colors, reinterpret_cast<double*>(ctx->d_f64b), opitch, s);
+    if (rc) return rc;
+    CK(cudaMemcpy2DAsync(out, out_stride2, ctx->d_f64b, opitch, opitch, n2, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return MR_OK;
+}
+
 // ------------------------------------------------------------------ polygon masks / polygon painting
 // (_polymask src/selectcolors.jl:559-563; (1 .- mask) .* A :480-481; rasterize!(...; fill = i) :494-496)
 static int polygons_dev(mr_ctx* ctx, const char* fn, int n_rings, const int32_t* offsets, const double* xy, const uint8_t* fill,

@@ -138,3 +138,5 @@ cudaError_t mr_launch_polygons(int n_rings, int n_edges, const int32_t* off, con
 // categorical erosion / dilation, one pass (mr_morph.cu)
 cudaError_t mr_launch_morph(bool dilate, const uint8_t* a, int64_t stride2, int64_t n1, int64_t n2, uint8_t* out,
                             int64_t out_stride2, int sm_count, cudaStream_t s, int* n_launches);
+cudaError_t mr_launch_recolor(const uint8_t* lab, int64_t stride2, int64_t n1, int64_t n2, int K, const double* colors_dev,
+                              double* out, int64_t out_stride2, int sm_count, cudaStream_t s, int* n_launches);

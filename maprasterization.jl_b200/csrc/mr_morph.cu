@@ -1,4 +1,5 @@
-// mr_morph.cu -- categorical erosion / dilation of a label plane: `_erode` (src/clean.jl:121-129), `_dilate` (:96-118)
+// mr_morph.cu -- label-plane helpers around the path: `_recolor` (display layers, at the end of the file) and the
+// categorical erosion / dilation of a label plane: `_erode` (src/clean.jl:121-129), `_dilate` (:96-118)
 // and their loop `_shrink_grow(A, i, j)` (:132-140; the reference's call sites are commented out,
 // src/selectcolors.jl:699, :703).  Moore(1) = the 8 neighbours without the centre in CartesianIndices order (d1
 // fastest); neighbours outside the image are missingval = 0 (decisions: Neighborhoods.jl 0.1 is not in the reference
@@ -132,7 +133,45 @@ __global__ void __launch_bounds__(256) k_morph(const uint8_t* __restrict__ a, in
     }
 }
 
+// `_recolor` (src/selectcolors.jl:650-655): label -> RGBA{Float64} display pixel (the category's mean colour, alpha 1;
+// label 0 or a label above K: the transparent pixel).  One thread = one pixel, two 16-byte stores; the colour table
+// in shared memory.  Bound: HBM, 33 B per pixel (32 of them written).
+__global__ void __launch_bounds__(256) k_recolor(const uint8_t* __restrict__ lab, int64_t stride2, int64_t n1, int64_t n2, int K,
+                                                 const double* __restrict__ colors, double* __restrict__ out, int64_t out_stride2) {
+    __shared__ double s_c[255 * 4];
+    for (int t = threadIdx.x; t < 4 * (K + 1); t += blockDim.x) {
+        const int c = t >> 2, ch = t & 3;
+        s_c[t] = c == 0 ? 0.0 : (ch == 3 ? 1.0 : __ldg(colors + 3 * (c - 1) + ch));
+    }
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n1) return;
+    for (int64_t j = blockIdx.y; j < n2; j += gridDim.y) {
+        int c = __ldg(lab + j * stride2 + i);
+        if (c > K) c = 0;
+        double* o = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(out) + j * out_stride2) + 4 * i;
+        if ((reinterpret_cast<uintptr_t>(o) & 15u) == 0) {
+            reinterpret_cast<double2*>(o)[0] = make_double2(s_c[4 * c], s_c[4 * c + 1]);
+            reinterpret_cast<double2*>(o)[1] = make_double2(s_c[4 * c + 2], s_c[4 * c + 3]);
+        } else {
+            o[0] = s_c[4 * c]; o[1] = s_c[4 * c + 1]; o[2] = s_c[4 * c + 2]; o[3] = s_c[4 * c + 3];
+        }
+    }
+}
+
 }  // namespace
+
+cudaError_t mr_launch_recolor(const uint8_t* lab, int64_t stride2, int64_t n1, int64_t n2, int K, const double* colors_dev,
+                              double* out, int64_t out_stride2, int sm_count, cudaStream_t s, int* n_launches) {
+    if (n1 <= 0 || n2 <= 0) return cudaSuccess;
+    const int64_t gx = (n1 + 255) / 256;
+    int64_t gy = ((int64_t)sm_count * 8 + gx - 1) / gx;
+    if (gy > n2) gy = n2;
+    if (gy > 65535) gy = 65535;
+    k_recolor<<<dim3((unsigned)gx, (unsigned)(gy < 1 ? 1 : gy)), 256, 0, s>>>(lab, stride2, n1, n2, K, colors_dev, out, out_stride2);
+    *n_launches += 1;
+    return cudaGetLastError();
+}
 
 cudaError_t mr_launch_morph(bool dilate, const uint8_t* a, int64_t stride2, int64_t n1, int64_t n2, uint8_t* out,
                             int64_t out_stride2, int sm_count, cudaStream_t s, int* n_launches) {

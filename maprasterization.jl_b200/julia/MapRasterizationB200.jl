@@ -22,7 +22,7 @@ using ColorTypes, FixedPointNumbers, Statistics
 import Neighborhoods: Window
 
 export categorize, clean, categorize_clean, categorize_u8, clean_u8, categorize_clean_u8, clean_segments,
-       clean_segments_u8, fill_gaps, fill_gaps_u8, blur, balance, stds, stripes, polymask, paint_polygons, shrink_grow, erode, dilate, rasterize, MapSelection, Context, MultiContext, Palette
+       clean_segments_u8, fill_gaps, fill_gaps_u8, blur, balance, stds, stripes, polymask, paint_polygons, shrink_grow, erode, dilate, recolor, rasterize, MapSelection, Context, MultiContext, Palette
 
 const libmaprast = get(ENV, "LIBMAPRAST", joinpath(@__DIR__, "..", "libmaprast.so"))
 const DEFAULT_CATEGORY_TOLERANCE = 2.0            # src/selectcolors.jl:1
@@ -410,6 +410,27 @@ function fill_gaps_u8(src::AbstractMatrix{<:Integer}; categories, stats::Palette
     return out
 end
 fill_gaps(src; kw...) = _rewrap(src, fill_gaps_u8(src; kw...))
+
+# ---- display layers (src/selectcolors.jl:650-655, 701-704) ------------------------------------------------
+"`_mean_color(A, pointvec)` (src/selectcolors.jl:701-704) as (r, g, b) Float64; the zero colour without points."
+function _mean_rgb(A::AbstractMatrix{<:Colorant}, pointvec)
+    st = _stats(A, pointvec)
+    return ismissing(st) ? (0.0, 0.0, 0.0) : (st[1].mean, st[2].mean, st[3].mean)
+end
+
+"`_recolor(categories, source, points)` (src/selectcolors.jl:650-655): `Matrix{RGBA{Float64}}`, transparent black for 0."
+function recolor(categories::AbstractMatrix{<:Integer}, source::AbstractMatrix{<:Colorant}, points; ctx::Context=default_context())
+    L = Matrix{UInt8}(categories)
+    n1, n2 = size(L)
+    cols = Float64[c for ps in points for c in _mean_rgb(source, ps)]          # K x 3, row = category
+    out = Matrix{RGBA{Float64}}(undef, n1, n2)
+    GC.@preserve L cols out begin
+        _check(ctx, ccall((:mr_recolor_host, libmaprast), Cint,
+            (Ptr{Cvoid}, Ptr{UInt8}, Int64, Int64, Int64, Cint, Ptr{Float64}, Ptr{Float64}, Int64),
+            ctx.ptr, pointer(L), n1, n2, n1, length(points), pointer(cols), Ptr{Float64}(pointer(out)), n1 * 32))
+    end
+    return _rebuild(categories, out)
+end
 
 # ---- categorical erosion / dilation (src/clean.jl:96-140) ------------------------------------------------
 "`_shrink_grow(A, i, j)` (src/clean.jl:132-140): `i` passes of `_erode` (:121-129), then `j` passes of `_dilate` (:96-118)."

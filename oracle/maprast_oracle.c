@@ -975,3 +975,18 @@ void mro_dilate(const uint8_t* a, int64_t n1, int64_t n2, int64_t stride2, uint8
             out[j * out_stride2 + i] = (uint8_t)v;
         }
 }
+
+/* `_recolor(categories, source, points)` (src/selectcolors.jl:650-655), the display layers of the GUI (:378-388):
+ * label c >= 1 -> RGBA(colors[c]) = (mean r, g, b of the category's clicked points, `_mean_color` :701-704, alpha 1),
+ * label 0 -> RGBA(RGB(0), 0).  colors: K x 3 doubles; out: 4 doubles per pixel.  Labels above K (a BoundsError in
+ * the reference) give the transparent pixel.  No arithmetic: the means are copied. */
+void mro_recolor(const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2, int K, const double* colors,
+                 double* out, int64_t out_stride2) {
+    for (int64_t j = 0; j < n2; ++j)
+        for (int64_t i = 0; i < n1; ++i) {
+            const int c = labels[j * stride2 + i];
+            double* o = (double*)((uint8_t*)out + j * out_stride2) + 4 * i;
+            if (c >= 1 && c <= K) { o[0] = colors[3 * (c - 1)]; o[1] = colors[3 * (c - 1) + 1]; o[2] = colors[3 * (c - 1) + 2]; o[3] = 1.0; }
+            else o[0] = o[1] = o[2] = o[3] = 0.0;
+        }
+}

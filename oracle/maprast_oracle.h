@@ -153,6 +153,10 @@ void mro_polygons(int n_rings, const int32_t* off, const double* xy, const uint8
 void mro_erode(const uint8_t* a, int64_t n1, int64_t n2, int64_t stride2, uint8_t* out, int64_t out_stride2);
 void mro_dilate(const uint8_t* a, int64_t n1, int64_t n2, int64_t stride2, uint8_t* out, int64_t out_stride2);
 
+/* _recolor (src/selectcolors.jl:650-655): labels -> RGBA{Float64} display layer (4 doubles per pixel) */
+void mro_recolor(const uint8_t* labels, int64_t n1, int64_t n2, int64_t stride2, int K, const double* colors,
+                 double* out, int64_t out_stride2);
+
 #ifdef __cplusplus
 }
 #endif

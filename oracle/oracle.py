@@ -67,6 +67,7 @@ def lib():
         L.mro_categorize_f64_image.argtypes = [C.c_void_p, _i64, _i64, _i64, C.c_int, _f64p, _f64p, _f64p, _i64,
                                                C.c_void_p, C.c_void_p, _u8p, _i64]
         L.mro_balance.argtypes = [_u8p, _i64, _i64, _i64, _f64p, C.c_void_p, _i64, C.c_void_p]
+        L.mro_recolor.argtypes = [C.c_void_p, _i64, _i64, _i64, C.c_int, _f64p, C.c_void_p, _i64]
         L.mro_erode.argtypes = [_u8p, _i64, _i64, _i64, _u8p, _i64]
         L.mro_dilate.argtypes = [_u8p, _i64, _i64, _i64, _u8p, _i64]
         L.mro_polygons.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, _i64, _i64, C.c_void_p, _i64]
@@ -246,6 +247,16 @@ def categorize_f64_image(px, mean, lo, hi, known_idx=None, known_cat=None):
         nk = ki.size
     lib().mro_categorize_f64_image(px.ctypes.data, n1, n2, n1 * 24, mean.shape[0], mean, lo, hi, nk,
                                    ki.ctypes.data if nk else None, kc.ctypes.data if nk else None, out.ctypes.data, n1)
+    return out
+
+
+def recolor(labels, colors):
+    """`_recolor` (src/selectcolors.jl:650-655): labels (n2, n1) uint8, colors (K, 3) -> (n2, n1, 4) float64 RGBA"""
+    labels = np.ascontiguousarray(labels, dtype=np.uint8)
+    colors = _f64(colors).reshape(-1, 3)
+    n2, n1 = labels.shape
+    out = np.empty((n2, n1, 4), dtype=np.float64)
+    lib().mro_recolor(labels.ctypes.data, n1, n2, n1, colors.shape[0], colors, out.ctypes.data, n1 * 32)
     return out
 
 

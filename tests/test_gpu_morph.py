@@ -34,3 +34,25 @@ def test_shrink_grow_device_entry_with_pitches(ctx, oracle):
     torch.cuda.synchronize()
     assert mismatches(d_out[:, :n1].cpu().numpy(), oracle.shrink_grow(A, 2, 3)) == 0
     assert bool((d_out[:, n1:] == 77).all())
+
+
+def test_recolor(ctx, mr, oracle):
+    """`_recolor` (src/selectcolors.jl:650-655): display layer of a label image, bit-identical copies of the mean colours"""
+    rng = np.random.default_rng(4)
+    n2, n1, K = 37, 301, 5
+    src = rng.random((n2, n1, 3))
+    points = [[(float(rng.integers(1, n1 + 1)), float(rng.integers(1, n2 + 1))) for _ in range(4)] for _ in range(K)]
+    points[2] = []                                            # a category without points: the zero colour
+    lab = rng.integers(0, K + 3, size=(n2, n1)).astype(np.uint8)      # labels above K: transparent
+    got = mr.recolor(lab, src, points, ctx=ctx)
+    colors = np.stack([mr.mean_color(src, ps) for ps in points])
+    want = oracle.recolor(lab, colors)
+    assert got.tobytes() == want.tobytes()
+    assert (got[lab == 0] == 0).all() and (got[(lab >= 1) & (lab <= K)][:, 3] == 1).all() and (colors[2] == 0).all()
+    d_lab = torch.from_numpy(lab).cuda()
+    d_out = torch.full((n2, n1 * 4 + 6), -7.0, dtype=torch.float64, device="cuda")
+    ctx._ck(ctx._L.mr_recolor_dev(ctx._h, d_lab.data_ptr(), n1, n2, n1, K, colors.ctypes.data, d_out.data_ptr(), (n1 * 4 + 6) * 8,
+                                  torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert d_out[:, :n1 * 4].cpu().numpy().reshape(n2, n1, 4).tobytes() == want.tobytes()
+    assert bool((d_out[:, n1 * 4:] == -7.0).all())
