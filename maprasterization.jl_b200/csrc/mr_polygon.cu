@@ -55,8 +55,8 @@ __global__ void __launch_bounds__(256) k_polygons_lines(int n_rings, int n_edges
                                                         const double* __restrict__ xy, const int32_t* __restrict__ ring_of,
                                                         const uint8_t* __restrict__ fill, int64_t n1, int64_t n2,
                                                         uint8_t* __restrict__ plane, int64_t stride2) {
-    extern __shared__ double s_x[];                        // [n_edges] crossings, ring p in [off[p], off[p] + s_cnt[p])
-    int* s_cnt = reinterpret_cast<int*>(s_x + n_edges);    // [n_rings]
+    extern __shared__ int s_x[];                           // [n_edges] crossing thresholds, ring p in [off[p], off[p] + s_cnt[p])
+    int* s_cnt = s_x + n_edges;                            // [n_rings]
     int* s_off = s_cnt + n_rings;                          // [n_rings]
     int* s_act = s_off + n_rings;                          // [n_rings] rings with crossings on this line, ascending
     __shared__ int s_nact;
@@ -75,7 +75,10 @@ __global__ void __launch_bounds__(256) k_polygons_lines(int n_rings, int n_edges
             if ((a2 > pj) != (b2 > pj)) {
                 const double t = __ddiv_rn(__dsub_rn(pj, a2), __dsub_rn(b2, a2));
                 const double x = __dadd_rn(a1, __dmul_rn(__dsub_rn(b1, a1), t));
-                s_x[v0 + atomicAdd(&s_cnt[p], 1)] = x;
+                // pixel i (0-based) is left of the crossing iff (double)(i + 1) < x  <=>  i < ceil(x) - 1: an integer
+                // threshold, clamped to the line (the pixel phase then needs no Float64 at all)
+                const double th = ceil(x) - 1.0;
+                s_x[v0 + atomicAdd(&s_cnt[p], 1)] = th < 0.0 ? 0 : (th > (double)n1 ? (int)n1 : (int)th);
             }
         }
         __syncthreads();
@@ -95,12 +98,11 @@ __global__ void __launch_bounds__(256) k_polygons_lines(int n_rings, int n_edges
             int hit[4] = {-1, -1, -1, -1};
             for (int a = 0; a < nact; ++a) {
                 const int p = s_act[a], c = s_cnt[p];
-                const double* x = s_x + s_off[p];
+                const int* x = s_x + s_off[p];
                 unsigned in = 0u;
                 for (int q = 0; q < c; ++q) {
-                    const double xq = x[q];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) in ^= ((double)(i + k + 1) < xq ? 1u : 0u) << k;
+                    const int left = x[q] - (int)i;             // how many of the four pixels lie left of the crossing
+                    in ^= (1u << (left < 0 ? 0 : (left > 4 ? 4 : left))) - 1u;
                 }
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
@@ -133,7 +135,7 @@ cudaError_t mr_launch_polygons(int n_rings, int n_edges, const int32_t* off, con
                                const int32_t* ring_of, const uint8_t* fill, int64_t n1, int64_t n2, uint8_t* plane,
                                int64_t stride2, int sm_count, cudaStream_t s, int* n_launches) {
     if (n1 <= 0 || n2 <= 0) return cudaSuccess;
-    const size_t smem = (size_t)n_edges * 8 + (size_t)n_rings * 12 + 16;
+    const size_t smem = (size_t)n_edges * 4 + (size_t)n_rings * 12 + 16;
     if (smem <= 40 * 1024) {          // the usual case: a handful of hand-drawn polygons
         const int64_t gx = (n1 + 256 * PXL - 1) / (256 * PXL);
         int64_t gy = ((int64_t)sm_count * 8 + gx - 1) / gx;
