@@ -725,7 +725,30 @@ def run_ours(args, rank, world, local_rank):
                     "roofline": {"bound": "fp64 issue (HBM figure for reference)",
                                  "algorithmic_bytes_per_px": bpp_alg, "achieved": bpp_alg * n1 * bl / (ms * 1e-3) / 1e9,
                                  "peak": peak, "unit": "GB/s", "frac": bpp_alg * n1 * bl / (ms * 1e-3) / 1e9 / peak}}
-            del f64, lab64, sdp, stp
+            # the reference's DEFAULT settings end to end on those lines (blur_repeat = 1, match = (:color, :std, :stripe),
+            # stripe_radius = 2): blur -> _stds -> _stripes -> PixelProp categorise -> _clean -> fill_gaps, device resident
+            pr64 = torch.empty((bl, n1), dtype=torch.uint8, device=dev)
+            fl64 = torch.empty((bl, n1), dtype=torch.uint8, device=dev)
+            cats64 = list(range(1, K + 1))
+            def _default_pipeline():
+                _blur(); _stds(); _stripes(); _props()
+                ctx.clean_segments_dev(lab64, n1, bl, n1, keep, 0.01, 20, pr64, n1)
+                ctx.fill_gaps_dev(pr64, n1, bl, n1, own, n1 * 3, 3, cats64, fl64, n1)
+            _default_pipeline()
+            torch.cuda.synchronize()
+            l0 = ctx.launch_count()
+            e0.record()
+            for _ in range(reps):
+                _default_pipeline()
+            e1.record()
+            torch.cuda.synchronize()
+            dp_ms = e0.elapsed_time(e1) / reps
+            res["next_rows"]["default_pipeline"] = {
+                "what": "the reference's default settings: blur -> _stds -> _stripes -> categorise (:color, :std, :stripe) -> _clean -> "
+                        f"fill_gaps, first {bl} lines, device resident",
+                "value": n1 * bl / (dp_ms * 1e-3) / 1e6, "unit": UNIT, "ms": dp_ms,
+                "gpu_launches_per_call": (ctx.launch_count() - l0) / reps}
+            del f64, lab64, sdp, stp, pr64, fl64
         # polygon mask of the "clean" / "fill" buttons (src/selectcolors.jl:559-563): 16 rings of 12 vertices over the sheet
         if not batch:
             prng = np.random.default_rng(17)
