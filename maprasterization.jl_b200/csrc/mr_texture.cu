@@ -19,7 +19,8 @@ __device__ __forceinline__ unsigned long long dbits(double v) { return (unsigned
 // neighbourhood values of the channel sit in registers, sums in CartesianIndices order (d1 fastest).
 // (ncu: L1 throughput 80 %, FP64 pipe 48 % -- the 8-byte loads of one channel use a quarter of every sector.  Putting
 // the three channels on neighbouring lanes for denser accesses was SLOWER, 3.8 -> 4.7 ms: three times the threads
-// repeat the address and bounds arithmetic.)
+// repeat the address and bounds arithmetic.  Eight pixels per thread (229 registers): 5.7 ms; capped at 128 registers
+// for four blocks per SM (spills): 4.2 ms.)
 constexpr int SPX = 4;
 __global__ void __launch_bounds__(128) k_stds_raw(const double* __restrict__ px, int64_t stride2, int64_t n1, int64_t n2,
                                                   double* __restrict__ out, int64_t out_stride2,
