@@ -14,11 +14,11 @@
 // RUN based: a cleaned map has long horizontal runs of equal labels (~30 pixels on the synthetic
 // sheets), so everything after the first two passes works on runs, not pixels:
 //
-//   k_count    (line, 4096-pixel chunk): number of run starts; per thread (16 pixels, one 16-byte load) the
+//   k_count_stage  (line, 4096-pixel chunk): number of run starts; per thread (16 pixels, one 16-byte load) the
 //              run-start mask and its offset in the chunk (`info`, 4 B per 16 pixels); the chunk's run starts
 //              and labels compacted into the chunk's staging slot.  THE ONLY PASS THAT READS THE LABELS.
 //   k_scan     exclusive scan of the chunk counts -> first run of every chunk / line
-//   k_fill     staging slots -> run arrays (start x, label, parent = self): work per run, not per pixel
+//   k_fill_runs  staging slots -> run arrays (start x, label, parent = self): work per run, not per pixel
 //   k_merge    one block per line: every run finds the runs of the previous line that overlap it
 //              (binary search in the sorted run starts) and unites with those of equal label
 //              (lock-free union-find, atomicMin links towards the smaller run index)
@@ -43,7 +43,7 @@ constexpr int BT = 256;           // threads per block
 constexpr int CH = PT * BT;       // pixels per chunk
 constexpr int UB = 2;             // chunks per block in the streaming kernels (count: 12 KB of shared memory each)
 
-// per-chunk staging written by k_count: the only pass over the label plane
+// per-chunk staging written by k_count_stage: the only pass over the label plane
 struct Stage {
     uint32_t* info;             // [chunk][BT]: run-start mask of the thread's 16 pixels | offset of its first run in the chunk << 16
     uint16_t* sx;               // [chunk][CH]: x - chunk start of the chunk's runs, in order (first `count` entries)
@@ -540,7 +540,7 @@ bool aligned16(const void* p, int64_t stride) { return ((uintptr_t)p % 16 == 0) 
 size_t mr_prune_cbase_bytes(int64_t n1, int64_t n2) {
     return ((size_t)((n1 + CH - 1) / CH) * (size_t)n2 + 1) * sizeof(uint32_t);
 }
-// staging of k_count: 4 B per 16 pixels (`info`) + 3 B per pixel slot of the chunk's compacted run starts / labels
+// staging of k_count_stage: 4 B per 16 pixels (`info`) + 3 B per pixel slot of the chunk's compacted run starts / labels
 size_t mr_prune_stage_bytes(int64_t n1, int64_t n2) {
     const size_t units = (size_t)((n1 + CH - 1) / CH) * (size_t)n2;
     return units * ((size_t)BT * 4 + (size_t)CH * 3) + 16;
