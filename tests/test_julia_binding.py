@@ -95,7 +95,10 @@ def test_julia_wrapper_covers_the_entry_points_it_documents():
     names = {c[0] for c in ccalls(JL)}
     for need in ("mr_create", "mr_destroy", "mr_last_error", "mr_set_palette", "mr_set_known", "mr_categorize_clean_host",
                  "mr_clean_host", "mr_clean_segments_host", "mr_fill_gaps_host", "mr_multi_create", "mr_multi_destroy",
-                 "mr_multi_set_palette", "mr_multi_set_known", "mr_multi_categorize_clean_host"):
+                 "mr_multi_set_palette", "mr_multi_set_known", "mr_multi_categorize_clean_host",
+                 "mr_blur_host", "mr_balance_host", "mr_categorize_clean_f64_host", "mr_stds_host", "mr_stripes_host",
+                 "mr_set_texture_stats", "mr_categorize_clean_props_host", "mr_polygons_host", "mr_shrink_grow_host",
+                 "mr_recolor_host"):
         assert need in names, f"the Julia wrapper never calls {need}"
     src = open(JL).read()
     # every entry point that runs with a known plane clears it again (stale points)
