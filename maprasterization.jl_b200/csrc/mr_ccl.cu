@@ -90,41 +90,6 @@ __device__ __forceinline__ void unite(uint32_t* parent, uint32_t a, uint32_t b) 
     }
 }
 
-// exclusive prefix over the block (BT = 256 threads) of UB independent values per thread (one barrier pair for all of them)
-__device__ __forceinline__ void block_exclusive_ub(const uint32_t (&v)[UB], uint32_t (&excl)[UB], uint32_t (&tot)[UB]) {
-    __shared__ uint32_t wsum[UB][BT / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t s[UB];
-#pragma unroll
-    for (int u = 0; u < UB; ++u) s[u] = v[u];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-#pragma unroll
-        for (int u = 0; u < UB; ++u) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, s[u], o);
-            if (lane >= o) s[u] += t;
-        }
-    }
-    if (lane == 31) {
-#pragma unroll
-        for (int u = 0; u < UB; ++u) wsum[u][warp] = s[u];
-    }
-    __syncthreads();
-    // the BT / 32 = 8 warp totals: lane l < 8 takes one, inclusive scan over those lanes, broadcast
-#pragma unroll
-    for (int u = 0; u < UB; ++u) {
-        uint32_t t = lane < BT / 32 ? wsum[u][lane] : 0u;
-#pragma unroll
-        for (int o = 1; o < BT / 32; o <<= 1) {
-            const uint32_t q = __shfl_up_sync(0xffffffffu, t, o);
-            if (lane >= o) t += q;
-        }
-        tot[u] = __shfl_sync(0xffffffffu, t, BT / 32 - 1);
-        const uint32_t before = __shfl_sync(0xffffffffu, t, (warp + 31) & 31);   // inclusive total of the warps below
-        excl[u] = (warp ? before : 0u) + s[u] - v[u];
-    }
-}
-
 // run-start mask of the 16 pixels in w[0..3] (byte-parallel): bit k <=> pixel k differs from the pixel before it;
 // prev = label of the pixel before w[0]'s first one (any value > 255: none)
 __device__ __forceinline__ uint32_t starts16(const uint32_t (&w)[4], uint32_t prev) {
@@ -140,66 +105,86 @@ __device__ __forceinline__ uint32_t starts16(const uint32_t (&w)[4], uint32_t pr
     return m;
 }
 
-// (A persistent variant that loads the next group of units while the current one is processed was measured:
-// 226 -> 275 us, twice the registers and half the resident blocks.)
-// grid: n2 * ceil(chunks / UB) blocks; block = UB consecutive chunks of one line.  The 16-byte loads of all
-// units are issued first; one block scan for all of them; the run starts / labels of a unit are compacted in
-// shared memory and leave as contiguous, coalesced stores.
-__global__ void __launch_bounds__(BT) k_count_stage(const uint8_t* __restrict__ lab, int64_t stride2, uint32_t n1, bool al16,
+// The only pass over the label plane.  Block = CT = 128 threads = two 4096-pixel chunk units of one line, 64 threads
+// (two warps) per unit; a thread owns GT = 4 groups of 16 consecutive pixels (four 16-byte loads issued together:
+// 64 contiguous bytes), so the scan, the left-neighbour exchange and the address arithmetic are paid once per 64
+// pixels (the 16-pixels-per-thread version was instruction bound: 250 instructions per 16 pixels, SM busy 82 %,
+// DRAM 28 %).  Per group: run-start mask (byte-parallel) and the `info` word (mask | offset of its first run in
+// the chunk); the run starts / labels of a unit are compacted in shared memory and leave as contiguous stores.
+constexpr int GT = 4;                 // groups of PT pixels per thread
+constexpr int CT = UB * (BT / GT);    // threads per block: BT / GT = 64 per unit
+__global__ void __launch_bounds__(CT) k_count_stage(const uint8_t* __restrict__ lab, int64_t stride2, uint32_t n1, bool al16,
                                                     uint32_t chunks, uint32_t n_units, uint32_t* __restrict__ cnt, Stage G) {
     __shared__ uint16_t s_x[UB][CH];
     __shared__ uint8_t s_l[UB][CH];
-    uint32_t w[UB][4], m[UB], pc[UB], excl[UB], tot[UB];
-#pragma unroll
-    const uint32_t groups = (chunks + UB - 1) / UB;          // blocks per line
+    __shared__ uint32_t s_w[UB][2];                       // run counts of the two warps of a unit
+    const uint32_t groups = (chunks + UB - 1) / UB;       // blocks per line
     const uint32_t y = blockIdx.x / groups, c0 = (blockIdx.x - y * groups) * UB;   // line, first chunk of this block (uniform)
-    const uint32_t unit0 = y * chunks + c0;
-    for (int u = 0; u < UB; ++u) {
-        m[u] = 0u;
-        w[u][0] = w[u][1] = w[u][2] = w[u][3] = 0u;
-        if (c0 + u < chunks) {   // block-uniform
-            const uint32_t x = (c0 + u) * CH + threadIdx.x * PT;
-            const uint8_t* line = lab + (int64_t)y * stride2;
-            const int nv = x >= n1 ? 0 : (n1 - x < (uint32_t)PT ? (int)(n1 - x) : PT);
-            if (nv == PT && al16) {
-                const uint4 v = *reinterpret_cast<const uint4*>(line + x);
-                w[u][0] = v.x; w[u][1] = v.y; w[u][2] = v.z; w[u][3] = v.w;
-            } else {
-                for (int k = 0; k < nv; ++k) w[u][k >> 2] |= (uint32_t)line[x + k] << (8 * (k & 3));
-            }
-            // label of the pixel before this thread's first one: the previous thread's last pixel
-            uint32_t prev = __shfl_up_sync(0xffffffffu, w[u][3] >> 24, 1);
-            if ((threadIdx.x & 31) == 0) prev = (x > 0 && nv > 0) ? (uint32_t)line[x - 1] : 0x100u;
-            if (x == 0) prev = 0x100u;
-            m[u] = starts16(w[u], prev) & (nv == PT ? 0xFFFFu : ((1u << nv) - 1u));
-        }
-        pc[u] = __popc(m[u]);
-    }
-    block_exclusive_ub(pc, excl, tot);
+    const int u = threadIdx.x / (BT / GT), tu = threadIdx.x % (BT / GT);           // unit of the block, thread within the unit
+    const int lane = threadIdx.x & 31, wu = tu >> 5;                               // warp within the unit
+    const bool live = c0 + u < chunks;                                             // warp-uniform
+    const uint32_t unit = y * chunks + c0 + u;
+    const uint32_t x0 = (c0 + u) * CH + tu * (GT * PT);                            // first pixel of this thread
+    const uint8_t* line = lab + (int64_t)y * stride2;
+    uint32_t w[GT][4], m[GT];
+    int nv[GT];
 #pragma unroll
-    for (int u = 0; u < UB; ++u) {
-        const uint32_t unit = unit0 + u;
-        if (c0 + u >= chunks) break;
-        G.info[(size_t)unit * BT + threadIdx.x] = m[u] | (excl[u] << 16);
-        if (threadIdx.x == 0) cnt[unit] = tot[u];
-        uint32_t mm = m[u], pos = excl[u];
-        while (mm) {
-            const int k = __ffs(mm) - 1;
-            mm &= mm - 1;
-            s_x[u][pos] = (uint16_t)(threadIdx.x * PT + k);
-            // byte k of the 16: the 8-byte half by two selects, the byte by one permute
-            s_l[u][pos] = (uint8_t)__byte_perm(k < 8 ? w[u][0] : w[u][2], k < 8 ? w[u][1] : w[u][3], (uint32_t)(k & 7));
-            ++pos;
+    for (int g = 0; g < GT; ++g) {
+        const uint32_t x = x0 + g * PT;
+        w[g][0] = w[g][1] = w[g][2] = w[g][3] = 0u;
+        nv[g] = (!live || x >= n1) ? 0 : (n1 - x < (uint32_t)PT ? (int)(n1 - x) : PT);
+        if (nv[g] == PT && al16) {
+            const uint4 v = *reinterpret_cast<const uint4*>(line + x);
+            w[g][0] = v.x; w[g][1] = v.y; w[g][2] = v.z; w[g][3] = v.w;
+        } else if (nv[g] > 0) {       // ragged end of the line / unaligned lines: byte loads (never for groups outside the line)
+#pragma unroll
+            for (int k = 0; k < PT; ++k)
+                if (k < nv[g]) w[g][k >> 2] |= (uint32_t)line[x + k] << (8 * (k & 3));
+        }
+    }
+    // label of the pixel before the thread's first one: the previous thread's last pixel (it has 64 valid pixels
+    // whenever this thread has any); first lane of a warp: from memory; first pixel of the line: none
+    uint32_t prev = __shfl_up_sync(0xffffffffu, w[GT - 1][3] >> 24, 1);
+    if (lane == 0) prev = (x0 > 0 && nv[0] > 0) ? (uint32_t)line[x0 - 1] : 0x100u;
+    if (x0 == 0) prev = 0x100u;
+    uint32_t pc = 0;
+#pragma unroll
+    for (int g = 0; g < GT; ++g) {
+        m[g] = starts16(w[g], g == 0 ? prev : (w[g - 1][3] >> 24)) & (nv[g] == PT ? 0xFFFFu : ((1u << nv[g]) - 1u));
+        pc += __popc(m[g]);
+    }
+    // exclusive prefix of pc over the 64 threads of the unit
+    uint32_t sc = pc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, sc, o);
+        if (lane >= o) sc += t;
+    }
+    if (lane == 31) s_w[u][wu] = sc;
+    __syncthreads();
+    const uint32_t tot = s_w[u][0] + s_w[u][1];
+    uint32_t pos = sc - pc + (wu ? s_w[u][0] : 0u);
+    if (live) {
+        if (tu == 0) cnt[unit] = tot;
+#pragma unroll
+        for (int g = 0; g < GT; ++g) {
+            G.info[(size_t)unit * BT + tu * GT + g] = m[g] | (pos << 16);
+            uint32_t mm = m[g];
+            while (mm) {
+                const int k = __ffs(mm) - 1;
+                mm &= mm - 1;
+                s_x[u][pos] = (uint16_t)((tu * GT + g) * PT + k);
+                // byte k of the 16: the 8-byte half by two selects, the byte by one permute
+                s_l[u][pos] = (uint8_t)__byte_perm(k < 8 ? w[g][0] : w[g][2], k < 8 ? w[g][1] : w[g][3], (uint32_t)(k & 7));
+                ++pos;
+            }
         }
     }
     __syncthreads();
-#pragma unroll
-    for (int u = 0; u < UB; ++u) {
-        const uint32_t unit = unit0 + u;
-        if (c0 + u >= chunks) break;
+    if (live) {
         uint16_t* sx = G.sx + (size_t)unit * CH;
         uint8_t* sl = G.sl + (size_t)unit * CH;
-        for (uint32_t j = threadIdx.x; j < tot[u]; j += BT) {
+        for (uint32_t j = tu; j < tot; j += BT / GT) {
             sx[j] = s_x[u][j];
             sl[j] = s_l[u][j];
         }
@@ -554,7 +539,7 @@ cudaError_t mr_launch_prune_count(const uint8_t* labels, int64_t n1, int64_t n2,
                                   void* stage_mem, cudaStream_t s, int* n_launches) {
     const uint32_t chunks = (uint32_t)((n1 + CH - 1) / CH);
     const uint32_t n_units = chunks * (uint32_t)n2;
-    k_count_stage<<<(unsigned)n2 * ((chunks + UB - 1) / UB), BT, 0, s>>>(labels, stride2, (uint32_t)n1, aligned16(labels, stride2), chunks,
+    k_count_stage<<<(unsigned)n2 * ((chunks + UB - 1) / UB), CT, 0, s>>>(labels, stride2, (uint32_t)n1, aligned16(labels, stride2), chunks,
                                                         n_units, cbase, make_stage(stage_mem, n1, n2));
     k_scan<<<1, 1024, 0, s>>>(cbase, (uint64_t)chunks * (uint64_t)n2);
     *n_launches += 2;
