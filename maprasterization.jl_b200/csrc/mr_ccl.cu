@@ -447,49 +447,51 @@ __global__ void k_runout(Runs R, uint32_t n, const SegRec* __restrict__ rec) {
 constexpr int PU = 4;
 __global__ void __launch_bounds__(BT) k_paint(uint32_t n1, uint32_t n_units, Runs R, Stage G, uint8_t* __restrict__ out,
                                               int64_t out_stride2, bool out_al16) {
+    const uint32_t groups = (R.chunks + PU - 1) / PU;          // blocks per line
+    const uint32_t y = blockIdx.x / groups, c0 = (blockIdx.x - y * groups) * PU;   // line, first chunk of this block (one division)
+    const uint32_t unit0 = y * R.chunks + c0;
     uint32_t inf[PU], run[PU];
     uint8_t cur[PU];
 #pragma unroll
     for (int u = 0; u < PU; ++u) {
-        const uint32_t unit = blockIdx.x * PU + u;
-        inf[u] = unit < n_units ? G.info[(size_t)unit * BT + threadIdx.x] : 0u;
-        run[u] = unit < n_units ? R.cbase[unit] : 0u;
+        const bool on = c0 + u < R.chunks;
+        inf[u] = on ? G.info[(size_t)(unit0 + u) * BT + threadIdx.x] : 0u;
+        run[u] = on ? R.cbase[unit0 + u] : 0u;
     }
 #pragma unroll
     for (int u = 0; u < PU; ++u) {
         run[u] += inf[u] >> 16;                                  // next run to start
         // the run that continues into this thread (none when its first pixel starts one, or outside the sheet)
-        cur[u] = ((inf[u] & 1u) || run[u] == 0u || blockIdx.x * PU + u >= n_units) ? (uint8_t)0 : R.out[run[u] - 1];
+        cur[u] = ((inf[u] & 1u) || run[u] == 0u || c0 + u >= R.chunks) ? (uint8_t)0 : R.out[run[u] - 1];
     }
+    uint8_t* row = out + (int64_t)y * out_stride2;
 #pragma unroll
     for (int u = 0; u < PU; ++u) {
-        const uint32_t unit = blockIdx.x * PU + u;
-        if (unit >= n_units) break;
-        const uint32_t y = unit / R.chunks, c = unit - y * R.chunks, x = c * CH + threadIdx.x * PT;
+        if (c0 + u >= R.chunks) break;
+        const uint32_t x = (c0 + u) * CH + threadIdx.x * PT;
         if (x >= n1) continue;
         const int nv = n1 - x < (uint32_t)PT ? (int)(n1 - x) : PT;
-        const uint32_t m = inf[u] & 0xFFFFu;
         // the continuing run's label everywhere, then every run start (0.5 per thread on a filtered sheet)
-        // overwrites the bytes from its pixel on: work per run, not per pixel
-        uint32_t r = run[u], mm = m;
-        uint32_t w[4];
-        w[0] = w[1] = w[2] = w[3] = (uint32_t)cur[u] * 0x01010101u;
+        // overwrites the bytes from its pixel on: work per run, not per pixel; the 16 bytes as two 64-bit halves
+        uint32_t r = run[u], mm = inf[u] & 0xFFFFu;
+        unsigned long long lo = (unsigned long long)cur[u] * 0x0101010101010101ull, hi = lo;
         while (mm) {
             const int k = __ffs(mm) - 1;
             mm &= mm - 1;
-            const uint32_t L4 = (uint32_t)R.out[r++] * 0x01010101u;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int d = k - 4 * j;                                  // first byte of word j to overwrite
-                const uint32_t keep = d <= 0 ? 0u : (d >= 4 ? 0xFFFFFFFFu : (0xFFFFFFFFu >> (8 * (4 - d))));
-                w[j] = (w[j] & keep) | (L4 & ~keep);
+            const unsigned long long L8 = (unsigned long long)R.out[r++] * 0x0101010101010101ull;
+            const unsigned long long keep = (1ull << (8 * (k & 7))) - 1ull;     // the bytes of the half before pixel k
+            if (k < 8) {
+                lo = (lo & keep) | (L8 & ~keep);
+                hi = L8;
+            } else {
+                hi = (hi & keep) | (L8 & ~keep);
             }
         }
-        uint8_t* dst = out + (int64_t)y * out_stride2 + x;
+        uint8_t* dst = row + x;
         if (nv == PT && out_al16) {
-            *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(dst) = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
         } else {
-            for (int k = 0; k < nv; ++k) dst[k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+            for (int k = 0; k < nv; ++k) dst[k] = (uint8_t)((k < 8 ? lo : hi) >> (8 * (k & 7)));
         }
     }
 }
@@ -588,7 +590,7 @@ cudaError_t mr_launch_prune_apply(int64_t n1, int64_t n2, const uint32_t* cbase,
     k_decide<<<(n_segments + 255) / 256, 256, 0, s>>>(r, n_segments, keep_dev, line_threshold, prune_threshold, d_conflict);
     k_runout<<<(n_runs + 255) / 256, 256, 0, s>>>(R, n_runs, r);
     const uint32_t n_units = R.chunks * (uint32_t)n2;
-    k_paint<<<(n_units + PU - 1) / PU, BT, 0, s>>>((uint32_t)n1, n_units, R, make_stage(const_cast<void*>(stage_mem), n1, n2), out,
+    k_paint<<<(unsigned)n2 * ((R.chunks + PU - 1) / PU), BT, 0, s>>>((uint32_t)n1, n_units, R, make_stage(const_cast<void*>(stage_mem), n1, n2), out,
                                                   out_stride2, aligned16(out, out_stride2));
     *n_launches += 3;
     return cudaGetLastError();
