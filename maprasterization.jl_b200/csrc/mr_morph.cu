@@ -51,10 +51,15 @@ __global__ void __launch_bounds__(256) k_morph(const uint8_t* __restrict__ a, in
             if (nv == 16 && al16) {
                 const uint4 v = __ldg(reinterpret_cast<const uint4*>(line + i0));
                 w[r][0] = v.x; w[r][1] = v.y; w[r][2] = v.z; w[r][3] = v.w;
-            } else {
-#pragma unroll
-                for (int k = 0; k < 16; ++k)
-                    if (k < nv) w[r][k >> 2] |= (uint32_t)__ldg(line + i0 + k) << (8 * (k & 3));
+            } else {   // ragged end of the line / unaligned lines.  A real loop: unrolled, the compiler predicated these 16
+                       // byte loads into the aligned path as well (a fifth of the kernel's instructions, all switched off)
+                unsigned long long lo = 0ull, hi = 0ull;
+#pragma unroll 1
+                for (int k = 0; k < nv; ++k) {
+                    const unsigned long long b = __ldg(line + i0 + k);
+                    if (k < 8) lo |= b << (8 * k); else hi |= b << (8 * (k - 8));
+                }
+                w[r][0] = (uint32_t)lo; w[r][1] = (uint32_t)(lo >> 32); w[r][2] = (uint32_t)hi; w[r][3] = (uint32_t)(hi >> 32);
             }
             if (i0 > 0) lb[r] = __ldg(line + i0 - 1);
             if (i0 + 16 < n1) rb[r] = __ldg(line + i0 + 16);
