@@ -109,21 +109,31 @@ __global__ void __launch_bounds__(256) k_morph(const uint8_t* __restrict__ a, in
                 };
                 // neighbours in CartesianIndices order: (-1,-1) (0,-1) (1,-1) (-1,0) (1,0) (-1,1) (0,1) (1,1)
                 const uint32_t h[8] = {px(0, k - 1), px(0, k), px(0, k + 1), px(1, k - 1), px(1, k + 1), px(2, k - 1), px(2, k), px(2, k + 1)};
-                int best = 0, bc = -1;
+                uint32_t first = 0;
 #pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    int c = 0;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) c += h[q] == h[t];
-                    if (c > bc) { bc = c; best = t; }           // findmax: first maximum
-                }
-                uint32_t v = 0, first = 0;
-#pragma unroll
-                for (int t = 7; t >= 0; --t) {
-                    if (t == best) v = h[t];
+                for (int t = 7; t >= 0; --t)
                     if (h[t] != 0) first = h[t];                 // ends as the first neighbour that is not 0
+                bool one = true;                                 // every neighbour is 0 or `first`
+#pragma unroll
+                for (int t = 0; t < 8; ++t) one = one && (h[t] == 0 || h[t] == first);
+                uint32_t val = first;
+                // One label besides 0 around the pixel (the usual case at a rim): the rule gives that label whatever the
+                // counts are -- if it is the first maximum it is taken, if 0 is, the first neighbour that is not 0 is.
+                if (!one) {
+                    int best = 0, bc = -1;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        int c = 0;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) c += h[q] == h[t];
+                        if (c > bc) { bc = c; best = t; }       // findmax: first maximum
+                    }
+                    uint32_t v = 0;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t)
+                        if (t == best) v = h[t];
+                    if (v != 0) val = v;
                 }
-                const uint32_t val = v != 0 ? v : first;
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                     if ((k >> 2) == q) res[q] |= val << (8 * (k & 3));
