@@ -142,3 +142,26 @@ def test_texture_stats_from_points(mr, oracle):
     assert np.array_equal(tlo[0], tex.stripe["min"][0] - tex.stripe["sd"][0] * 2.0)
     zero = mr.TextureStats.from_points(None, None, pts, tol)
     assert zero.std["mean"][0] == 0.0 and (zero.stripe["max"][0] == 0.0).all()
+
+
+def test_polygon_and_morph_host_logic(mr):
+    """host side of the polygon / erode / dilate mirrors: ring flattening, category of a ring, argument checks
+    (nothing here needs a GPU: the checks come before the context is created)"""
+    polys = [[[(100.0, 100.0)]], [[(1, 1), (5, 1), (3, 4)], [(2, 2), (3, 2), (3, 3), (2, 3)]], []]
+    rings, cats = mr.api._rings_of(polys)
+    assert len(rings) == 3 and cats == [1, 2, 2]
+    assert mr.api._rings_of(None) == ([], [])
+    with pytest.raises(ValueError):
+        mr.paint_polygons(np.zeros((3, 3)), polys)                 # float labels
+    with pytest.raises(ValueError):
+        mr.paint_polygons(np.full((3, 3), 255), polys)             # label 255
+    with pytest.raises(ValueError):
+        mr.shrink_grow(np.zeros((3, 3), dtype=np.int64), -1, 0)
+    with pytest.raises(ValueError):
+        mr.shrink_grow(np.zeros((3, 3), dtype=np.int64), 1, 1, missingval=7)
+    with pytest.raises(ValueError):
+        mr.recolor(np.zeros((3, 3), dtype=np.int64), np.zeros((3, 3, 3)), [])
+    assert (mr.mean_color(np.full((4, 4, 3), 0.25), []) == 0).all()             # no points: the zero colour
+    assert np.allclose(mr.mean_color(np.full((4, 4, 3), 0.25), [(1.0, 1.0), (2.0, 3.0)]), 0.25)
+    sel = mr.MapSelection(settings={}, points=[[]], polygons=polys)
+    assert sel.polygons is polys
