@@ -50,7 +50,7 @@ struct Stage {
     uint8_t* sl;                // [chunk][CH]: their labels
 };
 
-struct SegRec {                 // one per component
+struct SegRec {                 // one per component; 32 bytes, read and written as two uint4 (k_init_recs, k_decide, k_stats)
     unsigned int xmin, xmax, ymin, ymax;   // the box: one 16-byte read in k_stats
     unsigned int count;
     unsigned int cmin, cmax;    // known categories present: min / max of the non-zero ones
@@ -352,14 +352,11 @@ __device__ __forceinline__ uint32_t comp_id(const uint32_t* parent, uint32_t run
 __global__ void k_init_recs(SegRec* rec, unsigned int n, Runs R) {
     const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    SegRec r;
-    r.count = 0;
-    r.xmin = r.ymin = 0xffffffffu;
-    r.xmax = r.ymax = 0;
-    r.cmin = 0xffffffffu;
-    r.cmax = 0;
-    r.label = R.label[R.rootof[i]];   // the component's label = the label of any of its runs
-    rec[i] = r;
+    // two 16-byte stores: { xmin, xmax, ymin, ymax } { count, cmin, cmax, label }
+    const uint32_t label = R.label[R.rootof[i]];   // the component's label = the label of any of its runs
+    uint4* o = reinterpret_cast<uint4*>(rec + i);
+    o[0] = make_uint4(0xffffffffu, 0u, 0xffffffffu, 0u);
+    o[1] = make_uint4(0u, 0xffffffffu, 0u, label);
 }
 
 // one block per line.  (Grouping the runs of a warp by component -- match.any + redux -- before touching the
@@ -428,7 +425,12 @@ __global__ void k_decide(SegRec* __restrict__ rec, unsigned int n, const uint8_t
                          double line_threshold, double prune_threshold, unsigned int* conflict) {
     const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const SegRec r = rec[i];
+    SegRec r;
+    {   // two 16-byte loads
+        const uint4 a = reinterpret_cast<const uint4*>(rec + i)[0], b = reinterpret_cast<const uint4*>(rec + i)[1];
+        r.xmin = a.x; r.xmax = a.y; r.ymin = a.z; r.ymax = a.w;
+        r.count = b.x; r.cmin = b.y; r.cmax = b.z; r.label = b.w;
+    }
     const unsigned L = r.label;
     unsigned out = L;
     if (!keep[L]) {
