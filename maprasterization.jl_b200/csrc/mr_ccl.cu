@@ -309,11 +309,21 @@ __global__ void k_number_roots(uint32_t* __restrict__ parent, uint32_t n, unsign
         const uint32_t t = __shfl_up_sync(0xffffffffu, sc, o);
         if (lane >= o) sc += t;
     }
+    // one atomic per BLOCK on the single counter (raw label sheets have millions of roots: one atomic per warp
+    // serialised on that address, 174 us for 36 M runs)
+    __shared__ uint32_t s_wt[8], s_base;
     const uint32_t tot = __shfl_sync(0xffffffffu, sc, 31);
+    const int warp = threadIdx.x >> 5;
+    if (lane == 0) s_wt[warp] = tot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t all = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { const uint32_t t = s_wt[w]; s_wt[w] = all; all += t; }
+        s_base = all ? atomicAdd(n_roots, all) : 0u;
+    }
+    __syncthreads();
     if (!tot) return;
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(n_roots, tot);
-    uint32_t id = __shfl_sync(0xffffffffu, base, 0) + sc - c;
+    uint32_t id = s_base + s_wt[warp] + sc - c;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
         if ((rm >> k) & 1u) {
