@@ -124,3 +124,29 @@ def test_fused_then_segments_on_synthetic_sheet(ctx, mr, oracle):
     got, nseg = ctx.clean_segments_host(labels, keep, 0.01, 20)
     want, nseg_o = oracle.clean_segments(labels, None, range(1, spec["K"] + 1), 0.01, 20)
     assert mismatches(got, want) == 0 and nseg == nseg_o
+
+
+@pytest.mark.parametrize("R", [0, 2])
+def test_prune_at_sheet_width_against_the_sequential_oracle(ctx, mr, oracle, R):
+    """the segment prune at BASELINE config 2's line width (20000 pixels: five 4096-pixel chunks per line, the last one
+    ragged) on raw categorise-only labels (R = 0: about one speckle segment per 40 pixels) and on filtered labels:
+    labels and segment count identical to the literal sequential restatement"""
+    import torch
+    from maprast_b200 import synth
+    seed, palrgb, stats, spec = synth.config_workload(2)
+    n1, n2, K = spec["n1"], 1200, spec["K"]
+    ctx.set_palette(stats.mean, stats.lo, stats.hi)
+    ctx.palette = None
+    ctx.set_known(None)
+    px = torch.empty((n2, n1, 3), dtype=torch.uint8, device="cuda")
+    ctx.synth_scan_dev(seed, 0, palrgb, n1, spec["n2"], 0, n2, px, n1 * 3)
+    lab = torch.empty((n2, n1), dtype=torch.uint8, device="cuda")
+    ctx.categorize_clean_dev(px, n1, n2, n1 * 3, 3, R, lab, n1)
+    keep = np.zeros(256, dtype=np.uint8)
+    keep[1:K + 1] = 1
+    out = torch.empty_like(lab)
+    nseg = ctx.clean_segments_dev(lab, n1, n2, n1, keep, 0.01, 20, out, n1)
+    torch.cuda.synchronize()
+    want, want_seg = oracle.clean_segments(lab.cpu().numpy(), None, range(1, K + 1), 0.01, 20)
+    assert nseg == want_seg and nseg > (100000 if R == 0 else 1000)
+    assert mismatches(out.cpu().numpy(), want) == 0
