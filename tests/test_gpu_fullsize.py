@@ -70,3 +70,30 @@ def test_full_size_sheet(ctx, mr, oracle, cfg):
     hist = torch.bincount(out.flatten().to(torch.int64), minlength=spec["K"] + 1)
     assert int(hist.sum().item()) == n1 * n2 and int(hist[spec["K"] + 1:].sum().item()) == 0
     assert (hist[1:spec["K"] + 1] > 0).all()
+
+
+def test_widened_stages_at_sheet_width(ctx, mr, oracle):
+    """the stages around the hot path at BASELINE config 2's line width (20000 pixels, a few lines): texture planes bit
+    for bit, PixelProp labels, polygon mask, erode / dilate, display layer -- all against the oracle"""
+    rng = np.random.default_rng(77)
+    n1, n2, K = 20000, 7, 6
+    px = rng.random((n2, n1, 3))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        std_w, st_w = oracle.stds(px), oracle.stripes(px, 2)
+    std, st = ctx.stds_host(px), ctx.stripes_host(px, 2)
+    assert std.tobytes() == std_w.tobytes() and st.tobytes() == st_w.tobytes()
+    mean = rng.random((K, 3))
+    pal = mr.Palette(mean, mean - 0.3, mean + 0.3, np.zeros((K, 3)))
+    ctx.set_palette(pal.mean, pal.lo, pal.hi)
+    ctx.palette = None
+    ctx.set_known(None)
+    sdm, stm = np.full(K, float(std.mean())), np.zeros((K, 2))
+    sds, sts = (sdm, sdm - 1, sdm + 1), (stm, stm - 50, stm + 50)
+    ctx.set_texture_stats(*sds, *sts)
+    got = ctx.categorize_clean_props_host(px, std, st, 7, 0)
+    want = oracle.categorize_props_image(px, std, st, ("color", "std", "stripe"), pal.mean, pal.lo, pal.hi, sds, sts)
+    assert int((got != want).sum()) == 0 and len(np.unique(got)) > 3
+    rings = [[(10.0, 1.0), (19990.5, 2.0), (15000.0, 7.5), (300.0, 6.0)], [(5000.0, 0.0), (5100.0, 8.0), (4900.0, 8.0)]]
+    assert int((ctx.polygons_host(rings, (n2, n1)) != oracle.polygons(rings, (n2, n1))).sum()) == 0
+    assert int((ctx.shrink_grow_host(got, 1, 2) != oracle.shrink_grow(got, 1, 2)).sum()) == 0
+    assert ctx.recolor_host(got, mean).tobytes() == oracle.recolor(got, mean).tobytes()
